@@ -1,0 +1,155 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI (ctypes Engine), against the oracle and the
+golden fixtures written by the unmodified reference.  Integer sizes must be identical; NCD bit-exact."""
+import json
+import os
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import lib as olib
+from oracle import snacc_oracle
+from oracle.fasta_shim import COMPLEMENT_TABLE
+from oracle.make_golden import VECTOR_KINDS, synth_vector
+
+pytestmark = pytest.mark.gpu
+
+ALGOS = ["lz4", "gzip"]
+
+
+def _ref_len(data, algo):
+    return olib.ref_compressed_len(data, algo)
+
+
+@pytest.fixture(scope="module")
+def ref_sizes(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "reference_sizes.json")))
+
+
+@pytest.mark.parametrize("case", ["lz4", "lz4_rc", "gzip", "gzip_rc"])
+def test_fixture_matrix_equals_reference_golden(engine, golden_dir, ref_sizes, case):
+    """all singles + all ordered pairs of the committed FASTA fixtures == what the reference's own
+    compressed_size returned (incl. multi-record reverse complement done on the device)"""
+    from snacc_b200.pairwise_ncd import ncd_matrix
+    algo, rc = case.split("_")[0], case.endswith("_rc")
+    files = [Path(golden_dir) / "fasta" / f for f in ref_sizes["files"]]
+    labels, C, S, D = ncd_matrix(files, algo, reverse_complement=rc, engine=engine)
+    want = ref_sizes["cases"][case]
+    assert (C + 33).tolist() == want["C"]
+    assert (S + 33).tolist() == want["S"]
+    assert np.array_equal(D, np.array(want["D"]))
+    assert np.array_equal(engine.ncd(C, S), np.array(want["D"]))
+
+
+@pytest.mark.parametrize("case", ["lz4", "gzip_rc"])
+def test_cli_csv_is_byte_identical_to_reference_cli(golden_dir, tmp_path, case, monkeypatch):
+    from click.testing import CliRunner
+    from snacc_b200 import cli as gcli
+    algo, rc = case.split("_")[0], case.endswith("_rc")
+    d = Path(golden_dir) / "fasta"
+    files = [str(f) for f in sorted(d.iterdir()) if not f.name.startswith("big")]
+    out = tmp_path / "dist.csv"
+    monkeypatch.chdir(tmp_path)
+    args = files + ["-o", str(out), "-c", algo, "--no-show-progress"] + (["--reverse-compliment", "True"] if rc else [])
+    r = CliRunner().invoke(gcli.cli, args)
+    assert r.exit_code == 0, r.output
+    got = out.read_text().replace(str(d.absolute()) + "/", "")
+    assert got == (Path(golden_dir) / f"reference_cli_{case}.csv").read_text()
+    assert (tmp_path / "dist.md").exists()
+
+
+def test_single_job_shim_matches_reference_signature(golden_dir, ref_sizes):
+    import snacc_b200
+    f = Path(golden_dir) / "fasta" / "g1.fasta"
+    g = Path(golden_dir) / "fasta" / "multi.fa"
+    i, j = ref_sizes["files"].index("g1.fasta"), ref_sizes["files"].index("multi.fa")
+    assert snacc_b200.compressed_size(f, "lz4") == (f, ref_sizes["cases"]["lz4"]["C"][i])
+    assert snacc_b200.compressed_size((f, g), "lz4", reverse_complement=True) == ((f, g), ref_sizes["cases"]["lz4_rc"]["S"][i][j])
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_regime_boundaries_and_alphabets(engine, algo):
+    """lengths straddling every regime boundary x adversarial alphabets, singles and random pairs"""
+    rng = np.random.default_rng(5)
+    sizes = [1, 2, 3, 5, 12, 13, 300, 11000, 40000, 65274, 65535, 65536, 65537, 70000, 131072, 140000]
+    seqs = [synth_vector(kind, n, 17 * k + n) for k, kind in enumerate(VECTOR_KINDS) for n in sizes
+            if not (algo == "gzip" and n > 70000 and kind in ("run", "period", "low", "nrun"))]
+    engine.upload_sequences(seqs)
+    C = engine.single_sizes(algo)
+    ref = np.array([_ref_len(s, algo) for s in seqs])
+    assert np.array_equal(C, ref), np.nonzero(C != ref)[0][:10]
+    m = 400 if algo == "lz4" else 150
+    xs, ys = rng.integers(0, len(seqs), m), rng.integers(0, len(seqs), m)
+    S = engine.pair_sizes(algo, xs, ys)
+    refp = np.array([_ref_len(np.concatenate([seqs[a], seqs[b]]), algo) for a, b in zip(xs, ys)])
+    bad = np.nonzero(S != refp)[0]
+    assert bad.size == 0, [(int(xs[b]), int(ys[b]), seqs[xs[b]].size, seqs[ys[b]].size, int(S[b]), int(refp[b])) for b in bad[:5]]
+
+
+def test_on_device_reverse_complement(engine):
+    rng = np.random.default_rng(2)
+    alpha = np.frombuffer(b"ACGTacgtNnRYKMSWBDHVUu-*", dtype=np.uint8)
+    seqs, recs = [], []
+    for i in range(5):
+        rl = [int(v) for v in rng.integers(0, 400, size=int(rng.integers(1, 5)))]
+        rl[0] += 1
+        seqs.append(rng.choice(alpha, size=sum(rl)))
+        recs.append(rl)
+    engine.upload_sequences(seqs, reverse_complement=True, records=recs)
+    for i, (s, rl) in enumerate(zip(seqs, recs)):
+        raw, parts, pos = s.tobytes(), [], 0
+        for r in rl:
+            parts.append(raw[pos:pos + r].translate(COMPLEMENT_TABLE)[::-1])
+            pos += r
+        assert engine.download_sequence(i).tobytes() == b"".join(parts)
+
+
+def test_empty_sequence_is_value_error(engine):
+    with pytest.raises(ValueError):
+        engine.upload_sequences([b"ACGT", b""])
+
+
+def test_unsupported_codec_is_key_error(engine):
+    engine.upload_sequences([b"ACGTACGTACGT"])
+    with pytest.raises(KeyError):
+        engine.single_sizes("lzma")
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_small_stream_config_sample(engine, algo):
+    """c3 shape: dengue-sized (~11 kbp) genomes, random sample of pair jobs + all singles"""
+    from snacc_b200 import synth
+    g = synth.phylogeny(64, 10700, seed=3)
+    engine.upload_sequences(g)
+    C = engine.single_sizes(algo)
+    assert np.array_equal(C, np.array([_ref_len(s, algo) for s in g]))
+    rng = np.random.default_rng(3)
+    m = 3000 if algo == "lz4" else 300
+    xs, ys = rng.integers(0, 64, m), rng.integers(0, 64, m)
+    S = engine.pair_sizes(algo, xs, ys)
+    chk = rng.choice(m, size=min(m, 300), replace=False)
+    for k in chk:
+        assert S[k] == _ref_len(np.concatenate([g[xs[k]], g[ys[k]]]), algo)
+
+
+def test_full_size_genomes_lz4(engine):
+    """c4 shape at full length (5 Mbp): tile of ordered pairs vs the real liblz4, plus the size-independent
+    properties: prefix-checkpoint path == from-scratch path (single of a concatenated upload) and
+    determinism under a different number of streams in flight."""
+    from snacc_b200 import synth
+    g = synth.phylogeny(6, 5_000_000, seed=4, n_indels=2)
+    engine.upload_sequences(g)
+    C = engine.single_sizes("lz4")
+    assert np.array_equal(C, np.array([olib.ref_lz4f_size(s) for s in g]))
+    S = engine.tile_sizes("lz4", 0, 3, 0, 6)
+    ref = np.array([[olib.ref_lz4f_size(np.concatenate([g[i], g[j]])) for j in range(6)] for i in range(3)])
+    assert np.array_equal(S, ref)
+    engine.set_option("streams_in_flight", 8)
+    engine.set_option("invalidate_caches", 1)
+    assert np.array_equal(engine.tile_sizes("lz4", 0, 3, 0, 6), ref)
+    engine.set_option("streams_in_flight", 0)
+    # concatenation uploaded as ONE sequence takes the no-checkpoint route through the same kernel
+    engine.upload_sequences([np.concatenate([g[0], g[1]])])
+    assert engine.single_sizes("lz4")[0] == ref[0, 1]
+    D = engine.ncd(C[:3], S[:, :3])
+    assert np.array_equal(D, snacc_oracle.ncd_from_sizes(C[:3], S[:, :3]))

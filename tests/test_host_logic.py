@@ -1,0 +1,162 @@
+"""CPU: host-side mirror of the reference interface -- FASTA parsing, file discovery, NCD epilogue, CSV,
+CLI flag surface, and the world_size-2 row sharding over the gloo backend."""
+import os
+import socket
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import snacc_oracle
+from snacc_b200 import cli as gcli
+from snacc_b200 import fasta, pairwise_ncd, sharding
+
+
+def test_fasta_parser_matches_the_oracle_shim(golden_dir):
+    for f in sorted((Path(golden_dir) / "fasta").iterdir()):
+        data, recs = fasta.read_fasta(f)
+        assert data.tobytes().decode() == snacc_oracle.extract_sequences(f, False), f.name
+        assert pairwise_ncd.extract_sequences(f, False) == snacc_oracle.extract_sequences(f, False)
+        assert pairwise_ncd.extract_sequences(f, True) == snacc_oracle.extract_sequences(f, True)
+        assert sum(recs) == data.size
+
+
+def test_multi_record_offsets(golden_dir):
+    f = Path(golden_dir) / "fasta" / "multi.fa"
+    data, so, ro = fasta.load_corpus([f, f])
+    assert so.tolist() == [0, 850, 1700] and ro.tolist() == [0, 400, 700, 850, 1250, 1550, 1700]
+
+
+def test_empty_fasta_raises_value_error(tmp_path):
+    p = tmp_path / "empty.fa"
+    p.write_text("no header line here\nACGT\n")
+    with pytest.raises(ValueError):
+        fasta.load_corpus([p])
+    with pytest.raises(ValueError):
+        pairwise_ncd.extract_sequences(p)
+
+
+def test_unknown_algorithm_is_a_key_error(golden_dir):
+    f = Path(golden_dir) / "fasta" / "tiny.fa"
+    with pytest.raises(KeyError):
+        pairwise_ncd.compressed_size(f, "snappy")
+    with pytest.raises(KeyError):
+        pairwise_ncd.compressed_size(f, "lzma")      # valid for the reference, not on the GPU path: no fallback
+
+
+def test_compute_distance_matches_reference_branches():
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        x, y = (int(v) for v in rng.integers(50, 10_000_000, 2))
+        cxy, cyx = (int(v) for v in rng.integers(max(x, y), x + y + 100, 2))
+        assert pairwise_ncd.compute_distance(x, y, cxy, cyx) == snacc_oracle.compute_distance(x, y, cxy, cyx)
+    assert pairwise_ncd.compute_distance(1174721, 1173133, 1242873, 1242873) == 0.05936728806244206
+
+
+def test_vectorised_epilogue_is_bit_identical_to_the_scalar_formula():
+    rng = np.random.default_rng(1)
+    n = 23
+    C = rng.integers(1000, 5_000_000, n)
+    S = rng.integers(1000, 9_000_000, (n, n))
+    assert np.array_equal(sharding.ncd_host(C, S), snacc_oracle.ncd_from_sizes(C, S))
+
+
+def test_file_discovery_and_ordering(golden_dir, tmp_path):
+    d = Path(golden_dir) / "fasta"
+    (tmp_path / "notes.txt").write_text("x")
+    got = gcli.collect_files([str(d), str(d / "g1.fasta")])
+    assert got == snacc_oracle.sorted_files([d, d / "g1.fasta"])
+    assert [p.name for p in got][:3] == ["big1.fasta", "big2.fasta", "g1.fasta"]
+
+
+def test_csv_writer_matches_reference_layout(golden_dir, tmp_path):
+    d = Path(golden_dir) / "fasta"
+    files = [f for f in gcli.collect_files([str(d)]) if not f.name.startswith("big")]
+    C, S = snacc_oracle.size_tables(files, "lz4")
+    out = tmp_path / "x.csv"
+    gcli.write_distance_csv(files, sharding.ncd_host(C, S), out)
+    got = out.read_text().replace(str(d.absolute()) + "/", "")
+    assert got == (Path(golden_dir) / "reference_cli_lz4.csv").read_text()
+
+
+def test_cli_flag_surface():
+    names = {o for p in gcli.cli.params for o in p.opts}
+    for flag in ("-d", "-o", "-n", "-c", "-r", "-f", "-s", "--fast-mode", "--reverse-compliment", "--reverse_complement",
+                 "--log", "--show-progress"):
+        assert flag in names, flag
+
+
+def test_cli_rejects_unsupported_codec(golden_dir, tmp_path):
+    from click.testing import CliRunner
+    r = CliRunner().invoke(gcli.cli, [str(Path(golden_dir) / "fasta" / "tiny.fa"), "-o", str(tmp_path / "o.csv"),
+                                      "-c", "lzma"])
+    assert r.exit_code != 0 and "not supported on the GPU path" in r.output
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _oracle_size_fn(algorithm):
+    def fn(data, so, ro, rc, rows):
+        from oracle import lib
+        from oracle.fasta_shim import COMPLEMENT_TABLE
+        raw = data.tobytes()
+        seqs = []
+        so_l, ro_l = [int(v) for v in so], [int(v) for v in ro]
+        for i in range(len(so_l) - 1):
+            if rc:
+                parts = [raw[a:b].translate(COMPLEMENT_TABLE)[::-1] for a, b in zip(ro_l[:-1], ro_l[1:])
+                         if so_l[i] <= a and b <= so_l[i + 1] and b > a]
+                seqs.append(b"".join(parts))
+            else:
+                seqs.append(raw[so_l[i]:so_l[i + 1]])
+        C = np.array([lib.compressed_len(seqs[r], algorithm) for r in rows], dtype=np.int64)
+        S = np.array([[lib.compressed_len(seqs[r] + s, algorithm) for s in seqs] for r in rows],
+                     dtype=np.int64).reshape(len(rows), len(seqs))
+        return C, S
+    return fn
+
+
+def _worker(rank, world, port, files, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        labels, C, S, D = sharding.all_pairs(files, "lz4", True, False, size_fn=_oracle_size_fn("lz4"))
+        q.put((rank, C.tolist(), S.tolist(), D.tolist()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_sharding_world_size_2_gloo(golden_dir):
+    """N > 1 path on CPU: rank 0 parses + broadcasts, rows are split round-robin, one gather at the end."""
+    import torch.multiprocessing as mp
+    d = Path(golden_dir) / "fasta"
+    files = [f for f in gcli.collect_files([str(d)]) if not f.name.startswith("big")]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, files, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    C1, S1 = snacc_oracle.size_tables(files, "lz4", True)
+    for rank, C, S, D in res:
+        assert np.array_equal(np.array(C), C1) and np.array_equal(np.array(S), S1)
+        assert np.array_equal(np.array(D), snacc_oracle.ncd_from_sizes(C1, S1))
+
+
+def test_owned_rows_partition():
+    for n in (1, 7, 8, 512):
+        for w in (1, 2, 4, 8):
+            rows = np.concatenate([sharding.owned_rows(n, r, w) for r in range(w)])
+            assert sorted(rows.tolist()) == list(range(n))

@@ -1,0 +1,121 @@
+"""CPU: the oracle (C restatements) against the committed golden vectors produced by the unmodified
+reference (tests/golden, oracle/make_golden.py), against the real system codecs, and -- when the
+reference tree is present (build container) -- against the reference module itself."""
+import json
+import os
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import lib, ref_loader, snacc_oracle
+from oracle.make_golden import VECTOR_KINDS, VECTOR_SIZES, synth_vector
+
+
+@pytest.fixture(scope="module")
+def vectors(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "codec_vectors.json")))
+
+
+@pytest.fixture(scope="module")
+def ref_sizes(golden_dir):
+    return json.load(open(os.path.join(golden_dir, "reference_sizes.json")))
+
+
+def _vector(kind, n):
+    return synth_vector(kind, n, 1000 * VECTOR_KINDS.index(kind) + n % 997)
+
+
+@pytest.mark.parametrize("kind", VECTOR_KINDS)
+def test_lz4_restatement_matches_golden_vectors(vectors, kind):
+    for n, want in zip(VECTOR_SIZES, vectors["lz4"][kind]):
+        assert lib.lz4f_size(_vector(kind, n)) == want, (kind, n)
+
+
+@pytest.mark.parametrize("kind", VECTOR_KINDS)
+def test_deflate_restatement_matches_golden_vectors(vectors, kind):
+    for n, g, z in zip(VECTOR_SIZES, vectors["gzip"][kind], vectors["zlib"][kind]):
+        if n > 70000 and kind in ("low", "lower", "mut", "nrun"):
+            continue        # level 9 on these is slow on the CPU; covered at the smaller sizes
+        v = _vector(kind, n)
+        assert lib.deflate_size(v, 9) + 18 == g, (kind, n)
+        assert lib.deflate_size(v, 6) + 6 == z, (kind, n)
+
+
+def test_restatements_match_system_codecs_on_fresh_inputs():
+    rng = np.random.default_rng(99)
+    for kind in VECTOR_KINDS:
+        for n in rng.integers(1, 90000, size=3):
+            v = synth_vector(kind, int(n), int(n) + 5)
+            assert lib.lz4f_size(v) == lib.ref_lz4f_size(v)
+            assert lib.deflate_size(v, 9) == lib.ref_deflate_size(v, 9)
+            assert lib.deflate_size(v, 6) == lib.ref_deflate_size(v, 6)
+
+
+def test_frame_without_content_size_is_8_bytes_shorter():
+    v = synth_vector("dna", 5000, 1)
+    assert lib.lz4f_size(v, 0) + 8 == lib.lz4f_size(v, 1)
+    assert lib.ref_lz4f_size(v, 0) == lib.lz4f_size(v, 0)
+    assert lib.lz4f_size(b"", 1) == 11 == lib.ref_lz4f_size(b"", 1)
+
+
+def test_formula_known_answer(ref_sizes):
+    kat = ref_sizes["formula_kat"]
+    assert snacc_oracle.compute_distance(*kat["args"]) == kat["value"] == 0.05936728806244206
+
+
+@pytest.mark.parametrize("case", ["lz4", "lz4_rc", "gzip", "gzip_rc", "zlib", "zlib_rc"])
+def test_oracle_reproduces_reference_on_fixtures(ref_sizes, golden_dir, case):
+    """sizes (+33) and distances written by the reference's own compressed_size / compute_distance"""
+    algo, rc = case.split("_")[0], case.endswith("_rc")
+    files = [Path(golden_dir) / "fasta" / f for f in ref_sizes["files"]]
+    want = ref_sizes["cases"][case]
+    seqs = [snacc_oracle.extract_sequences(f, rc).encode() for f in files]
+    C = [lib.compressed_len(s, algo) + ref_sizes["bias"] for s in seqs]
+    assert C == want["C"]
+    small = [i for i, f in enumerate(files) if not f.name.startswith("big")]
+    for i in small:
+        for j in small:
+            assert lib.compressed_len(seqs[i] + seqs[j], algo) + 33 == want["S"][i][j]
+    big = [i for i, f in enumerate(files) if f.name.startswith("big")]
+    if algo == "lz4":
+        for i in big:
+            for j in big + small[:2]:
+                assert lib.compressed_len(seqs[i] + seqs[j], algo) + 33 == want["S"][i][j]
+    Cn, Sn = np.array(want["C"]) - 33, np.array(want["S"]) - 33
+    D = snacc_oracle.ncd_from_sizes(Cn, Sn)
+    assert np.array_equal(D, np.array(want["D"]))
+
+
+@pytest.mark.parametrize("case", ["lz4", "gzip_rc"])
+def test_oracle_csv_is_byte_identical_to_reference_cli(golden_dir, tmp_path, case):
+    algo, rc = case.split("_")[0], case.endswith("_rc")
+    fdir = Path(golden_dir) / "fasta"
+    files = [f for f in snacc_oracle.sorted_files([fdir]) if not f.name.startswith("big")]
+    C, S = snacc_oracle.size_tables(files, algo, rc)
+    out = tmp_path / "o.csv"
+    snacc_oracle.write_csv(files, snacc_oracle.ncd_from_sizes(C, S), out)
+    got = out.read_text().replace(str(fdir.absolute()) + "/", "")
+    assert got == (Path(golden_dir) / f"reference_cli_{case}.csv").read_text()
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree only exists in the build container")
+def test_against_unmodified_reference_module(ref_sizes):
+    ref = ref_loader.load_reference_pairwise_ncd()
+    sample = Path(ref_loader.REFERENCE_ROOT) / "test_dataset" / "sample.fa"
+    for case, want in ref_sizes["sample_fa"].items():
+        algo, rc = case.split("_")[0], case.endswith("_rc")
+        assert ref.compressed_size(sample, algo, reverse_complement=rc)[1] == want["C"]
+        assert snacc_oracle.compressed_size(sample, algo, rc)[1] == want["C"]
+        assert snacc_oracle.compressed_size((sample, sample), algo, rc)[1] == want["Cxx"]
+        assert snacc_oracle.compute_distance(want["C"], want["C"], want["Cxx"], want["Cxx"]) == want["ncd"]
+    assert ref.extract_sequences(sample, True) == snacc_oracle.extract_sequences(sample, True)
+
+
+def test_skew_transform_known_answer():
+    """_skew.csv = f_ln(base.csv) in the reference's test_dataset: -ln(1 - 0.000636747) = 0.00063695"""
+    from snacc_b200.skew_distance_metric import f_arctanh, f_inv, f_ln
+    assert abs(f_ln(np.float64(0.000636747)) - 0.00063695) < 5e-9
+    x = np.array([0.0, 0.25, 0.5])
+    assert np.array_equal(f_inv(x), x / (1 - x))
+    assert np.array_equal(f_arctanh(x), np.arctanh(x))
