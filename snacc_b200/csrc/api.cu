@@ -12,6 +12,8 @@
 #include "../../include/snacc_b200.h"
 #include "common.cuh"
 #include "lz4.cuh"
+#include "pack.cuh"
+#include "lz4_packed.cuh"
 #include "deflate.cuh"
 
 using namespace snacc;
@@ -41,6 +43,16 @@ struct snacc_ctx {
     int32_t n_slots = 0;
     uint8_t *d_ckpt_tab = nullptr;
     uint64_t *d_ckpt_total = nullptr;
+
+    // 2-bit packed copy + packed-path prefix checkpoints (lz4_packed.cuh)
+    int use_packed = 1;                    // option "lz4_packed": 0 forces the byte-wise kernels
+    int sm_count = 148;
+    uint64_t *d_pk_words = nullptr, *d_pk_woff = nullptr;
+    uint16_t *d_alias5 = nullptr, *d_alias4 = nullptr;
+    uint32_t *d_ck_tab = nullptr; PkState *d_ck_state = nullptr;
+    std::vector<uint8_t> h_packable, h_ck_have;   // per sequence; h_ck_have bit0: single-block regime, bit1: linked
+    PkAlphabet alphabet;
+    int64_t last_packed_jobs = 0, last_bytewise_jobs = 0;
 
     // working memory
     uint8_t *d_work = nullptr; size_t work_bytes = 0;
@@ -134,6 +146,13 @@ static void free_corpus(snacc_ctx *ctx)
     cudaFree(ctx->d_slot_of); ctx->d_slot_of = nullptr;
     cudaFree(ctx->d_ckpt_tab); ctx->d_ckpt_tab = nullptr;
     cudaFree(ctx->d_ckpt_total); ctx->d_ckpt_total = nullptr;
+    cudaFree(ctx->d_pk_words); ctx->d_pk_words = nullptr;
+    cudaFree(ctx->d_pk_woff); ctx->d_pk_woff = nullptr;
+    cudaFree(ctx->d_alias5); ctx->d_alias5 = nullptr;
+    cudaFree(ctx->d_alias4); ctx->d_alias4 = nullptr;
+    cudaFree(ctx->d_ck_tab); ctx->d_ck_tab = nullptr;
+    cudaFree(ctx->d_ck_state); ctx->d_ck_state = nullptr;
+    ctx->h_packable.clear(); ctx->h_ck_have.clear();
     ctx->n_seqs = 0; ctx->n_slots = 0;
     deflate_free_corpus(ctx->dfl);
 }
@@ -155,6 +174,7 @@ extern "C" int snacc_ctx_create(int device_id, snacc_ctx **out)
         delete ctx;
         return SNACC_ERR_CUDA;
     }
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device_id);
     uint8_t tab[256];
     build_complement_table(tab);
     if (cudaMemcpyToSymbol(c_complement, tab, 256) != cudaSuccess) { delete ctx; return SNACC_ERR_CUDA; }
@@ -175,6 +195,65 @@ extern "C" void snacc_ctx_destroy(snacc_ctx *ctx)
     cudaEventDestroy(ctx->evm0); cudaEventDestroy(ctx->evm1);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0b: measure the corpus alphabet on the device, then keep a 2-bit copy of every sequence that only
+// uses the four most frequent byte values (pack.cuh)
+// ---------------------------------------------------------------------------------------------
+static int pack_corpus(snacc_ctx *ctx)
+{
+    const int32_t n = ctx->n_seqs;
+    unsigned long long *d_hist = nullptr;
+    CK(cudaMalloc(&d_hist, 256 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(d_hist, 0, 256 * sizeof(unsigned long long), ctx->stream));
+    uint32_t max_len = 0;
+    for (int32_t i = 0; i < n; ++i) max_len = std::max(max_len, ctx->h_len[i]);
+    {
+        dim3 grid(std::min<uint32_t>((max_len + 65535) / 65536, 64), (unsigned)std::min<int32_t>(n, 1024));
+        pk_hist_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_corpus, ctx->d_off, ctx->d_len, n, d_hist);
+        CK(cudaGetLastError());
+    }
+    unsigned long long hist[256];
+    CK(cudaMemcpyAsync(hist, d_hist, sizeof hist, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_hist);
+    ctx->alphabet = pk_choose_alphabet(hist);
+    uint16_t a5[1024], a4[256];
+    pk_slot_lut(ctx->alphabet, false, a5);
+    pk_slot_lut(ctx->alphabet, true, a4);
+    CK(cudaMalloc(&ctx->d_alias5, sizeof a5));
+    CK(cudaMalloc(&ctx->d_alias4, sizeof a4));
+    CK(cudaMemcpyAsync(ctx->d_alias5, a5, sizeof a5, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_alias4, a4, sizeof a4, cudaMemcpyHostToDevice, ctx->stream));
+
+    PkCodes codes;
+    memcpy(codes.c, ctx->alphabet.code_of, 256);
+    std::vector<uint64_t> woff((size_t)n);
+    uint64_t w = 0;
+    for (int32_t i = 0; i < n; ++i) { woff[i] = w; w += pk_words(ctx->h_len[i]); }
+    int32_t *d_bad = nullptr;
+    CK(cudaMalloc(&ctx->d_pk_words, w * sizeof(uint64_t)));
+    CK(cudaMalloc(&ctx->d_pk_woff, sizeof(uint64_t) * n));
+    CK(cudaMalloc(&d_bad, sizeof(int32_t) * n));
+    CK(cudaMemsetAsync(d_bad, 0, sizeof(int32_t) * n, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_pk_woff, woff.data(), sizeof(uint64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        dim3 grid(std::min<uint32_t>((pk_words(max_len) + 255) / 256, 256), (unsigned)std::min<int32_t>(n, 4096));
+        pk_pack_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_corpus, ctx->d_off, ctx->d_len, ctx->d_pk_woff, n,
+                                                      ctx->d_pk_words, d_bad, codes);
+        CK(cudaGetLastError());
+    }
+    std::vector<int32_t> bad((size_t)n);
+    CK(cudaMemcpyAsync(bad.data(), d_bad, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMalloc(&ctx->d_ck_tab, (size_t)n * 2 * PK_CKPT_TAB * sizeof(uint32_t)));
+    CK(cudaMalloc(&ctx->d_ck_state, (size_t)n * 2 * sizeof(PkState)));
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_bad);
+    ctx->h_packable.assign(n, 0);
+    for (int32_t i = 0; i < n; ++i) ctx->h_packable[i] = bad[i] ? 0 : 1;
+    ctx->h_ck_have.assign(n, 0);
+    return SNACC_OK;
 }
 
 static int upload_impl(snacc_ctx *ctx, const void *bytes, bool on_device, const uint64_t *seq_offsets,
@@ -273,7 +352,7 @@ static int upload_impl(snacc_ctx *ctx, const void *bytes, bool on_device, const 
     ctx->n_seqs = n_seqs;
     CK(cudaStreamSynchronize(ctx->stream));
     cudaFree(d_src); cudaFree(d_rec_off); cudaFree(d_rec_dst);
-    return SNACC_OK;
+    return pack_corpus(ctx);
 }
 
 extern "C" int snacc_upload(snacc_ctx *ctx, const uint8_t *bytes, const uint64_t *seq_offsets, int32_t n_seqs,
@@ -350,28 +429,170 @@ static int lz4_prepare_prefixes(snacc_ctx *ctx, const int32_t *xs, int64_t n)
     return SNACC_OK;
 }
 
-static int run_lz4(snacc_ctx *ctx, const int32_t *h_x, int64_t n_jobs, bool pairs)
+// byte-wise kernels (lz4.cuh) on the jobs `sel` (host list; null = all n_jobs jobs) of the uploaded job arrays
+static int run_lz4_bytewise(snacc_ctx *ctx, const int32_t *h_x, const std::vector<int64_t> *sel, int64_t n_jobs,
+                            bool pairs)
 {
-    int r = lz4_prepare_prefixes(ctx, h_x, n_jobs);
+    const int64_t n = sel ? (int64_t)sel->size() : n_jobs;
+    if (n == 0) return SNACC_OK;
+    std::vector<int32_t> xs((size_t)n);
+    for (int64_t k = 0; k < n; ++k) xs[k] = h_x[sel ? (*sel)[k] : k];
+    int r = lz4_prepare_prefixes(ctx, xs.data(), n);
     if (r) return r;
     // linked-regime streams each own a 16 KiB table that is hit at random: keep the set L2 resident
     // (one warp per SM); single-block streams are short and want many more threads in flight
     bool any_linked = false;
-    for (int64_t k = 0; k < n_jobs && !any_linked; ++k) any_linked = ctx->h_len[h_x[k]] >= LZ4_BLOCK / 2;
+    for (int64_t k = 0; k < n && !any_linked; ++k) any_linked = ctx->h_len[xs[k]] >= LZ4_BLOCK / 2;
     int64_t inflight = ctx->streams_in_flight > 0 ? ctx->streams_in_flight : (any_linked ? 148 * 32 : 148 * 1024);
     const int threads = 32;
-    int64_t blocks = (std::min<int64_t>(inflight, n_jobs) + threads - 1) / threads;
+    int64_t blocks = (std::min<int64_t>(inflight, n) + threads - 1) / threads;
     if (blocks < 1) blocks = 1;
     r = ensure_work(ctx, (size_t)blocks * threads * LZ4_TABLE_BYTES);
     if (r) return r;
+    int64_t *d_sel = nullptr;
+    if (sel) {
+        CK(cudaMalloc(&d_sel, sizeof(int64_t) * n));
+        CK(cudaMemcpyAsync(d_sel, sel->data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    }
     CK(cudaMemsetAsync(ctx->d_counter, 0, sizeof(unsigned long long), ctx->stream));
-    CK(cudaEventRecord(ctx->evm0, ctx->stream));
+    if (!ctx->last_packed_jobs) CK(cudaEventRecord(ctx->evm0, ctx->stream));
     lz4_stream_kernel<<<(unsigned)blocks, threads, 0, ctx->stream>>>(
-        ctx->d_corpus, ctx->d_off, ctx->d_len, ctx->d_jobx, pairs ? ctx->d_joby : nullptr, n_jobs, ctx->d_slot_of,
+        ctx->d_corpus, ctx->d_off, ctx->d_len, ctx->d_jobx, pairs ? ctx->d_joby : nullptr, d_sel, n, ctx->d_slot_of,
         ctx->d_ckpt_tab, ctx->d_ckpt_total, ctx->d_work, ctx->d_counter, ctx->d_out);
-    CK(cudaEventRecord(ctx->evm1, ctx->stream));
+    if (!ctx->last_packed_jobs) CK(cudaEventRecord(ctx->evm1, ctx->stream));
+    ctx->last_launches++;
+    ctx->last_bytewise_jobs += n;
+    CK(cudaGetLastError());
+    if (d_sel) { CK(cudaStreamSynchronize(ctx->stream)); cudaFree(d_sel); }
+    return SNACC_OK;
+}
+
+// packed path, step 1: singles and/or prefix checkpoints of the listed sequences (lz4_pk_single_kernel)
+static int run_pk_single(snacc_ctx *ctx, const std::vector<int32_t> &seqs, const std::vector<int32_t> &want,
+                         const std::vector<int64_t> &out_idx)
+{
+    const int32_t n = (int32_t)seqs.size();
+    if (!n) return SNACC_OK;
+    int32_t *d_seqs = nullptr, *d_want = nullptr; int64_t *d_idx = nullptr;
+    CK(cudaMalloc(&d_seqs, sizeof(int32_t) * n));
+    CK(cudaMalloc(&d_want, sizeof(int32_t) * n));
+    CK(cudaMalloc(&d_idx, sizeof(int64_t) * n));
+    CK(cudaMemcpyAsync(d_seqs, seqs.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_want, want.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_idx, out_idx.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    const PkCorpus pc{ctx->d_pk_words, ctx->d_pk_woff, ctx->d_len};
+    lz4_pk_single_kernel<<<n, 64, 0, ctx->stream>>>(pc, d_seqs, d_want, n, ctx->d_ck_tab, ctx->d_ck_state, ctx->d_alias5,
+                                                    ctx->d_alias4, d_idx, ctx->d_out);
     ctx->last_launches++;
     CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_seqs); cudaFree(d_want); cudaFree(d_idx);
+    return SNACC_OK;
+}
+
+// tile geometry of lz4_pk_pair_kernel: linked regime 3 warps x 16 lanes (4 KiB table per stream),
+// single-block regime 12 warps x 32 lanes (512 B table per stream); both fill one SM's shared memory
+constexpr int PK_L_LANES = 16, PK_L_WARPS = 3, PK_S_LANES = 32, PK_S_WARPS = 12;
+constexpr size_t PK_L_SMEM = PK_RING_WORDS * 8 + 1024 * 2 + (size_t)PK_L_WARPS * 1024 * PK_L_LANES * 4;
+constexpr size_t PK_S_SMEM = PK_RING_WORDS * 8 + 256 * 2 + (size_t)PK_S_WARPS * 256 * PK_S_LANES * 2;
+
+struct PkJob { int32_t y, x; int64_t j; };
+
+static int run_pk_pairs(snacc_ctx *ctx, std::vector<PkJob> &jobs, bool u16)
+{
+    if (jobs.empty()) return SNACC_OK;
+    const int T = u16 ? PK_S_LANES * PK_S_WARPS : PK_L_LANES * PK_L_WARPS;
+    std::sort(jobs.begin(), jobs.end(), [&](const PkJob &a, const PkJob &b) {
+        const uint32_t la = ctx->h_len[a.y], lb = ctx->h_len[b.y];
+        return la != lb ? la > lb : a.y != b.y ? a.y < b.y : a.j < b.j;       // longest y first, jobs of one y together
+    });
+    std::vector<PkTile> tiles;
+    std::vector<int32_t> tx(jobs.size());
+    std::vector<int64_t> tout(jobs.size());
+    for (size_t k = 0; k < jobs.size();) {
+        size_t e = k;
+        while (e < jobs.size() && jobs[e].y == jobs[k].y) ++e;
+        // split the y group into near-equal tiles of at most T streams
+        const size_t cnt = e - k, nt = (cnt + T - 1) / T;
+        for (size_t t = 0; t < nt; ++t) {
+            const size_t a = k + cnt * t / nt, b = k + cnt * (t + 1) / nt;
+            tiles.push_back(PkTile{jobs[k].y, (int32_t)(b - a), (int64_t)a});
+        }
+        k = e;
+    }
+    for (size_t k = 0; k < jobs.size(); ++k) { tx[k] = jobs[k].x; tout[k] = jobs[k].j; }
+    PkTile *d_tiles = nullptr; int32_t *d_tx = nullptr; int64_t *d_tout = nullptr;
+    CK(cudaMalloc(&d_tiles, sizeof(PkTile) * tiles.size()));
+    CK(cudaMalloc(&d_tx, sizeof(int32_t) * tx.size()));
+    CK(cudaMalloc(&d_tout, sizeof(int64_t) * tout.size()));
+    CK(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(PkTile) * tiles.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_tx, tx.data(), sizeof(int32_t) * tx.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_tout, tout.data(), sizeof(int64_t) * tout.size(), cudaMemcpyHostToDevice, ctx->stream));
+    unsigned long long *counter = ctx->d_counter + (u16 ? 1 : 2);
+    CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream));
+    const PkCorpus pc{ctx->d_pk_words, ctx->d_pk_woff, ctx->d_len};
+    const int grid = (int)std::min<size_t>(tiles.size(), (size_t)ctx->sm_count);
+    CK(cudaEventRecord(ctx->evm0, ctx->stream));
+    if (u16) {
+        CK(cudaFuncSetAttribute(lz4_pk_pair_kernel<true, PK_S_LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_S_SMEM));
+        lz4_pk_pair_kernel<true, PK_S_LANES><<<grid, PK_S_WARPS * 32, PK_S_SMEM, ctx->stream>>>(
+            pc, d_tiles, (int32_t)tiles.size(), d_tx, d_tout, ctx->d_ck_tab, ctx->d_ck_state, ctx->d_alias4, counter, ctx->d_out);
+    } else {
+        CK(cudaFuncSetAttribute(lz4_pk_pair_kernel<false, PK_L_LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_L_SMEM));
+        lz4_pk_pair_kernel<false, PK_L_LANES><<<grid, PK_L_WARPS * 32, PK_L_SMEM, ctx->stream>>>(
+            pc, d_tiles, (int32_t)tiles.size(), d_tx, d_tout, ctx->d_ck_tab, ctx->d_ck_state, ctx->d_alias5, counter, ctx->d_out);
+    }
+    CK(cudaEventRecord(ctx->evm1, ctx->stream));
+    ctx->last_launches++;
+    ctx->last_packed_jobs += (int64_t)jobs.size();
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_tiles); cudaFree(d_tx); cudaFree(d_tout);
+    return SNACC_OK;
+}
+
+// LZ4 driver: jobs whose operands have a 2-bit copy take the packed tile kernels, the rest the byte-wise kernel
+static int run_lz4(snacc_ctx *ctx, const int32_t *h_x, const int32_t *h_y, int64_t n_jobs)
+{
+    const bool pairs = h_y != nullptr;
+    ctx->last_packed_jobs = ctx->last_bytewise_jobs = 0;
+    if (!ctx->use_packed) return run_lz4_bytewise(ctx, h_x, nullptr, n_jobs, pairs);
+    std::vector<int64_t> bytewise;
+    int r;
+    if (!pairs) {
+        std::vector<int32_t> seqs, want; std::vector<int64_t> idx;
+        for (int64_t k = 0; k < n_jobs; ++k) {
+            if (ctx->h_packable[h_x[k]]) { seqs.push_back(h_x[k]); want.push_back(0); idx.push_back(k); }
+            else bytewise.push_back(k);
+        }
+        ctx->last_packed_jobs = (int64_t)seqs.size();
+        CK(cudaEventRecord(ctx->evm0, ctx->stream));
+        r = run_pk_single(ctx, seqs, want, idx);
+        if (r) return r;
+        CK(cudaEventRecord(ctx->evm1, ctx->stream));
+    } else {
+        std::vector<PkJob> small, linked;
+        std::vector<int32_t> need((size_t)ctx->n_seqs, 0);
+        for (int64_t k = 0; k < n_jobs; ++k) {
+            const int32_t x = h_x[k], y = h_y[k];
+            if (!ctx->h_packable[x] || !ctx->h_packable[y] || ctx->h_len[y] < 16) { bytewise.push_back(k); continue; }
+            const bool u16 = (uint64_t)ctx->h_len[x] + ctx->h_len[y] <= LZ4_BLOCK;
+            (u16 ? small : linked).push_back(PkJob{y, x, k});
+            need[x] |= u16 ? 1 : 2;
+        }
+        std::vector<int32_t> seqs, want; std::vector<int64_t> idx;
+        for (int32_t s = 0; s < ctx->n_seqs; ++s) {
+            const int32_t missing = need[s] & ~ctx->h_ck_have[s];
+            if (missing) { seqs.push_back(s); want.push_back(missing); idx.push_back(-1); ctx->h_ck_have[s] |= (uint8_t)missing; }
+        }
+        r = run_pk_single(ctx, seqs, want, idx);
+        if (r) return r;
+        r = run_pk_pairs(ctx, small, true);
+        if (r) return r;
+        r = run_pk_pairs(ctx, linked, false);
+        if (r) return r;
+    }
+    if (!bytewise.empty()) return run_lz4_bytewise(ctx, h_x, &bytewise, n_jobs, pairs);
     return SNACC_OK;
 }
 
@@ -401,7 +622,7 @@ static int sizes_impl(snacc_ctx *ctx, int codec, const int32_t *xs, const int32_
     if (ys) CK(cudaMemcpyAsync(ctx->d_joby, ys, sizeof(int32_t) * n_jobs, cudaMemcpyHostToDevice, ctx->stream));
     ctx->last_launches = 0;
     CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (codec == SNACC_LZ4F) r = run_lz4(ctx, xs, n_jobs, ys != nullptr);
+    if (codec == SNACC_LZ4F) r = run_lz4(ctx, xs, ys, n_jobs);
     else {
         DeflateCorpus dc{ctx->d_corpus, ctx->d_off, ctx->d_len, ctx->h_off.data(), ctx->h_len.data(), ctx->n_seqs};
         r = deflate_run(ctx->dfl, dc, codec == SNACC_GZIP9 ? 9 : 6, xs, ys, ctx->d_jobx, ys ? ctx->d_joby : nullptr,
@@ -414,7 +635,19 @@ static int sizes_impl(snacc_ctx *ctx, int codec, const int32_t *xs, const int32_
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;
-    if (codec == SNACC_LZ4F) { CK(cudaEventElapsedTime(&ms, ctx->evm0, ctx->evm1)); ctx->last_main_ms = ms; }
+    if (codec == SNACC_LZ4F) {
+        CK(cudaEventElapsedTime(&ms, ctx->evm0, ctx->evm1)); ctx->last_main_ms = ms;
+        // packed pair streams that could not use their checkpoint exactly (-1) are redone byte-wise
+        std::vector<int64_t> redo;
+        if (ctx->last_packed_jobs && ys) for (int64_t k = 0; k < n_jobs; ++k) if (out[k] < 0) redo.push_back(k);
+        if (!redo.empty()) {
+            ctx->last_packed_jobs -= (int64_t)redo.size();
+            r = run_lz4_bytewise(ctx, xs, &redo, n_jobs, true);
+            if (r) return r;
+            CK(cudaMemcpyAsync(out, ctx->d_out, sizeof(int64_t) * n_jobs, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
     const int64_t wb = wrapper_bytes(codec);
     if (wb) for (int64_t k = 0; k < n_jobs; ++k) out[k] += wb;
     return SNACC_OK;
@@ -487,6 +720,8 @@ extern "C" int snacc_get_stat(const snacc_ctx *ctx, const char *name, double *ou
     if (!strcmp(name, "main_kernel_ms")) { *out = ctx->last_main_ms; return SNACC_OK; }
     if (!strcmp(name, "total_kernel_ms")) { *out = ctx->last_ms; return SNACC_OK; }
     if (!strcmp(name, "launches")) { *out = (double)ctx->last_launches; return SNACC_OK; }
+    if (!strcmp(name, "packed_jobs")) { *out = (double)ctx->last_packed_jobs; return SNACC_OK; }
+    if (!strcmp(name, "bytewise_jobs")) { *out = (double)ctx->last_bytewise_jobs; return SNACC_OK; }
     return SNACC_ERR_ARG;
 }
 
@@ -495,10 +730,12 @@ extern "C" int snacc_set_option(snacc_ctx *ctx, const char *name, int64_t value)
     if (!ctx || !name) return SNACC_ERR_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);
     if (!strcmp(name, "streams_in_flight")) { ctx->streams_in_flight = value; return SNACC_OK; }
+    if (!strcmp(name, "lz4_packed")) { ctx->use_packed = value ? 1 : 0; return SNACC_OK; }
     if (!strcmp(name, "invalidate_caches")) {
         // forget every per-sequence precomputation (prefix checkpoints ...) so the next sizes call
         // redoes the whole job; used by bench.py so that no step reuses work of an earlier step
         std::fill(ctx->ckpt_done.begin(), ctx->ckpt_done.end(), 0);
+        std::fill(ctx->h_ck_have.begin(), ctx->h_ck_have.end(), 0);
         deflate_invalidate(ctx->dfl);
         return SNACC_OK;
     }

@@ -35,6 +35,12 @@ struct Stream {
     uint32_t n;         // total length lx + ly
 };
 
+// 2-bit packed copy of a sequence (pack.cuh): base k sits in bits 2(k%32) of 64-bit word k/32; the word
+// count is even (16-byte vector copies) and PK_PAD_WORDS zero words follow, so reading 32 bases from any
+// position below len + 64 is legal.
+constexpr uint32_t PK_PAD_WORDS = 4;
+SNACC_HD uint32_t pk_words(uint32_t len) { return ((((len + 31) >> 5) + 1) & ~1u) + PK_PAD_WORDS; }
+
 SNACC_HD uint64_t ldu64(const uint8_t *p)
 {
     // unaligned 8-byte little-endian load built from two aligned 8-byte loads

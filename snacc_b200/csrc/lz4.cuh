@@ -219,9 +219,10 @@ __global__ void lz4_prefix_kernel(const uint8_t *__restrict__ corpus, const uint
 }
 
 // ---- K1/K2b: frame size of every job; persistent threads pull jobs from a counter ----
+// `sel` (optional): the launch covers jobs sel[0..n_jobs) of the job arrays instead of 0..n_jobs.
 __global__ void lz4_stream_kernel(const uint8_t *__restrict__ corpus, const uint64_t *__restrict__ off,
                                   const uint32_t *__restrict__ len, const int32_t *__restrict__ job_x,
-                                  const int32_t *__restrict__ job_y, int64_t n_jobs,
+                                  const int32_t *__restrict__ job_y, const int64_t *__restrict__ sel, int64_t n_jobs,
                                   const int32_t *__restrict__ slot_of, const uint8_t *__restrict__ ckpt_tab,
                                   const uint64_t *__restrict__ ckpt_total, uint8_t *__restrict__ work_tab,
                                   unsigned long long *__restrict__ counter, int64_t *__restrict__ out)
@@ -229,8 +230,9 @@ __global__ void lz4_stream_kernel(const uint8_t *__restrict__ corpus, const uint
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     uint8_t *mytab = work_tab + (size_t)tid * LZ4_TABLE_BYTES;
     for (;;) {
-        const long long j = (long long)atomicAdd(counter, 1ull);
-        if (j >= n_jobs) break;
+        const long long k = (long long)atomicAdd(counter, 1ull);
+        if (k >= n_jobs) break;
+        const long long j = sel ? sel[k] : k;
         const int32_t x = job_x[j];
         const int32_t y = job_y ? job_y[j] : -1;
         const Stream s = make_stream(corpus, off, len, x, y);

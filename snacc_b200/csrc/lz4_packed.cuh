@@ -1,0 +1,727 @@
+// lz4_packed.cuh -- LZ4-frame compressed-size kernels on 2-bit packed sequences (K1/K2 of SURVEY.md 2.3),
+// sm_100a.  This is the fast path of len(lz4framed.compress(b)) (reference call site
+// snacc/pairwise_ncd.py:80) for corpora whose sequences use at most four distinct byte values
+// (A/C/G/T genomes); everything else takes the byte-wise kernels of lz4.cuh.
+//
+// Why packing changes the design (DESIGN.md "LZ4 tile kernel"):
+//   * with <= 4 symbols the 5-byte (linked regime) / 4-byte (single-block regime) hash of LZ4 only ever
+//     sees 1024 / 256 distinct k-mers, so the 4096 x u32 / 8192 x u16 library table collapses to a table
+//     with one slot per distinct bucket the k-mers reach (a 1024-entry code -> slot map keeps k-mers that
+//     collide in the library's table colliding here too).  4 KiB (512 B) of state per stream
+//     instead of 16 KiB -> the table lives in SHARED MEMORY, bank-conflict free (entry e of lane l is word
+//     e*LANES + l);
+//   * 32 bases fit one 64-bit word: hash input, the 4-byte match test and the match extension are one
+//     XOR + count-trailing-zeros;
+//   * all streams of a CTA are pair jobs (x_i, y) that share y: y is staged once per CTA in a 128 Ki-base
+//     shared-memory ring (64 Ki back-reference window + read-ahead) and every stream resumes from the
+//     prefix checkpoint of its own x, taken right before the parse first looks at a byte of y.  Reads
+//     that fall outside the ring (early back-references into x, very long matches) take an exact
+//     global-memory path, so the ring is only ever a cache.
+//
+// The parse is the same flat probe loop as lz4.cuh (validated against liblz4 1.9.4), expressed as a
+// resumable state machine (PkState) so that a stream can stop at a ring refill and so that the prefix
+// pass can stop, without side effects, at the first iteration whose outcome depends on bytes >= xend.
+#pragma once
+#include "common.cuh"
+#include "lz4.cuh"
+#include <type_traits>
+
+namespace snacc {
+
+constexpr uint32_t PK_RING_WORDS = 4096;                 // 32 KiB: 131072 bases
+constexpr uint32_t PK_RING_BASES = PK_RING_WORDS * 32;
+constexpr uint32_t PK_CHUNK_BASES = 32768;               // refill granularity (keeps >= 96 Ki bases behind)
+constexpr uint32_t PK_GUARD = 128;                       // streams stop this far before the ring's end
+constexpr uint32_t PK_ABORT = 0xffffffffu;
+
+enum : uint32_t { PK_SEARCH = 0, PK_RETEST = 1, PK_BLOCK_START = 2, PK_DONE = 3 };
+
+// Parser state between two iterations of the probe loop.  Everything a stream needs to resume.
+struct PkState {
+    uint32_t ip, fip, step, nb;      // probe position (re-test mode) / forward position + skip counters (search mode)
+    uint32_t anchor, op;             // start of pending literals; payload bytes of the open block (PK_ABORT = aborted)
+    uint32_t bs, be, mfl1, mlim;     // open block [bs, be), mflimit+1, matchlimit
+    uint32_t budget, max_lhs;        // blen-1; largest left-hand side any output-budget test has seen in this block
+    uint32_t phase, pad_;
+    uint64_t total;                  // sum of (4 + stored payload) over closed blocks
+};
+
+// What one stream sees of its input: y through the shared ring, everything else through global memory.
+struct PkView {
+    const uint64_t *ring;            // PK_RING_WORDS words holding y offsets [rlo, rlo + rspan + 64)
+    uint32_t rlo, rspan;             // fast path iff (q - rlo) <= rspan (unsigned), q = p - lx
+    const uint64_t *xw, *yw;         // packed x / y in global memory (zero padded)
+    uint32_t lx;
+};
+
+SNACC_HD uint32_t pk_ctz64(uint64_t d)
+{
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__ffsll((long long)d) - 1;
+#else
+    return (uint32_t)__builtin_ctzll(d);
+#endif
+}
+
+SNACC_HD uint64_t pk_read(const uint64_t *w, uint32_t k)
+{
+    const uint32_t i = k >> 5, s = (k & 31) * 2;
+    const uint64_t a = SNACC_LDG(w + i), b = SNACC_LDG(w + i + 1);
+    return (a >> s) | ((b << 1) << (63 - s));
+}
+
+// exact path for anything outside the ring
+static __host__ __device__ __noinline__ uint64_t pk_get32_slow(const PkView &v, uint32_t p)
+{
+    if (p >= v.lx) return pk_read(v.yw, p - v.lx);
+    const uint64_t a = pk_read(v.xw, p);
+    const uint32_t k = v.lx - p;                 // bases of x available from p
+    if (k >= 32) return a;
+    const uint64_t b = SNACC_LDG(v.yw);          // straddles the x|y boundary
+    return (a & ((1ull << (2 * k)) - 1)) | (b << (2 * k));
+}
+
+// 32 bases of the stream starting at position p (base p in bits 0-1)
+SNACC_HD uint64_t pk_get32(const PkView &v, uint32_t p)
+{
+    const uint32_t q = p - v.lx;
+    if ((uint32_t)(q - v.rlo) <= v.rspan) {
+        const uint32_t i = q >> 5, s = (q & 31) * 2;
+        const uint64_t a = v.ring[i & (PK_RING_WORDS - 1)], b = v.ring[(i + 1) & (PK_RING_WORDS - 1)];
+        return (a >> s) | ((b << 1) << (63 - s));
+    }
+    return pk_get32_slow(v, p);
+}
+
+// Position table.  `lut` maps a k-mer code to its slot: codes whose real bytes fall into the same bucket
+// of the library's hash table share a slot (pack.cuh: pk_slot_lut), so the table behaves exactly like
+// the library's while holding at most 1024 (256) live entries.
+template <bool U16, int STRIDE> struct PkTab {
+    typedef typename std::conditional<U16, uint16_t, uint32_t>::type T;
+    static constexpr uint32_t K = U16 ? 4 : 5;
+    static constexpr uint32_t MASK = U16 ? 0xffu : 0x3ffu;
+    static constexpr uint32_t ENTRIES = MASK + 1;
+    T *t;
+    const uint16_t *lut;
+    SNACC_HD uint32_t slot(uint32_t c) const { return (uint32_t)lut[c] * STRIDE; }
+    SNACC_HD uint32_t get(uint32_t c) const { return t[slot(c)]; }
+    SNACC_HD void put(uint32_t c, uint32_t pos) { t[slot(c)] = (T)pos; }
+};
+
+SNACC_HD void pk_end_block(PkState &st)
+{
+    const uint32_t blen = st.be - st.bs;
+    uint32_t op = st.op;
+    if (op != PK_ABORT) {
+        const uint32_t last_run = st.be - st.anchor;
+        const uint32_t lhs = op + last_run + 1 + (last_run + 240) / 255;
+        st.max_lhs = tmax(st.max_lhs, lhs);
+        if (lhs > st.budget) op = PK_ABORT;
+        else op += 1 + (last_run >= 15 ? (last_run - 15) / 255 + 1 : 0) + last_run;
+    }
+    const uint32_t payload = (op == PK_ABORT || op >= blen) ? blen : op;
+    st.total += 4 + payload;
+    st.bs = st.be;
+    st.phase = PK_BLOCK_START;
+}
+
+SNACC_HD void pk_fresh(PkState &st)
+{
+    st = PkState();
+    st.phase = PK_BLOCK_START;
+}
+
+// position the next iteration will look at first (for the ring-refill stop test)
+SNACC_HD uint32_t pk_next_pos(const PkState &st)
+{
+    return st.phase == PK_SEARCH ? st.fip : st.phase == PK_RETEST ? st.ip : st.bs;
+}
+
+// One iteration of the probe loop (or one block start).  `n`: stream length (0xffffffff while the
+// prefix pass pretends the stream goes on).  DETECT: return true -- leaving state and table exactly as
+// they were before the call -- when the iteration would depend on a base at or beyond `xend`.
+template <bool U16, int STRIDE, bool DETECT>
+SNACC_HD bool pk_step(PkState &st, PkTab<U16, STRIDE> &tab, const PkView &v, uint32_t n, uint32_t xend)
+{
+    constexpr uint32_t K = PkTab<U16, STRIDE>::K, MASK = PkTab<U16, STRIDE>::MASK;
+    if (st.phase == PK_BLOCK_START) {
+        if (st.bs >= n) { st.phase = PK_DONE; return false; }
+        const uint32_t be = (n - st.bs > LZ4_BLOCK) ? st.bs + LZ4_BLOCK : n;
+        const uint32_t blen = be - st.bs;
+        if (DETECT && st.bs + K > xend) return true;
+        st.be = be; st.budget = blen - 1; st.anchor = st.bs; st.op = 0; st.max_lhs = 0;
+        if (blen >= LZ4_MINLENGTH) {
+            st.mfl1 = be - LZ4_MFLIMIT + 1; st.mlim = be - LZ4_LASTLITERALS;
+            tab.put((uint32_t)pk_get32(v, st.bs) & MASK, st.bs);
+            st.ip = st.bs; st.fip = st.bs + 1; st.step = 1; st.nb = 64;
+            st.phase = PK_SEARCH;
+        } else {
+            pk_end_block(st);
+        }
+        return false;
+    }
+    const bool searching = st.phase == PK_SEARCH;
+    PkState pre;
+    if (DETECT) pre = st;
+    uint32_t ip;
+    if (searching) {
+        ip = st.fip; st.fip += st.step; st.step = (st.nb++ >> 6);
+        if (DETECT && st.fip > xend) { st = pre; return true; }
+        if (st.fip > st.mfl1) { pk_end_block(st); return false; }
+    } else {
+        ip = st.ip;
+    }
+    if (DETECT && ip + K > xend) { st = pre; return true; }
+    uint64_t w = pk_get32(v, ip);
+    const uint32_t c = (uint32_t)w & MASK;
+    uint32_t m = tab.get(c);
+    const uint32_t old_m = m;
+    tab.put(c, ip);
+    bool hit = U16 || (m + LZ4_MAX_DISTANCE >= ip);
+    uint32_t common = 0;
+    if (hit) {
+        const uint64_t d = w ^ pk_get32(v, m);
+        common = d ? (pk_ctz64(d) >> 1) : 32;
+        hit = common >= 4;
+    }
+    if (hit) {
+        uint32_t op = st.op;
+        if (searching) {
+            bool moved = false;
+            while (ip > st.anchor && m > 0 && (((uint32_t)pk_get32(v, ip - 1) ^ (uint32_t)pk_get32(v, m - 1)) & 3) == 0) {
+                --ip; --m; moved = true;
+            }
+            const uint32_t lit = ip - st.anchor;
+            op += 1;
+            const uint32_t lhs = op + lit + 8 + lit / 255;
+            st.max_lhs = tmax(st.max_lhs, lhs);
+            if (lhs > st.budget) { st.op = PK_ABORT; pk_end_block(st); return false; }
+            if (lit >= 15) op += (lit - 15) / 255 + 1;
+            op += lit;
+            if (moved) {
+                w = pk_get32(v, ip);
+                const uint64_t d = w ^ pk_get32(v, m);
+                common = d ? (pk_ctz64(d) >> 1) : 32;
+            }
+        } else {
+            op += 1;                               // token with zero literals
+        }
+        op += 2;                                   // offset
+        uint32_t lim = st.mlim;
+        if (DETECT) lim = tmin(lim, xend);
+        if (common >= 32) {                        // long match: keep comparing 32 bases at a time
+            while (ip + common < lim) {
+                const uint64_t d = pk_get32(v, ip + common) ^ pk_get32(v, m + common);
+                if (d) { common += pk_ctz64(d) >> 1; break; }
+                common += 32;
+            }
+        }
+        const uint32_t mlen = tmin(common, lim - ip);
+        const uint32_t ip2 = ip + mlen;
+        if (DETECT && (ip2 >= xend || (ip2 < st.mfl1 && ip2 + K - 2 > xend))) {
+            tab.put(c, old_m); st = pre; return true;
+        }
+        const uint32_t mcode = mlen - 4;
+        const uint32_t lhs2 = op + 6 + (mcode + 240) / 255;
+        st.max_lhs = tmax(st.max_lhs, lhs2);
+        if (lhs2 > st.budget) { st.op = PK_ABORT; pk_end_block(st); return false; }
+        if (mcode >= 15) op += (mcode - 15) / 255 + 1;
+        st.op = op; st.anchor = ip2; st.ip = ip2;
+        if (ip2 >= st.mfl1) { pk_end_block(st); return false; }
+        const uint32_t off = mlen - 2;
+        const uint32_t c2 = (off + K <= 32) ? (uint32_t)(w >> (2 * off)) & MASK : (uint32_t)pk_get32(v, ip2 - 2) & MASK;
+        tab.put(c2, ip2 - 2);
+        st.phase = PK_RETEST;                      // immediate re-test at ip2
+    } else if (!searching) {
+        st.phase = PK_SEARCH; st.fip = ip + 1; st.step = 1; st.nb = 64;
+    }
+    return false;
+}
+
+#if defined(PK_COUNT_STEPS)
+static uint64_t pk_general_steps = 0, pk_lean_steps = 0, pk_turbo_steps = 0;
+#endif
+// ---- inner-loop helpers ------------------------------------------------------------------------
+// 16 bases starting at base index k of a packed array viewed as 32-bit words
+SNACC_HD uint32_t pk_fsr(uint32_t lo, uint32_t hi, uint32_t sh)
+{
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return (uint32_t)((((uint64_t)hi << 32) | lo) >> (sh & 31));
+#endif
+}
+SNACC_HD uint32_t pk_ctz32(uint32_t d)
+{
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__ffs((int)d) - 1;
+#else
+    return (uint32_t)__builtin_ctz(d);
+#endif
+}
+SNACC_HD uint32_t pk_ring16(const uint32_t *ring32, uint32_t q)
+{
+    const uint32_t i = q >> 4;
+    return pk_fsr(ring32[i & (2 * PK_RING_WORDS - 1)], ring32[(i + 1) & (2 * PK_RING_WORDS - 1)], (q & 15) * 2);
+}
+SNACC_HD uint32_t pk_glob16(const uint64_t *w, uint32_t k)
+{
+    const uint32_t *w32 = reinterpret_cast<const uint32_t *>(w);
+    const uint32_t i = k >> 4;
+    return pk_fsr(SNACC_LDG(w32 + i), SNACC_LDG(w32 + i + 1), (k & 15) * 2);
+}
+
+SNACC_HD uint64_t pk_ring_read(const uint64_t *ring, uint32_t q)
+{
+    const uint32_t i = q >> 5, s = (q & 31) * 2;
+    const uint64_t a = ring[i & (PK_RING_WORDS - 1)], b = ring[(i + 1) & (PK_RING_WORDS - 1)];
+    return (a >> s) | ((b << 1) << (63 - s));
+}
+SNACC_HD uint32_t pk_clz32(uint32_t d)
+{
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__clz((int)d);
+#else
+    return (uint32_t)__builtin_clz(d);
+#endif
+}
+
+SNACC_HD bool pk_all(uint32_t mask, bool pred)
+{
+#ifdef __CUDA_ARCH__
+    return __all_sync(mask, pred);
+#else
+    (void)mask; return pred;
+#endif
+}
+SNACC_HD bool pk_any(uint32_t mask, bool pred)
+{
+#ifdef __CUDA_ARCH__
+    return __any_sync(mask, pred);
+#else
+    (void)mask; return pred;
+#endif
+}
+
+template <bool U16, int STRIDE>
+static __host__ __device__ __noinline__ void pk_step_general(PkState &st, PkTab<U16, STRIDE> &tab, const PkView &v, uint32_t n)
+{
+    pk_step<U16, STRIDE, false>(st, tab, v, n, 0);
+}
+
+// ---- speculative inner loop ("turbo") ----------------------------------------------------------
+// One thread is one serial dependency chain: probe position -> table slot -> candidate -> compare ->
+// next probe position.  With a handful of warps per SM the issue slots are mostly idle, so this loop
+// spends instructions to shorten the chain: while the candidate of the current probe is being fetched
+// and compared, the table lookups for every likely NEXT probe position (p+1 after a miss, p+4 .. p+6
+// after a match of that length) are already in flight, taken from a 32-base register window; when the
+// match length arrives the right one is selected, patched if this iteration's second insert (p2-2) hit
+// the same slot, and the next compare starts at once.  The window also carries the 4 bases before p, so
+// catch-up over pending literals is a count-leading-zeros on the same XOR.
+//
+// The lanes of a warp run different streams, so the loop is kept WARP-UNIFORM: every lane of `mask`
+// executes every iteration (lanes that have reached `stop` idle), and the burst ends for all of them as
+// soon as one lane meets something the loop does not cover (end of block, candidate outside the ring,
+// match of 12+ bases, catch-up of 4+ bases, tight output budget, skip step > 1).  pk_run then gives every
+// lane one general pk_step -- in lock-step again -- and starts the next burst.  Without this the lanes
+// drift apart and the warp executes them one by one (measured: 4.3 of 16 lanes active per instruction).
+//
+// Exactness: the table sees precisely the library's sequence of reads and writes (speculative reads are
+// issued after the insert of p and corrected for the insert of p2-2); an iteration that cannot be
+// completed restores the one table entry it wrote and leaves the rest of the state untouched.
+SNACC_HD uint32_t pk_reduce_or(uint32_t mask, uint32_t v)
+{
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 800
+    return __reduce_or_sync(mask, v);
+#elif defined(__CUDA_ARCH__)
+    return (__any_sync(mask, v & 1) ? 1u : 0u) | (__any_sync(mask, v & 2) ? 2u : 0u);
+#else
+    (void)mask; return v;
+#endif
+}
+
+template <bool U16, int STRIDE>
+SNACC_HD void pk_turbo(PkState &st, PkTab<U16, STRIDE> &tab, const PkView &v, uint32_t stop, uint32_t mask, bool work)
+{
+    typedef typename PkTab<U16, STRIDE>::T T;
+    constexpr uint32_t MASK = PkTab<U16, STRIDE>::MASK;
+    const uint32_t lx = v.lx, rlo = v.rlo, rspan = v.rspan;
+    const uint64_t *ring = v.ring;
+    const uint32_t *ring32 = reinterpret_cast<const uint32_t *>(v.ring);
+    uint32_t p = st.phase == PK_SEARCH ? st.fip : st.ip;
+    uint32_t anchor = st.anchor, nb = st.nb, op = st.op;
+    const uint32_t lim = tmin(stop, st.mfl1 > 16 ? st.mfl1 - 16 : 0u);
+    const uint32_t op_lim = st.budget > 80 ? st.budget - 80 : 0u;
+    const bool fin = !work || p >= stop;
+    const bool ok0 = fin || (st.phase <= PK_RETEST && !(st.phase == PK_SEARCH && st.step != 1) &&
+                             (uint32_t)(p - 4 - lx - rlo) <= rspan);
+    if (!pk_all(mask, ok0) || pk_all(mask, fin)) return;
+    uint64_t W = 0;
+    uint32_t pw = p, slot = 0, m = 0;
+    if (!fin) {
+        W = pk_ring_read(ring, p - 4 - lx);                 // bases [pw-4, pw+28)
+        slot = tab.slot((uint32_t)(W >> 8) & MASK);
+        m = tab.t[slot];
+    }
+    bool blocked = false;
+    for (uint32_t it = 0;; ++it) {
+        // ---- may this lane take one more iteration?  (evaluated by every lane, every iteration)
+        const uint32_t pend = p - anchor;                   // pending literals; search mode iff != 0
+        const bool near = U16 || (p - m <= LZ4_MAX_DISTANCE);
+        const uint32_t qm4 = m - 4 - lx;
+        const bool live = !fin && p < stop;
+        const bool ok = !blocked && p < lim && op + pend + (pend >> 7) <= op_lim && nb <= 120 &&
+                        (!near || (uint32_t)(qm4 - rlo) <= rspan + 32);
+        const bool go = live && ok;
+        if ((it & 3) == 0) {
+            // warp vote every 4th iteration: leave when a live lane is stuck or nobody runs any more
+            // (a stuck lane simply idles for up to 3 iterations)
+            if (pk_reduce_or(mask, (go ? 2u : 0u) | ((live && !ok) ? 1u : 0u)) != 2u) break;
+        }
+        // ---- straight-line body; loads are harmless for any lane, stores and commits are predicated
+        const uint32_t sh = 2 * (p - pw);
+        const uint64_t Ws = W >> sh;                        // bases [p-4, p+28-(p-pw))
+        const uint32_t w16 = (uint32_t)Ws;
+        if (go) tab.t[slot] = (T)p;
+        const uint64_t Wn = pk_ring_read(ring, p - 4 - lx);
+        const uint32_t s1 = tab.slot((uint32_t)(Ws >> 10) & MASK), s2 = tab.slot((uint32_t)(Ws >> 12) & MASK);
+        const uint32_t s3 = tab.slot((uint32_t)(Ws >> 14) & MASK), s4 = tab.slot((uint32_t)(Ws >> 16) & MASK);
+        const uint32_t s5 = tab.slot((uint32_t)(Ws >> 18) & MASK), s6 = tab.slot((uint32_t)(Ws >> 20) & MASK);
+        const uint32_t s7 = tab.slot((uint32_t)(Ws >> 22) & MASK), s8 = tab.slot((uint32_t)(Ws >> 24) & MASK);
+        const uint32_t m1 = tab.t[s1], m4 = tab.t[s4], m5 = tab.t[s5], m6 = tab.t[s6], m7 = tab.t[s7], m8 = tab.t[s8];
+        const uint32_t x = w16 ^ pk_ring16(ring32, qm4);
+        const uint32_t fwd = x >> 8, back = x << 24;        // bases p.. ; base p-1 in the two top bits
+        uint32_t common = fwd ? (pk_ctz32(fwd) >> 1) : 12;
+        common = near ? common : 0;
+        uint32_t k = back ? (pk_clz32(back) >> 1) : 4;
+        k = pend ? k : 0;
+        const uint32_t kmax = tmin(pend, m);
+        const bool hit = common >= 4;
+        const bool bail = go && (common > 11 || (hit && k == 4 && kmax > 4));   // long match / long catch-up
+        if (bail) { tab.t[slot] = (T)m; blocked = true; }
+        const bool commit = go && !bail;
+        k = tmin(k, kmax);
+        const uint32_t lit = pend - k;
+        const uint32_t add = 3 + lit + (lit >= 15 ? (lit - 15) / 255 + 1 : 0);   // token + offset + literals
+        const uint32_t pn = hit ? p + common : p + 1;
+        uint32_t sp = common == 4 ? s2 : common == 5 ? s3 : common == 6 ? s4 : common == 7 ? s5 : s6;
+        uint32_t sn = common == 4 ? s4 : common == 5 ? s5 : common == 6 ? s6 : common == 7 ? s7 : s8;
+        uint32_t mn = common == 4 ? m4 : common == 5 ? m5 : common == 6 ? m6 : common == 7 ? m7 : m8;
+        if (commit && common > 8) {                         // 9..11: not speculated, look the slots up now
+            sp = tab.slot((uint32_t)(Ws >> (2 * (common + 2))) & MASK);
+            sn = tab.slot((uint32_t)(Ws >> (2 * (common + 4))) & MASK);
+            mn = tab.t[sn];
+        }
+        if (commit && hit) tab.t[sp] = (T)(pn - 2);
+        mn = sn == sp ? pn - 2 : mn;
+        if (commit) {
+#if defined(PK_COUNT_STEPS) && !defined(__CUDA_ARCH__)
+            ++pk_turbo_steps;
+#endif
+            op += hit ? add : 0;
+            nb = hit ? nb : (pend ? nb + 1 : 64);
+            anchor = hit ? pn : anchor;
+            m = hit ? mn : m1;
+            slot = hit ? sn : s1;
+            W = Wn; pw = p; p = pn;
+        }
+    }
+    if (work && st.phase <= PK_RETEST) {
+        if (p != anchor) { st.phase = PK_SEARCH; st.fip = p; st.step = 1; st.nb = nb; }
+        else             { st.phase = PK_RETEST; st.ip = p; }
+        st.anchor = anchor; st.op = op;
+    }
+}
+
+// Run the streams of the warp (lanes in `mask`, one stream each) until each one's next position reaches
+// its `stop` or it is done: turbo bursts, separated by one general pk_step for every lane.
+template <bool U16, int STRIDE>
+SNACC_HD void pk_run(PkState &st, PkTab<U16, STRIDE> &tab, const PkView &v, uint32_t n, uint32_t stop, uint32_t mask)
+{
+    for (;;) {
+        bool work = st.phase != PK_DONE && pk_next_pos(st) < stop;
+        if (!pk_any(mask, work)) return;
+        pk_turbo<U16, STRIDE>(st, tab, v, stop, mask, work);
+        work = st.phase != PK_DONE && pk_next_pos(st) < stop;
+        if (work) {
+#if defined(PK_COUNT_STEPS) && !defined(__CUDA_ARCH__)
+            ++pk_general_steps;
+#endif
+            pk_step_general<U16, STRIDE>(st, tab, v, n);
+        }
+    }
+}
+
+// Re-derive the open block's limits for the real stream length when a pair stream resumes from the
+// prefix checkpoint of x (taken with be = bs + 64 KiB).  Returns false when a budget test that passed in
+// the prefix pass could fail under the real, smaller budget (the job then takes the byte-wise kernel).
+SNACC_HD bool pk_resume(PkState &st, uint32_t n)
+{
+    if (st.phase == PK_BLOCK_START || st.phase == PK_DONE) return true;
+    const uint32_t be = (n - st.bs > LZ4_BLOCK) ? st.bs + LZ4_BLOCK : n;
+    st.be = be; st.budget = be - st.bs - 1;
+    st.mfl1 = be - LZ4_MFLIMIT + 1; st.mlim = be - LZ4_LASTLITERALS;
+    return st.max_lhs <= st.budget;
+}
+
+// bookkeeping of the ring window, identical on every thread of the CTA; the caller fills the word
+// range [w0, w1) that start()/advance() return
+struct PkRing {
+    uint32_t yw_total;     // words of y that may be loaded (incl. zero padding)
+    uint32_t hi_w;         // words [.., hi_w) loaded so far
+    SNACC_HD void start(uint32_t ly, uint32_t &w0, uint32_t &w1)
+    {
+        yw_total = pk_words(ly);
+        hi_w = tmin(yw_total, PK_RING_WORDS);
+        w0 = 0; w1 = hi_w;
+    }
+    SNACC_HD bool complete() const { return hi_w >= yw_total; }
+    SNACC_HD void advance(uint32_t &w0, uint32_t &w1)
+    {
+        w0 = hi_w;
+        hi_w = tmin(yw_total, hi_w + PK_CHUNK_BASES / 32);
+        w1 = hi_w;
+    }
+    SNACC_HD void view(PkView &v) const
+    {
+        const uint32_t lo_w = hi_w > PK_RING_WORDS ? hi_w - PK_RING_WORDS : 0;
+        v.rlo = lo_w * 32;
+        v.rspan = (hi_w - lo_w) * 32 - 64;       // hi_w - lo_w >= 6 words always (padding)
+    }
+    // streams may run while their next position is below this y offset
+    SNACC_HD uint32_t stop_q() const { return complete() ? 0xffffffffu : hi_w * 32 - PK_GUARD; }
+};
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------
+// device side
+// ------------------------------------------------------------------------------------------------
+struct PkCorpus {
+    const uint64_t *words;       // all packed sequences
+    const uint64_t *woff;        // word offset of sequence i
+    const uint32_t *len;         // bases
+};
+
+struct PkTile {                  // up to T pair jobs sharing y
+    int32_t y, count;
+    int64_t first;               // index of the tile's first job in tile_x / tile_out
+};
+
+// checkpoint storage: slot = seq * 2 + (linked ? 1 : 0); table stored as u32[1024] in both regimes
+constexpr uint32_t PK_CKPT_TAB = 1024;
+
+// cooperative ring fill: y words [w0, w1) -> ring; w0, w1 even
+__device__ __forceinline__ void pk_ring_fill(uint64_t *ring, const uint64_t *yw, uint32_t w0, uint32_t w1)
+{
+    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(yw);
+    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(ring);
+    for (uint32_t i = (w0 >> 1) + threadIdx.x; i < (w1 >> 1); i += blockDim.x)
+        dst[i & (PK_RING_WORDS / 2 - 1)] = __ldg(src + i);
+}
+
+// ---- pair tiles: one stream per thread, LANES active lanes per warp, tables in shared memory --------
+template <bool U16, int LANES>
+__global__ void __launch_bounds__(384, 1)
+lz4_pk_pair_kernel(PkCorpus pc, const PkTile *__restrict__ tiles, int32_t n_tiles, const int32_t *__restrict__ tile_x,
+                   const int64_t *__restrict__ tile_out, const uint32_t *__restrict__ ck_tab,
+                   const PkState *__restrict__ ck_state, const uint16_t *__restrict__ lut_g,
+                   unsigned long long *__restrict__ counter, int64_t *__restrict__ out)
+{
+    typedef PkTab<U16, LANES> Tab;
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint64_t *ring = reinterpret_cast<uint64_t *>(smem);
+    uint16_t *lut = reinterpret_cast<uint16_t *>(smem + PK_RING_WORDS * 8);
+    typename Tab::T *tabs = reinterpret_cast<typename Tab::T *>(smem + PK_RING_WORDS * 8 + Tab::ENTRIES * 2);
+    __shared__ int32_t s_tile;
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t slot = warp * LANES + lane;
+    for (uint32_t i = threadIdx.x; i < Tab::ENTRIES; i += blockDim.x) lut[i] = lut_g[i];
+    Tab tab;
+    tab.t = tabs + (size_t)warp * (Tab::ENTRIES * LANES) + lane;
+    tab.lut = lut;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = (int32_t)atomicAdd(counter, 1ull);
+        __syncthreads();
+        const int32_t tile = s_tile;
+        if (tile >= n_tiles) break;
+        const PkTile td = tiles[tile];
+        const uint32_t ly = pc.len[td.y];
+        const uint64_t *yw = pc.words + pc.woff[td.y];
+        PkRing rg;
+        uint32_t w0, w1;
+        rg.start(ly, w0, w1);
+        pk_ring_fill(ring, yw, w0, w1);
+
+        const bool has = lane < LANES && (int32_t)slot < td.count;
+        PkState st;
+        PkView v;
+        v.ring = ring; v.yw = yw; v.xw = yw; v.lx = 0;
+        uint32_t n = 0;
+        bool bail = false;
+        st.phase = PK_DONE; st.total = 0;
+        // each warp copies the checkpoint tables of its streams, one stream at a time (coalesced reads)
+        for (int k = 0; k < LANES; ++k) {
+            const int32_t sl = (int32_t)(warp * LANES + k);
+            if (sl >= td.count) break;
+            const int32_t x = tile_x[td.first + sl];
+            const uint32_t *src = ck_tab + (size_t)(2 * x + (U16 ? 0 : 1)) * PK_CKPT_TAB;
+            typename Tab::T *dst = tabs + (size_t)warp * (Tab::ENTRIES * LANES) + k;
+            for (uint32_t e = lane; e < Tab::ENTRIES; e += 32) dst[e * LANES] = (typename Tab::T)src[e];
+        }
+        if (has) {
+            const int32_t x = tile_x[td.first + slot];
+            st = ck_state[2 * x + (U16 ? 0 : 1)];
+            v.lx = pc.len[x];
+            v.xw = pc.words + pc.woff[x];
+            n = v.lx + ly;
+            bail = !pk_resume(st, n);
+            if (bail) st.phase = PK_DONE;
+        }
+        for (;;) {
+            __syncthreads();                       // ring (and on the first pass the tables) visible
+            rg.view(v);
+            const uint32_t stop_q = rg.stop_q();
+            const uint32_t stop = stop_q == 0xffffffffu ? 0xffffffffu : v.lx + stop_q;
+            const uint32_t lanes = __ballot_sync(0xffffffffu, has);
+            if (has) {
+                pk_run<U16, LANES>(st, tab, v, n, stop, lanes);
+            }
+            if (rg.complete()) break;
+            __syncthreads();                       // everyone is done reading the slots about to be replaced
+            rg.advance(w0, w1);
+            pk_ring_fill(ring, yw, w0, w1);
+        }
+        if (has) out[tile_out[td.first + slot]] = bail ? -1 : (int64_t)(st.total + lz4_frame_overhead(n));
+    }
+}
+
+// ---- singles + prefix checkpoints: one sequence per CTA, thread 0 parses, everyone refills the ring ----
+// For task t = sequence s: out[out_idx[t]] = frame size of s alone (its own regime; skipped when
+// out_idx[t] < 0); checkpoints of s as the x of a pair stream, for the regimes asked for in want[t]
+// (bit 0: single-block regime, bit 1: linked regime).
+struct PkSingleSmem {
+    uint32_t tab[1024];
+    uint32_t snap[1024];
+};
+
+template <bool U16, bool DETECT>
+__device__ void pk_single_run(PkState &st, PkTab<U16, 1> &tab, PkView &v, PkRing &rg, const uint64_t *yw, uint64_t *ring,
+                              uint32_t n, uint32_t xend, uint32_t snap_bs, PkState *snap_st, uint32_t *snap_tab)
+{
+    // CTA-uniform control flow: thread 0 parses, all threads take part in ring refills
+    __shared__ uint32_t s_more;
+    for (;;) {
+        __syncthreads();
+        rg.view(v);
+        const uint32_t stop = rg.stop_q();
+        if (threadIdx.x == 0) {
+            bool touched = false;
+            while (st.phase != PK_DONE && pk_next_pos(st) < stop) {
+                if (DETECT) {
+                    if (pk_step<U16, 1, true>(st, tab, v, n, xend)) { touched = true; break; }
+                    continue;
+                }
+                uint32_t limit = stop;
+                if (snap_st) {
+                    // stop at the start of the last block: its state is where the prefix pass resumes
+                    if (st.phase == PK_BLOCK_START && st.bs == snap_bs) {
+                        *snap_st = st;
+                        for (uint32_t e = 0; e < PkTab<U16, 1>::ENTRIES; ++e) snap_tab[e] = tab.t[e];
+                        snap_st = nullptr;
+                    } else {
+                        limit = tmin(stop, snap_bs);
+                    }
+                }
+                pk_run<U16, 1>(st, tab, v, n, limit, 1u);
+            }
+            s_more = (!touched && st.phase != PK_DONE && !rg.complete()) ? 1u : 0u;
+        }
+        __syncthreads();
+        if (!s_more) break;
+        uint32_t w0, w1;
+        rg.advance(w0, w1);
+        pk_ring_fill(ring, yw, w0, w1);
+    }
+}
+
+__global__ void __launch_bounds__(64)
+lz4_pk_single_kernel(PkCorpus pc, const int32_t *__restrict__ seqs, const int32_t *__restrict__ want, int32_t n_seqs,
+                     uint32_t *__restrict__ ck_tab, PkState *__restrict__ ck_state, const uint16_t *__restrict__ lut5_g,
+                     const uint16_t *__restrict__ lut4_g, const int64_t *__restrict__ out_idx,
+                     int64_t *__restrict__ out)
+{
+    __shared__ __align__(16) uint64_t ring[PK_RING_WORDS];
+    __shared__ uint32_t s_tab[1024];
+    __shared__ uint32_t s_snap[1024];
+    __shared__ uint16_t s_lut5[1024];
+    __shared__ uint16_t s_lut4[256];
+    for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) s_lut5[i] = lut5_g[i];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_lut4[i] = lut4_g[i];
+    for (int32_t t = blockIdx.x; t < n_seqs; t += gridDim.x) {
+        const int32_t s = seqs[t];
+        const int32_t wn = want[t];
+        const uint32_t len = pc.len[s];
+        const uint64_t *yw = pc.words + pc.woff[s];
+        PkView v;
+        v.ring = ring; v.yw = yw; v.xw = yw; v.lx = 0;
+        PkRing rg;
+        PkState st, snap;
+        PkTab<false, 1> tl; tl.t = s_tab; tl.lut = s_lut5;
+        PkTab<true, 1> ts; ts.t = reinterpret_cast<uint16_t *>(s_tab); ts.lut = s_lut4;
+        const bool linked_single = len > LZ4_BLOCK;
+        const uint32_t last_bs = (len / LZ4_BLOCK) * LZ4_BLOCK;
+
+        // (1) the sequence on its own
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) s_tab[i] = 0;
+        uint32_t w0, w1;
+        rg.start(len, w0, w1);
+        pk_ring_fill(ring, yw, w0, w1);
+        pk_fresh(st); pk_fresh(snap);
+        if (linked_single) pk_single_run<false, false>(st, tl, v, rg, yw, ring, len, 0, last_bs, &snap, s_snap);
+        else               pk_single_run<true, false>(st, ts, v, rg, yw, ring, len, 0, 0, nullptr, nullptr);
+        if (threadIdx.x == 0 && out_idx[t] >= 0) out[out_idx[t]] = (int64_t)(st.total + lz4_frame_overhead(len));
+
+        // (2) linked-regime checkpoint: from the snapshot at the last block start (or from scratch)
+        if (wn & 2) {
+            __syncthreads();
+            if (linked_single) {
+                // a sequence that is a whole number of blocks never reaches BLOCK_START(last_bs) before DONE
+                // inside the run above only if last_bs == len; pk_step turns that state into DONE, so the
+                // snapshot has been taken in both cases
+                for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) s_tab[i] = s_snap[i];
+                st = snap;
+            } else {
+                for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) s_tab[i] = 0;
+                pk_fresh(st);
+                rg.start(len, w0, w1);
+                pk_ring_fill(ring, yw, w0, w1);
+            }
+            pk_single_run<false, true>(st, tl, v, rg, yw, ring, 0xffffffffu, len, 0, nullptr, nullptr);
+            __syncthreads();
+            uint32_t *dst = ck_tab + (size_t)(2 * s + 1) * PK_CKPT_TAB;
+            for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) dst[i] = s_tab[i];
+            if (threadIdx.x == 0) ck_state[2 * s + 1] = st;
+        }
+        // (3) single-block-regime checkpoint (only meaningful when some pair stream with this x fits one block)
+        if ((wn & 1) && len < LZ4_BLOCK) {
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) s_tab[i] = 0;
+            pk_fresh(st);
+            rg.start(len, w0, w1);
+            pk_ring_fill(ring, yw, w0, w1);
+            pk_single_run<true, true>(st, ts, v, rg, yw, ring, 0xffffffffu, len, 0, nullptr, nullptr);
+            __syncthreads();
+            uint32_t *dst = ck_tab + (size_t)(2 * s) * PK_CKPT_TAB;
+            const uint16_t *t16 = reinterpret_cast<const uint16_t *>(s_tab);
+            for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) dst[i] = t16[i];
+            if (threadIdx.x == 0) ck_state[2 * s] = st;
+        }
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace snacc

@@ -1,6 +1,7 @@
 // tests/host_emu.cu -- TEST INFRASTRUCTURE.  Compiles the product's __host__ __device__ parse functions
 // (snacc_b200/csrc/*.cuh) for the CPU so the exact kernel logic can be checked against the oracle in the
 // GPU-less container.  Never loaded by the product package.
+#define PK_COUNT_STEPS 1
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -35,4 +36,132 @@ extern "C" int64_t emu_lz4_size(const uint8_t *x, uint32_t lx, const uint8_t *y,
     uint64_t r = lz4_frame_size(s, tab.data(), use ? ck.data() : nullptr, use ? ck_total : 0);
     free(px); free(py);
     return (int64_t)r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// packed (2-bit) LZ4 path: the same pk_step / PkRing / checkpoint logic the tile kernels run, driven
+// sequentially.  ring refills, the global-memory fallback, prefix checkpoints and resume are all exercised.
+// ---------------------------------------------------------------------------------------------
+#include "../snacc_b200/csrc/pack.cuh"
+#include "../snacc_b200/csrc/lz4_packed.cuh"
+
+static std::vector<uint64_t> pack_host(const PkAlphabet &a, const uint8_t *p, uint32_t n, bool &ok)
+{
+    std::vector<uint64_t> w(pk_words(n) + 2, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint8_t c = a.code_of[p[i]];
+        if (c > 3) { ok = false; return w; }
+        w[i >> 5] |= (uint64_t)c << (2 * (i & 31));
+    }
+    return w;
+}
+
+static void ring_fill_host(std::vector<uint64_t> &ring, const std::vector<uint64_t> &yw, uint32_t w0, uint32_t w1)
+{
+    for (uint32_t i = w0; i < w1; ++i) ring[i & (PK_RING_WORDS - 1)] = yw[i];
+}
+
+struct EmuCkpt { PkState st; std::vector<uint32_t> tab; };
+
+// run a stream until DONE (or until DETECT touches); mirrors pk_single_run / the pair kernel loop
+template <bool U16, bool DETECT>
+static bool emu_run(PkState &st, std::vector<uint32_t> &tab32, const uint16_t *alias, PkView &v, PkRing &rg,
+                    std::vector<uint64_t> &ring, const std::vector<uint64_t> &yw, uint32_t n, uint32_t xend,
+                    uint32_t snap_bs, EmuCkpt *snap)
+{
+    typedef PkTab<U16, 1> Tab;
+    Tab tab; tab.t = reinterpret_cast<typename Tab::T *>(tab32.data()); tab.lut = alias;
+    for (;;) {
+        rg.view(v);
+        const uint32_t sq = rg.stop_q();
+        const uint32_t stop = sq == 0xffffffffu ? sq : v.lx + sq;
+        while (st.phase != PK_DONE && pk_next_pos(st) < stop) {
+            if (DETECT) {
+                if (pk_step<U16, 1, true>(st, tab, v, n, xend)) return true;
+                continue;
+            }
+            uint32_t limit = stop;
+            if (snap) {
+                if (st.phase == PK_BLOCK_START && st.bs == snap_bs) { snap->st = st; snap->tab = tab32; snap = nullptr; }
+                else limit = tmin(stop, snap_bs);
+            }
+            pk_run<U16, 1>(st, tab, v, n, limit, 1u);
+        }
+        if (st.phase == PK_DONE || rg.complete()) return false;
+        uint32_t w0, w1;
+        rg.advance(w0, w1);
+        ring_fill_host(ring, yw, w0, w1);
+    }
+}
+
+// returns the size, -1 when the packed pair path bails out, -2 when the input is not packable
+extern "C" int64_t emu_lz4_packed(const uint8_t *x, uint32_t lx, const uint8_t *y, int64_t ly_)
+{
+    unsigned long long hist[256] = {0};
+    for (uint32_t i = 0; i < lx; ++i) hist[x[i]]++;
+    for (int64_t i = 0; i < ly_; ++i) hist[y[i]]++;
+    const PkAlphabet a = pk_choose_alphabet(hist);
+    bool ok = true;
+    std::vector<uint64_t> xw = pack_host(a, x, lx, ok);
+    std::vector<uint64_t> yw = ly_ >= 0 ? pack_host(a, y, (uint32_t)ly_, ok) : std::vector<uint64_t>();
+    if (!ok) return -2;
+    uint16_t alias5[1024], alias4[256];
+    pk_slot_lut(a, false, alias5);
+    pk_slot_lut(a, true, alias4);
+    std::vector<uint64_t> ring(PK_RING_WORDS, 0);
+    std::vector<uint32_t> tab(1024, 0);
+    PkView v; PkRing rg; PkState st; uint32_t w0, w1;
+
+    // ---- the sequence x on its own (kernel lz4_pk_single_kernel, step 1) ----
+    const bool linked_single = lx > LZ4_BLOCK;
+    const uint32_t last_bs = (lx / LZ4_BLOCK) * LZ4_BLOCK;
+    EmuCkpt snap; pk_fresh(snap.st); snap.tab.assign(1024, 0);
+    v.ring = ring.data(); v.yw = xw.data(); v.xw = xw.data(); v.lx = 0;
+    rg.start(lx, w0, w1); ring_fill_host(ring, xw, w0, w1);
+    pk_fresh(st);
+    if (linked_single) emu_run<false, false>(st, tab, alias5, v, rg, ring, xw, lx, 0, last_bs, &snap);
+    else               emu_run<true, false>(st, tab, alias4, v, rg, ring, xw, lx, 0, 0, nullptr);
+    const int64_t single = (int64_t)(st.total + lz4_frame_overhead(lx));
+    if (ly_ < 0) return single;
+
+    // ---- prefix checkpoint of x in the regime of the pair stream (steps 2 / 3) ----
+    const uint32_t ly = (uint32_t)ly_;
+    const uint32_t n = lx + ly;
+    const bool u16 = n <= LZ4_BLOCK;
+    if (ly < 16) return -1;          // host-side eligibility rule of the packed pair path
+    EmuCkpt ck;
+    if (!u16) {
+        if (linked_single) { tab = snap.tab; st = snap.st; }
+        else { tab.assign(1024, 0); pk_fresh(st); rg.start(lx, w0, w1); ring_fill_host(ring, xw, w0, w1); }
+        if (!emu_run<false, true>(st, tab, alias5, v, rg, ring, xw, 0xffffffffu, lx, 0, nullptr)) return -3;
+        ck.st = st; ck.tab = tab;
+    } else {
+        tab.assign(1024, 0); pk_fresh(st); rg.start(lx, w0, w1); ring_fill_host(ring, xw, w0, w1);
+        if (!emu_run<true, true>(st, tab, alias4, v, rg, ring, xw, 0xffffffffu, lx, 0, nullptr)) return -3;
+        ck.st = st; ck.tab.assign(1024, 0);
+        const uint16_t *t16 = reinterpret_cast<const uint16_t *>(tab.data());
+        for (int i = 0; i < 256; ++i) ck.tab[i] = t16[i];
+    }
+
+    // ---- the pair stream resumes from the checkpoint (kernel lz4_pk_pair_kernel) ----
+    st = ck.st;
+    if (!pk_resume(st, n)) return -1;
+    v.ring = ring.data(); v.yw = yw.data(); v.xw = xw.data(); v.lx = lx;
+    rg.start(ly, w0, w1); ring_fill_host(ring, yw, w0, w1);
+    if (u16) {
+        std::vector<uint32_t> t(1024, 0);
+        uint16_t *t16 = reinterpret_cast<uint16_t *>(t.data());
+        for (int i = 0; i < 256; ++i) t16[i] = (uint16_t)ck.tab[i];
+        emu_run<true, false>(st, t, alias4, v, rg, ring, yw, n, 0, 0, nullptr);
+    } else {
+        std::vector<uint32_t> t = ck.tab;
+        emu_run<false, false>(st, t, alias5, v, rg, ring, yw, n, 0, 0, nullptr);
+    }
+    return (int64_t)(st.total + lz4_frame_overhead(n));
+}
+
+extern "C" void emu_pk_counts(uint64_t *lean, uint64_t *general, uint64_t *turbo, int reset)
+{
+    *lean = pk_lean_steps; *general = pk_general_steps; *turbo = pk_turbo_steps;
+    if (reset) pk_lean_steps = pk_general_steps = pk_turbo_steps = 0;
 }
