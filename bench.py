@@ -1,17 +1,18 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the snacc all-pairs NCD hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--rows R] [--codec lz4|gzip]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--codec lz4|gzip]
 
 Workload (BASELINE.json configs[3], "c4"): 512 synthetic E. coli-sized (5 Mbp) mutated-phylogeny genomes,
-LZ4-frame NCD.  A *step* is one row band of the ordered-pair job matrix: R genomes x all 512 genomes
-(R + R*512 compressor jobs), per GPU; with N GPUs every rank takes its own R rows (weak scaling, no
-data-path collective).  Metric: NCD pairs/s, where -- as in SURVEY.md 8d -- a pair is an unordered
-{i,j} entry of the finished matrix and costs two ordered jobs under the reference's semantics
-(cli.py:120-136), so pairs = ordered pair jobs / 2.  `value` is timed with the corpus resident in HBM;
-`e2e` re-uploads the corpus from pinned host memory through the C ABI and reads the sizes back, every
-step.  Every step recomputes all per-genome prefix state (`invalidate_caches`): nothing is reused
-across steps.  One JSON line on stdout (rank 0).
+LZ4-frame NCD.  A *step* is the WHOLE job: C(i) for all 512 genomes, C(i.j) for all 512 x 512 ordered
+pairs (the reference's semantics, cli.py:104-136) and the float64 NCD matrix.  With N GPUs the rows of
+the job matrix are dealt round-robin to the ranks (strong scaling; no data-path collective, the row
+bands are all-gathered at the end of the step).  Metric: NCD pairs/s, where -- as in SURVEY.md 8d -- a
+pair is an unordered {i,j} entry of the finished matrix and costs two ordered compressor jobs, so
+pairs = ordered pair jobs / 2 (131072 per step).  `value` is timed with the corpus resident in HBM;
+`e2e` re-uploads the corpus from pinned host memory through the C ABI (and re-packs it) and reads the
+sizes back, every step.  Every step recomputes all per-genome prefix state (`invalidate_caches`):
+nothing is reused across steps.  One JSON line on stdout (rank 0).
 
 `--impl reference` times the reference's own CPU compressor calls (system liblz4 / zlib through
 oracle/ref_codecs.c, all host threads) on a bounded sample of the same workload.
@@ -36,10 +37,9 @@ CPU_SAMPLE_JOBS = 192
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="snacc_b200")
-    ap.add_argument("--rows", type=int, default=0, help="row band per step and per GPU (0 = default for the codec)")
     ap.add_argument("--codec", default="lz4", choices=["lz4", "gzip"])
     ap.add_argument("--genomes", type=int, default=N_GENOMES)
     ap.add_argument("--length", type=int, default=GENOME_LEN)
@@ -135,13 +135,13 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     codec = args.codec
     n, L = args.genomes, args.length
-    rows = args.rows or (8 if codec == "lz4" else 32)
-    workload = (f"c4: {n} x {L / 1e6:g} Mbp synthetic mutated-phylogeny genomes, {codec} NCD, "
-                f"step = {rows} rows x {n} cols of the ordered-pair matrix per GPU")
-    config = {"workload": workload, "n_genomes": n, "genome_len": L, "codec": codec, "rows_per_step_per_gpu": rows,
-              "seed": SEED, "pair_unit": "unordered {i,j}: ordered pair jobs / 2 (reference semantics, cli.py:120-136)",
-              "l2_policy": "inputs larger than L2 (corpus %.2f GB per GPU)" % (n * L / 1e9),
-              "sharding": f"rows round-robin over {world} rank(s), no data-path collective"}
+    workload = (f"c4: {n} x {L / 1e6:g} Mbp synthetic mutated-phylogeny genomes, {codec} NCD; step = the whole "
+                f"{n} x {n} ordered-pair matrix (N + N^2 compressor jobs, reference semantics cli.py:104-136) + float64 NCD")
+    config = {"workload": workload, "n_genomes": n, "genome_len": L, "codec": codec,
+              "seed": SEED, "pair_unit": "ordered pair jobs / 2 (an unordered {i,j} costs two ordered jobs, cli.py:120-136); N^2/2 per step",
+              "l2_policy": "inputs larger than L2 (corpus %.2f GB per GPU, replicated)" % (n * L / 1e9),
+              "sharding": f"rows i = rank (mod {world}) of the job matrix per rank, no data-path collective; "
+                          "row bands gathered with all_gather at the end of the step"}
 
     import numpy as np
 
@@ -162,7 +162,7 @@ def main():
         sample = f"{CPU_SAMPLE_JOBS} ordered pair jobs (rows 0-1 x first {need} genomes) per step, sequences pre-loaded"
         line = {"impl": "reference", "metric": "ncd_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": config, "algorithmic_GBps": tot_bytes / tot_t / 1e9,
                 "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "reference",
                                  "sample": sample},
@@ -200,25 +200,47 @@ def main():
     del corpus_dev
     torch.cuda.empty_cache()
 
-    def step_rows(step):
-        # rank r, step s: rows (s*world + r)*rows ... wrap around the matrix
-        base = ((step * world + rank) * rows) % n
-        return (np.arange(rows) + base) % n
+    my_rows = np.arange(rank, n, world, dtype=np.int32)          # rows i = rank (mod world): no data-path collective
+    xs = np.repeat(my_rows, n)
+    ys = np.tile(np.arange(n, dtype=np.int32), my_rows.size)
+    step_bytes = job_bytes(lengths, xs, ys)
 
-    def run_step(step, e2e):
-        rr = step_rows(step).astype(np.int32)
-        xs = np.repeat(rr, n)
-        ys = np.tile(np.arange(n, dtype=np.int32), rows)
+    def run_step(e2e):
+        """one full pass: C(i) for the rank's rows, S(i,j) for rows x all columns, gather, NCD on rank 0"""
         if e2e:
-            eng.upload(corpus_host.numpy(), so)          # H2D of the step's inputs from pinned memory
+            eng.upload(corpus_host.numpy(), so)          # H2D of the step's inputs from pinned memory (+ repack)
         else:
-            eng.set_option("invalidate_caches", 1)
-        c = eng.single_sizes(codec, rr)
+            eng.set_option("invalidate_caches", 1)       # nothing (prefix checkpoints ...) survives from the last step
+        c = eng.single_sizes(codec, my_rows)
         ms1, l1 = eng.stat("total_kernel_ms"), eng.stat("launches")
-        s = eng.pair_sizes(codec, xs, ys)                # D2H of the sizes inside
+        s = eng.pair_sizes(codec, xs, ys)                # sizes come back to the host inside (D2H)
         ms2, l2 = eng.stat("total_kernel_ms"), eng.stat("launches")
-        return {"kernel_ms": ms1 + ms2, "main_ms": eng.stat("main_kernel_ms"), "launches": int(l1 + l2),
-                "jobs": int(xs.size), "bytes": job_bytes(lengths, xs, ys), "check": int(s.sum() + c.sum())}
+        main_ms = eng.stat("main_kernel_ms")
+        packed = eng.stat("packed_jobs") if codec == "lz4" else 0
+        if world > 1:
+            # gather the row bands: rank r owns rows r, r+world, ...  (2 MiB of int64 at n = 512)
+            per = (n + world - 1) // world
+            cbuf = torch.zeros(per, dtype=torch.int64, device=dev); cbuf[:c.size] = torch.from_numpy(c).to(dev)
+            sbuf = torch.zeros(per * n, dtype=torch.int64, device=dev); sbuf[:s.size] = torch.from_numpy(s.ravel()).to(dev)
+            cg = [torch.empty_like(cbuf) for _ in range(world)]
+            sg = [torch.empty_like(sbuf) for _ in range(world)]
+            dist.all_gather(cg, cbuf)
+            dist.all_gather(sg, sbuf)
+            C = np.zeros(n, dtype=np.int64); S = np.zeros((n, n), dtype=np.int64)
+            for r in range(world):
+                rr = np.arange(r, n, world)
+                C[rr] = cg[r][:rr.size].cpu().numpy()
+                S[rr] = sg[r][:rr.size * n].cpu().numpy().reshape(rr.size, n)
+        else:
+            C, S = c, s.reshape(n, n)
+        launches = int(l1 + l2)
+        check = 0
+        if rank == 0:
+            D = eng.ncd(C, S)                            # float64 epilogue kernel, result read back
+            launches += 1
+            check = int(S.sum() + C.sum()) ^ int(np.float64(D.sum()).view(np.int64) & 0xffff)
+        return {"kernel_ms": ms1 + ms2, "main_ms": main_ms, "launches": launches, "jobs": int(xs.size),
+                "bytes": step_bytes, "check": check, "packed": int(packed)}
 
     def barrier():
         torch.cuda.synchronize()
@@ -227,24 +249,23 @@ def main():
         torch.cuda.synchronize()
 
     for w in range(args.warmup):
-        run_step(w, False)
+        run_step(False)
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
         sampler.start()
     t_start = time.perf_counter()
-    stats = [run_step(args.warmup + k, False) for k in range(args.steps)]
+    stats = [run_step(False) for _ in range(args.steps)]
     barrier()
     wall = time.perf_counter() - t_start
     clocks = sampler.stop() if rank == 0 else None
     dev_ms = sum(s["kernel_ms"] for s in stats)
-    # device time (CUDA events on the library's stream) is the timed quantity; wall is reported beside it
     # ---- e2e: host buffers, H2D + D2H inside the timed region ----
-    run_step(0, True)
+    run_step(True)
     barrier()
     t_e = time.perf_counter()
     for k in range(args.steps):
-        run_step(args.warmup + k, True)
+        run_step(True)
     barrier()
     e2e_wall = time.perf_counter() - t_e
 
@@ -252,10 +273,10 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_s, wall_s, e2e_s = [float(v) for v in t.tolist()]
-    jobs_total = sum(s["jobs"] for s in stats) * world
-    bytes_total = sum(s["bytes"] for s in stats) * world
+    pairs_per_step = n * n / 2                           # ordered pair jobs / 2 (same unit as the reference arm)
+    bytes_total = float(np.sum(lengths)) * 2 * n * args.steps
     timed_s = max(dev_s, 1e-9)
-    value = (jobs_total / 2) / wall_s
+    value = pairs_per_step * args.steps / wall_s
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -267,21 +288,23 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     main_ms = sum(s["main_ms"] for s in stats) / len(stats)
-    per_launch_bytes = stats[0]["bytes"]
+    per_launch_bytes = stats[0]["bytes"]                 # rank 0's pair-kernel launch: sum of len(x)+len(y) over its jobs
     achieved = per_launch_bytes / (main_ms * 1e-3) / 1e9
     line = {"metric": "ncd_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall_s / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
             "algorithmic_GBps": bytes_total / wall_s / 1e9,
             "device_ms_per_step": 1e3 * timed_s / args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "lz4_stream_kernel" if codec == "lz4" else "deflate_pair_kernel",
+                         "traffic": None, "kernel": "lz4_pk_pair_kernel<linked>" if codec == "lz4" else "deflate_pair_kernel",
                          "peak_source": peak_src,
                          "note": "achieved = algorithmic bytes of one launch (sum of len(x)+len(y) over its pair jobs) / "
                                  "its CUDA-event duration; the path is latency/integer bound, not HBM bound"},
-            "e2e": {"value": (jobs_total / 2) / e2e_s, "unit": "pairs/s",
-                    "h2d_bytes_per_step": int(corpus_host.numel() + so.nbytes + 2 * 4 * stats[0]["jobs"]),
-                    "d2h_bytes_per_step": int(8 * (stats[0]["jobs"] + rows))},
+            "e2e": {"value": pairs_per_step * args.steps / e2e_s, "unit": "pairs/s",
+                    "h2d_bytes_per_step": int(corpus_host.numel() + so.nbytes + 2 * 4 * stats[0]["jobs"] + 4 * my_rows.size
+                                              + 8 * (n * n + n)),
+                    "d2h_bytes_per_step": int(8 * (stats[0]["jobs"] + my_rows.size) + 8 * n * n)},
+            "packed_jobs_per_step": stats[0]["packed"],
             "gpu_launches": int(sum(s["launches"] for s in stats)),
             "clocks": clocks, "corpus_gen_s": gen_s, "checksum": stats[-1]["check"]}
     if not args.no_cpu_baseline and world == 1:

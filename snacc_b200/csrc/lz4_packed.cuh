@@ -329,6 +329,33 @@ static __host__ __device__ __noinline__ void pk_step_general(PkState &st, PkTab<
 // Exactness: the table sees precisely the library's sequence of reads and writes (speculative reads are
 // issued after the insert of p and corrected for the insert of p2-2); an iteration that cannot be
 // completed restores the one table entry it wrote and leaves the rest of the state untouched.
+// Shared-memory accessors of the turbo loop.  On the device they are explicit ld.shared / st.shared on
+// 32-bit shared-window addresses (the compiler otherwise re-derives the generic->shared base inside the
+// loop) and `selp` selects (it otherwise turns the 5-way selects into divergent branches); on the host --
+// the emulation used by the tests -- they are plain pointer accesses.
+#ifdef __CUDA_ARCH__
+typedef uint32_t pk_sptr;
+__device__ __forceinline__ pk_sptr pk_sptr_of(const void *p) { return (pk_sptr)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t pk_lds32(pk_sptr a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t pk_lds16(pk_sptr a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void pk_sts32(pk_sptr a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void pk_sts16(pk_sptr a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((uint16_t)v) : "memory"); }
+__device__ __forceinline__ uint32_t pk_sel(bool c, uint32_t a, uint32_t b)
+{
+    uint32_t r;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\tselp.u32 %0, %1, %2, q;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"((uint32_t)c));
+    return r;
+}
+#else
+typedef uintptr_t pk_sptr;
+inline pk_sptr pk_sptr_of(const void *p) { return (pk_sptr)p; }
+inline uint32_t pk_lds32(pk_sptr a) { return *reinterpret_cast<const uint32_t *>(a); }
+inline uint32_t pk_lds16(pk_sptr a) { return *reinterpret_cast<const uint16_t *>(a); }
+inline void pk_sts32(pk_sptr a, uint32_t v) { *reinterpret_cast<uint32_t *>(a) = v; }
+inline void pk_sts16(pk_sptr a, uint32_t v) { *reinterpret_cast<uint16_t *>(a) = (uint16_t)v; }
+inline uint32_t pk_sel(bool c, uint32_t a, uint32_t b) { return c ? a : b; }
+#endif
+
 SNACC_HD uint32_t pk_reduce_or(uint32_t mask, uint32_t v)
 {
 #if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 800
@@ -345,9 +372,9 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<U16, STRIDE> &tab, const PkView &v, ui
 {
     typedef typename PkTab<U16, STRIDE>::T T;
     constexpr uint32_t MASK = PkTab<U16, STRIDE>::MASK;
+    constexpr uint32_t ESZ = STRIDE * sizeof(T);            // bytes between two table entries of one lane
+    constexpr uint32_t RMASK = (2 * PK_RING_WORDS - 1) * 4; // byte-offset mask of the ring seen as u32 words
     const uint32_t lx = v.lx, rlo = v.rlo, rspan = v.rspan;
-    const uint64_t *ring = v.ring;
-    const uint32_t *ring32 = reinterpret_cast<const uint32_t *>(v.ring);
     uint32_t p = st.phase == PK_SEARCH ? st.fip : st.ip;
     uint32_t anchor = st.anchor, nb = st.nb, op = st.op;
     const uint32_t lim = tmin(stop, st.mfl1 > 16 ? st.mfl1 - 16 : 0u);
@@ -356,12 +383,23 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<U16, STRIDE> &tab, const PkView &v, ui
     const bool ok0 = fin || (st.phase <= PK_RETEST && !(st.phase == PK_SEARCH && st.step != 1) &&
                              (uint32_t)(p - 4 - lx - rlo) <= rspan);
     if (!pk_all(mask, ok0) || pk_all(mask, fin)) return;
-    uint64_t W = 0;
-    uint32_t pw = p, slot = 0, m = 0;
+    const pk_sptr ring_a = pk_sptr_of(v.ring), lut_a = pk_sptr_of(tab.lut), tab_a = pk_sptr_of(tab.t);
+#define PK_TLD(addr) (U16 ? pk_lds16(addr) : pk_lds32(addr))
+#define PK_TST(addr, val) do { if (U16) pk_sts16(addr, val); else pk_sts32(addr, val); } while (0)
+#define PK_SLOT(code) (tab_a + pk_lds16(lut_a + 2 * (code)) * ESZ)
+    // 32 bases starting at y offset q, as two 32-bit halves (three consecutive ring words)
+#define PK_RING32(q, lo, hi) do { const uint32_t j_ = ((q) >> 4) * 4, s_ = ((q) & 15) * 2;                      \
+        const uint32_t a_ = pk_lds32(ring_a + (j_ & RMASK)), b_ = pk_lds32(ring_a + ((j_ + 4) & RMASK)),       \
+                       c_ = pk_lds32(ring_a + ((j_ + 8) & RMASK));                                             \
+        lo = pk_fsr(a_, b_, s_); hi = pk_fsr(b_, c_, s_); } while (0)
+    uint32_t Wlo = 0, Whi = 0;                              // bases [pw-4, pw+28)
+    uint32_t pw = p;
+    pk_sptr slot = tab_a;
+    uint32_t m = 0;
     if (!fin) {
-        W = pk_ring_read(ring, p - 4 - lx);                 // bases [pw-4, pw+28)
-        slot = tab.slot((uint32_t)(W >> 8) & MASK);
-        m = tab.t[slot];
+        PK_RING32(p - 4 - lx, Wlo, Whi);
+        slot = PK_SLOT((Wlo >> 8) & MASK);
+        m = PK_TLD(slot);
     }
     bool blocked = false;
     for (uint32_t it = 0;; ++it) {
@@ -379,17 +417,23 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<U16, STRIDE> &tab, const PkView &v, ui
             if (pk_reduce_or(mask, (go ? 2u : 0u) | ((live && !ok) ? 1u : 0u)) != 2u) break;
         }
         // ---- straight-line body; loads are harmless for any lane, stores and commits are predicated
+        // candidate: 16 bases from m-4
+        uint32_t xm;
+        {
+            const uint32_t j = (qm4 >> 4) * 4;
+            xm = pk_fsr(pk_lds32(ring_a + (j & RMASK)), pk_lds32(ring_a + ((j + 4) & RMASK)), (qm4 & 15) * 2);
+        }
         const uint32_t sh = 2 * (p - pw);
-        const uint64_t Ws = W >> sh;                        // bases [p-4, p+28-(p-pw))
-        const uint32_t w16 = (uint32_t)Ws;
-        if (go) tab.t[slot] = (T)p;
-        const uint64_t Wn = pk_ring_read(ring, p - 4 - lx);
-        const uint32_t s1 = tab.slot((uint32_t)(Ws >> 10) & MASK), s2 = tab.slot((uint32_t)(Ws >> 12) & MASK);
-        const uint32_t s3 = tab.slot((uint32_t)(Ws >> 14) & MASK), s4 = tab.slot((uint32_t)(Ws >> 16) & MASK);
-        const uint32_t s5 = tab.slot((uint32_t)(Ws >> 18) & MASK), s6 = tab.slot((uint32_t)(Ws >> 20) & MASK);
-        const uint32_t s7 = tab.slot((uint32_t)(Ws >> 22) & MASK), s8 = tab.slot((uint32_t)(Ws >> 24) & MASK);
-        const uint32_t m1 = tab.t[s1], m4 = tab.t[s4], m5 = tab.t[s5], m6 = tab.t[s6], m7 = tab.t[s7], m8 = tab.t[s8];
-        const uint32_t x = w16 ^ pk_ring16(ring32, qm4);
+        const uint32_t Ws = pk_fsr(Wlo, Whi, sh), Wt = Whi >> sh;   // bases [p-4, p+12) and the 16 after them
+        if (go) PK_TST(slot, p);
+        // speculative table lookups: next probe at p+1 (miss) or p+4..p+8 (match of that length)
+        const pk_sptr s1 = PK_SLOT((Ws >> 10) & MASK), s2 = PK_SLOT((Ws >> 12) & MASK), s3 = PK_SLOT((Ws >> 14) & MASK);
+        const pk_sptr s4 = PK_SLOT((Ws >> 16) & MASK), s5 = PK_SLOT((Ws >> 18) & MASK), s6 = PK_SLOT((Ws >> 20) & MASK);
+        const pk_sptr s7 = PK_SLOT((Ws >> 22) & MASK), s8 = PK_SLOT(pk_fsr(Ws, Wt, 24) & MASK);
+        const uint32_t m1 = PK_TLD(s1), m4 = PK_TLD(s4), m5 = PK_TLD(s5), m6 = PK_TLD(s6), m7 = PK_TLD(s7), m8 = PK_TLD(s8);
+        uint32_t Nlo, Nhi;
+        PK_RING32(p - 4 - lx, Nlo, Nhi);                    // window for the next iteration
+        const uint32_t x = Ws ^ xm;
         const uint32_t fwd = x >> 8, back = x << 24;        // bases p.. ; base p-1 in the two top bits
         uint32_t common = fwd ? (pk_ctz32(fwd) >> 1) : 12;
         common = near ? common : 0;
@@ -398,21 +442,22 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<U16, STRIDE> &tab, const PkView &v, ui
         const uint32_t kmax = tmin(pend, m);
         const bool hit = common >= 4;
         const bool bail = go && (common > 11 || (hit && k == 4 && kmax > 4));   // long match / long catch-up
-        if (bail) { tab.t[slot] = (T)m; blocked = true; }
+        if (bail) { PK_TST(slot, m); blocked = true; }
         const bool commit = go && !bail;
         k = tmin(k, kmax);
         const uint32_t lit = pend - k;
         const uint32_t add = 3 + lit + (lit >= 15 ? (lit - 15) / 255 + 1 : 0);   // token + offset + literals
         const uint32_t pn = hit ? p + common : p + 1;
-        uint32_t sp = common == 4 ? s2 : common == 5 ? s3 : common == 6 ? s4 : common == 7 ? s5 : s6;
-        uint32_t sn = common == 4 ? s4 : common == 5 ? s5 : common == 6 ? s6 : common == 7 ? s7 : s8;
-        uint32_t mn = common == 4 ? m4 : common == 5 ? m5 : common == 6 ? m6 : common == 7 ? m7 : m8;
+        const bool c4 = common == 4, c5 = common == 5, c6 = common == 6, c7 = common == 7;
+        pk_sptr sp = (pk_sptr)pk_sel(c4, (uint32_t)s2, pk_sel(c5, (uint32_t)s3, pk_sel(c6, (uint32_t)s4, pk_sel(c7, (uint32_t)s5, (uint32_t)s6))));
+        pk_sptr sn = (pk_sptr)pk_sel(c4, (uint32_t)s4, pk_sel(c5, (uint32_t)s5, pk_sel(c6, (uint32_t)s6, pk_sel(c7, (uint32_t)s7, (uint32_t)s8))));
+        uint32_t mn = pk_sel(c4, m4, pk_sel(c5, m5, pk_sel(c6, m6, pk_sel(c7, m7, m8))));
         if (commit && common > 8) {                         // 9..11: not speculated, look the slots up now
-            sp = tab.slot((uint32_t)(Ws >> (2 * (common + 2))) & MASK);
-            sn = tab.slot((uint32_t)(Ws >> (2 * (common + 4))) & MASK);
-            mn = tab.t[sn];
+            sp = PK_SLOT(pk_fsr(Ws, Wt, 2 * (common + 2)) & MASK);
+            sn = PK_SLOT(pk_fsr(Ws, Wt, 2 * (common + 4)) & MASK);
+            mn = PK_TLD(sn);
         }
-        if (commit && hit) tab.t[sp] = (T)(pn - 2);
+        if (commit && hit) PK_TST(sp, pn - 2);
         mn = sn == sp ? pn - 2 : mn;
         if (commit) {
 #if defined(PK_COUNT_STEPS) && !defined(__CUDA_ARCH__)
@@ -423,9 +468,13 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<U16, STRIDE> &tab, const PkView &v, ui
             anchor = hit ? pn : anchor;
             m = hit ? mn : m1;
             slot = hit ? sn : s1;
-            W = Wn; pw = p; p = pn;
+            Wlo = Nlo; Whi = Nhi; pw = p; p = pn;
         }
     }
+#undef PK_TLD
+#undef PK_TST
+#undef PK_SLOT
+#undef PK_RING32
     if (work && st.phase <= PK_RETEST) {
         if (p != anchor) { st.phase = PK_SEARCH; st.fip = p; st.step = 1; st.nb = nb; }
         else             { st.phase = PK_RETEST; st.ip = p; }
