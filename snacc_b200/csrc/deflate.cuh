@@ -1,25 +1,931 @@
-// deflate.cuh -- raw-deflate compressed-size kernels (K3 of SURVEY.md 2.3), sm_100a.  [stub: filled next]
+// deflate.cuh -- raw-deflate compressed-size kernels (K3 of SURVEY.md 2.3), sm_100a.
+//
+// Reproduces the byte count of the reference's gzip.compress(b) (pairwise_ncd.py:74: zlib level 9,
+// raw + 18) and zlib.compress(b) (pairwise_ncd.py:78: level 6, raw + 6) as produced by CPython over
+// zlib 1.3 with memLevel 8, windowBits 15, default strategy.  Only bit COUNTS are produced.
+//
+// zlib's deflate_slow is a serial loop whose cost on DNA is the hash-chain walk (hundreds of
+// candidates per position).  The GPU design (DESIGN.md "deflate") separates what is parallel from what
+// is serial:
+//
+//   1. every position of a stream is inserted into the hash chains whatever the parse does, so
+//      "longest_match at position i" is a pure function of the bytes: F(i) = (length, distance) of the
+//      first longest candidate among the K most recent same-hash positions within MAX_DIST.  It is
+//      computed for ALL positions in parallel (dfl_match_kernel), one thread per position, candidates
+//      enumerated from a per-sequence index sorted by (hash, position) instead of a linked list;
+//   2. F of a sequence is the same in every stream that contains it, except near the x|y boundary:
+//      F_x(p) holds for p <= len(x)-258, F_y(q) for q >= 32507 (window entirely inside y).  It is computed
+//      once per SEQUENCE; each pair job only recomputes the junction (<= 257 + 32768 positions);
+//   3. what remains serial per stream is the lazy-evaluation state machine over F (one table read per
+//      step) plus the Huffman cost of each 16383-symbol block (dfl_parse_kernel, one thread per job);
+//      the parse of the x part is shared through a per-x checkpoint taken at the junction start.
+//
+// Rules restated from zlib 1.3 (each pinned by oracle/deflate_oracle.c against libz): hash =
+// ((b0<<10)^(b1<<5)^b2)&0x7fff; a search happens only if the chain head is within MAX_DIST (32506) and is
+// not stream position 0 (window index 0 doubles as NIL before the first slide); later candidates need
+// distance < MAX_DIST; at most max_chain candidates (quartered when prev_length >= good_length); a
+// candidate replaces the best only when strictly longer; the walk stops at nice_length; lengths are
+// capped by min(258, bytes left); a length-3 match farther than 4096 is dropped.
 #pragma once
 #include "common.cuh"
 #include <string>
+#include <vector>
 
 namespace snacc {
 
+constexpr uint32_t DFL_WSIZE = 32768, DFL_MIN_MATCH = 3, DFL_MAX_MATCH = 258;
+constexpr uint32_t DFL_MAX_DIST = DFL_WSIZE - (DFL_MAX_MATCH + DFL_MIN_MATCH + 1);   // 32506
+constexpr uint32_t DFL_TOO_FAR = 4096, DFL_HASH = 32768;
+constexpr uint32_t DFL_SYMS_PER_BLOCK = 16383;        // lit_bufsize - 1 at memLevel 8
+constexpr uint32_t DFL_JY = 32768;                    // junction: first DFL_JY positions of y ...
+constexpr uint32_t DFL_JX = 264;                      // ... and the last DFL_JX positions of x (>= 262: no end-of-input
+                                                      // effect of x alone may precede the junction)
+constexpr uint32_t DFL_QDIFF = 0x80000000u;           // F flag: the quartered-chain result differs
+
+struct DflConfig { int good_length, max_lazy, nice_length, max_chain; };
+SNACC_HD DflConfig dfl_config(int level)
+{
+    return level == 9 ? DflConfig{32, 258, 258, 4096} : DflConfig{8, 16, 128, 128};
+}
+
+SNACC_HD uint32_t dfl_hash3(uint32_t b0, uint32_t b1, uint32_t b2) { return ((b0 << 10) ^ (b1 << 5) ^ b2) & (DFL_HASH - 1); }
+
+// per-sequence index: positions sorted by (hash, position); bstart has DFL_HASH + 1 entries
+struct DflIndex {
+    const uint32_t *order;
+    const uint32_t *bstart;
+};
+
+// a stream (x, or x followed by y) with the indexes of its parts
+struct DflStream {
+    Stream s;
+    DflIndex ix, iy;      // iy unused for singles
+    bool pair;
+};
+
+SNACC_HD uint32_t dfl_hash_at(const Stream &s, uint32_t p)
+{
+    const uint32_t w = (uint32_t)ld64(s, p);
+    return dfl_hash3(w & 0xff, (w >> 8) & 0xff, (w >> 16) & 0xff);
+}
+
+// number of entries of [lo, hi) of `order` that are < key
+SNACC_HD uint32_t dfl_lower_bound(const uint32_t *order, uint32_t lo, uint32_t hi, uint32_t key)
+{
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (SNACC_LDG(order + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Candidates of stream position p with hash h, most recent first, as stream positions (0xffffffff = end).
+// Mirrors the order in which zlib's chain visits them: same-hash positions of y before p, then the two
+// positions lx-1, lx-2 whose hash straddles the boundary, then the same-hash positions of x.
+struct DflCandIter {
+    const DflStream *d;
+    uint32_t h, p;
+    uint32_t stage;       // 0: y bucket, 1: lx-1, 2: lx-2, 3: x bucket, 4: end
+    uint32_t ycur, ylo, xcur, xlo;
+    // hint: index of p itself inside its own bucket when the caller already knows it (0xffffffff: search)
+    SNACC_HD void init(const DflStream *ds, uint32_t pos, uint32_t hash, uint32_t hint)
+    {
+        d = ds; h = hash; p = pos;
+        const uint32_t lx = d->s.lx;
+        xlo = SNACC_LDG(d->ix.bstart + h);
+        const uint32_t xhi = SNACC_LDG(d->ix.bstart + h + 1);
+        ycur = ylo = 0;
+        if (d->pair && p >= lx) {
+            stage = 0;
+            ylo = SNACC_LDG(d->iy.bstart + h);
+            ycur = hint != 0xffffffffu ? hint : dfl_lower_bound(d->iy.order, ylo, SNACC_LDG(d->iy.bstart + h + 1), p - lx);
+            xcur = xhi;
+        } else if (d->pair && p + 2 >= lx) {
+            // lx-2, lx-1: not in x's index (their hash needs bytes of y); every indexed position of x precedes them
+            stage = p == lx - 1 ? 2 : 3;
+            xcur = xhi;
+        } else {
+            stage = 3;
+            xcur = hint != 0xffffffffu ? hint : dfl_lower_bound(d->ix.order, xlo, xhi, p);
+        }
+    }
+    SNACC_HD uint32_t next()
+    {
+        const uint32_t lx = d->s.lx;
+        for (;;) {
+            if (stage == 0) {
+                if (ycur > ylo) return lx + SNACC_LDG(d->iy.order + --ycur);
+                stage = 1;
+            } else if (stage == 1) {
+                stage = 2;
+                if (lx >= 1 && d->s.n - (lx - 1) >= 3 && dfl_hash_at(d->s, lx - 1) == h) return lx - 1;
+            } else if (stage == 2) {
+                stage = 3;
+                if (lx >= 2 && d->s.n - (lx - 2) >= 3 && dfl_hash_at(d->s, lx - 2) == h) return lx - 2;
+            } else if (stage == 3) {
+                if (xcur > xlo) return SNACC_LDG(d->ix.order + --xcur);
+                stage = 4;
+            } else {
+                return 0xffffffffu;
+            }
+        }
+    }
+};
+
+// common prefix length of stream[a..] and stream[b..] (b < a), at most maxcmp
+SNACC_HD uint32_t dfl_match_len(const Stream &s, uint32_t a, uint32_t b, uint32_t maxcmp)
+{
+    uint32_t len = 0;
+    while (len < maxcmp) {
+        const uint64_t d = ld64(s, a + len) ^ ld64(s, b + len);
+        if (d) { len += (uint32_t)(SNACC_FFS64(d) - 1) >> 3; break; }
+        len += 8;
+    }
+    return len < maxcmp ? len : maxcmp;
+}
+
+// base of zlib's window at a loop top with this strstart when input is still plentiful (oracle
+// fill_window): the first slide happens at the first loop top >= 65275, then one every 32768 positions
+SNACC_HD uint32_t dfl_window_base(uint32_t strstart)
+{
+    return strstart < 65275u ? 0u : DFL_WSIZE * ((strstart - 65275u) / DFL_WSIZE + 1);
+}
+
+// longest_match over the first `chain` candidates; returns (len << 16) | dist, 0 when there is no match of
+// 3+ bytes (or no search at all).  `base`: window base at this loop top (positions <= base are NIL).  When
+// `quarter` is non-null it also receives the result restricted to the first chain/4 candidates.
+SNACC_HD uint32_t dfl_longest(const DflStream &d, uint32_t p, uint32_t base, uint32_t chain, uint32_t nice, uint32_t hint,
+                              uint32_t *quarter)
+{
+    const Stream &s = d.s;
+    if (quarter) *quarter = 0;
+    if (s.n - p < DFL_MIN_MATCH) return 0;                 // the string at p is not even inserted
+    const uint32_t maxcmp = tmin(DFL_MAX_MATCH, s.n - p);
+    const uint32_t nice_match = tmin(nice, maxcmp);
+    const uint32_t h = dfl_hash_at(s, p);
+    DflCandIter it;
+    it.init(&d, p, h, hint);
+    uint32_t c = it.next();
+    // chain head: must exist, not be NIL and be within MAX_DIST
+    if (c == 0xffffffffu || c <= base || p - c > DFL_MAX_DIST) return 0;
+    const uint32_t limit = (p - base > DFL_MAX_DIST) ? p - DFL_MAX_DIST : base;
+    const uint64_t scan = ld64(s, p);
+    uint32_t best = 2, bdist = 0, qbest = 0;
+    const uint32_t qcount = chain >> 2;
+    uint32_t count = 0;
+    for (;;) {
+        // quick test on the first 8 bytes, full compare only when they all agree
+        const uint64_t x = scan ^ ld64(s, c);
+        uint32_t len = x ? (uint32_t)(SNACC_FFS64(x) - 1) >> 3 : 8 + dfl_match_len(s, p + 8, c + 8, maxcmp > 8 ? maxcmp - 8 : 0);
+        if (len > maxcmp) len = maxcmp;
+        if (len > best) {
+            best = len; bdist = p - c;
+            if (len >= nice_match) { ++count; break; }
+        }
+        ++count;
+        if (count == qcount) qbest = best > 2 ? (best << 16) | bdist : 0;
+        if (count >= chain) break;
+        c = it.next();
+        if (c == 0xffffffffu || c <= limit) break;
+    }
+    const uint32_t full = best > 2 ? (best << 16) | bdist : 0;
+    if (quarter) *quarter = count <= qcount ? full : qbest;
+    return full;
+}
+
+// F word of a position: the full-chain result, flagged when the quartered chain gives something else
+SNACC_HD uint32_t dfl_f_word(const DflStream &d, uint32_t p, const DflConfig &c, uint32_t hint, uint32_t *qword)
+{
+    uint32_t q;
+    const uint32_t f = dfl_longest(d, p, dfl_window_base(p), (uint32_t)c.max_chain, (uint32_t)c.nice_length, hint, &q);
+    if (qword) *qword = q;
+    return q != f ? f | DFL_QDIFF : f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Huffman block cost (trees.c: _tr_flush_block and helpers), bit counts only
+// ------------------------------------------------------------------------------------------------
+constexpr int DFL_L_CODES = 286, DFL_D_CODES = 30, DFL_BL_CODES = 19, DFL_HEAP = 2 * DFL_L_CODES + 1;
+
+struct DflNode { uint16_t freq, dad, len; };
+
+struct DflTrees {                      // scratch of one block flush
+    DflNode ltree[DFL_HEAP];
+    DflNode dtree[2 * DFL_D_CODES + 1];
+    DflNode bltree[2 * DFL_BL_CODES + 1];
+    int32_t heap[DFL_HEAP];
+    uint8_t depth[DFL_HEAP];
+    uint16_t bl_count[16];
+    int32_t heap_len, heap_max;
+    uint64_t opt_len, static_len;
+};
+
+SNACC_HD int dfl_extra_lbits(int code) { return code < 8 ? 0 : code == 28 ? 0 : (code - 4) >> 2; }
+SNACC_HD int dfl_extra_dbits(int code) { return code < 4 ? 0 : (code - 2) >> 1; }
+SNACC_HD int dfl_static_llen(int n) { return n <= 143 ? 8 : n <= 255 ? 9 : n <= 279 ? 7 : 8; }
+SNACC_HD int dfl_length_code(uint32_t len_minus3)
+{
+    // trees.c length_code[]: codes 0..27 cover 2^extra lengths each, 258 has its own code 28
+    if (len_minus3 == 255) return 28;
+    if (len_minus3 < 8) return (int)len_minus3;
+    const int k = 31 - (int)
+#ifdef __CUDA_ARCH__
+        __clz((int)len_minus3);
+#else
+        __builtin_clz(len_minus3);
+#endif
+    // len_minus3 in [2^k, 2^(k+1)): extra bits k-2, four codes per k
+    return 4 * (k - 1) + (int)((len_minus3 >> (k - 2)) & 3);
+}
+SNACC_HD int dfl_dist_code(uint32_t d /* distance - 1 */)
+{
+    if (d < 4) return (int)d;
+    const int k = 31 - (int)
+#ifdef __CUDA_ARCH__
+        __clz((int)d);
+#else
+        __builtin_clz(d);
+#endif
+    return 2 * k + (int)((d >> (k - 1)) & 1);
+}
+
+struct DflTreeDesc { DflNode *tree; int max_code; int kind; int elems; int max_length; };   // kind 0: literal/length, 1: distance, 2: bit lengths
+
+SNACC_HD bool dfl_smaller(const DflTrees &t, const DflNode *tree, int n, int m)
+{
+    return tree[n].freq < tree[m].freq || (tree[n].freq == tree[m].freq && t.depth[n] <= t.depth[m]);
+}
+
+SNACC_HD void dfl_pqdownheap(DflTrees &t, DflNode *tree, int k)
+{
+    const int v = t.heap[k];
+    int j = k << 1;
+    while (j <= t.heap_len) {
+        if (j < t.heap_len && dfl_smaller(t, tree, t.heap[j + 1], t.heap[j])) j++;
+        if (dfl_smaller(t, tree, v, t.heap[j])) break;
+        t.heap[k] = t.heap[j]; k = j;
+        j <<= 1;
+    }
+    t.heap[k] = v;
+}
+
+SNACC_HD int dfl_xbits(const DflTreeDesc &d, int n)
+{
+    if (d.kind == 0) return n >= 257 ? dfl_extra_lbits(n - 257) : 0;
+    if (d.kind == 1) return dfl_extra_dbits(n);
+    return n == 16 ? 2 : n == 17 ? 3 : n == 18 ? 7 : 0;
+}
+SNACC_HD int dfl_slen(const DflTreeDesc &d, int n) { return d.kind == 0 ? dfl_static_llen(n) : 5; }
+
+static __host__ __device__ void dfl_gen_bitlen(DflTrees &t, DflTreeDesc &desc)
+{
+    DflNode *tree = desc.tree;
+    const int max_code = desc.max_code, max_length = desc.max_length;
+    int h, n, m, bits, overflow = 0;
+    for (bits = 0; bits <= 15; bits++) t.bl_count[bits] = 0;
+    tree[t.heap[t.heap_max]].len = 0;
+    for (h = t.heap_max + 1; h < DFL_HEAP; h++) {
+        n = t.heap[h];
+        bits = tree[tree[n].dad].len + 1;
+        if (bits > max_length) bits = max_length, overflow++;
+        tree[n].len = (uint16_t)bits;
+        if (n > max_code) continue;
+        t.bl_count[bits]++;
+        const int xbits = dfl_xbits(desc, n);
+        const uint64_t f = tree[n].freq;
+        t.opt_len += f * (unsigned)(bits + xbits);
+        if (desc.kind != 2) t.static_len += f * (unsigned)(dfl_slen(desc, n) + xbits);
+    }
+    if (overflow == 0) return;
+    do {
+        bits = max_length - 1;
+        while (t.bl_count[bits] == 0) bits--;
+        t.bl_count[bits]--;
+        t.bl_count[bits + 1] += 2;
+        t.bl_count[max_length]--;
+        overflow -= 2;
+    } while (overflow > 0);
+    for (bits = max_length; bits != 0; bits--) {
+        n = t.bl_count[bits];
+        while (n != 0) {
+            m = t.heap[--h];
+            if (m > max_code) continue;
+            if ((unsigned)tree[m].len != (unsigned)bits) {
+                t.opt_len += ((uint64_t)bits - tree[m].len) * tree[m].freq;
+                tree[m].len = (uint16_t)bits;
+            }
+            n--;
+        }
+    }
+}
+
+static __host__ __device__ void dfl_build_tree(DflTrees &t, DflTreeDesc &desc)
+{
+    DflNode *tree = desc.tree;
+    const int elems = desc.elems;
+    int n, m, max_code = -1, node;
+    t.heap_len = 0; t.heap_max = DFL_HEAP;
+    for (n = 0; n < elems; n++) {
+        if (tree[n].freq != 0) { t.heap[++t.heap_len] = max_code = n; t.depth[n] = 0; }
+        else tree[n].len = 0;
+    }
+    while (t.heap_len < 2) {
+        node = t.heap[++t.heap_len] = (max_code < 2 ? ++max_code : 0);
+        tree[node].freq = 1;
+        t.depth[node] = 0;
+        t.opt_len--;
+        if (desc.kind != 2) t.static_len -= (uint64_t)dfl_slen(desc, node);
+    }
+    desc.max_code = max_code;
+    for (n = t.heap_len / 2; n >= 1; n--) dfl_pqdownheap(t, tree, n);
+    node = elems;
+    do {
+        n = t.heap[1];
+        t.heap[1] = t.heap[t.heap_len--];
+        dfl_pqdownheap(t, tree, 1);
+        m = t.heap[1];
+        t.heap[--t.heap_max] = n;
+        t.heap[--t.heap_max] = m;
+        tree[node].freq = (uint16_t)(tree[n].freq + tree[m].freq);
+        t.depth[node] = (uint8_t)((t.depth[n] >= t.depth[m] ? t.depth[n] : t.depth[m]) + 1);
+        tree[n].dad = tree[m].dad = (uint16_t)node;
+        t.heap[1] = node++;
+        dfl_pqdownheap(t, tree, 1);
+    } while (t.heap_len >= 2);
+    t.heap[--t.heap_max] = t.heap[1];
+    dfl_gen_bitlen(t, desc);
+}
+
+static __host__ __device__ void dfl_scan_tree(DflTrees &t, DflNode *tree, int max_code)
+{
+    int n, prevlen = -1, curlen, nextlen = tree[0].len, count = 0, max_count = 7, min_count = 4;
+    if (nextlen == 0) max_count = 138, min_count = 3;
+    tree[max_code + 1].len = 0xffff;
+    for (n = 0; n <= max_code; n++) {
+        curlen = nextlen; nextlen = tree[n + 1].len;
+        if (++count < max_count && curlen == nextlen) continue;
+        else if (count < min_count) t.bltree[curlen].freq += (uint16_t)count;
+        else if (curlen != 0) {
+            if (curlen != prevlen) t.bltree[curlen].freq++;
+            t.bltree[16].freq++;
+        } else if (count <= 10) t.bltree[17].freq++;
+        else t.bltree[18].freq++;
+        count = 0; prevlen = curlen;
+        if (nextlen == 0) max_count = 138, min_count = 3;
+        else if (curlen == nextlen) max_count = 6, min_count = 3;
+        else max_count = 7, min_count = 4;
+    }
+}
+
+// Bits of one block given its symbol frequencies (lfreq[286] incl. END_BLOCK = 1, dfreq[30]); `bits` is
+// the running total (the stored form aligns it).
+static __host__ __device__ void dfl_flush_block(DflTrees &t, const uint16_t *lfreq, int lstride, const uint16_t *dfreq,
+                                                int dstride, uint64_t stored_len, bool can_store, bool last, uint64_t &bits)
+{
+    const uint8_t bl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    for (int n = 0; n < DFL_L_CODES; n++) t.ltree[n].freq = lfreq[n * lstride];
+    for (int n = 0; n < DFL_D_CODES; n++) t.dtree[n].freq = dfreq[n * dstride];
+    for (int n = 0; n < DFL_BL_CODES; n++) t.bltree[n].freq = 0;
+    t.opt_len = t.static_len = 0;
+    DflTreeDesc ld{t.ltree, 0, 0, DFL_L_CODES, 15}, dd{t.dtree, 0, 1, DFL_D_CODES, 15}, bd{t.bltree, 0, 2, DFL_BL_CODES, 7};
+    dfl_build_tree(t, ld);
+    dfl_build_tree(t, dd);
+    dfl_scan_tree(t, t.ltree, ld.max_code);
+    dfl_scan_tree(t, t.dtree, dd.max_code);
+    dfl_build_tree(t, bd);
+    int max_blindex;
+    for (max_blindex = DFL_BL_CODES - 1; max_blindex >= 3; max_blindex--)
+        if (t.bltree[bl_order[max_blindex]].len != 0) break;
+    t.opt_len += 3 * ((uint64_t)max_blindex + 1) + 5 + 5 + 4;
+    uint64_t opt_lenb = (t.opt_len + 3 + 7) >> 3;
+    const uint64_t static_lenb = (t.static_len + 3 + 7) >> 3;
+    if (static_lenb <= opt_lenb) opt_lenb = static_lenb;
+    if (stored_len + 4 <= opt_lenb && can_store) {
+        bits += 3;
+        bits = (bits + 7) & ~7ull;
+        bits += 32 + 8 * stored_len;
+    } else if (static_lenb == opt_lenb) {
+        bits += 3 + t.static_len;
+    } else {
+        bits += 3 + t.opt_len;
+    }
+    if (last) bits = (bits + 7) & ~7ull;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the serial part: deflate_slow's lazy evaluation over the F table
+// ------------------------------------------------------------------------------------------------
+struct DflParseState {                 // everything a stream needs to resume (the per-x checkpoint)
+    uint32_t strstart, match_start, match_length, match_available;
+    uint32_t sym_count, base, read, block_start;     // base/read: zlib's window refill state (oracle fill_window)
+    uint64_t bits;
+};
+SNACC_HD void dfl_parse_fresh(DflParseState &st)
+{
+    st = DflParseState();
+    st.match_length = DFL_MIN_MATCH - 1;
+}
+
+// where F of stream position p lives
+struct DflFView {
+    const uint32_t *fx;      // F of x alone, valid for p < jx0
+    const uint32_t *fy;      // F of y alone, valid for p >= lx + DFL_JY
+    const uint32_t *fj;      // junction of this pair: positions [jx0, jend)
+    uint32_t jx0, jend, lx;
+    // optional second tables holding the quartered-chain result of the flagged positions (level 6, where
+    // prev_length >= good_length is the common case); null: recompute on demand
+    const uint32_t *qx, *qy, *qj;
+};
+SNACC_HD uint32_t dfl_f_at(const DflFView &v, uint32_t p)
+{
+    if (p < v.jx0) return SNACC_LDG(v.fx + p);
+    if (p < v.jend) return SNACC_LDG(v.fj + (p - v.jx0));
+    return SNACC_LDG(v.fy + (p - v.lx));
+}
+SNACC_HD uint32_t dfl_q_at(const DflFView &v, uint32_t p)
+{
+    if (p < v.jx0) return SNACC_LDG(v.qx + p);
+    if (p < v.jend) return SNACC_LDG(v.qj + (p - v.jx0));
+    return SNACC_LDG(v.qy + (p - v.lx));
+}
+
+// Run deflate_slow from `st` until strstart >= stop (loop-top granularity) or the stream ends; lfreq/dfreq
+// are the open block's counters (strided so that a kernel can keep them in shared memory).  At the end of
+// the stream the last block is flushed and the function returns true.
+template <class TallyT>
+static __host__ __device__ bool dfl_parse(const DflStream &d, const DflFView &fv, const DflConfig &c, DflParseState &st,
+                                          TallyT *lfreq, int lstride, TallyT *dfreq, int dstride, DflTrees &tr, uint32_t stop)
+{
+    const Stream &s = d.s;
+    const uint32_t n = s.n;
+    uint32_t strstart = st.strstart, match_start = st.match_start, match_length = st.match_length;
+    uint32_t match_available = st.match_available, sym_count = st.sym_count;
+    uint32_t base = st.base, read = st.read, block_start = st.block_start;
+    uint64_t bits = st.bits;
+    bool done = false;
+#define DFL_FLUSH(last_) do {                                                                                   \
+        dfl_flush_block(tr, lfreq, lstride, dfreq, dstride, strstart - block_start, block_start >= base, (last_), bits); \
+        for (int n_ = 0; n_ < DFL_L_CODES; n_++) lfreq[n_ * lstride] = 0;                                        \
+        for (int n_ = 0; n_ < DFL_D_CODES; n_++) dfreq[n_ * dstride] = 0;                                        \
+        lfreq[256 * lstride] = 1; sym_count = 0; block_start = strstart; } while (0)
+    for (;;) {
+        if (strstart >= stop && strstart < n) break;
+        // fill_window: slide and read ahead exactly as zlib does when all input is available
+        if (read - strstart < DFL_MAX_MATCH + DFL_MIN_MATCH + 1) {
+            for (;;) {
+                uint32_t more = 2 * DFL_WSIZE - (read - base);
+                if (strstart - base >= DFL_WSIZE + DFL_MAX_DIST) { base += DFL_WSIZE; more += DFL_WSIZE; }
+                if (read == n) break;
+                read += tmin(n - read, more);
+                if (!(read - strstart < DFL_MAX_MATCH + DFL_MIN_MATCH + 1 && read != n)) break;
+            }
+            if (read == strstart) { done = true; break; }
+        }
+        const uint32_t prev_length = match_length, prev_match = match_start;
+        match_length = DFL_MIN_MATCH - 1;
+        if (prev_length < (uint32_t)c.max_lazy) {
+            uint32_t f;
+            if (base != dfl_window_base(strstart)) {
+                // end of input: zlib slid the window one position early; the tables assume the regular schedule
+                uint32_t q;
+                f = dfl_longest(d, strstart, base, (uint32_t)c.max_chain, (uint32_t)c.nice_length, 0xffffffffu, &q);
+                if (prev_length >= (uint32_t)c.good_length) f = q;
+            } else {
+                f = dfl_f_at(fv, strstart);
+                if (prev_length >= (uint32_t)c.good_length && (f & DFL_QDIFF)) {  // quartered chain: second table or on demand
+                    if (fv.qx) f = dfl_q_at(fv, strstart);
+                    else dfl_longest(d, strstart, base, (uint32_t)c.max_chain, (uint32_t)c.nice_length, 0xffffffffu, &f);
+                }
+                f &= ~DFL_QDIFF;
+            }
+            const uint32_t len = f >> 16, dist = f & 0xffff;
+            if (len > prev_length) {
+                match_length = len; match_start = strstart - dist;
+                if (len == DFL_MIN_MATCH && dist > DFL_TOO_FAR) match_length = DFL_MIN_MATCH - 1;
+            }
+            // otherwise zlib's longest_match returns prev_length (or no search happens): either way the branch
+            // below is taken exactly as with MIN_MATCH-1
+        }
+        if (prev_length >= DFL_MIN_MATCH && match_length <= prev_length) {
+            lfreq[(dfl_length_code(prev_length - DFL_MIN_MATCH) + 257) * lstride]++;
+            dfreq[dfl_dist_code(strstart - 1 - prev_match - 1) * dstride]++;
+            const bool bflush = ++sym_count == DFL_SYMS_PER_BLOCK;
+            strstart += prev_length - 1;
+            match_available = 0;
+            match_length = DFL_MIN_MATCH - 1;
+            if (bflush) DFL_FLUSH(false);
+        } else if (match_available) {
+            lfreq[ld8(s, strstart - 1) * lstride]++;
+            const bool bflush = ++sym_count == DFL_SYMS_PER_BLOCK;
+            if (bflush) DFL_FLUSH(false);
+            strstart++;
+        } else {
+            match_available = 1;
+            strstart++;
+        }
+    }
+    if (done) {
+        if (match_available) { lfreq[ld8(s, strstart - 1) * lstride]++; ++sym_count; match_available = 0; }
+        DFL_FLUSH(true);
+    }
+#undef DFL_FLUSH
+    st.strstart = strstart; st.match_start = match_start; st.match_length = match_length;
+    st.match_available = match_available; st.sym_count = sym_count; st.block_start = block_start; st.bits = bits;
+    st.base = base; st.read = read;
+    return done;
+}
+
+
+// resume a pair stream from the checkpoint of its x (taken at the first loop top >= jx0 of x alone)
+SNACC_HD void dfl_resume(DflParseState &st, uint32_t n)
+{
+    // zlib has always read up to base + 64 KiB (or everything); x alone had stopped at its own end
+    const uint64_t want = (uint64_t)st.base + 2 * DFL_WSIZE;
+    st.read = want < n ? (uint32_t)want : n;
+}
+SNACC_HD uint32_t dfl_jx0(uint32_t lx) { return lx > DFL_JX ? lx - DFL_JX : 0; }
+SNACC_HD uint32_t dfl_jlen(uint32_t lx, uint32_t ly) { return (lx - dfl_jx0(lx)) + tmin(ly, DFL_JY); }
+constexpr uint32_t DFL_JSTRIDE = DFL_JX + DFL_JY;
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+struct DflCorpus {
+    const uint8_t *corpus; const uint64_t *off; const uint32_t *len;   // padded byte corpus (api.cu)
+    const uint64_t *poff;        // per sequence: offset of its slice in `order` / F arrays
+    uint32_t *order;             // all sequences
+    uint32_t *bstart;            // per sequence DFL_HASH + 1 entries
+};
+
+SNACC_HD Stream dfl_make_stream(const DflCorpus &c, int32_t x, int32_t y)
+{
+    Stream s;
+    s.x = c.corpus + c.off[x];
+    s.lx = c.len[x];
+    if (y >= 0) { s.y = c.corpus + c.off[y]; s.n = s.lx + c.len[y]; }
+    else        { s.y = s.x + s.lx;          s.n = s.lx; }
+    return s;
+}
+__device__ __forceinline__ DflStream dfl_make(const DflCorpus &c, int32_t x, int32_t y)
+{
+    DflStream d;
+    d.s = dfl_make_stream(c, x, y);
+    d.pair = y >= 0;
+    d.ix.order = c.order + c.poff[x]; d.ix.bstart = c.bstart + (size_t)x * (DFL_HASH + 1);
+    if (y >= 0) { d.iy.order = c.order + c.poff[y]; d.iy.bstart = c.bstart + (size_t)y * (DFL_HASH + 1); }
+    else d.iy = d.ix;
+    return d;
+}
+
+// K3a: index of one sequence per CTA (one warp): counting sort of its positions by hash, stable.
+// tmp: per position scratch (the F slice is used) receiving the rank inside the bucket.
+__global__ void __launch_bounds__(32)
+dfl_index_kernel(DflCorpus c, const int32_t *__restrict__ seqs, int32_t n_seqs, uint32_t *__restrict__ tmp)
+{
+    extern __shared__ uint32_t cnt[];                    // DFL_HASH counters
+    const uint32_t lane = threadIdx.x;
+    for (int32_t t = blockIdx.x; t < n_seqs; t += gridDim.x) {
+        const int32_t sq = seqs[t];
+        const uint8_t *p = c.corpus + c.off[sq];
+        const uint32_t len = c.len[sq];
+        const uint32_t nidx = len >= 3 ? len - 2 : 0;    // positions with 3 bytes left are inserted
+        uint32_t *rank = tmp + c.poff[sq];
+        uint32_t *order = c.order + c.poff[sq];
+        uint32_t *bstart = c.bstart + (size_t)sq * (DFL_HASH + 1);
+        for (uint32_t i = lane; i < DFL_HASH; i += 32) cnt[i] = 0;
+        __syncwarp();
+        for (uint32_t base = 0; base < nidx; base += 32) {
+            const uint32_t i = base + lane;
+            const bool ok = i < nidx;
+            const uint32_t h = ok ? dfl_hash3(p[i], p[i + 1], p[i + 2]) : 0xffffffffu - lane;
+            const uint32_t peers = __match_any_sync(0xffffffffu, h);
+            if (ok) {
+                const uint32_t before = __popc(peers & ((1u << lane) - 1));
+                rank[i] = cnt[h] + before;
+            }
+            __syncwarp();
+            if (ok && (peers >> lane) <= 1u) cnt[h] += __popc(peers);   // highest lane of the group updates
+            __syncwarp();
+        }
+        // exclusive scan of the counters -> bucket starts
+        uint32_t carry = 0;
+        for (uint32_t b0 = 0; b0 < DFL_HASH; b0 += 32) {
+            const uint32_t v = cnt[b0 + lane];
+            uint32_t inc = v;
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if ((int)lane >= o) inc += u; }
+            const uint32_t ex = carry + inc - v;
+            bstart[b0 + lane] = ex;
+            cnt[b0 + lane] = ex;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) bstart[DFL_HASH] = carry;
+        __syncwarp();
+        for (uint32_t i = lane; i < nidx; i += 32) {
+            const uint32_t h = dfl_hash3(p[i], p[i + 1], p[i + 2]);
+            order[cnt[h] + rank[i]] = i;
+        }
+        __syncwarp();
+    }
+}
+
+// K3b: F of every position of the listed sequences (each alone); thread per index entry so that the
+// threads of a warp walk overlapping slices of the same bucket
+__global__ void __launch_bounds__(256)
+dfl_match_kernel(DflCorpus c, const int32_t *__restrict__ seqs, int32_t n_seqs, int level, uint32_t *__restrict__ F,
+                 uint32_t *__restrict__ FQ)
+{
+    const DflConfig cfg = dfl_config(level);
+    for (int32_t t = blockIdx.y; t < n_seqs; t += gridDim.y) {
+        const int32_t sq = seqs[t];
+        const DflStream d = dfl_make(c, sq, -1);
+        const uint32_t len = d.s.n;
+        const uint32_t nidx = len >= 3 ? len - 2 : 0;
+        uint32_t *f = F + c.poff[sq];
+        uint32_t *fq = FQ ? FQ + c.poff[sq] : nullptr;
+        for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < len; k += gridDim.x * blockDim.x) {
+            if (k >= nidx) { f[k] = 0; if (fq) fq[k] = 0; continue; }       // the last two positions: no string, no search
+            const uint32_t p = d.ix.order[k];
+            uint32_t q;
+            f[p] = dfl_f_word(d, p, cfg, k, &q);
+            if (fq) fq[p] = q;
+        }
+    }
+}
+
+struct DflPair { int32_t x, y; };
+
+// K3c: junction F of a batch of pair streams: positions [jx0, lx + min(ly, DFL_JY))
+__global__ void __launch_bounds__(256)
+dfl_junction_kernel(DflCorpus c, const DflPair *__restrict__ pairs, int32_t n_pairs, int level, uint32_t *__restrict__ FJ,
+                    uint32_t *__restrict__ FJQ)
+{
+    const DflConfig cfg = dfl_config(level);
+    for (int32_t b = blockIdx.y; b < n_pairs; b += gridDim.y) {
+        const DflStream d = dfl_make(c, pairs[b].x, pairs[b].y);
+        const uint32_t lx = d.s.lx, jx0 = dfl_jx0(lx), jlen = dfl_jlen(lx, d.s.n - lx);
+        uint32_t *f = FJ + (size_t)b * DFL_JSTRIDE;
+        uint32_t *fq = FJQ ? FJQ + (size_t)b * DFL_JSTRIDE : nullptr;
+        for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < jlen; u += gridDim.x * blockDim.x) {
+            uint32_t q;
+            f[u] = dfl_f_word(d, jx0 + u, cfg, 0xffffffffu, &q);
+            if (fq) fq[u] = q;
+        }
+    }
+}
+
+// K3d: the serial parse, one stream per thread.  kind 0: sequence alone -> size; kind 1: x alone up to its
+// junction -> checkpoint; kind 2: pair stream resumed from the checkpoint of x -> size.
+struct DflCkpt {
+    DflParseState st;
+    uint16_t lfreq[DFL_L_CODES];
+    uint16_t dfreq[DFL_D_CODES];
+};
+struct DflJob { int32_t x, y, kind, fj; int64_t out; };     // fj: slot of the pair in the junction batch
+
+constexpr int DFL_PARSE_THREADS = 64;
+
+__global__ void __launch_bounds__(DFL_PARSE_THREADS)
+dfl_parse_kernel(DflCorpus c, const DflJob *__restrict__ jobs, int64_t n_jobs, int level, const uint32_t *__restrict__ F,
+                 const uint32_t *__restrict__ FQ, const uint32_t *__restrict__ FJ, const uint32_t *__restrict__ FJQ,
+                 DflCkpt *__restrict__ ckpt, DflTrees *__restrict__ scratch,
+                 unsigned long long *__restrict__ counter, int64_t *__restrict__ out)
+{
+    __shared__ uint16_t s_l[DFL_L_CODES * DFL_PARSE_THREADS];
+    __shared__ uint16_t s_d[DFL_D_CODES * DFL_PARSE_THREADS];
+    const DflConfig cfg = dfl_config(level);
+    const int T = DFL_PARSE_THREADS, tid = threadIdx.x;
+    uint16_t *lf = s_l + tid, *df = s_d + tid;
+    DflTrees &tr = scratch[(size_t)blockIdx.x * T + tid];
+    for (;;) {
+        const long long j = (long long)atomicAdd(counter, 1ull);
+        if (j >= n_jobs) break;
+        const DflJob jb = jobs[j];
+        const DflStream d = dfl_make(c, jb.x, jb.kind == 2 ? jb.y : -1);
+        const uint32_t lx = d.s.lx;
+        DflFView fv;
+        fv.fx = F + c.poff[jb.x]; fv.lx = lx;
+        fv.qx = FQ ? FQ + c.poff[jb.x] : nullptr; fv.qy = fv.qj = fv.qx;
+        DflParseState st;
+        if (jb.kind == 2) {
+            fv.fy = F + c.poff[jb.y];
+            fv.fj = FJ + (size_t)jb.fj * DFL_JSTRIDE;
+            if (FQ) { fv.qy = FQ + c.poff[jb.y]; fv.qj = FJQ + (size_t)jb.fj * DFL_JSTRIDE; }
+            fv.jx0 = dfl_jx0(lx); fv.jend = fv.jx0 + dfl_jlen(lx, d.s.n - lx);
+            const DflCkpt &ck = ckpt[jb.x];
+            st = ck.st;
+            dfl_resume(st, d.s.n);
+            for (int k = 0; k < DFL_L_CODES; ++k) lf[k * T] = ck.lfreq[k];
+            for (int k = 0; k < DFL_D_CODES; ++k) df[k * T] = ck.dfreq[k];
+        } else {
+            fv.fy = fv.fj = fv.fx; fv.jx0 = fv.jend = lx;     // everything from F of the sequence
+            dfl_parse_fresh(st);
+            for (int k = 0; k < DFL_L_CODES; ++k) lf[k * T] = 0;
+            for (int k = 0; k < DFL_D_CODES; ++k) df[k * T] = 0;
+            lf[256 * T] = 1;
+        }
+        const uint32_t stop = jb.kind == 1 ? dfl_jx0(lx) : 0xffffffffu;
+        dfl_parse(d, fv, cfg, st, lf, T, df, T, tr, stop);
+        if (jb.kind == 1) {
+            DflCkpt &ck = ckpt[jb.x];
+            ck.st = st;
+            for (int k = 0; k < DFL_L_CODES; ++k) ck.lfreq[k] = lf[k * T];
+            for (int k = 0; k < DFL_D_CODES; ++k) ck.dfreq[k] = df[k * T];
+        } else {
+            out[jb.out] = (int64_t)(st.bits >> 3);
+        }
+    }
+}
+#endif  // __CUDACC__
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------------------------------------
+// host-side orchestration (called from api.cu with the context lock held)
+// ------------------------------------------------------------------------------------------------
 struct DeflateCorpus {
     const uint8_t *d_corpus; const uint64_t *d_off; const uint32_t *d_len;
     const uint64_t *h_off; const uint32_t *h_len; int32_t n_seqs;
 };
-struct DeflateState { int dummy = 0; };
 
-static inline void deflate_free_corpus(DeflateState &) {}
-static inline void deflate_free_work(DeflateState &) {}
-static inline void deflate_invalidate(DeflateState &) {}
-static inline int deflate_run(DeflateState &, const DeflateCorpus &, int, const int32_t *, const int32_t *,
-                              const int32_t *, const int32_t *, int64_t, int64_t *, cudaStream_t, int64_t,
-                              int64_t *, std::string &err)
+struct DeflateState {
+    // per-corpus
+    uint64_t *d_poff = nullptr; std::vector<uint64_t> h_poff; uint64_t total = 0;
+    uint32_t *d_order = nullptr, *d_bstart = nullptr;
+    std::vector<uint8_t> indexed;                  // per sequence
+    uint32_t *d_F[2] = {nullptr, nullptr};         // level 9, level 6
+    uint32_t *d_FQ = nullptr, *d_FJQ = nullptr;    // level 6 only: quartered-chain tables
+    std::vector<uint8_t> have_F[2], have_ck[2];
+    DflCkpt *d_ckpt[2] = {nullptr, nullptr};
+    int32_t n_seqs = 0;
+    // working memory
+    DflTrees *d_scratch = nullptr; size_t scratch_n = 0;
+    uint32_t *d_FJ = nullptr; size_t fj_pairs = 0;
+    double main_ms = 0.0;
+};
+
+static inline void deflate_free_corpus(DeflateState &st)
 {
-    err = "deflate codecs are not built into this library yet";
-    return -4;
+    cudaFree(st.d_poff); cudaFree(st.d_order); cudaFree(st.d_bstart);
+    cudaFree(st.d_FQ); st.d_FQ = nullptr;
+    for (int l = 0; l < 2; ++l) { cudaFree(st.d_F[l]); cudaFree(st.d_ckpt[l]); st.d_F[l] = nullptr; st.d_ckpt[l] = nullptr;
+                                  st.have_F[l].clear(); st.have_ck[l].clear(); }
+    st.d_poff = nullptr; st.d_order = nullptr; st.d_bstart = nullptr; st.indexed.clear(); st.h_poff.clear();
+    st.n_seqs = 0; st.total = 0;
 }
+static inline void deflate_free_work(DeflateState &st)
+{
+    cudaFree(st.d_scratch); cudaFree(st.d_FJ); cudaFree(st.d_FJQ);
+    st.d_scratch = nullptr; st.d_FJ = nullptr; st.d_FJQ = nullptr; st.scratch_n = 0; st.fj_pairs = 0;
+}
+static inline void deflate_invalidate(DeflateState &st)
+{
+    std::fill(st.indexed.begin(), st.indexed.end(), 0);
+    for (int l = 0; l < 2; ++l) {
+        std::fill(st.have_F[l].begin(), st.have_F[l].end(), 0);
+        std::fill(st.have_ck[l].begin(), st.have_ck[l].end(), 0);
+    }
+}
+
+#define DCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+        char b_[512]; snprintf(b_, sizeof b_, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+        err = b_; return -1; } } while (0)
+
+template <typename T> static int dfl_upload(std::string &err, cudaStream_t stream, const std::vector<T> &h, T **d)
+{
+    *d = nullptr;
+    if (h.empty()) return 0;
+    DCK(cudaMalloc(d, sizeof(T) * h.size()));
+    DCK(cudaMemcpyAsync(*d, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, stream));
+    return 0;
+}
+
+// sizes of the raw deflate streams of the jobs (x alone when ys == nullptr) into d_out[0..n_jobs)
+static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, const int32_t *xs, const int32_t *ys,
+                       const int32_t *, const int32_t *, int64_t n_jobs, int64_t *d_out, cudaStream_t stream,
+                       int64_t, int64_t *launches, std::string &err)
+{
+    const int li = level == 9 ? 0 : 1;
+    const int32_t ns = dc.n_seqs;
+    if (st.n_seqs != ns || !st.d_poff) {
+        deflate_free_corpus(st);
+        st.n_seqs = ns;
+        st.h_poff.assign(ns, 0);
+        uint64_t t = 0;
+        for (int32_t i = 0; i < ns; ++i) { st.h_poff[i] = t; t += ((uint64_t)dc.h_len[i] + 3) & ~3ull; }
+        st.total = t;
+        DCK(cudaMalloc(&st.d_poff, sizeof(uint64_t) * ns));
+        DCK(cudaMemcpyAsync(st.d_poff, st.h_poff.data(), sizeof(uint64_t) * ns, cudaMemcpyHostToDevice, stream));
+        DCK(cudaMalloc(&st.d_order, sizeof(uint32_t) * (t + 4)));
+        DCK(cudaMalloc(&st.d_bstart, sizeof(uint32_t) * (size_t)ns * (DFL_HASH + 1)));
+        st.indexed.assign(ns, 0);
+        for (int l = 0; l < 2; ++l) { st.have_F[l].assign(ns, 0); st.have_ck[l].assign(ns, 0); }
+    }
+    if (!st.d_F[li]) {
+        DCK(cudaMalloc(&st.d_F[li], sizeof(uint32_t) * (st.total + 4)));
+        DCK(cudaMalloc(&st.d_ckpt[li], sizeof(DflCkpt) * ns));
+        if (level != 9) DCK(cudaMalloc(&st.d_FQ, sizeof(uint32_t) * (st.total + 4)));
+    }
+    uint32_t *FQ = level != 9 ? st.d_FQ : nullptr;
+    DflCorpus c{dc.d_corpus, dc.d_off, dc.d_len, st.d_poff, st.d_order, st.d_bstart};
+
+    // ---- per-sequence state the jobs need: index, F (this level), checkpoint of every x of a pair ----
+    std::vector<int32_t> need_idx, need_f, need_ck;
+    {
+        std::vector<uint8_t> used(ns, 0), isx(ns, 0);
+        for (int64_t k = 0; k < n_jobs; ++k) { used[xs[k]] = 1; if (ys) { used[ys[k]] = 1; isx[xs[k]] = 1; } }
+        for (int32_t i = 0; i < ns; ++i) {
+            if (!used[i]) continue;
+            if (!st.indexed[i]) { need_idx.push_back(i); st.indexed[i] = 1; st.have_F[0][i] = st.have_F[1][i] = 0; }
+            if (!st.have_F[li][i]) { need_f.push_back(i); st.have_F[li][i] = 1; st.have_ck[li][i] = 0; }
+            if (isx[i] && !st.have_ck[li][i]) { need_ck.push_back(i); st.have_ck[li][i] = 1; }
+        }
+    }
+    uint32_t max_len = 0;
+    for (int32_t i : need_f) max_len = std::max(max_len, dc.h_len[i]);
+    if (!need_idx.empty()) {
+        int32_t *d_list = nullptr;
+        if (dfl_upload(err, stream, need_idx, &d_list)) return -1;
+        DCK(cudaFuncSetAttribute(dfl_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DFL_HASH * 4)));
+        // the F slice of this level doubles as rank scratch; it is recomputed right below
+        dfl_index_kernel<<<(unsigned)std::min<size_t>(need_idx.size(), 148 * 4), 32, DFL_HASH * 4, stream>>>(
+            c, d_list, (int32_t)need_idx.size(), st.d_F[li]);
+        DCK(cudaGetLastError());
+        ++*launches;
+        DCK(cudaStreamSynchronize(stream));
+        cudaFree(d_list);
+    }
+    if (!need_f.empty()) {
+        int32_t *d_list = nullptr;
+        if (dfl_upload(err, stream, need_f, &d_list)) return -1;
+        dim3 grid(std::max(1u, std::min((max_len + 255) / 256, 4096u)), (unsigned)std::min<size_t>(need_f.size(), 64));
+        dfl_match_kernel<<<grid, 256, 0, stream>>>(c, d_list, (int32_t)need_f.size(), level, st.d_F[li], FQ);
+        DCK(cudaGetLastError());
+        ++*launches;
+        DCK(cudaStreamSynchronize(stream));
+        cudaFree(d_list);
+    }
+    // ---- parse jobs ----
+    const int parse_blocks = 148 * 4;
+    if (st.scratch_n < (size_t)parse_blocks * DFL_PARSE_THREADS) {
+        cudaFree(st.d_scratch); st.d_scratch = nullptr;
+        st.scratch_n = (size_t)parse_blocks * DFL_PARSE_THREADS;
+        DCK(cudaMalloc(&st.d_scratch, sizeof(DflTrees) * st.scratch_n));
+    }
+    unsigned long long *d_counter = nullptr;
+    DCK(cudaMalloc(&d_counter, sizeof(unsigned long long)));
+    auto run_parse = [&](const std::vector<DflJob> &jobs) -> int {
+        if (jobs.empty()) return 0;
+        DflJob *d_jobs = nullptr;
+        if (dfl_upload(err, stream, jobs, &d_jobs)) return -1;
+        DCK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream));
+        const int blocks = (int)std::min<size_t>((jobs.size() + DFL_PARSE_THREADS - 1) / DFL_PARSE_THREADS, parse_blocks);
+        dfl_parse_kernel<<<blocks, DFL_PARSE_THREADS, 0, stream>>>(c, d_jobs, (int64_t)jobs.size(), level, st.d_F[li], FQ, st.d_FJ,
+                                                                  FQ ? st.d_FJQ : nullptr, st.d_ckpt[li], st.d_scratch, d_counter, d_out);
+        DCK(cudaGetLastError());
+        ++*launches;
+        DCK(cudaStreamSynchronize(stream));
+        cudaFree(d_jobs);
+        return 0;
+    };
+    int rc = 0;
+    if (!ys) {
+        std::vector<DflJob> jobs((size_t)n_jobs);
+        for (int64_t k = 0; k < n_jobs; ++k) jobs[k] = DflJob{xs[k], -1, 0, 0, k};
+        rc = run_parse(jobs);
+    } else {
+        std::vector<DflJob> jobs;
+        for (int32_t i : need_ck) jobs.push_back(DflJob{i, -1, 1, 0, 0});
+        rc = run_parse(jobs);
+        // pairs in batches: junction F of the batch, then its parses
+        const size_t batch = 2048;
+        if (!rc && st.fj_pairs < batch) {
+            cudaFree(st.d_FJ); st.d_FJ = nullptr;
+            st.fj_pairs = batch;
+            DCK(cudaMalloc(&st.d_FJ, sizeof(uint32_t) * batch * DFL_JSTRIDE));
+        }
+        if (!rc && FQ && !st.d_FJQ) DCK(cudaMalloc(&st.d_FJQ, sizeof(uint32_t) * batch * DFL_JSTRIDE));
+        for (int64_t b0 = 0; !rc && b0 < n_jobs; b0 += (int64_t)batch) {
+            const int64_t nb = std::min<int64_t>((int64_t)batch, n_jobs - b0);
+            std::vector<DflPair> pairs((size_t)nb);
+            jobs.assign((size_t)nb, DflJob());
+            for (int64_t k = 0; k < nb; ++k) {
+                pairs[k] = DflPair{xs[b0 + k], ys[b0 + k]};
+                jobs[k] = DflJob{xs[b0 + k], ys[b0 + k], 2, (int32_t)k, b0 + k};
+            }
+            DflPair *d_pairs = nullptr;
+            if (dfl_upload(err, stream, pairs, &d_pairs)) { rc = -1; break; }
+            dim3 grid((DFL_JSTRIDE + 255) / 256, (unsigned)std::min<int64_t>(nb, 4096));
+            dfl_junction_kernel<<<grid, 256, 0, stream>>>(c, d_pairs, (int32_t)nb, level, st.d_FJ, FQ ? st.d_FJQ : nullptr);
+            if (cudaGetLastError() != cudaSuccess) { err = "dfl_junction_kernel launch failed"; rc = -1; }
+            ++*launches;
+            if (!rc) rc = run_parse(jobs);
+            cudaFree(d_pairs);
+        }
+    }
+    cudaFree(d_counter);
+    return rc;
+}
+#undef DCK
+#endif  // __CUDACC__
 
 }  // namespace snacc

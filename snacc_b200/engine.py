@@ -126,6 +126,8 @@ class Engine:
         so[1:] = np.cumsum([a.size for a in arrs])
         data = np.concatenate(arrs) if arrs else np.zeros(0, np.uint8)
         ro = None
+        if records is None and reverse_complement:
+            records = [[a.size] for a in arrs]          # one record per sequence
         if records is not None:
             flat = [l for rl in records for l in rl]
             ro = np.zeros(len(flat) + 1, dtype=np.uint64)

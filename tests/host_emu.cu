@@ -165,3 +165,75 @@ extern "C" void emu_pk_counts(uint64_t *lean, uint64_t *general, uint64_t *turbo
     *lean = pk_lean_steps; *general = pk_general_steps; *turbo = pk_turbo_steps;
     if (reset) pk_lean_steps = pk_general_steps = pk_turbo_steps = 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// deflate path: the same index / F table / junction / checkpoint / parse logic the kernels run
+// ---------------------------------------------------------------------------------------------
+#include "../snacc_b200/csrc/deflate.cuh"
+
+struct EmuIndex { std::vector<uint32_t> order, bstart; };
+static EmuIndex emu_index(const uint8_t *p, uint32_t len)
+{
+    EmuIndex ix; ix.bstart.assign(DFL_HASH + 1, 0);
+    const uint32_t nidx = len >= 3 ? len - 2 : 0;
+    ix.order.assign(nidx + 4, 0);
+    std::vector<uint32_t> cnt(DFL_HASH, 0);
+    for (uint32_t i = 0; i < nidx; ++i) cnt[dfl_hash3(p[i], p[i + 1], p[i + 2])]++;
+    uint32_t acc = 0;
+    for (uint32_t h = 0; h < DFL_HASH; ++h) { ix.bstart[h] = acc; acc += cnt[h]; cnt[h] = ix.bstart[h]; }
+    ix.bstart[DFL_HASH] = acc;
+    for (uint32_t i = 0; i < nidx; ++i) ix.order[cnt[dfl_hash3(p[i], p[i + 1], p[i + 2])]++] = i;
+    return ix;
+}
+
+static std::vector<uint32_t> emu_F_single(const DflStream &d, const DflConfig &cfg)
+{
+    std::vector<uint32_t> F(d.s.n + 4, 0);
+    const uint32_t nidx = d.s.n >= 3 ? d.s.n - 2 : 0;
+    for (uint32_t k = 0; k < nidx; ++k) { const uint32_t p = d.ix.order[k]; F[p] = dfl_f_word(d, p, cfg, k, nullptr); }
+    return F;
+}
+
+// returns the raw deflate size of x (ly < 0) or of x followed by y
+extern "C" int64_t emu_deflate_size(const uint8_t *x, uint32_t lx, const uint8_t *y, int64_t ly_, int level)
+{
+    const DflConfig cfg = dfl_config(level);
+    uint8_t *px = padded_copy(x, lx);
+    uint8_t *py = ly_ >= 0 ? padded_copy(y, (uint64_t)ly_) : nullptr;
+    EmuIndex ix = emu_index(px, lx), iy;
+    if (ly_ >= 0) iy = emu_index(py, (uint32_t)ly_);
+    DflTrees *tr = new DflTrees();
+    std::vector<uint16_t> lf(DFL_L_CODES, 0), df(DFL_D_CODES, 0);
+    // x alone
+    DflStream dx; dx.s.x = px; dx.s.lx = lx; dx.s.y = px + lx; dx.s.n = lx; dx.pair = false;
+    dx.ix.order = ix.order.data(); dx.ix.bstart = ix.bstart.data(); dx.iy = dx.ix;
+    std::vector<uint32_t> Fx = emu_F_single(dx, cfg);
+    DflFView fv; fv.fx = fv.fy = fv.fj = Fx.data(); fv.jx0 = fv.jend = fv.lx = lx; fv.qx = fv.qy = fv.qj = nullptr;
+    DflParseState st;
+    int64_t result;
+    if (ly_ < 0) {
+        dfl_parse_fresh(st); lf[256] = 1;
+        dfl_parse(dx, fv, cfg, st, lf.data(), 1, df.data(), 1, *tr, 0xffffffffu);
+        result = (int64_t)(st.bits >> 3);
+    } else {
+        const uint32_t ly = (uint32_t)ly_;
+        // checkpoint of x: parse x alone up to its junction
+        dfl_parse_fresh(st); lf[256] = 1;
+        dfl_parse(dx, fv, cfg, st, lf.data(), 1, df.data(), 1, *tr, dfl_jx0(lx));
+        // y alone
+        DflStream dy; dy.s.x = py; dy.s.lx = ly; dy.s.y = py + ly; dy.s.n = ly; dy.pair = false;
+        dy.ix.order = iy.order.data(); dy.ix.bstart = iy.bstart.data(); dy.iy = dy.ix;
+        std::vector<uint32_t> Fy = emu_F_single(dy, cfg);
+        // pair stream: junction F, then resume
+        DflStream d; d.s.x = px; d.s.lx = lx; d.s.y = py; d.s.n = lx + ly; d.pair = true; d.ix = dx.ix; d.iy = dy.ix;
+        const uint32_t jx0 = dfl_jx0(lx), jlen = dfl_jlen(lx, ly);
+        std::vector<uint32_t> FJ(jlen + 4, 0);
+        for (uint32_t u = 0; u < jlen; ++u) FJ[u] = dfl_f_word(d, jx0 + u, cfg, 0xffffffffu, nullptr);
+        fv.fx = Fx.data(); fv.fy = Fy.data(); fv.fj = FJ.data(); fv.jx0 = jx0; fv.jend = jx0 + jlen; fv.lx = lx;
+        dfl_resume(st, d.s.n);
+        dfl_parse(d, fv, cfg, st, lf.data(), 1, df.data(), 1, *tr, 0xffffffffu);
+        result = (int64_t)(st.bits >> 3);
+    }
+    delete tr; free(px); free(py);
+    return result;
+}

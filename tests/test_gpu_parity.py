@@ -14,7 +14,7 @@ from oracle.make_golden import VECTOR_KINDS, synth_vector
 
 pytestmark = pytest.mark.gpu
 
-ALGOS = ["lz4", "gzip"]
+ALGOS = ["lz4", "gzip", "zlib"]
 
 
 def _ref_len(data, algo):
@@ -153,3 +153,38 @@ def test_full_size_genomes_lz4(engine):
     assert engine.single_sizes("lz4")[0] == ref[0, 1]
     D = engine.ncd(C[:3], S[:, :3])
     assert np.array_equal(D, snacc_oracle.ncd_from_sizes(C[:3], S[:, :3]))
+
+
+def test_packed_and_bytewise_lz4_paths_agree(engine):
+    """the 2-bit tile kernels and the byte-wise kernels are two independent implementations of the same
+    frame size; mixed corpus (a sequence with N falls back to the byte-wise path inside the same call)"""
+    from snacc_b200 import synth
+    g = synth.phylogeny(12, 150000, seed=9) + [synth_vector("nrun", 90000, 5)]
+    engine.upload_sequences(g)
+    n = len(g)
+    S = engine.tile_sizes("lz4", 0, n, 0, n)
+    assert engine.stat("packed_jobs") == 144 and engine.stat("bytewise_jobs") == n * n - 144
+    engine.set_option("lz4_packed", 0)
+    try:
+        S2 = engine.tile_sizes("lz4", 0, n, 0, n)
+    finally:
+        engine.set_option("lz4_packed", 1)
+    assert np.array_equal(S, S2)
+    chk = np.random.default_rng(1).integers(0, n, size=(40, 2))
+    for i, j in chk:
+        assert S[i, j] == olib.ref_lz4f_size(np.concatenate([g[i], g[j]]))
+
+
+def test_megabase_genomes_gzip(engine):
+    """c2 shape (scaled to 1.2 Mbp so that zlib finishes in seconds): all singles, a tile of pairs, warm caches"""
+    from snacc_b200 import synth
+    g = synth.phylogeny(4, 1_200_000, seed=6, n_indels=2)
+    engine.upload_sequences(g)
+    C = engine.single_sizes("gzip")
+    assert np.array_equal(C, np.array([_ref_len(s, "gzip") for s in g]))
+    S = engine.tile_sizes("gzip", 0, 2, 0, 4)
+    ref = np.array([[_ref_len(np.concatenate([g[i], g[j]]), "gzip") for j in range(4)] for i in range(2)])
+    assert np.array_equal(S, ref)
+    assert np.array_equal(engine.tile_sizes("gzip", 0, 2, 0, 4), ref)          # checkpoints and tables reused
+    engine.set_option("invalidate_caches", 1)
+    assert np.array_equal(engine.tile_sizes("gzip", 0, 2, 0, 4), ref)          # and rebuilt

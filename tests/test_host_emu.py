@@ -21,11 +21,15 @@ def emu():
     src = os.path.join(HERE, "host_emu.cu")
     deps = [src] + _build.HEADERS
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-        subprocess.check_call([_build._nvcc(), "-O2", "-std=c++17", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC",
+        subprocess.check_call([_build._nvcc(), "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
                                "-shared", "-o", so, src])
     e = ctypes.CDLL(so)
     e.emu_lz4_size.restype = ctypes.c_int64
     e.emu_lz4_size.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int64]
+    e.emu_lz4_packed.restype = ctypes.c_int64
+    e.emu_lz4_packed.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int64]
+    e.emu_deflate_size.restype = ctypes.c_int64
+    e.emu_deflate_size.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]
     return e
 
 
@@ -54,3 +58,121 @@ def test_lz4_related_genomes_cross_boundary_matches(emu):
     for a in g:
         for b in g:
             assert lz4_emu(emu, a, b) == lib.ref_lz4f_size(np.concatenate([a, b]))
+
+
+# ---- packed (2-bit) LZ4 tile-kernel logic: ring refills, global fallback, prefix checkpoints, turbo loop ----
+def _call2(fn, x, y, *extra):
+    x = np.ascontiguousarray(x, dtype=np.uint8)
+    if y is None:
+        return fn(x.ctypes.data, x.size, None, -1, *extra)
+    y = np.ascontiguousarray(y, dtype=np.uint8)
+    return fn(x.ctypes.data, x.size, y.ctypes.data, y.size, *extra)
+
+
+def _dna(n, seed, alphabet=b"ACGT", p=None):
+    return np.frombuffer(alphabet, dtype=np.uint8)[np.random.default_rng(seed).choice(len(alphabet), size=n, p=p)]
+
+
+def _four_symbol_vector(kind, n, seed):
+    if kind == "run":
+        return np.full(n, 65, np.uint8)
+    if kind == "period":
+        return np.frombuffer((b"ACGTTGCA" * (n // 8 + 1))[:n], dtype=np.uint8).copy()
+    if kind == "two":
+        return _dna(n, seed, b"AT")
+    if kind == "skew":
+        return _dna(n, seed, b"ACGT", [0.85, 0.05, 0.05, 0.05])
+    if kind == "lower":
+        return _dna(n, seed, b"acgt")
+    if kind == "repeat":
+        return np.tile(_dna(max(1, n // 7), seed), 8)[:n].copy()
+    if kind == "longrep":
+        u = _dna(max(1, n // 2 + 3), seed)
+        return np.concatenate([u, u])[:n].copy()
+    return _dna(n, seed)
+
+
+def test_lz4_packed_logic_regime_boundaries(emu):
+    bad = []
+    for lx in [1, 5, 12, 13, 20, 700, 11000, 40000, 65519, 65520, 65535, 65536, 65537, 65540, 70000, 131071, 131072, 131073,
+               150000, 300000]:
+        x = _dna(lx, lx)
+        if _call2(emu.emu_lz4_packed, x, None) != lib.lz4f_size(x):
+            bad.append(("single", lx))
+        for ly in [16, 17, 100, 9000, 25000, 65536, 80000, 200000]:
+            y = _dna(ly, ly + 3)
+            if _call2(emu.emu_lz4_packed, x, y) != lib.ref_lz4f_size(np.concatenate([x, y])):
+                bad.append(("pair", lx, ly))
+    assert not bad, bad[:10]
+
+
+@pytest.mark.parametrize("kind", ["run", "period", "two", "skew", "lower", "repeat", "longrep"])
+def test_lz4_packed_logic_adversarial_four_symbol_inputs(emu, kind):
+    bad = []
+    for lx in [1, 13, 300, 11000, 65535, 65536, 65537, 100000, 140000]:
+        x = _four_symbol_vector(kind, lx, lx)
+        if _call2(emu.emu_lz4_packed, x, None) != lib.ref_lz4f_size(x):
+            bad.append(("single", lx))
+        for ly in [16, 300, 30000, 65536, 100000]:
+            for k2 in (kind, "skew"):
+                y = _four_symbol_vector(k2, ly, ly + 5)
+                z = np.concatenate([x, y])
+                if len(set(z.tolist())) > 4:
+                    continue
+                if _call2(emu.emu_lz4_packed, x, y) != lib.ref_lz4f_size(z):
+                    bad.append(("pair", k2, lx, ly))
+        got = _call2(emu.emu_lz4_packed, x, x)
+        if got != lib.ref_lz4f_size(np.concatenate([x, x])) and not (lx < 16 and got == -1):
+            bad.append(("self", lx))
+    assert not bad, bad[:10]
+
+
+def test_lz4_packed_related_genomes(emu):
+    from snacc_b200 import synth
+    g = synth.phylogeny(4, 40000, seed=3) + synth.phylogeny(3, 200000, seed=4)
+    for a in g:
+        for b in g:
+            assert _call2(emu.emu_lz4_packed, a, b) == lib.ref_lz4f_size(np.concatenate([a, b]))
+
+
+def test_lz4_packed_refuses_more_than_four_symbols(emu):
+    assert _call2(emu.emu_lz4_packed, np.frombuffer(b"ACGTNACGTNACGTNACGT", dtype=np.uint8), None) == -2
+
+
+# ---- deflate: index + F tables + junction + x checkpoint + lazy parse + block cost, as the kernels do it ----
+@pytest.mark.parametrize("level", [9, 6])
+def test_deflate_logic_boundaries(emu, level):
+    bad = []
+    for lx in [1, 2, 3, 5, 100, 300, 5000, 32506, 32768, 65274, 65275, 65400, 70000]:
+        x = _dna(lx, lx)
+        if _call2(emu.emu_deflate_size, x, None, level) != lib.ref_deflate_size(x, level):
+            bad.append(("single", lx))
+        for ly in [1, 2, 3, 100, 5000, 33000]:
+            y = _dna(ly, ly + 1)
+            if _call2(emu.emu_deflate_size, x, y, level) != lib.ref_deflate_size(np.concatenate([x, y]), level):
+                bad.append(("pair", lx, ly))
+    assert not bad, bad[:10]
+
+
+@pytest.mark.parametrize("kind", VECTOR_KINDS)
+def test_deflate_logic_alphabets(emu, kind):
+    bad = []
+    for level in (9, 6):
+        for lx in [13, 300, 9000, 33000]:
+            x = synth_vector(kind, lx, lx + 1)
+            if _call2(emu.emu_deflate_size, x, None, level) != lib.ref_deflate_size(x, level):
+                bad.append(("single", level, lx))
+            for ly in [40, 9000, 34000]:
+                y = synth_vector(kind, ly, ly + 7)
+                if _call2(emu.emu_deflate_size, x, y, level) != lib.ref_deflate_size(np.concatenate([x, y]), level):
+                    bad.append(("pair", level, lx, ly))
+    assert not bad, bad[:10]
+
+
+def test_deflate_logic_related_genomes_long_matches_across_the_boundary(emu):
+    from snacc_b200 import synth
+    g = synth.phylogeny(3, 40000, seed=3)
+    for level in (9, 6):
+        for a in g:
+            for b in g:
+                assert _call2(emu.emu_deflate_size, a, b, level) == lib.ref_deflate_size(np.concatenate([a, b]), level)
