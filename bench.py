@@ -179,6 +179,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"                # keep NCCL's version banner off stdout: ONE JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 

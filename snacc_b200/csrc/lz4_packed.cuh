@@ -101,9 +101,10 @@ template <bool U16, int STRIDE> struct PkTab {
     static constexpr uint32_t K = U16 ? 4 : 5;
     static constexpr uint32_t MASK = U16 ? 0xffu : 0x3ffu;
     static constexpr uint32_t ENTRIES = MASK + 1;
+    static constexpr uint32_t ESZ = STRIDE * sizeof(T);   // bytes between two slots of one lane
     T *t;
-    const uint16_t *lut;
-    SNACC_HD uint32_t slot(uint32_t c) const { return (uint32_t)lut[c] * STRIDE; }
+    const uint16_t *lut;                                  // code -> BYTE offset of the slot (slot index * ESZ)
+    SNACC_HD uint32_t slot(uint32_t c) const { return (uint32_t)lut[c] / (uint32_t)sizeof(T); }
     SNACC_HD uint32_t get(uint32_t c) const { return t[slot(c)]; }
     SNACC_HD void put(uint32_t c, uint32_t pos) { t[slot(c)] = (T)pos; }
 };
@@ -346,8 +347,10 @@ __device__ __forceinline__ uint32_t pk_sel(bool c, uint32_t a, uint32_t b)
     asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\tselp.u32 %0, %1, %2, q;\n\t}" : "=r"(r) : "r"(a), "r"(b), "r"((uint32_t)c));
     return r;
 }
+__device__ __forceinline__ pk_sptr pk_opaque(pk_sptr a) { pk_sptr r; asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(a)); return r; }
 #else
 typedef uintptr_t pk_sptr;
+inline pk_sptr pk_opaque(pk_sptr a) { return a; }
 inline pk_sptr pk_sptr_of(const void *p) { return (pk_sptr)p; }
 inline uint32_t pk_lds32(pk_sptr a) { return *reinterpret_cast<const uint32_t *>(a); }
 inline uint32_t pk_lds16(pk_sptr a) { return *reinterpret_cast<const uint16_t *>(a); }
@@ -372,7 +375,6 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<U16, STRIDE> &tab, const PkView &v, ui
 {
     typedef typename PkTab<U16, STRIDE>::T T;
     constexpr uint32_t MASK = PkTab<U16, STRIDE>::MASK;
-    constexpr uint32_t ESZ = STRIDE * sizeof(T);            // bytes between two table entries of one lane
     constexpr uint32_t RMASK = (2 * PK_RING_WORDS - 1) * 4; // byte-offset mask of the ring seen as u32 words
     const uint32_t lx = v.lx, rlo = v.rlo, rspan = v.rspan;
     uint32_t p = st.phase == PK_SEARCH ? st.fip : st.ip;
@@ -383,10 +385,13 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<U16, STRIDE> &tab, const PkView &v, ui
     const bool ok0 = fin || (st.phase <= PK_RETEST && !(st.phase == PK_SEARCH && st.step != 1) &&
                              (uint32_t)(p - 4 - lx - rlo) <= rspan);
     if (!pk_all(mask, ok0) || pk_all(mask, fin)) return;
-    const pk_sptr ring_a = pk_sptr_of(v.ring), lut_a = pk_sptr_of(tab.lut), tab_a = pk_sptr_of(tab.t);
+    // (pk_opaque: keep the three base addresses in registers -- the compiler otherwise re-derives them from
+    // SR_CgaCtaId inside the loop)
+    const pk_sptr ring_a = pk_opaque(pk_sptr_of(v.ring)), lut_a = pk_opaque(pk_sptr_of(tab.lut)),
+                  tab_a = pk_opaque(pk_sptr_of(tab.t));
 #define PK_TLD(addr) (U16 ? pk_lds16(addr) : pk_lds32(addr))
 #define PK_TST(addr, val) do { if (U16) pk_sts16(addr, val); else pk_sts32(addr, val); } while (0)
-#define PK_SLOT(code) (tab_a + pk_lds16(lut_a + 2 * (code)) * ESZ)
+#define PK_SLOT(code) (tab_a + pk_lds16(lut_a + 2 * (code)))
     // 32 bases starting at y offset q, as two 32-bit halves (three consecutive ring words)
 #define PK_RING32(q, lo, hi) do { const uint32_t j_ = ((q) >> 4) * 4, s_ = ((q) & 15) * 2;                      \
         const uint32_t a_ = pk_lds32(ring_a + (j_ & RMASK)), b_ = pk_lds32(ring_a + ((j_ + 4) & RMASK)),       \
@@ -585,7 +590,7 @@ lz4_pk_pair_kernel(PkCorpus pc, const PkTile *__restrict__ tiles, int32_t n_tile
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t slot = warp * LANES + lane;
-    for (uint32_t i = threadIdx.x; i < Tab::ENTRIES; i += blockDim.x) lut[i] = lut_g[i];
+    for (uint32_t i = threadIdx.x; i < Tab::ENTRIES; i += blockDim.x) lut[i] = (uint16_t)(lut_g[i] * Tab::ESZ);
     Tab tab;
     tab.t = tabs + (size_t)warp * (Tab::ENTRIES * LANES) + lane;
     tab.lut = lut;
@@ -707,8 +712,8 @@ lz4_pk_single_kernel(PkCorpus pc, const int32_t *__restrict__ seqs, const int32_
     __shared__ uint32_t s_snap[1024];
     __shared__ uint16_t s_lut5[1024];
     __shared__ uint16_t s_lut4[256];
-    for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) s_lut5[i] = lut5_g[i];
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_lut4[i] = lut4_g[i];
+    for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) s_lut5[i] = (uint16_t)(lut5_g[i] * 4);   // byte offsets
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_lut4[i] = (uint16_t)(lut4_g[i] * 2);
     for (int32_t t = blockIdx.x; t < n_seqs; t += gridDim.x) {
         const int32_t s = seqs[t];
         const int32_t wn = want[t];

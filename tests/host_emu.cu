@@ -70,7 +70,9 @@ static bool emu_run(PkState &st, std::vector<uint32_t> &tab32, const uint16_t *a
                     uint32_t snap_bs, EmuCkpt *snap)
 {
     typedef PkTab<U16, 1> Tab;
-    Tab tab; tab.t = reinterpret_cast<typename Tab::T *>(tab32.data()); tab.lut = alias;
+    uint16_t lutb[1024];                                  // the kernels keep BYTE offsets in the shared-memory map
+    for (uint32_t i = 0; i < Tab::ENTRIES; ++i) lutb[i] = (uint16_t)(alias[i] * Tab::ESZ);
+    Tab tab; tab.t = reinterpret_cast<typename Tab::T *>(tab32.data()); tab.lut = lutb;
     for (;;) {
         rg.view(v);
         const uint32_t sq = rg.stop_q();
