@@ -52,6 +52,7 @@ struct snacc_ctx {
     uint32_t *d_ck_tab = nullptr; PkState *d_ck_state = nullptr;
     std::vector<uint8_t> h_packable, h_ck_have;   // per sequence; h_ck_have bit0: single-block regime, bit1: linked
     PkAlphabet alphabet;
+    uint32_t nslot5 = 1024;                // distinct hash buckets the 1024 5-mers of the alphabet reach
     int64_t last_packed_jobs = 0, last_bytewise_jobs = 0;
 
     // working memory
@@ -220,7 +221,7 @@ static int pack_corpus(snacc_ctx *ctx)
     cudaFree(d_hist);
     ctx->alphabet = pk_choose_alphabet(hist);
     uint16_t a5[1024], a4[256];
-    pk_slot_lut(ctx->alphabet, false, a5);
+    ctx->nslot5 = pk_slot_lut(ctx->alphabet, false, a5);
     pk_slot_lut(ctx->alphabet, true, a4);
     CK(cudaMalloc(&ctx->d_alias5, sizeof a5));
     CK(cudaMalloc(&ctx->d_alias4, sizeof a4));
@@ -490,10 +491,12 @@ static int run_pk_single(snacc_ctx *ctx, const std::vector<int32_t> &seqs, const
     return SNACC_OK;
 }
 
-// tile geometry of lz4_pk_pair_kernel: linked regime 3 warps x 16 lanes (4 KiB table per stream),
-// single-block regime 12 warps x 32 lanes (512 B table per stream); both fill one SM's shared memory
-constexpr int PK_L_LANES = 16, PK_L_WARPS = 3, PK_S_LANES = 32, PK_S_WARPS = 12;
-constexpr size_t PK_L_SMEM = PK_RING_WORDS * 8 + 1024 * 2 + (size_t)PK_L_WARPS * 1024 * PK_L_LANES * 4;
+// tile geometry of lz4_pk_pair_kernel.  Linked regime: 16 lanes per warp, 16-bit slots + epoch bit plane
+// (PkTab KIND 2: 2 bytes + 1 bit per slot, as many slots as the alphabet's 5-mers reach), as many warps as
+// fit one SM's shared memory (6 for A/C/G/T: 96 streams).  Single-block regime: 12 warps x 32 lanes,
+// 512 B table per stream.
+constexpr int PK_S_LANES = 32, PK_S_WARPS = 12;
+constexpr size_t PK_SMEM_MAX = 232448 - 16;       // 227 KiB per CTA minus the kernel's static shared memory
 constexpr size_t PK_S_SMEM = PK_RING_WORDS * 8 + 256 * 2 + (size_t)PK_S_WARPS * 256 * PK_S_LANES * 2;
 
 struct PkJob { int32_t y, x; int64_t j; };
@@ -501,7 +504,16 @@ struct PkJob { int32_t y, x; int64_t j; };
 static int run_pk_pairs(snacc_ctx *ctx, std::vector<PkJob> &jobs, bool u16)
 {
     if (jobs.empty()) return SNACC_OK;
-    const int T = u16 ? PK_S_LANES * PK_S_WARPS : PK_L_LANES * PK_L_WARPS;
+    // linked regime: as many streams as one SM's shared memory holds (A/C/G/T: 894 slots -> 1900 B per stream
+    // -> 104 streams = 4 warps x 26 lanes; a full 1024-slot alphabet: 90 -> 2 warps x 32 lanes)
+    const uint32_t nslot = (ctx->nslot5 + 1) & ~1u;
+    const size_t l_stream = (size_t)nslot * 2 + ((nslot + 31) / 32) * 4;            // bytes of table per linked stream
+    const size_t l_fixed = PK_RING_WORDS * 8 + 1024 * 2;
+    const size_t l_fit = (PK_SMEM_MAX - l_fixed) / l_stream;
+    const int l_lanes = l_fit >= 104 ? 26 : 32;
+    const int l_warps = l_fit >= 104 ? 4 : (int)std::max<size_t>(1, l_fit / 32);
+    const size_t l_smem = l_fixed + (size_t)l_warps * l_lanes * l_stream;
+    const int T = u16 ? PK_S_LANES * PK_S_WARPS : l_lanes * l_warps;
     std::sort(jobs.begin(), jobs.end(), [&](const PkJob &a, const PkJob &b) {
         const uint32_t la = ctx->h_len[a.y], lb = ctx->h_len[b.y];
         return la != lb ? la > lb : a.y != b.y ? a.y < b.y : a.j < b.j;       // longest y first, jobs of one y together
@@ -534,13 +546,22 @@ static int run_pk_pairs(snacc_ctx *ctx, std::vector<PkJob> &jobs, bool u16)
     const int grid = (int)std::min<size_t>(tiles.size(), (size_t)ctx->sm_count);
     CK(cudaEventRecord(ctx->evm0, ctx->stream));
     if (u16) {
-        CK(cudaFuncSetAttribute(lz4_pk_pair_kernel<true, PK_S_LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_S_SMEM));
-        lz4_pk_pair_kernel<true, PK_S_LANES><<<grid, PK_S_WARPS * 32, PK_S_SMEM, ctx->stream>>>(
-            pc, d_tiles, (int32_t)tiles.size(), d_tx, d_tout, ctx->d_ck_tab, ctx->d_ck_state, ctx->d_alias4, counter, ctx->d_out);
+        CK(cudaFuncSetAttribute(lz4_pk_pair_kernel<1, PK_S_LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_S_SMEM));
+        lz4_pk_pair_kernel<1, PK_S_LANES><<<grid, PK_S_WARPS * 32, PK_S_SMEM, ctx->stream>>>(
+            pc, d_tiles, (int32_t)tiles.size(), d_tx, d_tout, ctx->d_ck_tab, ctx->d_ck_state, ctx->d_alias4, 256, counter,
+            ctx->d_out);
     } else {
-        CK(cudaFuncSetAttribute(lz4_pk_pair_kernel<false, PK_L_LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_L_SMEM));
-        lz4_pk_pair_kernel<false, PK_L_LANES><<<grid, PK_L_WARPS * 32, PK_L_SMEM, ctx->stream>>>(
-            pc, d_tiles, (int32_t)tiles.size(), d_tx, d_tout, ctx->d_ck_tab, ctx->d_ck_state, ctx->d_alias5, counter, ctx->d_out);
+        if (l_lanes == 26) {
+            CK(cudaFuncSetAttribute(lz4_pk_pair_kernel<2, 26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l_smem));
+            lz4_pk_pair_kernel<2, 26><<<grid, l_warps * 32, l_smem, ctx->stream>>>(
+                pc, d_tiles, (int32_t)tiles.size(), d_tx, d_tout, ctx->d_ck_tab, ctx->d_ck_state, ctx->d_alias5, nslot, counter,
+                ctx->d_out);
+        } else {
+            CK(cudaFuncSetAttribute(lz4_pk_pair_kernel<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l_smem));
+            lz4_pk_pair_kernel<2, 32><<<grid, l_warps * 32, l_smem, ctx->stream>>>(
+                pc, d_tiles, (int32_t)tiles.size(), d_tx, d_tout, ctx->d_ck_tab, ctx->d_ck_state, ctx->d_alias5, nslot, counter,
+                ctx->d_out);
+        }
     }
     CK(cudaEventRecord(ctx->evm1, ctx->stream));
     ctx->last_launches++;

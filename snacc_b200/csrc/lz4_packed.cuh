@@ -95,18 +95,90 @@ SNACC_HD uint64_t pk_get32(const PkView &v, uint32_t p)
 
 // Position table.  `lut` maps a k-mer code to its slot: codes whose real bytes fall into the same bucket
 // of the library's hash table share a slot (pack.cuh: pk_slot_lut), so the table behaves exactly like
-// the library's while holding at most 1024 (256) live entries.
-template <bool U16, int STRIDE> struct PkTab {
-    typedef typename std::conditional<U16, uint16_t, uint32_t>::type T;
+// the library's while holding at most 1024 (256) live entries.  Three storage kinds:
+//   KIND 0  linked regime, 32-bit positions                                  (4 B per slot)
+//   KIND 1  single-block regime, 16-bit positions (streams <= 64 KiB)         (2 B per slot)
+//   KIND 2  linked regime, 17 bits per slot: the low 16 bits of the position plus an epoch bit
+//           (bit 16 of the position) kept in a separate bit plane            (2 B + 1 bit per slot)
+// KIND 2 is what lets twice as many streams stay resident per SM.  It is exact because a candidate only
+// counts when it is at most 65535 behind the probe: with p = probe position, d' = (p - low16) mod 65536 and
+// m' = p - d', the slot holds a usable candidate iff d' != 0 and bit 16 of m' equals the stored epoch bit --
+// PROVIDED no slot is ever 131072 or more positions old.  That is guaranteed by a rolling sweep: slots are
+// visited round-robin, at least one per ~40 positions of progress (one per vote in the turbo loop, 1 + adv/40
+// per general step, everything after a match longer than 4096), and a visited slot that is out of reach is
+// rewritten to "current position - 65536".  A full cycle therefore takes at most ~40 K positions, so a slot
+// is never older than 65536 + 40 K + 4 K < 131072 when it is read.
+template <int KIND, int STRIDE> struct PkTab {
+    static constexpr bool U16 = KIND == 1;
+    typedef typename std::conditional<KIND == 0, uint32_t, uint16_t>::type T;
     static constexpr uint32_t K = U16 ? 4 : 5;
     static constexpr uint32_t MASK = U16 ? 0xffu : 0x3ffu;
     static constexpr uint32_t ENTRIES = MASK + 1;
     static constexpr uint32_t ESZ = STRIDE * sizeof(T);   // bytes between two slots of one lane
     T *t;
+    uint32_t *ep;                                         // KIND 2: epoch bit plane, word w of this lane at ep[w * STRIDE]
+    uint32_t nslot;                                       // KIND 2: slots actually stored
+    uint32_t cur, last_pos;                               // KIND 2: rolling-sweep cursor and the position it was last advanced at
     const uint16_t *lut;                                  // code -> BYTE offset of the slot (slot index * ESZ)
     SNACC_HD uint32_t slot(uint32_t c) const { return (uint32_t)lut[c] / (uint32_t)sizeof(T); }
-    SNACC_HD uint32_t get(uint32_t c) const { return t[slot(c)]; }
-    SNACC_HD void put(uint32_t c, uint32_t pos) { t[slot(c)] = (T)pos; }
+    // candidate of code c for a probe at position ip; false: nothing within reach
+    SNACC_HD bool lookup(uint32_t c, uint32_t ip, uint32_t &m) const
+    {
+        const uint32_t sl = slot(c);
+        if (KIND == 0) { m = t[sl]; return m + LZ4_MAX_DISTANCE >= ip; }
+        if (KIND == 1) { m = t[sl]; return true; }
+        const uint32_t idx = sl / STRIDE;
+        const uint32_t e = (ep[(idx >> 5) * STRIDE] >> (idx & 31)) & 1;
+        const uint32_t d = (ip - t[sl]) & 0xffffu;
+        m = ip - d;
+        return d != 0 && (((m >> 16) ^ e) & 1) == 0;
+    }
+    SNACC_HD void put(uint32_t c, uint32_t pos)
+    {
+        const uint32_t sl = slot(c);
+        t[sl] = (T)pos;
+        if (KIND == 2) {
+            const uint32_t idx = sl / STRIDE;
+            uint32_t &w = ep[(idx >> 5) * STRIDE];
+            w = (w & ~(1u << (idx & 31))) | (((pos >> 16) & 1) << (idx & 31));
+        }
+    }
+    // KIND 2 rolling sweep: retire slot `cur` if it is out of reach of a probe at ip, then move on
+    SNACC_HD void sweep_one(uint32_t ip)
+    {
+        if (KIND != 2) return;
+        const uint32_t idx = cur;
+        cur = cur + 1 == nslot ? 0 : cur + 1;
+        uint32_t &w = ep[(idx >> 5) * STRIDE];
+        const uint32_t e = (w >> (idx & 31)) & 1;
+        const uint32_t d = (ip - t[idx * STRIDE]) & 0xffffu;
+        const uint32_t m = ip - d;
+        if (!(d != 0 && (((m >> 16) ^ e) & 1) == 0)) {
+            t[idx * STRIDE] = (T)ip;                                                  // low 16 bits of ip - 65536
+            w = (w & ~(1u << (idx & 31))) | ((((ip >> 16) & 1) ^ 1) << (idx & 31));
+        }
+    }
+    // as many slots as the progress since the last call asks for
+    SNACC_HD void sweep_progress(uint32_t ip)
+    {
+        if (KIND != 2) return;
+        const uint32_t adv = ip - last_pos;
+        last_pos = ip;
+        uint32_t k = adv > 4096 ? nslot : 1 + adv / 40;
+        if (ip < 65536u) return;                           // nothing can be out of reach yet (and "0" means position 0)
+        for (; k; --k) sweep_one(ip);
+    }
+    // KIND 2: store an absolute position coming from a 32-bit checkpoint table, for a stream whose open
+    // block starts at bs
+    SNACC_HD void import_slot(uint32_t idx, uint32_t pos, uint32_t bs)
+    {
+        if (KIND != 2) { t[idx * STRIDE] = (T)pos; return; }
+        const bool live = pos + LZ4_MAX_DISTANCE >= bs;
+        const uint32_t store = live ? pos : bs - 65536u;
+        t[idx * STRIDE] = (T)store;
+        uint32_t &w = ep[(idx >> 5) * STRIDE];
+        w = (w & ~(1u << (idx & 31))) | (((store >> 16) & 1) << (idx & 31));
+    }
 };
 
 SNACC_HD void pk_end_block(PkState &st)
@@ -141,10 +213,11 @@ SNACC_HD uint32_t pk_next_pos(const PkState &st)
 // One iteration of the probe loop (or one block start).  `n`: stream length (0xffffffff while the
 // prefix pass pretends the stream goes on).  DETECT: return true -- leaving state and table exactly as
 // they were before the call -- when the iteration would depend on a base at or beyond `xend`.
-template <bool U16, int STRIDE, bool DETECT>
-SNACC_HD bool pk_step(PkState &st, PkTab<U16, STRIDE> &tab, const PkView &v, uint32_t n, uint32_t xend)
+template <int KIND, int STRIDE, bool DETECT>
+SNACC_HD bool pk_step(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, uint32_t n, uint32_t xend)
 {
-    constexpr uint32_t K = PkTab<U16, STRIDE>::K, MASK = PkTab<U16, STRIDE>::MASK;
+    constexpr uint32_t K = PkTab<KIND, STRIDE>::K, MASK = PkTab<KIND, STRIDE>::MASK;
+    tab.sweep_progress(pk_next_pos(st));
     if (st.phase == PK_BLOCK_START) {
         if (st.bs >= n) { st.phase = PK_DONE; return false; }
         const uint32_t be = (n - st.bs > LZ4_BLOCK) ? st.bs + LZ4_BLOCK : n;
@@ -175,10 +248,10 @@ SNACC_HD bool pk_step(PkState &st, PkTab<U16, STRIDE> &tab, const PkView &v, uin
     if (DETECT && ip + K > xend) { st = pre; return true; }
     uint64_t w = pk_get32(v, ip);
     const uint32_t c = (uint32_t)w & MASK;
-    uint32_t m = tab.get(c);
+    uint32_t m;
+    bool hit = tab.lookup(c, ip, m);
     const uint32_t old_m = m;
     tab.put(c, ip);
-    bool hit = U16 || (m + LZ4_MAX_DISTANCE >= ip);
     uint32_t common = 0;
     if (hit) {
         const uint64_t d = w ^ pk_get32(v, m);
@@ -304,10 +377,10 @@ SNACC_HD bool pk_any(uint32_t mask, bool pred)
 #endif
 }
 
-template <bool U16, int STRIDE>
-static __host__ __device__ __noinline__ void pk_step_general(PkState &st, PkTab<U16, STRIDE> &tab, const PkView &v, uint32_t n)
+template <int KIND, int STRIDE>
+static __host__ __device__ __noinline__ void pk_step_general(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, uint32_t n)
 {
-    pk_step<U16, STRIDE, false>(st, tab, v, n, 0);
+    pk_step<KIND, STRIDE, false>(st, tab, v, n, 0);
 }
 
 // ---- speculative inner loop ("turbo") ----------------------------------------------------------
@@ -370,11 +443,14 @@ SNACC_HD uint32_t pk_reduce_or(uint32_t mask, uint32_t v)
 #endif
 }
 
-template <bool U16, int STRIDE>
-SNACC_HD void pk_turbo(PkState &st, PkTab<U16, STRIDE> &tab, const PkView &v, uint32_t stop, uint32_t mask, bool work)
+template <int KIND, int STRIDE>
+SNACC_HD void pk_turbo(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, uint32_t stop, uint32_t mask, bool work)
 {
-    typedef typename PkTab<U16, STRIDE>::T T;
-    constexpr uint32_t MASK = PkTab<U16, STRIDE>::MASK;
+    typedef PkTab<KIND, STRIDE> Tab;
+    constexpr bool U16 = Tab::U16;
+    constexpr uint32_t MASK = Tab::MASK;
+    constexpr uint32_t ESZ = Tab::ESZ;                      // bytes between two slots of one lane
+    constexpr uint32_t EWB = STRIDE * 4;                    // KIND 2: bytes between two epoch words of one lane
     constexpr uint32_t RMASK = (2 * PK_RING_WORDS - 1) * 4; // byte-offset mask of the ring seen as u32 words
     const uint32_t lx = v.lx, rlo = v.rlo, rspan = v.rspan;
     uint32_t p = st.phase == PK_SEARCH ? st.fip : st.ip;
@@ -385,32 +461,34 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<U16, STRIDE> &tab, const PkView &v, ui
     const bool ok0 = fin || (st.phase <= PK_RETEST && !(st.phase == PK_SEARCH && st.step != 1) &&
                              (uint32_t)(p - 4 - lx - rlo) <= rspan);
     if (!pk_all(mask, ok0) || pk_all(mask, fin)) return;
-    // (pk_opaque: keep the three base addresses in registers -- the compiler otherwise re-derives them from
+    // (pk_opaque: keep the base addresses in registers -- the compiler otherwise re-derives them from
     // SR_CgaCtaId inside the loop)
     const pk_sptr ring_a = pk_opaque(pk_sptr_of(v.ring)), lut_a = pk_opaque(pk_sptr_of(tab.lut)),
-                  tab_a = pk_opaque(pk_sptr_of(tab.t));
-#define PK_TLD(addr) (U16 ? pk_lds16(addr) : pk_lds32(addr))
-#define PK_TST(addr, val) do { if (U16) pk_sts16(addr, val); else pk_sts32(addr, val); } while (0)
-#define PK_SLOT(code) (tab_a + pk_lds16(lut_a + 2 * (code)))
+                  tab_a = pk_opaque(pk_sptr_of(tab.t)), ep_a = KIND == 2 ? pk_opaque(pk_sptr_of(tab.ep)) : 0;
+#define PK_TLD(addr) (KIND == 0 ? pk_lds32(addr) : pk_lds16(addr))
+#define PK_TST(addr, val) do { if (KIND == 0) pk_sts32(addr, val); else pk_sts16(addr, val); } while (0)
+#define PK_OFF(code) pk_lds16(lut_a + 2 * (code))            /* slot handle: byte offset of the slot */
+#define PK_EWA(off) (ep_a + (((off) / ESZ) >> 5) * EWB)      /* address of the epoch word of a slot */
+#define PK_EBIT(off) ((((off) / ESZ)) & 31)
     // 32 bases starting at y offset q, as two 32-bit halves (three consecutive ring words)
 #define PK_RING32(q, lo, hi) do { const uint32_t j_ = ((q) >> 4) * 4, s_ = ((q) & 15) * 2;                      \
         const uint32_t a_ = pk_lds32(ring_a + (j_ & RMASK)), b_ = pk_lds32(ring_a + ((j_ + 4) & RMASK)),       \
                        c_ = pk_lds32(ring_a + ((j_ + 8) & RMASK));                                             \
         lo = pk_fsr(a_, b_, s_); hi = pk_fsr(b_, c_, s_); } while (0)
     uint32_t Wlo = 0, Whi = 0;                              // bases [pw-4, pw+28)
-    uint32_t pw = p;
-    pk_sptr slot = tab_a;
-    uint32_t m = 0;
+    uint32_t pw = p, soff = 0, m = 0, scur = tab.cur;
+    bool near = false;                                      // the slot of p holds a candidate within reach
     if (!fin) {
         PK_RING32(p - 4 - lx, Wlo, Whi);
-        slot = PK_SLOT((Wlo >> 8) & MASK);
-        m = PK_TLD(slot);
+        const uint32_t c0 = (Wlo >> 8) & MASK;
+        soff = tab.lut[c0];
+        near = tab.lookup(c0, p, m);
     }
     bool blocked = false;
-    for (uint32_t it = 0;; ++it) {
+    uint32_t it = 0;
+    for (;; ++it) {
         // ---- may this lane take one more iteration?  (evaluated by every lane, every iteration)
         const uint32_t pend = p - anchor;                   // pending literals; search mode iff != 0
-        const bool near = U16 || (p - m <= LZ4_MAX_DISTANCE);
         const uint32_t qm4 = m - 4 - lx;
         const bool live = !fin && p < stop;
         const bool ok = !blocked && p < lim && op + pend + (pend >> 7) <= op_lim && nb <= 120 &&
@@ -420,6 +498,18 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<U16, STRIDE> &tab, const PkView &v, ui
             // warp vote every 4th iteration: leave when a live lane is stuck or nobody runs any more
             // (a stuck lane simply idles for up to 3 iterations)
             if (pk_reduce_or(mask, (go ? 2u : 0u) | ((live && !ok) ? 1u : 0u)) != 2u) break;
+            if (KIND == 2 && p >= 65536u) {                 // rolling sweep: one slot per vote (PkTab comment)
+                const uint32_t so = scur * ESZ;
+                scur = scur + 1 == tab.nslot ? 0 : scur + 1;
+                const uint32_t rv = pk_lds16(tab_a + so), ew = pk_lds32(PK_EWA(so));
+                const uint32_t d = (p - rv) & 0xffffu;
+                const bool reach = d != 0 && ((((p - d) >> 16) ^ (ew >> PK_EBIT(so))) & 1) == 0;
+                // never touch the slot of the pending probe: its candidate is already in registers
+                if (!reach && so != soff) {
+                    pk_sts16(tab_a + so, p);
+                    pk_sts32(PK_EWA(so), (ew & ~(1u << PK_EBIT(so))) | ((((p >> 16) & 1) ^ 1) << PK_EBIT(so)));
+                }
+            }
         }
         // ---- straight-line body; loads are harmless for any lane, stores and commits are predicated
         // candidate: 16 bases from m-4
@@ -430,12 +520,30 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<U16, STRIDE> &tab, const PkView &v, ui
         }
         const uint32_t sh = 2 * (p - pw);
         const uint32_t Ws = pk_fsr(Wlo, Whi, sh), Wt = Whi >> sh;   // bases [p-4, p+12) and the 16 after them
-        if (go) PK_TST(slot, p);
+        // first insert: slot of p <- p (remember what it held, an unfinished iteration puts it back)
+        const pk_sptr slot = tab_a + soff;
+        uint32_t raw_old = 0, ew_old = 0;
+        if (KIND == 2) {
+            raw_old = pk_lds16(slot); ew_old = pk_lds32(PK_EWA(soff));
+            if (go) {
+                pk_sts16(slot, p);
+                pk_sts32(PK_EWA(soff), (ew_old & ~(1u << PK_EBIT(soff))) | (((p >> 16) & 1) << PK_EBIT(soff)));
+            }
+        } else {
+            raw_old = m;
+            if (go) PK_TST(slot, p);
+        }
         // speculative table lookups: next probe at p+1 (miss) or p+4..p+8 (match of that length)
-        const pk_sptr s1 = PK_SLOT((Ws >> 10) & MASK), s2 = PK_SLOT((Ws >> 12) & MASK), s3 = PK_SLOT((Ws >> 14) & MASK);
-        const pk_sptr s4 = PK_SLOT((Ws >> 16) & MASK), s5 = PK_SLOT((Ws >> 18) & MASK), s6 = PK_SLOT((Ws >> 20) & MASK);
-        const pk_sptr s7 = PK_SLOT((Ws >> 22) & MASK), s8 = PK_SLOT(pk_fsr(Ws, Wt, 24) & MASK);
-        const uint32_t m1 = PK_TLD(s1), m4 = PK_TLD(s4), m5 = PK_TLD(s5), m6 = PK_TLD(s6), m7 = PK_TLD(s7), m8 = PK_TLD(s8);
+        const uint32_t o1 = PK_OFF((Ws >> 10) & MASK), o2 = PK_OFF((Ws >> 12) & MASK), o3 = PK_OFF((Ws >> 14) & MASK);
+        const uint32_t o4 = PK_OFF((Ws >> 16) & MASK), o5 = PK_OFF((Ws >> 18) & MASK), o6 = PK_OFF((Ws >> 20) & MASK);
+        const uint32_t o7 = PK_OFF((Ws >> 22) & MASK), o8 = PK_OFF(pk_fsr(Ws, Wt, 24) & MASK);
+        const uint32_t m1 = PK_TLD(tab_a + o1), m4 = PK_TLD(tab_a + o4), m5 = PK_TLD(tab_a + o5), m6 = PK_TLD(tab_a + o6),
+                       m7 = PK_TLD(tab_a + o7), m8 = PK_TLD(tab_a + o8);
+        uint32_t e1 = 0, e4 = 0, e5 = 0, e6 = 0, e7 = 0, e8 = 0;
+        if (KIND == 2) {
+            e1 = pk_lds32(PK_EWA(o1)); e4 = pk_lds32(PK_EWA(o4)); e5 = pk_lds32(PK_EWA(o5));
+            e6 = pk_lds32(PK_EWA(o6)); e7 = pk_lds32(PK_EWA(o7)); e8 = pk_lds32(PK_EWA(o8));
+        }
         uint32_t Nlo, Nhi;
         PK_RING32(p - 4 - lx, Nlo, Nhi);                    // window for the next iteration
         const uint32_t x = Ws ^ xm;
@@ -447,23 +555,48 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<U16, STRIDE> &tab, const PkView &v, ui
         const uint32_t kmax = tmin(pend, m);
         const bool hit = common >= 4;
         const bool bail = go && (common > 11 || (hit && k == 4 && kmax > 4));   // long match / long catch-up
-        if (bail) { PK_TST(slot, m); blocked = true; }
+        if (bail) {
+            if (KIND == 2) { pk_sts16(slot, raw_old); pk_sts32(PK_EWA(soff), ew_old); }
+            else PK_TST(slot, raw_old);
+            blocked = true;
+        }
         const bool commit = go && !bail;
         k = tmin(k, kmax);
         const uint32_t lit = pend - k;
         const uint32_t add = 3 + lit + (lit >= 15 ? (lit - 15) / 255 + 1 : 0);   // token + offset + literals
         const uint32_t pn = hit ? p + common : p + 1;
         const bool c4 = common == 4, c5 = common == 5, c6 = common == 6, c7 = common == 7;
-        pk_sptr sp = (pk_sptr)pk_sel(c4, (uint32_t)s2, pk_sel(c5, (uint32_t)s3, pk_sel(c6, (uint32_t)s4, pk_sel(c7, (uint32_t)s5, (uint32_t)s6))));
-        pk_sptr sn = (pk_sptr)pk_sel(c4, (uint32_t)s4, pk_sel(c5, (uint32_t)s5, pk_sel(c6, (uint32_t)s6, pk_sel(c7, (uint32_t)s7, (uint32_t)s8))));
+        uint32_t sp = pk_sel(c4, o2, pk_sel(c5, o3, pk_sel(c6, o4, pk_sel(c7, o5, o6))));      // slot of the insert pn-2
+        uint32_t sn = pk_sel(c4, o4, pk_sel(c5, o5, pk_sel(c6, o6, pk_sel(c7, o7, o8))));      // slot of pn
         uint32_t mn = pk_sel(c4, m4, pk_sel(c5, m5, pk_sel(c6, m6, pk_sel(c7, m7, m8))));
+        uint32_t en = KIND == 2 ? pk_sel(c4, e4, pk_sel(c5, e5, pk_sel(c6, e6, pk_sel(c7, e7, e8)))) : 0;
         if (commit && common > 8) {                         // 9..11: not speculated, look the slots up now
-            sp = PK_SLOT(pk_fsr(Ws, Wt, 2 * (common + 2)) & MASK);
-            sn = PK_SLOT(pk_fsr(Ws, Wt, 2 * (common + 4)) & MASK);
-            mn = PK_TLD(sn);
+            sp = PK_OFF(pk_fsr(Ws, Wt, 2 * (common + 2)) & MASK);
+            sn = PK_OFF(pk_fsr(Ws, Wt, 2 * (common + 4)) & MASK);
+            mn = PK_TLD(tab_a + sn);
+            if (KIND == 2) en = pk_lds32(PK_EWA(sn));
         }
-        if (commit && hit) PK_TST(sp, pn - 2);
-        mn = sn == sp ? pn - 2 : mn;
+        sn = hit ? sn : o1; mn = hit ? mn : m1; en = hit ? en : e1;
+        if (commit && hit) {                                // second insert: slot of pn-2 <- pn-2
+            if (KIND == 2) {
+                pk_sts16(tab_a + sp, pn - 2);
+                const uint32_t w2 = pk_lds32(PK_EWA(sp));
+                pk_sts32(PK_EWA(sp), (w2 & ~(1u << PK_EBIT(sp))) | ((((pn - 2) >> 16) & 1) << PK_EBIT(sp)));
+            } else {
+                PK_TST(tab_a + sp, pn - 2);
+            }
+        }
+        // candidate of the next probe: the speculative read, unless the second insert just overwrote that slot
+        uint32_t mnext; bool nnext;
+        if (KIND == 2) {
+            const uint32_t d = (pn - mn) & 0xffffu;
+            mnext = pn - d;
+            nnext = d != 0 && ((((mnext >> 16) ^ (en >> PK_EBIT(sn))) & 1) == 0);
+        } else {
+            mnext = mn;
+            nnext = U16 || (pn - mn <= LZ4_MAX_DISTANCE);
+        }
+        if (hit && sn == sp) { mnext = pn - 2; nnext = true; }
         if (commit) {
 #if defined(PK_COUNT_STEPS) && !defined(__CUDA_ARCH__)
             ++pk_turbo_steps;
@@ -471,37 +604,39 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<U16, STRIDE> &tab, const PkView &v, ui
             op += hit ? add : 0;
             nb = hit ? nb : (pend ? nb + 1 : 64);
             anchor = hit ? pn : anchor;
-            m = hit ? mn : m1;
-            slot = hit ? sn : s1;
+            m = mnext; near = nnext; soff = sn;
             Wlo = Nlo; Whi = Nhi; pw = p; p = pn;
         }
     }
 #undef PK_TLD
 #undef PK_TST
-#undef PK_SLOT
+#undef PK_OFF
+#undef PK_EWA
+#undef PK_EBIT
 #undef PK_RING32
     if (work && st.phase <= PK_RETEST) {
         if (p != anchor) { st.phase = PK_SEARCH; st.fip = p; st.step = 1; st.nb = nb; }
         else             { st.phase = PK_RETEST; st.ip = p; }
         st.anchor = anchor; st.op = op;
+        if (KIND == 2 && it) { tab.cur = scur; tab.last_pos = p; }
     }
 }
 
 // Run the streams of the warp (lanes in `mask`, one stream each) until each one's next position reaches
 // its `stop` or it is done: turbo bursts, separated by one general pk_step for every lane.
-template <bool U16, int STRIDE>
-SNACC_HD void pk_run(PkState &st, PkTab<U16, STRIDE> &tab, const PkView &v, uint32_t n, uint32_t stop, uint32_t mask)
+template <int KIND, int STRIDE>
+SNACC_HD void pk_run(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, uint32_t n, uint32_t stop, uint32_t mask)
 {
     for (;;) {
         bool work = st.phase != PK_DONE && pk_next_pos(st) < stop;
         if (!pk_any(mask, work)) return;
-        pk_turbo<U16, STRIDE>(st, tab, v, stop, mask, work);
+        pk_turbo<KIND, STRIDE>(st, tab, v, stop, mask, work);
         work = st.phase != PK_DONE && pk_next_pos(st) < stop;
         if (work) {
 #if defined(PK_COUNT_STEPS) && !defined(__CUDA_ARCH__)
             ++pk_general_steps;
 #endif
-            pk_step_general<U16, STRIDE>(st, tab, v, n);
+            pk_step_general<KIND, STRIDE>(st, tab, v, n);
         }
     }
 }
@@ -574,25 +709,34 @@ __device__ __forceinline__ void pk_ring_fill(uint64_t *ring, const uint64_t *yw,
 }
 
 // ---- pair tiles: one stream per thread, LANES active lanes per warp, tables in shared memory --------
-template <bool U16, int LANES>
+// KIND: table storage (PkTab).  nslot: slots per stream (KIND 2: what pk_slot_lut needs, rounded up to 32).
+// shared memory: ring | code->slot map | position tables (warp-major, lane-interleaved) | epoch planes
+template <int KIND, int LANES>
 __global__ void __launch_bounds__(384, 1)
 lz4_pk_pair_kernel(PkCorpus pc, const PkTile *__restrict__ tiles, int32_t n_tiles, const int32_t *__restrict__ tile_x,
                    const int64_t *__restrict__ tile_out, const uint32_t *__restrict__ ck_tab,
-                   const PkState *__restrict__ ck_state, const uint16_t *__restrict__ lut_g,
+                   const PkState *__restrict__ ck_state, const uint16_t *__restrict__ lut_g, uint32_t nslot,
                    unsigned long long *__restrict__ counter, int64_t *__restrict__ out)
 {
-    typedef PkTab<U16, LANES> Tab;
+    typedef PkTab<KIND, LANES> Tab;
+    constexpr bool U16 = Tab::U16;
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t *ring = reinterpret_cast<uint64_t *>(smem);
     uint16_t *lut = reinterpret_cast<uint16_t *>(smem + PK_RING_WORDS * 8);
     typename Tab::T *tabs = reinterpret_cast<typename Tab::T *>(smem + PK_RING_WORDS * 8 + Tab::ENTRIES * 2);
+    const uint32_t n_warps = blockDim.x >> 5;
+    if (KIND != 2) nslot = Tab::ENTRIES;
+    const uint32_t nw = (nslot + 31) >> 5;                 // epoch words per stream
+    uint32_t *eps = reinterpret_cast<uint32_t *>(tabs + (size_t)n_warps * nslot * LANES);
     __shared__ int32_t s_tile;
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t slot = warp * LANES + lane;
     for (uint32_t i = threadIdx.x; i < Tab::ENTRIES; i += blockDim.x) lut[i] = (uint16_t)(lut_g[i] * Tab::ESZ);
     Tab tab;
-    tab.t = tabs + (size_t)warp * (Tab::ENTRIES * LANES) + lane;
+    tab.t = tabs + (size_t)warp * (nslot * LANES) + lane;
+    tab.ep = eps + (size_t)warp * (nw * LANES) + lane;
+    tab.nslot = nslot;
     tab.lut = lut;
 
     for (;;) {
@@ -616,14 +760,24 @@ lz4_pk_pair_kernel(PkCorpus pc, const PkTile *__restrict__ tiles, int32_t n_tile
         uint32_t n = 0;
         bool bail = false;
         st.phase = PK_DONE; st.total = 0;
-        // each warp copies the checkpoint tables of its streams, one stream at a time (coalesced reads)
+        // each warp copies the checkpoint tables of its streams, one stream at a time (coalesced reads);
+        // KIND 2 converts the 32-bit checkpoint positions relative to the stream's open block
         for (int k = 0; k < LANES; ++k) {
             const int32_t sl = (int32_t)(warp * LANES + k);
             if (sl >= td.count) break;
             const int32_t x = tile_x[td.first + sl];
             const uint32_t *src = ck_tab + (size_t)(2 * x + (U16 ? 0 : 1)) * PK_CKPT_TAB;
-            typename Tab::T *dst = tabs + (size_t)warp * (Tab::ENTRIES * LANES) + k;
-            for (uint32_t e = lane; e < Tab::ENTRIES; e += 32) dst[e * LANES] = (typename Tab::T)src[e];
+            Tab tk = tab;
+            tk.t = tabs + (size_t)warp * (nslot * LANES) + k;
+            tk.ep = eps + (size_t)warp * (nw * LANES) + k;
+            const uint32_t bs = ck_state[2 * x + (U16 ? 0 : 1)].bs;
+            if (KIND == 2) {
+                // one lane per epoch word so that the read-modify-writes of import_slot never collide
+                for (uint32_t wd = lane; wd < nw; wd += 32)
+                    for (uint32_t e = wd * 32; e < tmin(wd * 32 + 32, nslot); ++e) tk.import_slot(e, src[e], bs);
+            } else {
+                for (uint32_t e = lane; e < nslot; e += 32) tk.import_slot(e, src[e], bs);
+            }
         }
         if (has) {
             const int32_t x = tile_x[td.first + slot];
@@ -633,6 +787,7 @@ lz4_pk_pair_kernel(PkCorpus pc, const PkTile *__restrict__ tiles, int32_t n_tile
             n = v.lx + ly;
             bail = !pk_resume(st, n);
             if (bail) st.phase = PK_DONE;
+            tab.cur = 0; tab.last_pos = pk_next_pos(st);
         }
         for (;;) {
             __syncthreads();                       // ring (and on the first pass the tables) visible
@@ -641,7 +796,7 @@ lz4_pk_pair_kernel(PkCorpus pc, const PkTile *__restrict__ tiles, int32_t n_tile
             const uint32_t stop = stop_q == 0xffffffffu ? 0xffffffffu : v.lx + stop_q;
             const uint32_t lanes = __ballot_sync(0xffffffffu, has);
             if (has) {
-                pk_run<U16, LANES>(st, tab, v, n, stop, lanes);
+                pk_run<KIND, LANES>(st, tab, v, n, stop, lanes);
             }
             if (rg.complete()) break;
             __syncthreads();                       // everyone is done reading the slots about to be replaced
@@ -661,8 +816,8 @@ struct PkSingleSmem {
     uint32_t snap[1024];
 };
 
-template <bool U16, bool DETECT>
-__device__ void pk_single_run(PkState &st, PkTab<U16, 1> &tab, PkView &v, PkRing &rg, const uint64_t *yw, uint64_t *ring,
+template <int KIND, bool DETECT>
+__device__ void pk_single_run(PkState &st, PkTab<KIND, 1> &tab, PkView &v, PkRing &rg, const uint64_t *yw, uint64_t *ring,
                               uint32_t n, uint32_t xend, uint32_t snap_bs, PkState *snap_st, uint32_t *snap_tab)
 {
     // CTA-uniform control flow: thread 0 parses, all threads take part in ring refills
@@ -675,7 +830,7 @@ __device__ void pk_single_run(PkState &st, PkTab<U16, 1> &tab, PkView &v, PkRing
             bool touched = false;
             while (st.phase != PK_DONE && pk_next_pos(st) < stop) {
                 if (DETECT) {
-                    if (pk_step<U16, 1, true>(st, tab, v, n, xend)) { touched = true; break; }
+                    if (pk_step<KIND, 1, true>(st, tab, v, n, xend)) { touched = true; break; }
                     continue;
                 }
                 uint32_t limit = stop;
@@ -683,13 +838,13 @@ __device__ void pk_single_run(PkState &st, PkTab<U16, 1> &tab, PkView &v, PkRing
                     // stop at the start of the last block: its state is where the prefix pass resumes
                     if (st.phase == PK_BLOCK_START && st.bs == snap_bs) {
                         *snap_st = st;
-                        for (uint32_t e = 0; e < PkTab<U16, 1>::ENTRIES; ++e) snap_tab[e] = tab.t[e];
+                        for (uint32_t e = 0; e < PkTab<KIND, 1>::ENTRIES; ++e) snap_tab[e] = tab.t[e];
                         snap_st = nullptr;
                     } else {
                         limit = tmin(stop, snap_bs);
                     }
                 }
-                pk_run<U16, 1>(st, tab, v, n, limit, 1u);
+                pk_run<KIND, 1>(st, tab, v, n, limit, 1u);
             }
             s_more = (!touched && st.phase != PK_DONE && !rg.complete()) ? 1u : 0u;
         }
@@ -723,8 +878,8 @@ lz4_pk_single_kernel(PkCorpus pc, const int32_t *__restrict__ seqs, const int32_
         v.ring = ring; v.yw = yw; v.xw = yw; v.lx = 0;
         PkRing rg;
         PkState st, snap;
-        PkTab<false, 1> tl; tl.t = s_tab; tl.lut = s_lut5;
-        PkTab<true, 1> ts; ts.t = reinterpret_cast<uint16_t *>(s_tab); ts.lut = s_lut4;
+        PkTab<0, 1> tl; tl.t = s_tab; tl.lut = s_lut5; tl.ep = nullptr; tl.nslot = 1024; tl.cur = tl.last_pos = 0;
+        PkTab<1, 1> ts; ts.t = reinterpret_cast<uint16_t *>(s_tab); ts.lut = s_lut4; ts.ep = nullptr; ts.nslot = 256; ts.cur = ts.last_pos = 0;
         const bool linked_single = len > LZ4_BLOCK;
         const uint32_t last_bs = (len / LZ4_BLOCK) * LZ4_BLOCK;
 
@@ -735,8 +890,8 @@ lz4_pk_single_kernel(PkCorpus pc, const int32_t *__restrict__ seqs, const int32_
         rg.start(len, w0, w1);
         pk_ring_fill(ring, yw, w0, w1);
         pk_fresh(st); pk_fresh(snap);
-        if (linked_single) pk_single_run<false, false>(st, tl, v, rg, yw, ring, len, 0, last_bs, &snap, s_snap);
-        else               pk_single_run<true, false>(st, ts, v, rg, yw, ring, len, 0, 0, nullptr, nullptr);
+        if (linked_single) pk_single_run<0, false>(st, tl, v, rg, yw, ring, len, 0, last_bs, &snap, s_snap);
+        else               pk_single_run<1, false>(st, ts, v, rg, yw, ring, len, 0, 0, nullptr, nullptr);
         if (threadIdx.x == 0 && out_idx[t] >= 0) out[out_idx[t]] = (int64_t)(st.total + lz4_frame_overhead(len));
 
         // (2) linked-regime checkpoint: from the snapshot at the last block start (or from scratch)
@@ -754,7 +909,7 @@ lz4_pk_single_kernel(PkCorpus pc, const int32_t *__restrict__ seqs, const int32_
                 rg.start(len, w0, w1);
                 pk_ring_fill(ring, yw, w0, w1);
             }
-            pk_single_run<false, true>(st, tl, v, rg, yw, ring, 0xffffffffu, len, 0, nullptr, nullptr);
+            pk_single_run<0, true>(st, tl, v, rg, yw, ring, 0xffffffffu, len, 0, nullptr, nullptr);
             __syncthreads();
             uint32_t *dst = ck_tab + (size_t)(2 * s + 1) * PK_CKPT_TAB;
             for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) dst[i] = s_tab[i];
@@ -767,7 +922,7 @@ lz4_pk_single_kernel(PkCorpus pc, const int32_t *__restrict__ seqs, const int32_
             pk_fresh(st);
             rg.start(len, w0, w1);
             pk_ring_fill(ring, yw, w0, w1);
-            pk_single_run<true, true>(st, ts, v, rg, yw, ring, 0xffffffffu, len, 0, nullptr, nullptr);
+            pk_single_run<1, true>(st, ts, v, rg, yw, ring, 0xffffffffu, len, 0, nullptr, nullptr);
             __syncthreads();
             uint32_t *dst = ck_tab + (size_t)(2 * s) * PK_CKPT_TAB;
             const uint16_t *t16 = reinterpret_cast<const uint16_t *>(s_tab);

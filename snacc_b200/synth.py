@@ -60,6 +60,22 @@ def phylogeny_torch(n_genomes, length, seed, device, sub_rate=0.01, n_indels=4, 
     return out
 
 
+def stale_slot_stream(seed):
+    """Test input for the LZ4 table encoding: ACGT stretches separated by A/T-only stretches of 66 k - 300 k bases, so
+    that every hash-table slot of a k-mer containing C or G goes out of reach -- far more than 131072 positions --
+    before it is probed again.  Returns (x, y)."""
+    rng = np.random.default_rng(seed)
+
+    def seg(alphabet, n):
+        return np.frombuffer(alphabet, dtype=np.uint8)[rng.integers(0, len(alphabet), n)]
+
+    parts = []
+    for _ in range(8):
+        parts.append(seg(b"ACGT", int(rng.integers(60000, 120000))))
+        parts.append(seg(b"AT", int(rng.integers(66000, 300000))))
+    return seg(b"ACGT", int(rng.integers(1000, 200000))), np.concatenate(parts)
+
+
 def write_fasta(path, name, seq, width=70):
     s = bytes(seq).decode("ascii")
     with open(path, "w") as fh:

@@ -64,36 +64,40 @@ static void ring_fill_host(std::vector<uint64_t> &ring, const std::vector<uint64
 struct EmuCkpt { PkState st; std::vector<uint32_t> tab; };
 
 // run a stream until DONE (or until DETECT touches); mirrors pk_single_run / the pair kernel loop
-template <bool U16, bool DETECT>
-static bool emu_run(PkState &st, std::vector<uint32_t> &tab32, const uint16_t *alias, PkView &v, PkRing &rg,
+template <int KIND, bool DETECT>
+static bool emu_run(PkState &st, PkTab<KIND, 1> &tab, std::vector<uint32_t> *tab32, PkView &v, PkRing &rg,
                     std::vector<uint64_t> &ring, const std::vector<uint64_t> &yw, uint32_t n, uint32_t xend,
                     uint32_t snap_bs, EmuCkpt *snap)
 {
-    typedef PkTab<U16, 1> Tab;
-    uint16_t lutb[1024];                                  // the kernels keep BYTE offsets in the shared-memory map
-    for (uint32_t i = 0; i < Tab::ENTRIES; ++i) lutb[i] = (uint16_t)(alias[i] * Tab::ESZ);
-    Tab tab; tab.t = reinterpret_cast<typename Tab::T *>(tab32.data()); tab.lut = lutb;
     for (;;) {
         rg.view(v);
         const uint32_t sq = rg.stop_q();
         const uint32_t stop = sq == 0xffffffffu ? sq : v.lx + sq;
         while (st.phase != PK_DONE && pk_next_pos(st) < stop) {
             if (DETECT) {
-                if (pk_step<U16, 1, true>(st, tab, v, n, xend)) return true;
+                if (pk_step<KIND, 1, true>(st, tab, v, n, xend)) return true;
                 continue;
             }
             uint32_t limit = stop;
             if (snap) {
-                if (st.phase == PK_BLOCK_START && st.bs == snap_bs) { snap->st = st; snap->tab = tab32; snap = nullptr; }
+                if (st.phase == PK_BLOCK_START && st.bs == snap_bs) { snap->st = st; snap->tab = *tab32; snap = nullptr; }
                 else limit = tmin(stop, snap_bs);
             }
-            pk_run<U16, 1>(st, tab, v, n, limit, 1u);
+            pk_run<KIND, 1>(st, tab, v, n, limit, 1u);
         }
         if (st.phase == PK_DONE || rg.complete()) return false;
         uint32_t w0, w1;
         rg.advance(w0, w1);
         ring_fill_host(ring, yw, w0, w1);
     }
+}
+
+// the kernels keep BYTE offsets in the shared-memory code->slot map
+template <int KIND> static std::vector<uint16_t> emu_lut(const uint16_t *raw)
+{
+    std::vector<uint16_t> l(PkTab<KIND, 1>::ENTRIES);
+    for (size_t i = 0; i < l.size(); ++i) l[i] = (uint16_t)(raw[i] * PkTab<KIND, 1>::ESZ);
+    return l;
 }
 
 // returns the size, -1 when the packed pair path bails out, -2 when the input is not packable
@@ -107,11 +111,14 @@ extern "C" int64_t emu_lz4_packed(const uint8_t *x, uint32_t lx, const uint8_t *
     std::vector<uint64_t> xw = pack_host(a, x, lx, ok);
     std::vector<uint64_t> yw = ly_ >= 0 ? pack_host(a, y, (uint32_t)ly_, ok) : std::vector<uint64_t>();
     if (!ok) return -2;
-    uint16_t alias5[1024], alias4[256];
-    pk_slot_lut(a, false, alias5);
-    pk_slot_lut(a, true, alias4);
+    uint16_t raw5[1024], raw4[256];
+    const uint32_t nslot5 = pk_slot_lut(a, false, raw5);
+    pk_slot_lut(a, true, raw4);
+    const std::vector<uint16_t> lut32 = emu_lut<0>(raw5), lut16 = emu_lut<1>(raw4), lut17 = emu_lut<2>(raw5);
     std::vector<uint64_t> ring(PK_RING_WORDS, 0);
     std::vector<uint32_t> tab(1024, 0);
+    PkTab<0, 1> t32; t32.t = tab.data(); t32.ep = nullptr; t32.nslot = 1024; t32.cur = t32.last_pos = 0; t32.lut = lut32.data();
+    PkTab<1, 1> t16; t16.t = reinterpret_cast<uint16_t *>(tab.data()); t16.ep = nullptr; t16.nslot = 256; t16.cur = t16.last_pos = 0; t16.lut = lut16.data();
     PkView v; PkRing rg; PkState st; uint32_t w0, w1;
 
     // ---- the sequence x on its own (kernel lz4_pk_single_kernel, step 1) ----
@@ -121,8 +128,8 @@ extern "C" int64_t emu_lz4_packed(const uint8_t *x, uint32_t lx, const uint8_t *
     v.ring = ring.data(); v.yw = xw.data(); v.xw = xw.data(); v.lx = 0;
     rg.start(lx, w0, w1); ring_fill_host(ring, xw, w0, w1);
     pk_fresh(st);
-    if (linked_single) emu_run<false, false>(st, tab, alias5, v, rg, ring, xw, lx, 0, last_bs, &snap);
-    else               emu_run<true, false>(st, tab, alias4, v, rg, ring, xw, lx, 0, 0, nullptr);
+    if (linked_single) emu_run<0, false>(st, t32, &tab, v, rg, ring, xw, lx, 0, last_bs, &snap);
+    else               emu_run<1, false>(st, t16, &tab, v, rg, ring, xw, lx, 0, 0, nullptr);
     const int64_t single = (int64_t)(st.total + lz4_frame_overhead(lx));
     if (ly_ < 0) return single;
 
@@ -135,14 +142,16 @@ extern "C" int64_t emu_lz4_packed(const uint8_t *x, uint32_t lx, const uint8_t *
     if (!u16) {
         if (linked_single) { tab = snap.tab; st = snap.st; }
         else { tab.assign(1024, 0); pk_fresh(st); rg.start(lx, w0, w1); ring_fill_host(ring, xw, w0, w1); }
-        if (!emu_run<false, true>(st, tab, alias5, v, rg, ring, xw, 0xffffffffu, lx, 0, nullptr)) return -3;
+        t32.t = tab.data();
+        if (!emu_run<0, true>(st, t32, &tab, v, rg, ring, xw, 0xffffffffu, lx, 0, nullptr)) return -3;
         ck.st = st; ck.tab = tab;
     } else {
         tab.assign(1024, 0); pk_fresh(st); rg.start(lx, w0, w1); ring_fill_host(ring, xw, w0, w1);
-        if (!emu_run<true, true>(st, tab, alias4, v, rg, ring, xw, 0xffffffffu, lx, 0, nullptr)) return -3;
+        t16.t = reinterpret_cast<uint16_t *>(tab.data());
+        if (!emu_run<1, true>(st, t16, &tab, v, rg, ring, xw, 0xffffffffu, lx, 0, nullptr)) return -3;
         ck.st = st; ck.tab.assign(1024, 0);
-        const uint16_t *t16 = reinterpret_cast<const uint16_t *>(tab.data());
-        for (int i = 0; i < 256; ++i) ck.tab[i] = t16[i];
+        const uint16_t *p16 = reinterpret_cast<const uint16_t *>(tab.data());
+        for (int i = 0; i < 256; ++i) ck.tab[i] = p16[i];
     }
 
     // ---- the pair stream resumes from the checkpoint (kernel lz4_pk_pair_kernel) ----
@@ -152,20 +161,20 @@ extern "C" int64_t emu_lz4_packed(const uint8_t *x, uint32_t lx, const uint8_t *
     rg.start(ly, w0, w1); ring_fill_host(ring, yw, w0, w1);
     if (u16) {
         std::vector<uint32_t> t(1024, 0);
-        uint16_t *t16 = reinterpret_cast<uint16_t *>(t.data());
-        for (int i = 0; i < 256; ++i) t16[i] = (uint16_t)ck.tab[i];
-        emu_run<true, false>(st, t, alias4, v, rg, ring, yw, n, 0, 0, nullptr);
+        uint16_t *p16 = reinterpret_cast<uint16_t *>(t.data());
+        for (int i = 0; i < 256; ++i) p16[i] = (uint16_t)ck.tab[i];
+        t16.t = p16;
+        emu_run<1, false>(st, t16, &t, v, rg, ring, yw, n, 0, 0, nullptr);
     } else {
-        std::vector<uint32_t> t = ck.tab;
-        emu_run<false, false>(st, t, alias5, v, rg, ring, yw, n, 0, 0, nullptr);
+        // linked regime: 16-bit slots + epoch bit plane (PkTab KIND 2), imported from the 32-bit checkpoint
+        const uint32_t nslot = (nslot5 + 1) & ~1u;
+        std::vector<uint16_t> lo(nslot, 0);
+        std::vector<uint32_t> ep((nslot + 31) / 32, 0);
+        PkTab<2, 1> t17; t17.t = lo.data(); t17.ep = ep.data(); t17.nslot = nslot; t17.cur = 0; t17.last_pos = pk_next_pos(st); t17.lut = lut17.data();
+        for (uint32_t e = 0; e < nslot; ++e) t17.import_slot(e, ck.tab[e], ck.st.bs);
+        emu_run<2, false>(st, t17, nullptr, v, rg, ring, yw, n, 0, 0, nullptr);
     }
     return (int64_t)(st.total + lz4_frame_overhead(n));
-}
-
-extern "C" void emu_pk_counts(uint64_t *lean, uint64_t *general, uint64_t *turbo, int reset)
-{
-    *lean = pk_lean_steps; *general = pk_general_steps; *turbo = pk_turbo_steps;
-    if (reset) pk_lean_steps = pk_general_steps = pk_turbo_steps = 0;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -188,3 +188,19 @@ def test_megabase_genomes_gzip(engine):
     assert np.array_equal(engine.tile_sizes("gzip", 0, 2, 0, 4), ref)          # checkpoints and tables reused
     engine.set_option("invalidate_caches", 1)
     assert np.array_equal(engine.tile_sizes("gzip", 0, 2, 0, 4), ref)          # and rebuilt
+
+
+def test_lz4_stale_table_slots(engine):
+    """A/T-only stretches of 66 k - 300 k bases between ACGT stretches: slots of k-mers with C/G age far beyond the
+    131072 positions the 17-bit slot encoding can tell apart; the rolling sweep must have retired them"""
+    from snacc_b200 import synth
+    seqs = []
+    for seed in range(3):
+        x, y = synth.stale_slot_stream(seed)
+        seqs += [x, y]
+    engine.upload_sequences(seqs)
+    n = len(seqs)
+    S = engine.tile_sizes("lz4", 0, n, 0, n)
+    assert engine.stat("packed_jobs") == n * n
+    ref = np.array([[olib.ref_lz4f_size(np.concatenate([a, b])) for b in seqs] for a in seqs])
+    assert np.array_equal(S, ref)

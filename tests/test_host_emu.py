@@ -176,3 +176,11 @@ def test_deflate_logic_related_genomes_long_matches_across_the_boundary(emu):
         for a in g:
             for b in g:
                 assert _call2(emu.emu_deflate_size, a, b, level) == lib.ref_deflate_size(np.concatenate([a, b]), level)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_lz4_packed_17bit_slots_never_resurrect_stale_candidates(emu, seed):
+    """the 16-bit + epoch-bit table (PkTab KIND 2) relies on the rolling sweep; without it this input gives wrong sizes"""
+    from snacc_b200 import synth
+    x, y = synth.stale_slot_stream(seed)
+    assert _call2(emu.emu_lz4_packed, x, y) == lib.ref_lz4f_size(np.concatenate([x, y]))
