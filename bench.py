@@ -6,8 +6,8 @@
 Workload (BASELINE.json configs[3], "c4"): 512 synthetic E. coli-sized (5 Mbp) mutated-phylogeny genomes,
 LZ4-frame NCD.  A *step* is the WHOLE job: C(i) for all 512 genomes, C(i.j) for all 512 x 512 ordered
 pairs (the reference's semantics, cli.py:104-136) and the float64 NCD matrix.  With N GPUs the rows of
-the job matrix are dealt round-robin to the ranks (strong scaling; no data-path collective, the row
-bands are all-gathered at the end of the step).  Metric: NCD pairs/s, where -- as in SURVEY.md 8d -- a
+the job matrix are split into one contiguous band per rank (strong scaling; no data-path collective, the
+row bands are all-gathered at the end of the step).  Metric: NCD pairs/s, where -- as in SURVEY.md 8d -- a
 pair is an unordered {i,j} entry of the finished matrix and costs two ordered compressor jobs, so
 pairs = ordered pair jobs / 2 (131072 per step).  `value` is timed with the corpus resident in HBM;
 `e2e` re-uploads the corpus from pinned host memory through the C ABI (and re-packs it) and reads the
@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--genomes", type=int, default=N_GENOMES)
     ap.add_argument("--length", type=int, default=GENOME_LEN)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--config", default="c4", choices=["c4", "c3"],
+                    help="c4 (default, the headline): 512 x 5 Mbp; c3: 10,000 x ~11 kbp viral genomes (BASELINE.json configs[2])")
+    ap.add_argument("--band", type=int, default=0, help="rows per library call (0 = the rank's whole band, 1024 for c3)")
     return ap.parse_args()
 
 
@@ -134,13 +137,15 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     codec = args.codec
+    if args.config == "c3" and args.genomes == N_GENOMES and args.length == GENOME_LEN:
+        args.genomes, args.length = 10_000, 10_700
     n, L = args.genomes, args.length
-    workload = (f"c4: {n} x {L / 1e6:g} Mbp synthetic mutated-phylogeny genomes, {codec} NCD; step = the whole "
+    workload = (f"{args.config}: {n} x {L / 1e6:g} Mbp synthetic mutated-phylogeny genomes, {codec} NCD; step = the whole "
                 f"{n} x {n} ordered-pair matrix (N + N^2 compressor jobs, reference semantics cli.py:104-136) + float64 NCD")
     config = {"workload": workload, "n_genomes": n, "genome_len": L, "codec": codec,
               "seed": SEED, "pair_unit": "ordered pair jobs / 2 (an unordered {i,j} costs two ordered jobs, cli.py:120-136); N^2/2 per step",
               "l2_policy": "inputs larger than L2 (corpus %.2f GB per GPU, replicated)" % (n * L / 1e9),
-              "sharding": f"rows i = rank (mod {world}) of the job matrix per rank, no data-path collective; "
+              "sharding": f"contiguous row band [r*N/{world}, (r+1)*N/{world}) of the job matrix per rank, no data-path collective; "
                           "row bands gathered with all_gather at the end of the step"}
 
     import numpy as np
@@ -202,10 +207,9 @@ def main():
     del corpus_dev
     torch.cuda.empty_cache()
 
-    my_rows = np.arange(rank, n, world, dtype=np.int32)          # rows i = rank (mod world): no data-path collective
-    xs = np.repeat(my_rows, n)
-    ys = np.tile(np.arange(n, dtype=np.int32), my_rows.size)
-    step_bytes = job_bytes(lengths, xs, ys)
+    my_rows = np.arange(rank * n // world, (rank + 1) * n // world, dtype=np.int32)   # contiguous band: a rectangle
+    step_jobs = int(my_rows.size) * n
+    step_bytes = float(n * np.sum(lengths[my_rows]) + my_rows.size * np.sum(lengths))
 
     def run_step(e2e):
         """one full pass: C(i) for the rank's rows, S(i,j) for rows x all columns, gather, NCD on rank 0"""
@@ -215,12 +219,16 @@ def main():
             eng.set_option("invalidate_caches", 1)       # nothing (prefix checkpoints ...) survives from the last step
         c = eng.single_sizes(codec, my_rows)
         ms1, l1 = eng.stat("total_kernel_ms"), eng.stat("launches")
-        s = eng.pair_sizes(codec, xs, ys)                # sizes come back to the host inside (D2H)
-        ms2, l2 = eng.stat("total_kernel_ms"), eng.stat("launches")
-        main_ms = eng.stat("main_kernel_ms")
-        packed = eng.stat("packed_jobs") if codec == "lz4" else 0
+        band = args.band or (1024 if args.config == "c3" else int(my_rows.size))
+        s = np.empty((my_rows.size, n), dtype=np.int64)
+        ms2 = l2 = main_ms = packed = 0
+        for a in range(0, my_rows.size, band):           # sizes come back to the host inside (D2H)
+            nb = min(band, my_rows.size - a)
+            s[a:a + nb] = eng.tile_sizes(codec, int(my_rows[a]), nb, 0, n)
+            ms2 += eng.stat("total_kernel_ms"); l2 += eng.stat("launches"); main_ms += eng.stat("main_kernel_ms")
+            packed += eng.stat("packed_jobs") if codec == "lz4" else 0
         if world > 1:
-            # gather the row bands: rank r owns rows r, r+world, ...  (2 MiB of int64 at n = 512)
+            # gather the row bands: rank r owns rows [r*n/world, (r+1)*n/world)  (2 MiB of int64 at n = 512)
             per = (n + world - 1) // world
             cbuf = torch.zeros(per, dtype=torch.int64, device=dev); cbuf[:c.size] = torch.from_numpy(c).to(dev)
             sbuf = torch.zeros(per * n, dtype=torch.int64, device=dev); sbuf[:s.size] = torch.from_numpy(s.ravel()).to(dev)
@@ -230,7 +238,7 @@ def main():
             dist.all_gather(sg, sbuf)
             C = np.zeros(n, dtype=np.int64); S = np.zeros((n, n), dtype=np.int64)
             for r in range(world):
-                rr = np.arange(r, n, world)
+                rr = np.arange(r * n // world, (r + 1) * n // world)
                 C[rr] = cg[r][:rr.size].cpu().numpy()
                 S[rr] = sg[r][:rr.size * n].cpu().numpy().reshape(rr.size, n)
         else:
@@ -241,7 +249,7 @@ def main():
             D = eng.ncd(C, S)                            # float64 epilogue kernel, result read back
             launches += 1
             check = int(S.sum() + C.sum()) ^ int(np.float64(D.sum()).view(np.int64) & 0xffff)
-        return {"kernel_ms": ms1 + ms2, "main_ms": main_ms, "launches": launches, "jobs": int(xs.size),
+        return {"kernel_ms": ms1 + ms2, "main_ms": main_ms, "launches": launches, "jobs": step_jobs,
                 "bytes": step_bytes, "check": check, "packed": int(packed)}
 
     def barrier():
@@ -298,13 +306,13 @@ def main():
             "algorithmic_GBps": bytes_total / wall_s / 1e9,
             "device_ms_per_step": 1e3 * timed_s / args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "lz4_pk_pair_kernel<linked>" if codec == "lz4" else "deflate_pair_kernel",
+                         "traffic": None, "kernel": ("lz4_pk_pair_kernel<linked>" if args.config == "c4" else "lz4_pk_pair_kernel<single-block>")
+                                   if codec == "lz4" else "dfl_parse_kernel",
                          "peak_source": peak_src,
                          "note": "achieved = algorithmic bytes of one launch (sum of len(x)+len(y) over its pair jobs) / "
                                  "its CUDA-event duration; the path is latency/integer bound, not HBM bound"},
             "e2e": {"value": pairs_per_step * args.steps / e2e_s, "unit": "pairs/s",
-                    "h2d_bytes_per_step": int(corpus_host.numel() + so.nbytes + 2 * 4 * stats[0]["jobs"] + 4 * my_rows.size
-                                              + 8 * (n * n + n)),
+                    "h2d_bytes_per_step": int(corpus_host.numel() + so.nbytes + 4 * my_rows.size + 8 * (n * n + n)),
                     "d2h_bytes_per_step": int(8 * (stats[0]["jobs"] + my_rows.size) + 8 * n * n)},
             "packed_jobs_per_step": stats[0]["packed"],
             "gpu_launches": int(sum(s["launches"] for s in stats)),

@@ -501,19 +501,77 @@ constexpr size_t PK_S_SMEM = PK_RING_WORDS * 8 + 256 * 2 + (size_t)PK_S_WARPS * 
 
 struct PkJob { int32_t y, x; int64_t j; };
 
+struct PkGeometry { uint32_t nslot; int lanes, warps; size_t smem; int T; };
+
+static PkGeometry pk_geometry(const snacc_ctx *ctx, bool u16)
+{
+    PkGeometry g;
+    if (u16) { g.nslot = 256; g.lanes = PK_S_LANES; g.warps = PK_S_WARPS; g.smem = PK_S_SMEM; g.T = PK_S_LANES * PK_S_WARPS; return g; }
+    // linked regime: as many streams as one SM's shared memory holds (A/C/G/T: 894 slots -> 1900 B per stream
+    // -> 104 streams = 4 warps x 26 lanes; a full 1024-slot alphabet: 90 -> 2 warps x 32 lanes)
+    g.nslot = (ctx->nslot5 + 1) & ~1u;
+    const size_t l_stream = (size_t)g.nslot * 2 + ((g.nslot + 31) / 32) * 4;        // bytes of table per linked stream
+    const size_t l_fixed = PK_RING_WORDS * 8 + 1024 * 2;
+    const size_t l_fit = (PK_SMEM_MAX - l_fixed) / l_stream;
+    g.lanes = l_fit >= 104 ? 26 : 32;
+    g.warps = l_fit >= 104 ? 4 : (int)std::max<size_t>(1, l_fit / 32);
+    g.smem = l_fixed + (size_t)g.warps * g.lanes * l_stream;
+    g.T = g.lanes * g.warps;
+    return g;
+}
+
+// split `cnt` jobs of one y into near-equal tiles of at most T streams
+static void pk_split(std::vector<PkTile> &tiles, int32_t y, size_t first, size_t cnt, int T)
+{
+    const size_t nt = (cnt + T - 1) / T;
+    for (size_t t = 0; t < nt; ++t) {
+        const size_t a = first + cnt * t / nt, b = first + cnt * (t + 1) / nt;
+        tiles.push_back(PkTile{y, (int32_t)(b - a), (int64_t)a});
+    }
+}
+
+// launch lz4_pk_pair_kernel on prepared tiles; tout empty = rectangle mode (out_stride, col0)
+static int pk_launch(snacc_ctx *ctx, bool u16, const PkGeometry &g, const std::vector<PkTile> &tiles,
+                     const std::vector<int32_t> &tx, const std::vector<int64_t> &tout, int64_t out_stride, int32_t col0,
+                     int64_t n_jobs)
+{
+    PkTile *d_tiles = nullptr; int32_t *d_tx = nullptr; int64_t *d_tout = nullptr;
+    CK(cudaMalloc(&d_tiles, sizeof(PkTile) * tiles.size()));
+    CK(cudaMalloc(&d_tx, sizeof(int32_t) * tx.size()));
+    CK(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(PkTile) * tiles.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_tx, tx.data(), sizeof(int32_t) * tx.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (!tout.empty()) {
+        CK(cudaMalloc(&d_tout, sizeof(int64_t) * tout.size()));
+        CK(cudaMemcpyAsync(d_tout, tout.data(), sizeof(int64_t) * tout.size(), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    unsigned long long *counter = ctx->d_counter + (u16 ? 1 : 2);
+    CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream));
+    const PkCorpus pc{ctx->d_pk_words, ctx->d_pk_woff, ctx->d_len};
+    const int grid = (int)std::min<size_t>(tiles.size(), (size_t)ctx->sm_count);
+    const int32_t nt = (int32_t)tiles.size();
+    CK(cudaEventRecord(ctx->evm0, ctx->stream));
+#define PK_GO(KIND_, LANES_, lut_) do {                                                                              \
+        CK(cudaFuncSetAttribute(lz4_pk_pair_kernel<KIND_, LANES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem)); \
+        lz4_pk_pair_kernel<KIND_, LANES_><<<grid, g.warps * 32, g.smem, ctx->stream>>>(                                \
+            pc, d_tiles, nt, d_tx, d_tout, ctx->d_ck_tab, ctx->d_ck_state, lut_, g.nslot, out_stride, col0, counter, ctx->d_out); \
+    } while (0)
+    if (u16) PK_GO(1, PK_S_LANES, ctx->d_alias4);
+    else if (g.lanes == 26) PK_GO(2, 26, ctx->d_alias5);
+    else PK_GO(2, 32, ctx->d_alias5);
+#undef PK_GO
+    CK(cudaEventRecord(ctx->evm1, ctx->stream));
+    ctx->last_launches++;
+    ctx->last_packed_jobs += n_jobs;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_tiles); cudaFree(d_tx); cudaFree(d_tout);
+    return SNACC_OK;
+}
+
 static int run_pk_pairs(snacc_ctx *ctx, std::vector<PkJob> &jobs, bool u16)
 {
     if (jobs.empty()) return SNACC_OK;
-    // linked regime: as many streams as one SM's shared memory holds (A/C/G/T: 894 slots -> 1900 B per stream
-    // -> 104 streams = 4 warps x 26 lanes; a full 1024-slot alphabet: 90 -> 2 warps x 32 lanes)
-    const uint32_t nslot = (ctx->nslot5 + 1) & ~1u;
-    const size_t l_stream = (size_t)nslot * 2 + ((nslot + 31) / 32) * 4;            // bytes of table per linked stream
-    const size_t l_fixed = PK_RING_WORDS * 8 + 1024 * 2;
-    const size_t l_fit = (PK_SMEM_MAX - l_fixed) / l_stream;
-    const int l_lanes = l_fit >= 104 ? 26 : 32;
-    const int l_warps = l_fit >= 104 ? 4 : (int)std::max<size_t>(1, l_fit / 32);
-    const size_t l_smem = l_fixed + (size_t)l_warps * l_lanes * l_stream;
-    const int T = u16 ? PK_S_LANES * PK_S_WARPS : l_lanes * l_warps;
+    const PkGeometry g = pk_geometry(ctx, u16);
     std::sort(jobs.begin(), jobs.end(), [&](const PkJob &a, const PkJob &b) {
         const uint32_t la = ctx->h_len[a.y], lb = ctx->h_len[b.y];
         return la != lb ? la > lb : a.y != b.y ? a.y < b.y : a.j < b.j;       // longest y first, jobs of one y together
@@ -524,52 +582,55 @@ static int run_pk_pairs(snacc_ctx *ctx, std::vector<PkJob> &jobs, bool u16)
     for (size_t k = 0; k < jobs.size();) {
         size_t e = k;
         while (e < jobs.size() && jobs[e].y == jobs[k].y) ++e;
-        // split the y group into near-equal tiles of at most T streams
-        const size_t cnt = e - k, nt = (cnt + T - 1) / T;
-        for (size_t t = 0; t < nt; ++t) {
-            const size_t a = k + cnt * t / nt, b = k + cnt * (t + 1) / nt;
-            tiles.push_back(PkTile{jobs[k].y, (int32_t)(b - a), (int64_t)a});
-        }
+        pk_split(tiles, jobs[k].y, k, e - k, g.T);
         k = e;
     }
     for (size_t k = 0; k < jobs.size(); ++k) { tx[k] = jobs[k].x; tout[k] = jobs[k].j; }
-    PkTile *d_tiles = nullptr; int32_t *d_tx = nullptr; int64_t *d_tout = nullptr;
-    CK(cudaMalloc(&d_tiles, sizeof(PkTile) * tiles.size()));
-    CK(cudaMalloc(&d_tx, sizeof(int32_t) * tx.size()));
-    CK(cudaMalloc(&d_tout, sizeof(int64_t) * tout.size()));
-    CK(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(PkTile) * tiles.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_tx, tx.data(), sizeof(int32_t) * tx.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(d_tout, tout.data(), sizeof(int64_t) * tout.size(), cudaMemcpyHostToDevice, ctx->stream));
-    unsigned long long *counter = ctx->d_counter + (u16 ? 1 : 2);
-    CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream));
-    const PkCorpus pc{ctx->d_pk_words, ctx->d_pk_woff, ctx->d_len};
-    const int grid = (int)std::min<size_t>(tiles.size(), (size_t)ctx->sm_count);
-    CK(cudaEventRecord(ctx->evm0, ctx->stream));
-    if (u16) {
-        CK(cudaFuncSetAttribute(lz4_pk_pair_kernel<1, PK_S_LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PK_S_SMEM));
-        lz4_pk_pair_kernel<1, PK_S_LANES><<<grid, PK_S_WARPS * 32, PK_S_SMEM, ctx->stream>>>(
-            pc, d_tiles, (int32_t)tiles.size(), d_tx, d_tout, ctx->d_ck_tab, ctx->d_ck_state, ctx->d_alias4, 256, counter,
-            ctx->d_out);
-    } else {
-        if (l_lanes == 26) {
-            CK(cudaFuncSetAttribute(lz4_pk_pair_kernel<2, 26>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l_smem));
-            lz4_pk_pair_kernel<2, 26><<<grid, l_warps * 32, l_smem, ctx->stream>>>(
-                pc, d_tiles, (int32_t)tiles.size(), d_tx, d_tout, ctx->d_ck_tab, ctx->d_ck_state, ctx->d_alias5, nslot, counter,
-                ctx->d_out);
-        } else {
-            CK(cudaFuncSetAttribute(lz4_pk_pair_kernel<2, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)l_smem));
-            lz4_pk_pair_kernel<2, 32><<<grid, l_warps * 32, l_smem, ctx->stream>>>(
-                pc, d_tiles, (int32_t)tiles.size(), d_tx, d_tout, ctx->d_ck_tab, ctx->d_ck_state, ctx->d_alias5, nslot, counter,
-                ctx->d_out);
-        }
+    return pk_launch(ctx, u16, g, tiles, tx, tout, 0, 0, (int64_t)jobs.size());
+}
+
+// make sure the listed sequences have their packed prefix checkpoint for the regimes in `need` (bit 0 / bit 1)
+static int pk_ensure_ckpts(snacc_ctx *ctx, const std::vector<int32_t> &need)
+{
+    std::vector<int32_t> seqs, want; std::vector<int64_t> idx;
+    for (int32_t s = 0; s < ctx->n_seqs; ++s) {
+        const int32_t missing = need[s] & ~ctx->h_ck_have[s];
+        if (missing) { seqs.push_back(s); want.push_back(missing); idx.push_back(-1); ctx->h_ck_have[s] |= (uint8_t)missing; }
     }
-    CK(cudaEventRecord(ctx->evm1, ctx->stream));
-    ctx->last_launches++;
-    ctx->last_packed_jobs += (int64_t)jobs.size();
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_tiles); cudaFree(d_tx); cudaFree(d_tout);
-    return SNACC_OK;
+    return run_pk_single(ctx, seqs, want, idx);
+}
+
+// Rectangle rows [row0, row0+n_rows) x cols [col0, col0+n_cols) of the ordered-pair matrix on the packed path
+// without building per-job arrays (c3: 10^8 jobs).  Returns 1 when the rectangle is not uniform enough (some
+// sequence outside the alphabet, a y shorter than 16, or pairs on both sides of the 64 KiB regime boundary):
+// the caller then takes the per-job path.
+static int run_pk_rect(snacc_ctx *ctx, int32_t row0, int32_t n_rows, int32_t col0, int32_t n_cols)
+{
+    uint32_t min_x = 0xffffffffu, max_x = 0, min_y = 0xffffffffu, max_y = 0;
+    for (int32_t r = row0; r < row0 + n_rows; ++r) {
+        if (!ctx->h_packable[r]) return 1;
+        min_x = std::min(min_x, ctx->h_len[r]); max_x = std::max(max_x, ctx->h_len[r]);
+    }
+    for (int32_t c = col0; c < col0 + n_cols; ++c) {
+        if (!ctx->h_packable[c]) return 1;
+        min_y = std::min(min_y, ctx->h_len[c]); max_y = std::max(max_y, ctx->h_len[c]);
+    }
+    if (min_y < 16) return 1;
+    const bool all_small = (uint64_t)max_x + max_y <= LZ4_BLOCK, all_linked = (uint64_t)min_x + min_y > LZ4_BLOCK;
+    if (!all_small && !all_linked) return 1;
+    const bool u16 = all_small;
+    std::vector<int32_t> need((size_t)ctx->n_seqs, 0);
+    for (int32_t r = row0; r < row0 + n_rows; ++r) need[r] = u16 ? 1 : 2;
+    int rc = pk_ensure_ckpts(ctx, need);
+    if (rc) return rc;
+    const PkGeometry g = pk_geometry(ctx, u16);
+    std::vector<int32_t> cols((size_t)n_cols), tx((size_t)n_rows);
+    for (int32_t c = 0; c < n_cols; ++c) cols[c] = col0 + c;
+    std::stable_sort(cols.begin(), cols.end(), [&](int32_t a, int32_t b) { return ctx->h_len[a] > ctx->h_len[b]; });
+    for (int32_t r = 0; r < n_rows; ++r) tx[r] = row0 + r;
+    std::vector<PkTile> tiles;
+    for (int32_t y : cols) pk_split(tiles, y, 0, (size_t)n_rows, g.T);
+    return pk_launch(ctx, u16, g, tiles, tx, std::vector<int64_t>(), n_cols, col0, (int64_t)n_rows * n_cols);
 }
 
 // LZ4 driver: jobs whose operands have a 2-bit copy take the packed tile kernels, the rest the byte-wise kernel
@@ -601,12 +662,7 @@ static int run_lz4(snacc_ctx *ctx, const int32_t *h_x, const int32_t *h_y, int64
             (u16 ? small : linked).push_back(PkJob{y, x, k});
             need[x] |= u16 ? 1 : 2;
         }
-        std::vector<int32_t> seqs, want; std::vector<int64_t> idx;
-        for (int32_t s = 0; s < ctx->n_seqs; ++s) {
-            const int32_t missing = need[s] & ~ctx->h_ck_have[s];
-            if (missing) { seqs.push_back(s); want.push_back(missing); idx.push_back(-1); ctx->h_ck_have[s] |= (uint8_t)missing; }
-        }
-        r = run_pk_single(ctx, seqs, want, idx);
+        r = pk_ensure_ckpts(ctx, need);
         if (r) return r;
         r = run_pk_pairs(ctx, small, true);
         if (r) return r;
@@ -686,11 +742,61 @@ extern "C" int snacc_pair_sizes(snacc_ctx *ctx, int codec, const int32_t *xs, co
     return sizes_impl(ctx, codec, xs, ys, n_jobs, out);
 }
 
+// rectangle on the packed LZ4 path; returns 1 when the rectangle has to take the per-job path
+static int tile_sizes_rect(snacc_ctx *ctx, int32_t row0, int32_t n_rows, int32_t col0, int32_t n_cols, int64_t *out)
+{
+    std::unique_lock<std::mutex> lock(ctx->mu);
+    ctx->err.clear();
+    if (!ctx->n_seqs || !ctx->use_packed) return 1;
+    if (row0 + n_rows > ctx->n_seqs || col0 + n_cols > ctx->n_seqs) return 1;      // the per-job path reports the error
+    const int64_t n = (int64_t)n_rows * n_cols;
+    if (n == 0) return 1;
+    CK(cudaSetDevice(ctx->device));
+    if (n > ctx->out_cap) {
+        cudaFree(ctx->d_out); ctx->d_out = nullptr; ctx->out_cap = 0;
+        CK(cudaMalloc(&ctx->d_out, sizeof(int64_t) * n));
+        ctx->out_cap = n;
+    }
+    ctx->last_launches = 0;
+    ctx->last_packed_jobs = ctx->last_bytewise_jobs = 0;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    int r = run_pk_rect(ctx, row0, n_rows, col0, n_cols);
+    if (r) return r;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaMemcpyAsync(out, ctx->d_out, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); ctx->last_ms = ms;
+    CK(cudaEventElapsedTime(&ms, ctx->evm0, ctx->evm1)); ctx->last_main_ms = ms;
+    // streams that could not use their checkpoint exactly (-1): redo those jobs on the per-job path
+    std::vector<int64_t> redo;
+    for (int64_t k = 0; k < n; ++k) if (out[k] < 0) redo.push_back(k);
+    if (!redo.empty()) {
+        std::vector<int32_t> xs(redo.size()), ys(redo.size());
+        std::vector<int64_t> got(redo.size());
+        for (size_t k = 0; k < redo.size(); ++k) { xs[k] = row0 + (int32_t)(redo[k] / n_cols); ys[k] = col0 + (int32_t)(redo[k] % n_cols); }
+        const int64_t packed = ctx->last_packed_jobs - (int64_t)redo.size();
+        ctx->use_packed = 0;
+        lock.unlock();
+        r = sizes_impl(ctx, SNACC_LZ4F, xs.data(), ys.data(), (int64_t)redo.size(), got.data());
+        lock.lock();
+        ctx->use_packed = 1;
+        if (r) return r;
+        for (size_t k = 0; k < redo.size(); ++k) out[redo[k]] = got[k];
+        ctx->last_packed_jobs = packed; ctx->last_bytewise_jobs = (int64_t)redo.size();
+    }
+    return SNACC_OK;
+}
+
 extern "C" int snacc_tile_sizes(snacc_ctx *ctx, int codec, int32_t row0, int32_t n_rows, int32_t col0,
                                 int32_t n_cols, int64_t *out)
 {
     if (!ctx) return SNACC_ERR_ARG;
     if (n_rows < 0 || n_cols < 0 || row0 < 0 || col0 < 0) return SNACC_ERR_ARG;
+    if (codec == SNACC_LZ4F && out) {
+        const int r = tile_sizes_rect(ctx, row0, n_rows, col0, n_cols, out);
+        if (r != 1) return r;
+    }
     const int64_t n = (int64_t)n_rows * n_cols;
     std::vector<int32_t> xs((size_t)n), ys((size_t)n);
     for (int32_t r = 0; r < n_rows; ++r)

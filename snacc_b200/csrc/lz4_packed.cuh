@@ -709,14 +709,16 @@ __device__ __forceinline__ void pk_ring_fill(uint64_t *ring, const uint64_t *yw,
 }
 
 // ---- pair tiles: one stream per thread, LANES active lanes per warp, tables in shared memory --------
-// KIND: table storage (PkTab).  nslot: slots per stream (KIND 2: what pk_slot_lut needs, rounded up to 32).
+// KIND: table storage (PkTab).  nslot: slots per stream (KIND 2: what pk_slot_lut needs, rounded up to 2).
+// tile_out == nullptr: rectangle mode -- the tile's jobs are rows first .. first+count-1 of tile_x against
+// column y, and results go to out[(first + k) * out_stride + (y - col0)] (no per-job arrays on the host).
 // shared memory: ring | code->slot map | position tables (warp-major, lane-interleaved) | epoch planes
 template <int KIND, int LANES>
 __global__ void __launch_bounds__(384, 1)
 lz4_pk_pair_kernel(PkCorpus pc, const PkTile *__restrict__ tiles, int32_t n_tiles, const int32_t *__restrict__ tile_x,
                    const int64_t *__restrict__ tile_out, const uint32_t *__restrict__ ck_tab,
                    const PkState *__restrict__ ck_state, const uint16_t *__restrict__ lut_g, uint32_t nslot,
-                   unsigned long long *__restrict__ counter, int64_t *__restrict__ out)
+                   int64_t out_stride, int32_t col0, unsigned long long *__restrict__ counter, int64_t *__restrict__ out)
 {
     typedef PkTab<KIND, LANES> Tab;
     constexpr bool U16 = Tab::U16;
@@ -803,7 +805,11 @@ lz4_pk_pair_kernel(PkCorpus pc, const PkTile *__restrict__ tiles, int32_t n_tile
             rg.advance(w0, w1);
             pk_ring_fill(ring, yw, w0, w1);
         }
-        if (has) out[tile_out[td.first + slot]] = bail ? -1 : (int64_t)(st.total + lz4_frame_overhead(n));
+        if (has) {
+            // explicit output index per job, or (rectangle mode) row-major position of (x, y) in the rectangle
+            const int64_t oi = tile_out ? tile_out[td.first + slot] : (td.first + slot) * out_stride + (td.y - col0);
+            out[oi] = bail ? -1 : (int64_t)(st.total + lz4_frame_overhead(n));
+        }
     }
 }
 

@@ -92,8 +92,8 @@ def compute_distance(x, y, cxy, cyx):
 
 
 def _row_partition(n, world):
-    """rows owned by each rank: round-robin, which balances bytes when lengths are similar"""
-    return [np.arange(r, n, world, dtype=np.int64) for r in range(world)]
+    """rows owned by each rank: contiguous bands (see sharding.owned_rows)"""
+    return [np.arange(r * n // world, (r + 1) * n // world, dtype=np.int64) for r in range(world)]
 
 
 def ncd_matrix(files, algorithm, reverse_complement=False, fast_mode=False, gpus=None, engine=None,

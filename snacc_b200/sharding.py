@@ -1,8 +1,8 @@
 """Row sharding of the ordered-pair job matrix across GPUs.
 
 Jobs are independent: there is no data-path collective.  The corpus is replicated (one broadcast), rank
-r owns rows ``r, r+W, r+2W, ...`` of S (so every x prefix state is built by exactly one rank), and the
-int64 row blocks are gathered at the end.  With ``torch.distributed`` uninitialised this is the
+r owns the contiguous row band ``[r*N/W, (r+1)*N/W)`` of S (so every x prefix state is built by exactly one
+rank), and the int64 row blocks are gathered at the end.  With ``torch.distributed`` uninitialised this is the
 single-GPU path.  The same code runs under the ``gloo`` backend on CPU for the host-logic tests, with
 ``size_fn`` standing in for the GPU engine.
 """
@@ -23,7 +23,9 @@ def _dist():
 
 
 def owned_rows(n, rank, world):
-    return np.arange(rank, n, world, dtype=np.int64)
+    """contiguous row band of rank `rank`: a rectangle of the job matrix, which the library runs without
+    per-job arrays (snacc_tile_sizes)"""
+    return np.arange(rank * n // world, (rank + 1) * n // world, dtype=np.int64)
 
 
 def broadcast_corpus(files, dist, device=None):
@@ -119,10 +121,8 @@ def all_pairs(files, algorithm, reverse_complement, fast_mode, engine=None, rows
                 for i, r in enumerate(rr):
                     S_rows[a + i, r:] = vals[k:k + n - r]
                     k += n - r
-            else:
-                xs = np.repeat(rr.astype(np.int32), n)
-                ys = np.tile(np.arange(n, dtype=np.int32), rr.size)
-                S_rows[a:a + rr.size] = engine.pair_sizes(algorithm, xs, ys).reshape(rr.size, n)
+            elif rr.size:
+                S_rows[a:a + rr.size] = engine.tile_sizes(algorithm, int(rr[0]), int(rr.size), 0, n)
     else:
         if dist:
             t, so, ro = broadcast_corpus(files, dist, None)
