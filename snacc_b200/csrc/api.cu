@@ -712,6 +712,7 @@ static int sizes_impl(snacc_ctx *ctx, int codec, const int32_t *xs, const int32_
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_ms = ms;
+    if (codec != SNACC_LZ4F) ctx->last_main_ms = ctx->dfl.main_ms;
     if (codec == SNACC_LZ4F) {
         CK(cudaEventElapsedTime(&ms, ctx->evm0, ctx->evm1)); ctx->last_main_ms = ms;
         // packed pair streams that could not use their checkpoint exactly (-1) are redone byte-wise

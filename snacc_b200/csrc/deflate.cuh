@@ -436,11 +436,32 @@ struct DflFView {
     // prev_length >= good_length is the common case); null: recompute on demand
     const uint32_t *qx, *qy, *qj;
 };
-SNACC_HD uint32_t dfl_f_at(const DflFView &v, uint32_t p)
+// The parse reads F at nearly consecutive positions (two reads per emitted match, a match is ~9 bytes on DNA) and
+// each read is a dependent DRAM round trip, so the last 32-byte sector (8 entries) is kept in registers.
+// All three tables start on 32-byte boundaries and are padded to a multiple of 8 entries.
+struct DflFCache { const uint32_t *base; uint32_t v[8]; };
+SNACC_HD uint32_t dfl_f_cached(DflFCache &c, const uint32_t *tab, uint32_t i)
 {
-    if (p < v.jx0) return SNACC_LDG(v.fx + p);
-    if (p < v.jend) return SNACC_LDG(v.fj + (p - v.jx0));
-    return SNACC_LDG(v.fy + (p - v.lx));
+    const uint32_t *blk = tab + (i & ~7u);
+    if (blk != c.base) {
+        c.base = blk;
+#ifdef __CUDA_ARCH__
+        const uint4 a = __ldg(reinterpret_cast<const uint4 *>(blk)), b = __ldg(reinterpret_cast<const uint4 *>(blk) + 1);
+        c.v[0] = a.x; c.v[1] = a.y; c.v[2] = a.z; c.v[3] = a.w; c.v[4] = b.x; c.v[5] = b.y; c.v[6] = b.z; c.v[7] = b.w;
+#else
+        for (int k = 0; k < 8; ++k) c.v[k] = blk[k];
+#endif
+    }
+    const uint32_t k = i & 7;
+    const uint32_t lo = (k & 1) ? ((k & 2) ? c.v[3] : c.v[1]) : ((k & 2) ? c.v[2] : c.v[0]);
+    const uint32_t hi = (k & 1) ? ((k & 2) ? c.v[7] : c.v[5]) : ((k & 2) ? c.v[6] : c.v[4]);
+    return (k & 4) ? hi : lo;
+}
+SNACC_HD uint32_t dfl_f_at(const DflFView &v, uint32_t p, DflFCache &c)
+{
+    if (p < v.jx0) return dfl_f_cached(c, v.fx, p);
+    if (p < v.jend) return dfl_f_cached(c, v.fj, p - v.jx0);
+    return dfl_f_cached(c, v.fy, p - v.lx);
 }
 SNACC_HD uint32_t dfl_q_at(const DflFView &v, uint32_t p)
 {
@@ -463,6 +484,8 @@ static __host__ __device__ bool dfl_parse(const DflStream &d, const DflFView &fv
     uint32_t base = st.base, read = st.read, block_start = st.block_start;
     uint64_t bits = st.bits;
     bool done = false;
+    DflFCache fc;
+    fc.base = nullptr;
 #define DFL_FLUSH(last_) do {                                                                                   \
         dfl_flush_block(tr, lfreq, lstride, dfreq, dstride, strstart - block_start, block_start >= base, (last_), bits); \
         for (int n_ = 0; n_ < DFL_L_CODES; n_++) lfreq[n_ * lstride] = 0;                                        \
@@ -491,7 +514,7 @@ static __host__ __device__ bool dfl_parse(const DflStream &d, const DflFView &fv
                 f = dfl_longest(d, strstart, base, (uint32_t)c.max_chain, (uint32_t)c.nice_length, 0xffffffffu, &q);
                 if (prev_length >= (uint32_t)c.good_length) f = q;
             } else {
-                f = dfl_f_at(fv, strstart);
+                f = dfl_f_at(fv, strstart, fc);
                 if (prev_length >= (uint32_t)c.good_length && (f & DFL_QDIFF)) {  // quartered chain: second table or on demand
                     if (fv.qx) f = dfl_q_at(fv, strstart);
                     else dfl_longest(d, strstart, base, (uint32_t)c.max_chain, (uint32_t)c.nice_length, 0xffffffffu, &f);
@@ -546,6 +569,7 @@ SNACC_HD void dfl_resume(DflParseState &st, uint32_t n)
 SNACC_HD uint32_t dfl_jx0(uint32_t lx) { return lx > DFL_JX ? lx - DFL_JX : 0; }
 SNACC_HD uint32_t dfl_jlen(uint32_t lx, uint32_t ly) { return (lx - dfl_jx0(lx)) + tmin(ly, DFL_JY); }
 constexpr uint32_t DFL_JSTRIDE = DFL_JX + DFL_JY;
+static_assert(DFL_JSTRIDE % 8 == 0, "junction slices must start on 32-byte boundaries (DflFCache)");
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------
@@ -811,19 +835,19 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
         st.n_seqs = ns;
         st.h_poff.assign(ns, 0);
         uint64_t t = 0;
-        for (int32_t i = 0; i < ns; ++i) { st.h_poff[i] = t; t += ((uint64_t)dc.h_len[i] + 3) & ~3ull; }
+        for (int32_t i = 0; i < ns; ++i) { st.h_poff[i] = t; t += ((uint64_t)dc.h_len[i] + 7) & ~7ull; }
         st.total = t;
         DCK(cudaMalloc(&st.d_poff, sizeof(uint64_t) * ns));
         DCK(cudaMemcpyAsync(st.d_poff, st.h_poff.data(), sizeof(uint64_t) * ns, cudaMemcpyHostToDevice, stream));
-        DCK(cudaMalloc(&st.d_order, sizeof(uint32_t) * (t + 4)));
+        DCK(cudaMalloc(&st.d_order, sizeof(uint32_t) * (t + 16)));
         DCK(cudaMalloc(&st.d_bstart, sizeof(uint32_t) * (size_t)ns * (DFL_HASH + 1)));
         st.indexed.assign(ns, 0);
         for (int l = 0; l < 2; ++l) { st.have_F[l].assign(ns, 0); st.have_ck[l].assign(ns, 0); }
     }
     if (!st.d_F[li]) {
-        DCK(cudaMalloc(&st.d_F[li], sizeof(uint32_t) * (st.total + 4)));
+        DCK(cudaMalloc(&st.d_F[li], sizeof(uint32_t) * (st.total + 16)));
         DCK(cudaMalloc(&st.d_ckpt[li], sizeof(DflCkpt) * ns));
-        if (level != 9) DCK(cudaMalloc(&st.d_FQ, sizeof(uint32_t) * (st.total + 4)));
+        if (level != 9) DCK(cudaMalloc(&st.d_FQ, sizeof(uint32_t) * (st.total + 16)));
     }
     uint32_t *FQ = level != 9 ? st.d_FQ : nullptr;
     DflCorpus c{dc.d_corpus, dc.d_off, dc.d_len, st.d_poff, st.d_order, st.d_bstart};
@@ -873,17 +897,25 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
     }
     unsigned long long *d_counter = nullptr;
     DCK(cudaMalloc(&d_counter, sizeof(unsigned long long)));
+    st.main_ms = 0.0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    DCK(cudaEventCreate(&e0)); DCK(cudaEventCreate(&e1));
     auto run_parse = [&](const std::vector<DflJob> &jobs) -> int {
         if (jobs.empty()) return 0;
         DflJob *d_jobs = nullptr;
         if (dfl_upload(err, stream, jobs, &d_jobs)) return -1;
         DCK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream));
+        DCK(cudaEventRecord(e0, stream));
         const int blocks = (int)std::min<size_t>((jobs.size() + DFL_PARSE_THREADS - 1) / DFL_PARSE_THREADS, parse_blocks);
         dfl_parse_kernel<<<blocks, DFL_PARSE_THREADS, 0, stream>>>(c, d_jobs, (int64_t)jobs.size(), level, st.d_F[li], FQ, st.d_FJ,
                                                                   FQ ? st.d_FJQ : nullptr, st.d_ckpt[li], st.d_scratch, d_counter, d_out);
         DCK(cudaGetLastError());
+        DCK(cudaEventRecord(e1, stream));
         ++*launches;
         DCK(cudaStreamSynchronize(stream));
+        float ms = 0.f;
+        DCK(cudaEventElapsedTime(&ms, e0, e1));
+        st.main_ms += ms;                                 // the parse kernel is the dominant one
         cudaFree(d_jobs);
         return 0;
     };
@@ -923,6 +955,7 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
         }
     }
     cudaFree(d_counter);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
     return rc;
 }
 #undef DCK

@@ -199,7 +199,7 @@ static EmuIndex emu_index(const uint8_t *p, uint32_t len)
 
 static std::vector<uint32_t> emu_F_single(const DflStream &d, const DflConfig &cfg)
 {
-    std::vector<uint32_t> F(d.s.n + 4, 0);
+    std::vector<uint32_t> F(d.s.n + 16, 0);
     const uint32_t nidx = d.s.n >= 3 ? d.s.n - 2 : 0;
     for (uint32_t k = 0; k < nidx; ++k) { const uint32_t p = d.ix.order[k]; F[p] = dfl_f_word(d, p, cfg, k, nullptr); }
     return F;
@@ -238,7 +238,7 @@ extern "C" int64_t emu_deflate_size(const uint8_t *x, uint32_t lx, const uint8_t
         // pair stream: junction F, then resume
         DflStream d; d.s.x = px; d.s.lx = lx; d.s.y = py; d.s.n = lx + ly; d.pair = true; d.ix = dx.ix; d.iy = dy.ix;
         const uint32_t jx0 = dfl_jx0(lx), jlen = dfl_jlen(lx, ly);
-        std::vector<uint32_t> FJ(jlen + 4, 0);
+        std::vector<uint32_t> FJ(jlen + 16, 0);
         for (uint32_t u = 0; u < jlen; ++u) FJ[u] = dfl_f_word(d, jx0 + u, cfg, 0xffffffffu, nullptr);
         fv.fx = Fx.data(); fv.fy = Fy.data(); fv.fj = FJ.data(); fv.jx0 = jx0; fv.jend = jx0 + jlen; fv.lx = lx;
         dfl_resume(st, d.s.n);
