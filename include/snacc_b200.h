@@ -102,10 +102,13 @@ int snacc_ncd(snacc_ctx *ctx, const int64_t *C, const int64_t *S, int32_t n, int
  * sizes call, and the number of kernel launches it made */
 int snacc_last_kernel_ms(const snacc_ctx *ctx, double *ms, int64_t *launches);
 /* named statistics of the last sizes call: "main_kernel_ms" (dominant kernel only), "total_kernel_ms",
- * "launches" */
+ * "launches", "packed_jobs", "bytewise_jobs", "deflate_serial_jobs" (pair streams of a deflate call that took
+ * the full serial parse after their canonical-stream shortcut met a block that might be stored) */
 int snacc_get_stat(const snacc_ctx *ctx, const char *name, double *out);
 /* tunables: 0 = default.  `streams_in_flight` bounds the number of concurrently parsed streams;
- * `invalidate_caches` (any value) drops every per-sequence precomputation so the next call redoes it. */
+ * `invalidate_caches` (any value) drops every per-sequence precomputation so the next call redoes it;
+ * `lz4_packed` 0 forces the byte-wise LZ4 kernels; `deflate_canonical` 0 makes every deflate pair stream take
+ * the full serial parse instead of the canonical symbol stream of y (both are for tests: same results). */
 int snacc_set_option(snacc_ctx *ctx, const char *name, int64_t value);
 
 #ifdef __cplusplus

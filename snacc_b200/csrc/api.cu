@@ -854,6 +854,7 @@ extern "C" int snacc_get_stat(const snacc_ctx *ctx, const char *name, double *ou
     if (!strcmp(name, "launches")) { *out = (double)ctx->last_launches; return SNACC_OK; }
     if (!strcmp(name, "packed_jobs")) { *out = (double)ctx->last_packed_jobs; return SNACC_OK; }
     if (!strcmp(name, "bytewise_jobs")) { *out = (double)ctx->last_bytewise_jobs; return SNACC_OK; }
+    if (!strcmp(name, "deflate_serial_jobs")) { *out = (double)ctx->dfl.serial_jobs; return SNACC_OK; }
     return SNACC_ERR_ARG;
 }
 
@@ -863,6 +864,7 @@ extern "C" int snacc_set_option(snacc_ctx *ctx, const char *name, int64_t value)
     std::lock_guard<std::mutex> lock(ctx->mu);
     if (!strcmp(name, "streams_in_flight")) { ctx->streams_in_flight = value; return SNACC_OK; }
     if (!strcmp(name, "lz4_packed")) { ctx->use_packed = value ? 1 : 0; return SNACC_OK; }
+    if (!strcmp(name, "deflate_canonical")) { ctx->dfl.use_canon = value ? 1 : 0; return SNACC_OK; }
     if (!strcmp(name, "invalidate_caches")) {
         // forget every per-sequence precomputation (prefix checkpoints ...) so the next sizes call
         // redoes the whole job; used by bench.py so that no step reuses work of an earlier step

@@ -380,7 +380,8 @@ static __host__ __device__ void dfl_scan_tree(DflTrees &t, DflNode *tree, int ma
 // Bits of one block given its symbol frequencies (lfreq[286] incl. END_BLOCK = 1, dfreq[30]); `bits` is
 // the running total (the stored form aligns it).
 static __host__ __device__ void dfl_flush_block(DflTrees &t, const uint16_t *lfreq, int lstride, const uint16_t *dfreq,
-                                                int dstride, uint64_t stored_len, bool can_store, bool last, uint64_t &bits)
+                                                int dstride, uint64_t stored_len, bool can_store, bool last, uint64_t &bits,
+                                                bool *stored_cand = nullptr)
 {
     const uint8_t bl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     for (int n = 0; n < DFL_L_CODES; n++) t.ltree[n].freq = lfreq[n * lstride];
@@ -400,6 +401,7 @@ static __host__ __device__ void dfl_flush_block(DflTrees &t, const uint16_t *lfr
     uint64_t opt_lenb = (t.opt_len + 3 + 7) >> 3;
     const uint64_t static_lenb = (t.static_len + 3 + 7) >> 3;
     if (static_lenb <= opt_lenb) opt_lenb = static_lenb;
+    if (stored_cand) *stored_cand = stored_len + 4 <= opt_lenb;    // the stored form would win if the window still holds the block
     if (stored_len + 4 <= opt_lenb && can_store) {
         bits += 3;
         bits = (bits + 7) & ~7ull;
@@ -410,6 +412,72 @@ static __host__ __device__ void dfl_flush_block(DflTrees &t, const uint16_t *lfr
         bits += 3 + t.opt_len;
     }
     if (last) bits = (bits + 7) & ~7ull;
+}
+
+// ------------------------------------------------------------------------------------------------
+// canonical symbol stream of a sequence
+// ------------------------------------------------------------------------------------------------
+// deflate_slow's state right after it has emitted a match is just the position: match_available = 0,
+// match_length = MIN_MATCH-1 (so prev_match is dead).  From such a loop top the symbols it emits are a pure
+// function of F, and F_y(q) is the same in every stream that contains y once q >= DFL_JY.  So as soon as the
+// parse of x.y stands, at y offset q >= DFL_JY, on a position where the parse of y ALONE also stood right
+// after a match, the two emit the same symbols for the rest of y -- only the block boundaries (every 16383
+// symbols, counted from wherever the pair stream's open block began) and the end-of-input window slide
+// (a function of the absolute position) differ.  The parse of y alone is therefore recorded once per
+// sequence: end offset and (length code, distance code) of every symbol, plus cumulative symbol
+// histograms every DFL_CUM_G symbols.  A pair stream parses its junction serially, finds the
+// synchronisation point (binary search in `end`), takes the histogram of each of its remaining blocks as
+// a difference of two cumulative rows and only returns to the serial parser for the last DFL_TAIL bytes.
+// A block for which zlib would consider the stored form (never on DNA) sends the job back to the full
+// serial parse: whether that form is allowed depends on the window position, which the shortcut does not
+// track.
+constexpr uint32_t DFL_CUM_G = 256;                    // symbols per cumulative-histogram row
+constexpr uint32_t DFL_CUM_W = 320;                    // row width: 286 literal/length + 30 distance counters, padded
+constexpr uint32_t DFL_TAIL = 1024;                    // bytes of y always left to the serial parser (>= 262 + 258)
+constexpr uint32_t DFL_CANON_MIN = DFL_JY + 4 * DFL_TAIL;   // shorter y: plain serial parse
+constexpr uint32_t DFL_LIT = 31;                       // distance-code field of a literal
+constexpr uint32_t DFL_NONE = 0xffffffffu;
+
+struct DflRec {                        // where the parse of a sequence alone records its symbols
+    uint32_t *end; uint16_t *code;     // end offset after the symbol; lcode | dcode << 9
+    uint32_t cap, n;                   // n = DFL_NONE after an overflow
+};
+SNACC_HD void dfl_rec_emit(DflRec *r, uint32_t code, uint32_t end)
+{
+    if (!r || r->n == DFL_NONE) return;
+    if (r->n >= r->cap) { r->n = DFL_NONE; return; }
+    r->end[r->n] = end; r->code[r->n] = (uint16_t)code; r->n++;
+}
+
+struct DflCanon {
+    const uint32_t *end; const uint16_t *code;
+    const uint32_t *cum;               // row j: counts of the symbols [0, j * DFL_CUM_G)
+    uint32_t n_sym;                    // 0: not available
+};
+
+// index of the canonical symbol that is a match and ends at y offset q, or DFL_NONE
+SNACC_HD uint32_t dfl_canon_find(const DflCanon &cn, uint32_t q)
+{
+    uint32_t lo = 0, hi = cn.n_sym;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (SNACC_LDG(cn.end + mid) < q) lo = mid + 1; else hi = mid;
+    }
+    if (lo < cn.n_sym && SNACC_LDG(cn.end + lo) == q && (SNACC_LDG(cn.code + lo) >> 9) != DFL_LIT) return lo;
+    return DFL_NONE;
+}
+
+// histogram of the canonical symbols [0, t) into acc[DFL_L_CODES + DFL_D_CODES]
+SNACC_HD void dfl_cum_at(const DflCanon &cn, uint32_t t, uint32_t *acc)
+{
+    const uint32_t row = t / DFL_CUM_G;
+    const uint32_t *src = cn.cum + (size_t)row * DFL_CUM_W;
+    for (int c = 0; c < DFL_L_CODES + DFL_D_CODES; ++c) acc[c] = SNACC_LDG(src + c);
+    for (uint32_t k = row * DFL_CUM_G; k < t; ++k) {
+        const uint32_t code = SNACC_LDG(cn.code + k);
+        acc[code & 511]++;
+        if ((code >> 9) != DFL_LIT) acc[DFL_L_CODES + (code >> 9)]++;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -473,9 +541,15 @@ SNACC_HD uint32_t dfl_q_at(const DflFView &v, uint32_t p)
 // Run deflate_slow from `st` until strstart >= stop (loop-top granularity) or the stream ends; lfreq/dfreq
 // are the open block's counters (strided so that a kernel can keep them in shared memory).  At the end of
 // the stream the last block is flushed and the function returns true.
+// rec: record every emitted symbol (the parse of a sequence alone).  canon: the canonical stream of y; the
+// function returns 2 -- with *sync_k = index of the canonical symbol just reproduced -- at the first match
+// that ends at a stream position >= sync_from where the canonical parse also ended a match.
+// Returns 0 when it stopped at `stop`, 1 when the stream is finished.
 template <class TallyT>
-static __host__ __device__ bool dfl_parse(const DflStream &d, const DflFView &fv, const DflConfig &c, DflParseState &st,
-                                          TallyT *lfreq, int lstride, TallyT *dfreq, int dstride, DflTrees &tr, uint32_t stop)
+static __host__ __device__ int dfl_parse(const DflStream &d, const DflFView &fv, const DflConfig &c, DflParseState &st,
+                                         TallyT *lfreq, int lstride, TallyT *dfreq, int dstride, DflTrees &tr, uint32_t stop,
+                                         DflRec *rec = nullptr, const DflCanon *canon = nullptr, uint32_t sync_from = 0,
+                                         uint32_t *sync_k = nullptr)
 {
     const Stream &s = d.s;
     const uint32_t n = s.n;
@@ -483,7 +557,7 @@ static __host__ __device__ bool dfl_parse(const DflStream &d, const DflFView &fv
     uint32_t match_available = st.match_available, sym_count = st.sym_count;
     uint32_t base = st.base, read = st.read, block_start = st.block_start;
     uint64_t bits = st.bits;
-    bool done = false;
+    bool done = false, synced = false;
     DflFCache fc;
     fc.base = nullptr;
 #define DFL_FLUSH(last_) do {                                                                                   \
@@ -530,16 +604,25 @@ static __host__ __device__ bool dfl_parse(const DflStream &d, const DflFView &fv
             // below is taken exactly as with MIN_MATCH-1
         }
         if (prev_length >= DFL_MIN_MATCH && match_length <= prev_length) {
-            lfreq[(dfl_length_code(prev_length - DFL_MIN_MATCH) + 257) * lstride]++;
-            dfreq[dfl_dist_code(strstart - 1 - prev_match - 1) * dstride]++;
+            const uint32_t lc = (uint32_t)dfl_length_code(prev_length - DFL_MIN_MATCH) + 257;
+            const uint32_t dcd = (uint32_t)dfl_dist_code(strstart - 1 - prev_match - 1);
+            lfreq[lc * lstride]++;
+            dfreq[dcd * dstride]++;
             const bool bflush = ++sym_count == DFL_SYMS_PER_BLOCK;
             strstart += prev_length - 1;
             match_available = 0;
             match_length = DFL_MIN_MATCH - 1;
+            dfl_rec_emit(rec, lc | (dcd << 9), strstart);
             if (bflush) DFL_FLUSH(false);
+            if (canon && strstart >= sync_from) {
+                const uint32_t k = dfl_canon_find(*canon, strstart - s.lx);
+                if (k != DFL_NONE) { *sync_k = k; synced = true; break; }
+            }
         } else if (match_available) {
-            lfreq[ld8(s, strstart - 1) * lstride]++;
+            const uint32_t lit = ld8(s, strstart - 1);
+            lfreq[lit * lstride]++;
             const bool bflush = ++sym_count == DFL_SYMS_PER_BLOCK;
+            dfl_rec_emit(rec, lit | (DFL_LIT << 9), strstart);
             if (bflush) DFL_FLUSH(false);
             strstart++;
         } else {
@@ -548,14 +631,93 @@ static __host__ __device__ bool dfl_parse(const DflStream &d, const DflFView &fv
         }
     }
     if (done) {
-        if (match_available) { lfreq[ld8(s, strstart - 1) * lstride]++; ++sym_count; match_available = 0; }
+        if (match_available) {
+            const uint32_t lit = ld8(s, strstart - 1);
+            lfreq[lit * lstride]++; ++sym_count; match_available = 0;
+            dfl_rec_emit(rec, lit | (DFL_LIT << 9), strstart);
+        }
         DFL_FLUSH(true);
     }
 #undef DFL_FLUSH
     st.strstart = strstart; st.match_start = match_start; st.match_length = match_length;
     st.match_available = match_available; st.sym_count = sym_count; st.block_start = block_start; st.bits = bits;
     st.base = base; st.read = read;
-    return done;
+    return done ? 1 : synced ? 2 : 0;
+}
+
+// After dfl_parse returned 2 at canonical symbol k_sync: account every block of the pair stream that ends
+// before the tail from the cumulative histograms and leave `st` at the loop top that follows the last
+// canonical match ending at or before ly - DFL_TAIL.  Returns 1 when it advanced, 0 when there was nothing
+// to skip, -1 when a block would consider the stored form (the job then takes the full serial parse).
+// accA/accB: two scratch rows of DFL_L_CODES + DFL_D_CODES counters.
+template <class TallyT>
+static __host__ __device__ int dfl_canon_blocks(const DflCanon &cn, uint32_t lx, uint32_t n, uint32_t k_sync, DflParseState &st,
+                                                TallyT *lfreq, int lstride, TallyT *dfreq, int dstride, DflTrees &tr,
+                                                uint32_t *accA, uint32_t *accB)
+{
+    const uint32_t ly = n - lx, lim = ly - DFL_TAIL;
+    uint32_t lo = 0, hi = cn.n_sym;                        // first symbol that ends beyond lim
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (SNACC_LDG(cn.end + mid) <= lim) lo = mid + 1; else hi = mid;
+    }
+    if (lo == 0) return 0;
+    uint32_t kt = lo - 1;
+    while (kt > k_sync && (SNACC_LDG(cn.code + kt) >> 9) == DFL_LIT) --kt;
+    if (kt <= k_sync) return 0;
+    uint32_t t = k_sync + 1;
+    const uint32_t t_end = kt + 1;
+    uint32_t *a = accA, *b = accB;
+    dfl_cum_at(cn, t, a);
+    for (;;) {
+        const uint32_t need = DFL_SYMS_PER_BLOCK - st.sym_count;
+        const bool flush = t + need <= t_end;
+        const uint32_t t2 = flush ? t + need : t_end;
+        dfl_cum_at(cn, t2, b);
+        for (int k = 0; k < DFL_L_CODES; ++k) lfreq[k * lstride] += (TallyT)(b[k] - a[k]);
+        for (int k = 0; k < DFL_D_CODES; ++k) dfreq[k * dstride] += (TallyT)(b[DFL_L_CODES + k] - a[DFL_L_CODES + k]);
+        st.sym_count += t2 - t;
+        if (flush) {
+            const uint32_t e2 = lx + SNACC_LDG(cn.end + t2 - 1);
+            bool cand = false;
+            dfl_flush_block(tr, lfreq, lstride, dfreq, dstride, e2 - st.block_start, true, false, st.bits, &cand);
+            if (cand) return -1;
+            for (int k = 0; k < DFL_L_CODES; ++k) lfreq[k * lstride] = 0;
+            for (int k = 0; k < DFL_D_CODES; ++k) dfreq[k * dstride] = 0;
+            lfreq[256 * lstride] = 1; st.sym_count = 0; st.block_start = e2;
+        }
+        uint32_t *sw = a; a = b; b = sw;
+        t = t2;
+        if (!flush) break;
+    }
+    st.strstart = lx + SNACC_LDG(cn.end + t_end - 1);
+    st.match_available = 0; st.match_length = DFL_MIN_MATCH - 1; st.match_start = 0;
+    st.base = dfl_window_base(st.strstart);                // a regular loop top: strstart <= n - DFL_TAIL
+    const uint64_t want = (uint64_t)st.base + 2 * DFL_WSIZE;
+    st.read = want < n ? (uint32_t)want : n;
+    return 1;
+}
+
+// The whole pair stream x.y from the checkpoint of x (already in st / lfreq / dfreq).  Returns 0 when the job
+// has to take the full serial parse (cn = null) instead, 1 when it was parsed serially, 2 when blocks were
+// taken from the canonical stream.
+template <class TallyT>
+static __host__ __device__ int dfl_pair_stream(const DflStream &d, const DflFView &fv, const DflConfig &c, DflParseState &st,
+                                                TallyT *lfreq, int lstride, TallyT *dfreq, int dstride, DflTrees &tr,
+                                                const DflCanon *cn, uint32_t *accA, uint32_t *accB)
+{
+    const uint32_t lx = d.s.lx, n = d.s.n;
+    const bool use = cn && cn->n_sym != 0 && n - lx >= DFL_CANON_MIN;
+    uint32_t k_sync = 0;
+    int r = dfl_parse(d, fv, c, st, lfreq, lstride, dfreq, dstride, tr, 0xffffffffu, (DflRec *)nullptr, use ? cn : nullptr,
+                      lx + DFL_JY, &k_sync);
+    if (r == 2) {
+        const int b = dfl_canon_blocks(*cn, lx, n, k_sync, st, lfreq, lstride, dfreq, dstride, tr, accA, accB);
+        if (b < 0) return 0;
+        dfl_parse(d, fv, c, st, lfreq, lstride, dfreq, dstride, tr, 0xffffffffu);
+        return b ? 2 : 1;
+    }
+    return 1;
 }
 
 
@@ -698,8 +860,11 @@ dfl_junction_kernel(DflCorpus c, const DflPair *__restrict__ pairs, int32_t n_pa
     }
 }
 
-// K3d: the serial parse, one stream per thread.  kind 0: sequence alone -> size; kind 1: x alone up to its
-// junction -> checkpoint; kind 2: pair stream resumed from the checkpoint of x -> size.
+// K3d: the serial parse, one stream per thread.
+//   kind 3  a sequence alone: size -> seq_size, checkpoint at its junction start (what a pair stream x.* resumes
+//           from) -> ckpt, canonical symbol stream -> canon pool
+//   kind 2  pair stream resumed from the checkpoint of x, remaining blocks of y from the canonical stream of y
+//   kind 4  pair stream resumed from the checkpoint of x, full serial parse (fallback of kind 2)
 struct DflCkpt {
     DflParseState st;
     uint16_t lfreq[DFL_L_CODES];
@@ -707,12 +872,28 @@ struct DflCkpt {
 };
 struct DflJob { int32_t x, y, kind, fj; int64_t out; };     // fj: slot of the pair in the junction batch
 
+struct DflCanonPool {
+    uint32_t *end; uint16_t *code; uint32_t *cum;
+    const uint64_t *soff;        // per sequence: first symbol slot
+    const uint32_t *cap;         // per sequence: symbol slots
+    const uint64_t *roff;        // per sequence: first cumulative row
+    uint32_t *n_sym;             // per sequence: symbols recorded (0: none / overflow)
+    int64_t *seq_size;           // per sequence: raw deflate size of the sequence alone
+};
+__device__ __forceinline__ DflCanon dfl_canon_of(const DflCanonPool &cp, int32_t s)
+{
+    DflCanon cn;
+    cn.end = cp.end + cp.soff[s]; cn.code = cp.code + cp.soff[s];
+    cn.cum = cp.cum + cp.roff[s] * DFL_CUM_W; cn.n_sym = cp.n_sym[s];
+    return cn;
+}
+
 constexpr int DFL_PARSE_THREADS = 64;
 
 __global__ void __launch_bounds__(DFL_PARSE_THREADS)
 dfl_parse_kernel(DflCorpus c, const DflJob *__restrict__ jobs, int64_t n_jobs, int level, const uint32_t *__restrict__ F,
                  const uint32_t *__restrict__ FQ, const uint32_t *__restrict__ FJ, const uint32_t *__restrict__ FJQ,
-                 DflCkpt *__restrict__ ckpt, DflTrees *__restrict__ scratch,
+                 DflCkpt *__restrict__ ckpt, DflCanonPool cp, DflTrees *__restrict__ scratch,
                  unsigned long long *__restrict__ counter, int64_t *__restrict__ out)
 {
     __shared__ uint16_t s_l[DFL_L_CODES * DFL_PARSE_THREADS];
@@ -721,17 +902,19 @@ dfl_parse_kernel(DflCorpus c, const DflJob *__restrict__ jobs, int64_t n_jobs, i
     const int T = DFL_PARSE_THREADS, tid = threadIdx.x;
     uint16_t *lf = s_l + tid, *df = s_d + tid;
     DflTrees &tr = scratch[(size_t)blockIdx.x * T + tid];
+    uint32_t accA[DFL_L_CODES + DFL_D_CODES], accB[DFL_L_CODES + DFL_D_CODES];
     for (;;) {
         const long long j = (long long)atomicAdd(counter, 1ull);
         if (j >= n_jobs) break;
         const DflJob jb = jobs[j];
-        const DflStream d = dfl_make(c, jb.x, jb.kind == 2 ? jb.y : -1);
+        const bool pair = jb.kind != 3;
+        const DflStream d = dfl_make(c, jb.x, pair ? jb.y : -1);
         const uint32_t lx = d.s.lx;
         DflFView fv;
         fv.fx = F + c.poff[jb.x]; fv.lx = lx;
         fv.qx = FQ ? FQ + c.poff[jb.x] : nullptr; fv.qy = fv.qj = fv.qx;
         DflParseState st;
-        if (jb.kind == 2) {
+        if (pair) {
             fv.fy = F + c.poff[jb.y];
             fv.fj = FJ + (size_t)jb.fj * DFL_JSTRIDE;
             if (FQ) { fv.qy = FQ + c.poff[jb.y]; fv.qj = FJQ + (size_t)jb.fj * DFL_JSTRIDE; }
@@ -741,24 +924,72 @@ dfl_parse_kernel(DflCorpus c, const DflJob *__restrict__ jobs, int64_t n_jobs, i
             dfl_resume(st, d.s.n);
             for (int k = 0; k < DFL_L_CODES; ++k) lf[k * T] = ck.lfreq[k];
             for (int k = 0; k < DFL_D_CODES; ++k) df[k * T] = ck.dfreq[k];
+            DflCanon cn;
+            cn.n_sym = 0;
+            if (jb.kind == 2) cn = dfl_canon_of(cp, jb.y);
+            const int how = dfl_pair_stream(d, fv, cfg, st, lf, T, df, T, tr, jb.kind == 2 ? &cn : nullptr, accA, accB);
+            out[jb.out] = how ? (int64_t)(st.bits >> 3) : -2;
         } else {
             fv.fy = fv.fj = fv.fx; fv.jx0 = fv.jend = lx;     // everything from F of the sequence
             dfl_parse_fresh(st);
             for (int k = 0; k < DFL_L_CODES; ++k) lf[k * T] = 0;
             for (int k = 0; k < DFL_D_CODES; ++k) df[k * T] = 0;
             lf[256 * T] = 1;
-        }
-        const uint32_t stop = jb.kind == 1 ? dfl_jx0(lx) : 0xffffffffu;
-        dfl_parse(d, fv, cfg, st, lf, T, df, T, tr, stop);
-        if (jb.kind == 1) {
+            DflRec rec{cp.end + cp.soff[jb.x], cp.code + cp.soff[jb.x], cp.cap[jb.x], 0};
+            int r = dfl_parse(d, fv, cfg, st, lf, T, df, T, tr, dfl_jx0(lx), &rec);
             DflCkpt &ck = ckpt[jb.x];
-            ck.st = st;
+            ck.st = st;                                        // (r == 1 only for an empty sequence: never resumed)
             for (int k = 0; k < DFL_L_CODES; ++k) ck.lfreq[k] = lf[k * T];
             for (int k = 0; k < DFL_D_CODES; ++k) ck.dfreq[k] = df[k * T];
-        } else {
-            out[jb.out] = (int64_t)(st.bits >> 3);
+            if (r == 0) dfl_parse(d, fv, cfg, st, lf, T, df, T, tr, 0xffffffffu, &rec);
+            cp.n_sym[jb.x] = rec.n == DFL_NONE ? 0u : rec.n;
+            cp.seq_size[jb.x] = (int64_t)(st.bits >> 3);
         }
     }
+}
+
+// K3e: cumulative symbol histograms of the canonical streams.  Step 1: histogram of every complete chunk of
+// DFL_CUM_G symbols into row chunk+1; step 2: running sum down the rows (row 0 = zeros).
+__global__ void __launch_bounds__(64)
+dfl_cum_chunk_kernel(DflCanonPool cp, const int32_t *__restrict__ seqs, int32_t n_seqs)
+{
+    __shared__ uint32_t h[DFL_CUM_W];
+    for (int32_t t = blockIdx.y; t < n_seqs; t += gridDim.y) {
+        const int32_t sq = seqs[t];
+        const uint32_t n_sym = cp.n_sym[sq];
+        const uint16_t *code = cp.code + cp.soff[sq];
+        uint32_t *cum = cp.cum + cp.roff[sq] * DFL_CUM_W;
+        for (uint32_t chunk = blockIdx.x; (chunk + 1) * DFL_CUM_G <= n_sym; chunk += gridDim.x) {
+            for (uint32_t i = threadIdx.x; i < DFL_CUM_W; i += blockDim.x) h[i] = 0;
+            __syncthreads();
+            for (uint32_t k = threadIdx.x; k < DFL_CUM_G; k += blockDim.x) {
+                const uint32_t cd = code[chunk * DFL_CUM_G + k];
+                atomicAdd(&h[cd & 511], 1u);
+                if ((cd >> 9) != DFL_LIT) atomicAdd(&h[DFL_L_CODES + (cd >> 9)], 1u);
+            }
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < DFL_CUM_W; i += blockDim.x) cum[(size_t)(chunk + 1) * DFL_CUM_W + i] = h[i];
+            __syncthreads();
+        }
+    }
+}
+__global__ void __launch_bounds__(DFL_CUM_W)
+dfl_cum_scan_kernel(DflCanonPool cp, const int32_t *__restrict__ seqs, int32_t n_seqs)
+{
+    for (int32_t t = blockIdx.x; t < n_seqs; t += gridDim.x) {
+        const int32_t sq = seqs[t];
+        const uint32_t rows = cp.n_sym[sq] / DFL_CUM_G;          // rows 1 .. rows hold chunk histograms
+        uint32_t *cum = cp.cum + cp.roff[sq] * DFL_CUM_W + threadIdx.x;
+        uint32_t acc = 0;
+        cum[0] = 0;
+        for (uint32_t r = 1; r <= rows; ++r) { acc += cum[(size_t)r * DFL_CUM_W]; cum[(size_t)r * DFL_CUM_W] = acc; }
+    }
+}
+__global__ void dfl_gather_sizes_kernel(const int64_t *__restrict__ seq_size, const int32_t *__restrict__ xs, int64_t n,
+                                        int64_t *__restrict__ out)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = seq_size[xs[k]];
 }
 #endif  // __CUDACC__
 
@@ -778,21 +1009,37 @@ struct DeflateState {
     std::vector<uint8_t> indexed;                  // per sequence
     uint32_t *d_F[2] = {nullptr, nullptr};         // level 9, level 6
     uint32_t *d_FQ = nullptr, *d_FJQ = nullptr;    // level 6 only: quartered-chain tables
-    std::vector<uint8_t> have_F[2], have_ck[2];
+    std::vector<uint8_t> have_F[2], have_prep[2];
     DflCkpt *d_ckpt[2] = {nullptr, nullptr};
+    // canonical symbol streams (per level): pools + per-sequence geometry (shared by both levels)
+    uint64_t *d_soff = nullptr, *d_roff = nullptr; uint32_t *d_cap = nullptr;
+    uint64_t sym_total = 0, row_total = 0;
+    uint32_t *d_sym_end[2] = {nullptr, nullptr}; uint16_t *d_sym_code[2] = {nullptr, nullptr};
+    uint32_t *d_cum[2] = {nullptr, nullptr}; uint32_t *d_nsym[2] = {nullptr, nullptr};
+    int64_t *d_seq_size[2] = {nullptr, nullptr};
     int32_t n_seqs = 0;
     // working memory
     DflTrees *d_scratch = nullptr; size_t scratch_n = 0;
     uint32_t *d_FJ = nullptr; size_t fj_pairs = 0;
     double main_ms = 0.0;
+    int use_canon = 1;                             // 0: every pair stream takes the full serial parse (tests)
+    int64_t serial_jobs = 0;                       // pair jobs of the last call that fell back to it
 };
 
 static inline void deflate_free_corpus(DeflateState &st)
 {
     cudaFree(st.d_poff); cudaFree(st.d_order); cudaFree(st.d_bstart);
     cudaFree(st.d_FQ); st.d_FQ = nullptr;
-    for (int l = 0; l < 2; ++l) { cudaFree(st.d_F[l]); cudaFree(st.d_ckpt[l]); st.d_F[l] = nullptr; st.d_ckpt[l] = nullptr;
-                                  st.have_F[l].clear(); st.have_ck[l].clear(); }
+    cudaFree(st.d_soff); cudaFree(st.d_roff); cudaFree(st.d_cap);
+    st.d_soff = st.d_roff = nullptr; st.d_cap = nullptr;
+    for (int l = 0; l < 2; ++l) {
+        cudaFree(st.d_F[l]); cudaFree(st.d_ckpt[l]); st.d_F[l] = nullptr; st.d_ckpt[l] = nullptr;
+        cudaFree(st.d_sym_end[l]); cudaFree(st.d_sym_code[l]); cudaFree(st.d_cum[l]); cudaFree(st.d_nsym[l]);
+        cudaFree(st.d_seq_size[l]);
+        st.d_sym_end[l] = nullptr; st.d_sym_code[l] = nullptr; st.d_cum[l] = nullptr; st.d_nsym[l] = nullptr;
+        st.d_seq_size[l] = nullptr;
+        st.have_F[l].clear(); st.have_prep[l].clear();
+    }
     st.d_poff = nullptr; st.d_order = nullptr; st.d_bstart = nullptr; st.indexed.clear(); st.h_poff.clear();
     st.n_seqs = 0; st.total = 0;
 }
@@ -806,7 +1053,7 @@ static inline void deflate_invalidate(DeflateState &st)
     std::fill(st.indexed.begin(), st.indexed.end(), 0);
     for (int l = 0; l < 2; ++l) {
         std::fill(st.have_F[l].begin(), st.have_F[l].end(), 0);
-        std::fill(st.have_ck[l].begin(), st.have_ck[l].end(), 0);
+        std::fill(st.have_prep[l].begin(), st.have_prep[l].end(), 0);
     }
 }
 
@@ -823,9 +1070,11 @@ template <typename T> static int dfl_upload(std::string &err, cudaStream_t strea
     return 0;
 }
 
+constexpr size_t DFL_BATCH = 8192;                 // pair streams per junction batch (1.08 GB of junction F)
+
 // sizes of the raw deflate streams of the jobs (x alone when ys == nullptr) into d_out[0..n_jobs)
 static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, const int32_t *xs, const int32_t *ys,
-                       const int32_t *, const int32_t *, int64_t n_jobs, int64_t *d_out, cudaStream_t stream,
+                       const int32_t *d_xs, const int32_t *, int64_t n_jobs, int64_t *d_out, cudaStream_t stream,
                        int64_t, int64_t *launches, std::string &err)
 {
     const int li = level == 9 ? 0 : 1;
@@ -834,34 +1083,59 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
         deflate_free_corpus(st);
         st.n_seqs = ns;
         st.h_poff.assign(ns, 0);
-        uint64_t t = 0;
-        for (int32_t i = 0; i < ns; ++i) { st.h_poff[i] = t; t += ((uint64_t)dc.h_len[i] + 7) & ~7ull; }
-        st.total = t;
+        std::vector<uint64_t> soff(ns), roff(ns);
+        std::vector<uint32_t> cap(ns);
+        uint64_t t = 0, sy = 0, ro = 0;
+        for (int32_t i = 0; i < ns; ++i) {
+            st.h_poff[i] = t; t += ((uint64_t)dc.h_len[i] + 7) & ~7ull;
+            // canonical stream: room for one symbol per 4 bytes (DNA needs one per ~9); a sequence that needs more
+            // simply has no canonical stream and its pair jobs take the serial parse
+            cap[i] = (dc.h_len[i] / 4 + 1024 + DFL_CUM_G - 1) / DFL_CUM_G * DFL_CUM_G;
+            soff[i] = sy; sy += cap[i];
+            roff[i] = ro; ro += cap[i] / DFL_CUM_G + 1;
+        }
+        st.total = t; st.sym_total = sy; st.row_total = ro;
         DCK(cudaMalloc(&st.d_poff, sizeof(uint64_t) * ns));
         DCK(cudaMemcpyAsync(st.d_poff, st.h_poff.data(), sizeof(uint64_t) * ns, cudaMemcpyHostToDevice, stream));
+        DCK(cudaMalloc(&st.d_soff, sizeof(uint64_t) * ns));
+        DCK(cudaMalloc(&st.d_roff, sizeof(uint64_t) * ns));
+        DCK(cudaMalloc(&st.d_cap, sizeof(uint32_t) * ns));
+        DCK(cudaMemcpyAsync(st.d_soff, soff.data(), sizeof(uint64_t) * ns, cudaMemcpyHostToDevice, stream));
+        DCK(cudaMemcpyAsync(st.d_roff, roff.data(), sizeof(uint64_t) * ns, cudaMemcpyHostToDevice, stream));
+        DCK(cudaMemcpyAsync(st.d_cap, cap.data(), sizeof(uint32_t) * ns, cudaMemcpyHostToDevice, stream));
+        DCK(cudaStreamSynchronize(stream));
         DCK(cudaMalloc(&st.d_order, sizeof(uint32_t) * (t + 16)));
         DCK(cudaMalloc(&st.d_bstart, sizeof(uint32_t) * (size_t)ns * (DFL_HASH + 1)));
         st.indexed.assign(ns, 0);
-        for (int l = 0; l < 2; ++l) { st.have_F[l].assign(ns, 0); st.have_ck[l].assign(ns, 0); }
+        for (int l = 0; l < 2; ++l) { st.have_F[l].assign(ns, 0); st.have_prep[l].assign(ns, 0); }
     }
     if (!st.d_F[li]) {
         DCK(cudaMalloc(&st.d_F[li], sizeof(uint32_t) * (st.total + 16)));
         DCK(cudaMalloc(&st.d_ckpt[li], sizeof(DflCkpt) * ns));
         if (level != 9) DCK(cudaMalloc(&st.d_FQ, sizeof(uint32_t) * (st.total + 16)));
+        DCK(cudaMalloc(&st.d_sym_end[li], sizeof(uint32_t) * (st.sym_total + 16)));
+        DCK(cudaMalloc(&st.d_sym_code[li], sizeof(uint16_t) * (st.sym_total + 16)));
+        DCK(cudaMalloc(&st.d_cum[li], sizeof(uint32_t) * st.row_total * DFL_CUM_W));
+        DCK(cudaMalloc(&st.d_nsym[li], sizeof(uint32_t) * ns));
+        DCK(cudaMalloc(&st.d_seq_size[li], sizeof(int64_t) * ns));
+        DCK(cudaMemsetAsync(st.d_nsym[li], 0, sizeof(uint32_t) * ns, stream));
     }
     uint32_t *FQ = level != 9 ? st.d_FQ : nullptr;
     DflCorpus c{dc.d_corpus, dc.d_off, dc.d_len, st.d_poff, st.d_order, st.d_bstart};
+    DflCanonPool cp{st.d_sym_end[li], st.d_sym_code[li], st.d_cum[li], st.d_soff, st.d_cap, st.d_roff, st.d_nsym[li],
+                    st.d_seq_size[li]};
 
-    // ---- per-sequence state the jobs need: index, F (this level), checkpoint of every x of a pair ----
-    std::vector<int32_t> need_idx, need_f, need_ck;
+    // ---- per-sequence state the jobs need: index, F (this level), and the parse of the sequence alone
+    //      (size, checkpoint, canonical symbol stream) ----
+    std::vector<int32_t> need_idx, need_f, need_prep;
     {
-        std::vector<uint8_t> used(ns, 0), isx(ns, 0);
-        for (int64_t k = 0; k < n_jobs; ++k) { used[xs[k]] = 1; if (ys) { used[ys[k]] = 1; isx[xs[k]] = 1; } }
+        std::vector<uint8_t> used(ns, 0);
+        for (int64_t k = 0; k < n_jobs; ++k) { used[xs[k]] = 1; if (ys) used[ys[k]] = 1; }
         for (int32_t i = 0; i < ns; ++i) {
             if (!used[i]) continue;
             if (!st.indexed[i]) { need_idx.push_back(i); st.indexed[i] = 1; st.have_F[0][i] = st.have_F[1][i] = 0; }
-            if (!st.have_F[li][i]) { need_f.push_back(i); st.have_F[li][i] = 1; st.have_ck[li][i] = 0; }
-            if (isx[i] && !st.have_ck[li][i]) { need_ck.push_back(i); st.have_ck[li][i] = 1; }
+            if (!st.have_F[li][i]) { need_f.push_back(i); st.have_F[li][i] = 1; st.have_prep[li][i] = 0; }
+            if (!st.have_prep[li][i]) { need_prep.push_back(i); st.have_prep[li][i] = 1; }
         }
     }
     uint32_t max_len = 0;
@@ -898,6 +1172,7 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
     unsigned long long *d_counter = nullptr;
     DCK(cudaMalloc(&d_counter, sizeof(unsigned long long)));
     st.main_ms = 0.0;
+    st.serial_jobs = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     DCK(cudaEventCreate(&e0)); DCK(cudaEventCreate(&e1));
     auto run_parse = [&](const std::vector<DflJob> &jobs) -> int {
@@ -908,7 +1183,8 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
         DCK(cudaEventRecord(e0, stream));
         const int blocks = (int)std::min<size_t>((jobs.size() + DFL_PARSE_THREADS - 1) / DFL_PARSE_THREADS, parse_blocks);
         dfl_parse_kernel<<<blocks, DFL_PARSE_THREADS, 0, stream>>>(c, d_jobs, (int64_t)jobs.size(), level, st.d_F[li], FQ, st.d_FJ,
-                                                                  FQ ? st.d_FJQ : nullptr, st.d_ckpt[li], st.d_scratch, d_counter, d_out);
+                                                                  FQ ? st.d_FJQ : nullptr, st.d_ckpt[li], cp, st.d_scratch,
+                                                                  d_counter, d_out);
         DCK(cudaGetLastError());
         DCK(cudaEventRecord(e1, stream));
         ++*launches;
@@ -920,38 +1196,72 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
         return 0;
     };
     int rc = 0;
-    if (!ys) {
-        std::vector<DflJob> jobs((size_t)n_jobs);
-        for (int64_t k = 0; k < n_jobs; ++k) jobs[k] = DflJob{xs[k], -1, 0, 0, k};
-        rc = run_parse(jobs);
-    } else {
+    if (!need_prep.empty()) {
         std::vector<DflJob> jobs;
-        for (int32_t i : need_ck) jobs.push_back(DflJob{i, -1, 1, 0, 0});
+        for (int32_t i : need_prep) jobs.push_back(DflJob{i, -1, 3, 0, 0});
         rc = run_parse(jobs);
+        if (!rc) {
+            int32_t *d_list = nullptr;
+            if (dfl_upload(err, stream, need_prep, &d_list)) return -1;
+            uint32_t max_rows = 1;
+            for (int32_t i : need_prep) max_rows = std::max(max_rows, dc.h_len[i] / 4 / DFL_CUM_G + 8);
+            dim3 grid(std::min(max_rows, 2048u), (unsigned)std::min<size_t>(need_prep.size(), 64));
+            dfl_cum_chunk_kernel<<<grid, 64, 0, stream>>>(cp, d_list, (int32_t)need_prep.size());
+            dfl_cum_scan_kernel<<<(unsigned)std::min<size_t>(need_prep.size(), 148 * 4), DFL_CUM_W, 0, stream>>>(
+                cp, d_list, (int32_t)need_prep.size());
+            DCK(cudaGetLastError());
+            *launches += 2;
+            DCK(cudaStreamSynchronize(stream));
+            cudaFree(d_list);
+        }
+    }
+    if (rc) { /* fall through to cleanup */ }
+    else if (!ys) {
+        dfl_gather_sizes_kernel<<<(unsigned)((n_jobs + 255) / 256), 256, 0, stream>>>(st.d_seq_size[li], d_xs, n_jobs, d_out);
+        if (cudaGetLastError() != cudaSuccess) { err = "dfl_gather_sizes_kernel launch failed"; rc = -1; }
+        ++*launches;
+    } else {
         // pairs in batches: junction F of the batch, then its parses
-        const size_t batch = 2048;
-        if (!rc && st.fj_pairs < batch) {
+        const size_t batch = DFL_BATCH;
+        if (st.fj_pairs < batch) {
             cudaFree(st.d_FJ); st.d_FJ = nullptr;
             st.fj_pairs = batch;
             DCK(cudaMalloc(&st.d_FJ, sizeof(uint32_t) * batch * DFL_JSTRIDE));
         }
-        if (!rc && FQ && !st.d_FJQ) DCK(cudaMalloc(&st.d_FJQ, sizeof(uint32_t) * batch * DFL_JSTRIDE));
-        for (int64_t b0 = 0; !rc && b0 < n_jobs; b0 += (int64_t)batch) {
-            const int64_t nb = std::min<int64_t>((int64_t)batch, n_jobs - b0);
-            std::vector<DflPair> pairs((size_t)nb);
-            jobs.assign((size_t)nb, DflJob());
-            for (int64_t k = 0; k < nb; ++k) {
-                pairs[k] = DflPair{xs[b0 + k], ys[b0 + k]};
-                jobs[k] = DflJob{xs[b0 + k], ys[b0 + k], 2, (int32_t)k, b0 + k};
+        if (FQ && !st.d_FJQ) DCK(cudaMalloc(&st.d_FJQ, sizeof(uint32_t) * batch * DFL_JSTRIDE));
+        std::vector<DflJob> jobs;
+        auto run_pairs = [&](const std::vector<int64_t> *subset, int kind) -> int {
+            const int64_t total = subset ? (int64_t)subset->size() : n_jobs;
+            for (int64_t b0 = 0; b0 < total; b0 += (int64_t)batch) {
+                const int64_t nb = std::min<int64_t>((int64_t)batch, total - b0);
+                std::vector<DflPair> pairs((size_t)nb);
+                jobs.assign((size_t)nb, DflJob());
+                for (int64_t k = 0; k < nb; ++k) {
+                    const int64_t j = subset ? (*subset)[b0 + k] : b0 + k;
+                    pairs[k] = DflPair{xs[j], ys[j]};
+                    jobs[k] = DflJob{xs[j], ys[j], kind, (int32_t)k, j};
+                }
+                DflPair *d_pairs = nullptr;
+                if (dfl_upload(err, stream, pairs, &d_pairs)) return -1;
+                dim3 grid((DFL_JSTRIDE + 255) / 256, (unsigned)std::min<int64_t>(nb, 4096));
+                dfl_junction_kernel<<<grid, 256, 0, stream>>>(c, d_pairs, (int32_t)nb, level, st.d_FJ, FQ ? st.d_FJQ : nullptr);
+                if (cudaGetLastError() != cudaSuccess) { err = "dfl_junction_kernel launch failed"; cudaFree(d_pairs); return -1; }
+                ++*launches;
+                const int r = run_parse(jobs);
+                cudaFree(d_pairs);
+                if (r) return r;
             }
-            DflPair *d_pairs = nullptr;
-            if (dfl_upload(err, stream, pairs, &d_pairs)) { rc = -1; break; }
-            dim3 grid((DFL_JSTRIDE + 255) / 256, (unsigned)std::min<int64_t>(nb, 4096));
-            dfl_junction_kernel<<<grid, 256, 0, stream>>>(c, d_pairs, (int32_t)nb, level, st.d_FJ, FQ ? st.d_FJQ : nullptr);
-            if (cudaGetLastError() != cudaSuccess) { err = "dfl_junction_kernel launch failed"; rc = -1; }
-            ++*launches;
-            if (!rc) rc = run_parse(jobs);
-            cudaFree(d_pairs);
+            return 0;
+        };
+        rc = run_pairs(nullptr, st.use_canon ? 2 : 4);
+        if (!rc && st.use_canon) {
+            // jobs whose shortcut met a block that might be stored (-2): full serial parse
+            std::vector<int64_t> h_out((size_t)n_jobs), redo;
+            DCK(cudaMemcpyAsync(h_out.data(), d_out, sizeof(int64_t) * n_jobs, cudaMemcpyDeviceToHost, stream));
+            DCK(cudaStreamSynchronize(stream));
+            for (int64_t k = 0; k < n_jobs; ++k) if (h_out[k] == -2) redo.push_back(k);
+            st.serial_jobs = (int64_t)redo.size();
+            if (!redo.empty()) rc = run_pairs(&redo, 4);
         }
     }
     cudaFree(d_counter);

@@ -205,10 +205,17 @@ static std::vector<uint32_t> emu_F_single(const DflStream &d, const DflConfig &c
     return F;
 }
 
-// returns the raw deflate size of x (ly < 0) or of x followed by y
-extern "C" int64_t emu_deflate_size(const uint8_t *x, uint32_t lx, const uint8_t *y, int64_t ly_, int level)
+// canonical symbol stream of a sequence alone, built the way dfl_parse_kernel (kind 3) + the dfl_cum kernels do
+struct EmuCanon { std::vector<uint32_t> end, cum; std::vector<uint16_t> code; uint32_t n_sym = 0; };
+
+// returns the raw deflate size of x (ly < 0) or of x followed by y.  use_canon: take the remaining blocks of y
+// from the canonical stream of y (the product path); info[0] = 1 when the shortcut was taken, info[1] = 1 when a
+// block that might be stored sent the job back to the serial parse
+extern "C" int64_t emu_deflate_size_ex(const uint8_t *x, uint32_t lx, const uint8_t *y, int64_t ly_, int level, int use_canon,
+                                       int32_t *info)
 {
     const DflConfig cfg = dfl_config(level);
+    if (info) info[0] = info[1] = 0;
     uint8_t *px = padded_copy(x, lx);
     uint8_t *py = ly_ >= 0 ? padded_copy(y, (uint64_t)ly_) : nullptr;
     EmuIndex ix = emu_index(px, lx), iy;
@@ -223,8 +230,12 @@ extern "C" int64_t emu_deflate_size(const uint8_t *x, uint32_t lx, const uint8_t
     DflParseState st;
     int64_t result;
     if (ly_ < 0) {
+        // kind 3: checkpoint stop in the middle, symbols recorded -- the size must not care
+        std::vector<uint32_t> rend(lx / 4 + 1024); std::vector<uint16_t> rcode(lx / 4 + 1024);
+        DflRec rec{rend.data(), rcode.data(), (uint32_t)rend.size(), 0};
         dfl_parse_fresh(st); lf[256] = 1;
-        dfl_parse(dx, fv, cfg, st, lf.data(), 1, df.data(), 1, *tr, 0xffffffffu);
+        if (dfl_parse(dx, fv, cfg, st, lf.data(), 1, df.data(), 1, *tr, dfl_jx0(lx), &rec) == 0)
+            dfl_parse(dx, fv, cfg, st, lf.data(), 1, df.data(), 1, *tr, 0xffffffffu, &rec);
         result = (int64_t)(st.bits >> 3);
     } else {
         const uint32_t ly = (uint32_t)ly_;
@@ -235,6 +246,32 @@ extern "C" int64_t emu_deflate_size(const uint8_t *x, uint32_t lx, const uint8_t
         DflStream dy; dy.s.x = py; dy.s.lx = ly; dy.s.y = py + ly; dy.s.n = ly; dy.pair = false;
         dy.ix.order = iy.order.data(); dy.ix.bstart = iy.bstart.data(); dy.iy = dy.ix;
         std::vector<uint32_t> Fy = emu_F_single(dy, cfg);
+        EmuCanon ec;
+        if (use_canon) {
+            const uint32_t cap = (ly / 4 + 1024 + DFL_CUM_G - 1) / DFL_CUM_G * DFL_CUM_G;
+            ec.end.assign(cap + 16, 0); ec.code.assign(cap + 16, 0);
+            DflRec rec{ec.end.data(), ec.code.data(), cap, 0};
+            DflFView fy; fy.fx = fy.fy = fy.fj = Fy.data(); fy.jx0 = fy.jend = fy.lx = ly; fy.qx = fy.qy = fy.qj = nullptr;
+            DflParseState sy; dfl_parse_fresh(sy);
+            std::vector<uint16_t> l2(DFL_L_CODES, 0), d2(DFL_D_CODES, 0); l2[256] = 1;
+            DflTrees *t2 = new DflTrees();
+            if (dfl_parse(dy, fy, cfg, sy, l2.data(), 1, d2.data(), 1, *t2, dfl_jx0(ly), &rec) == 0)
+                dfl_parse(dy, fy, cfg, sy, l2.data(), 1, d2.data(), 1, *t2, 0xffffffffu, &rec);
+            delete t2;
+            ec.n_sym = rec.n == DFL_NONE ? 0 : rec.n;
+            const uint32_t rows = ec.n_sym / DFL_CUM_G;
+            ec.cum.assign((size_t)(cap / DFL_CUM_G + 1) * DFL_CUM_W, 0);
+            for (uint32_t r = 1; r <= rows; ++r) {                       // dfl_cum_chunk_kernel + dfl_cum_scan_kernel
+                uint32_t *row = ec.cum.data() + (size_t)r * DFL_CUM_W;
+                const uint32_t *prev = row - DFL_CUM_W;
+                for (uint32_t c = 0; c < DFL_CUM_W; ++c) row[c] = prev[c];
+                for (uint32_t k = (r - 1) * DFL_CUM_G; k < r * DFL_CUM_G; ++k) {
+                    const uint32_t cd = ec.code[k];
+                    row[cd & 511]++;
+                    if ((cd >> 9) != DFL_LIT) row[DFL_L_CODES + (cd >> 9)]++;
+                }
+            }
+        }
         // pair stream: junction F, then resume
         DflStream d; d.s.x = px; d.s.lx = lx; d.s.y = py; d.s.n = lx + ly; d.pair = true; d.ix = dx.ix; d.iy = dy.ix;
         const uint32_t jx0 = dfl_jx0(lx), jlen = dfl_jlen(lx, ly);
@@ -242,9 +279,27 @@ extern "C" int64_t emu_deflate_size(const uint8_t *x, uint32_t lx, const uint8_t
         for (uint32_t u = 0; u < jlen; ++u) FJ[u] = dfl_f_word(d, jx0 + u, cfg, 0xffffffffu, nullptr);
         fv.fx = Fx.data(); fv.fy = Fy.data(); fv.fj = FJ.data(); fv.jx0 = jx0; fv.jend = jx0 + jlen; fv.lx = lx;
         dfl_resume(st, d.s.n);
-        dfl_parse(d, fv, cfg, st, lf.data(), 1, df.data(), 1, *tr, 0xffffffffu);
+        const DflParseState st0 = st;
+        const std::vector<uint16_t> lf0 = lf, df0 = df;
+        DflCanon cn; cn.end = ec.end.data(); cn.code = ec.code.data(); cn.cum = ec.cum.data(); cn.n_sym = ec.n_sym;
+        std::vector<uint32_t> accA(DFL_CUM_W), accB(DFL_CUM_W);
+        const uint32_t strstart0 = st.strstart;
+        const int how = dfl_pair_stream(d, fv, cfg, st, lf.data(), 1, df.data(), 1, *tr, use_canon ? &cn : nullptr, accA.data(), accB.data());
+        (void)strstart0;
+        if (!how) {
+            if (info) info[1] = 1;
+            st = st0; lf = lf0; df = df0;
+            dfl_pair_stream(d, fv, cfg, st, lf.data(), 1, df.data(), 1, *tr, (const DflCanon *)nullptr, accA.data(), accB.data());
+        } else if (info) {
+            info[0] = how == 2;
+        }
         result = (int64_t)(st.bits >> 3);
     }
     delete tr; free(px); free(py);
     return result;
+}
+
+extern "C" int64_t emu_deflate_size(const uint8_t *x, uint32_t lx, const uint8_t *y, int64_t ly_, int level)
+{
+    return emu_deflate_size_ex(x, lx, y, ly_, level, 1, nullptr);
 }

@@ -188,6 +188,16 @@ def test_megabase_genomes_gzip(engine):
     assert np.array_equal(engine.tile_sizes("gzip", 0, 2, 0, 4), ref)          # checkpoints and tables reused
     engine.set_option("invalidate_caches", 1)
     assert np.array_equal(engine.tile_sizes("gzip", 0, 2, 0, 4), ref)          # and rebuilt
+    assert engine.stat("deflate_serial_jobs") == 0                             # every pair stream used the canonical stream of y
+    engine.set_option("deflate_canonical", 0)                                  # the full serial parse gives the same sizes
+    try:
+        assert np.array_equal(engine.tile_sizes("gzip", 0, 2, 0, 4), ref)
+    finally:
+        engine.set_option("deflate_canonical", 1)
+    Sz = engine.tile_sizes("zlib", 1, 2, 0, 3)
+    refz = np.array([[_ref_len(np.concatenate([g[i], g[j]]), "zlib") for j in range(3)] for i in (1, 2)])
+    assert np.array_equal(Sz, refz)
+    assert np.array_equal(engine.single_sizes("zlib"), np.array([_ref_len(s, "zlib") for s in g]))
 
 
 def test_lz4_stale_table_slots(engine):

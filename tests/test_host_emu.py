@@ -30,6 +30,9 @@ def emu():
     e.emu_lz4_packed.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int64]
     e.emu_deflate_size.restype = ctypes.c_int64
     e.emu_deflate_size.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]
+    e.emu_deflate_size_ex.restype = ctypes.c_int64
+    e.emu_deflate_size_ex.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_void_p]
     return e
 
 
@@ -184,3 +187,37 @@ def test_lz4_packed_17bit_slots_never_resurrect_stale_candidates(emu, seed):
     from snacc_b200 import synth
     x, y = synth.stale_slot_stream(seed)
     assert _call2(emu.emu_lz4_packed, x, y) == lib.ref_lz4f_size(np.concatenate([x, y]))
+
+
+def _deflate_ex(emu, x, y, level, canon):
+    info = (ctypes.c_int32 * 2)()
+    x = np.ascontiguousarray(x, dtype=np.uint8)
+    y = np.ascontiguousarray(y, dtype=np.uint8)
+    r = emu.emu_deflate_size_ex(x.ctypes.data, x.size, y.ctypes.data, y.size, level, canon, info)
+    return r, info[0], info[1]
+
+
+@pytest.mark.parametrize("level", [9, 6])
+def test_deflate_canonical_symbol_stream_shortcut(emu, level):
+    """pair streams whose y is long enough take their blocks from the recorded parse of y alone (dfl_pair_stream): the
+    synchronisation point, block boundaries that fall inside the shortcut (y > 150 kbp: several 16383-symbol blocks), the
+    tail handed back to the serial parser, window-slide phases of x, and inputs for which there is no canonical stream"""
+    from snacc_b200 import synth
+    cases = []
+    for lx, ly in [(5000, 40000), (70000, 37000), (300, 200000), (100000, 400000), (65275, 36864), (65274, 36865),
+                   (50000, 36863), (1, 50000), (32506, 45000)]:
+        cases.append((_dna(lx, lx), _dna(ly, ly + 1), ly >= 36864))
+    rng = np.random.default_rng(9)
+    cases.append((rng.integers(65, 67, 30000).astype(np.uint8), rng.integers(65, 67, 120000).astype(np.uint8), True))
+    cases.append((rng.integers(65, 81, 30000).astype(np.uint8), rng.integers(65, 81, 90000).astype(np.uint8), None))
+    cases.append((rng.integers(0, 256, 30000).astype(np.uint8), rng.integers(0, 256, 90000).astype(np.uint8), False))
+    g = synth.phylogeny(2, 120000, seed=3)
+    cases += [(g[0], g[1], True), (g[1], g[1], True)]
+    bad = []
+    for x, y, expect_used in cases:
+        ref = lib.ref_deflate_size(np.concatenate([x, y]), level)
+        r, used, fell_back = _deflate_ex(emu, x, y, level, 1)
+        r0, used0, _ = _deflate_ex(emu, x, y, level, 0)
+        if r != ref or r0 != ref or used0 or (expect_used is not None and bool(used) != expect_used):
+            bad.append((x.size, y.size, ref, r, r0, used, fell_back))
+    assert not bad, bad
