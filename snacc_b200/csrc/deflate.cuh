@@ -154,11 +154,15 @@ SNACC_HD uint32_t dfl_window_base(uint32_t strstart)
 // longest_match over the first `chain` candidates; returns (len << 16) | dist, 0 when there is no match of
 // 3+ bytes (or no search at all).  `base`: window base at this loop top (positions <= base are NIL).  When
 // `quarter` is non-null it also receives the result restricted to the first chain/4 candidates.
+// `visit` (optional) receives how the walk went: number of candidates visited, DFL_V_NICE when it stopped at
+// nice_length, DFL_V_HEADFAR when there was no search because the chain head is farther than MAX_DIST.
+constexpr uint32_t DFL_V_COUNT = 0x1fffu, DFL_V_HEADFAR = 0x4000u, DFL_V_NICE = 0x8000u;
 SNACC_HD uint32_t dfl_longest(const DflStream &d, uint32_t p, uint32_t base, uint32_t chain, uint32_t nice, uint32_t hint,
-                              uint32_t *quarter)
+                              uint32_t *quarter, uint32_t *visit = nullptr)
 {
     const Stream &s = d.s;
     if (quarter) *quarter = 0;
+    if (visit) *visit = 0;
     if (s.n - p < DFL_MIN_MATCH) return 0;                 // the string at p is not even inserted
     const uint32_t maxcmp = tmin(DFL_MAX_MATCH, s.n - p);
     const uint32_t nice_match = tmin(nice, maxcmp);
@@ -167,12 +171,14 @@ SNACC_HD uint32_t dfl_longest(const DflStream &d, uint32_t p, uint32_t base, uin
     it.init(&d, p, h, hint);
     uint32_t c = it.next();
     // chain head: must exist, not be NIL and be within MAX_DIST
-    if (c == 0xffffffffu || c <= base || p - c > DFL_MAX_DIST) return 0;
+    if (c == 0xffffffffu || c <= base) return 0;
+    if (p - c > DFL_MAX_DIST) { if (visit) *visit = DFL_V_HEADFAR; return 0; }
     const uint32_t limit = (p - base > DFL_MAX_DIST) ? p - DFL_MAX_DIST : base;
     const uint64_t scan = ld64(s, p);
     uint32_t best = 2, bdist = 0, qbest = 0;
     const uint32_t qcount = chain >> 2;
     uint32_t count = 0;
+    bool nice_stop = false;
     for (;;) {
         // quick test on the first 8 bytes, full compare only when they all agree
         const uint64_t x = scan ^ ld64(s, c);
@@ -180,7 +186,7 @@ SNACC_HD uint32_t dfl_longest(const DflStream &d, uint32_t p, uint32_t base, uin
         if (len > maxcmp) len = maxcmp;
         if (len > best) {
             best = len; bdist = p - c;
-            if (len >= nice_match) { ++count; break; }
+            if (len >= nice_match) { ++count; nice_stop = true; break; }
         }
         ++count;
         if (count == qcount) qbest = best > 2 ? (best << 16) | bdist : 0;
@@ -190,14 +196,104 @@ SNACC_HD uint32_t dfl_longest(const DflStream &d, uint32_t p, uint32_t base, uin
     }
     const uint32_t full = best > 2 ? (best << 16) | bdist : 0;
     if (quarter) *quarter = count <= qcount ? full : qbest;
+    if (visit) *visit = count | (nice_stop ? DFL_V_NICE : 0u);
     return full;
 }
 
+// longest_match of a position p = lx + q in the head of y of a pair stream, continued from the walk that
+// the same position had in y ALONE (f_s = its F word, visit = how that walk went, q_s = its quartered result
+// when q_known).  For q < DFL_JY the candidates inside y are visited in the same order, with the same
+// distance rules, in both streams -- except y's position 0, which is NIL in y alone and an ordinary
+// candidate here -- so the walk only has to go on where the other one ran out of y: position 0 of y, the
+// two positions whose hash straddles the boundary, then x's bucket.  Returns the F word (QDIFF flag set
+// when the quartered result differs or cannot be told without a second walk); *quarter = quartered result
+// (exact whenever q_known).
+SNACC_HD uint32_t dfl_longest_cont(const DflStream &d, uint32_t p, uint32_t chain, uint32_t nice, uint32_t f_s, uint32_t visit,
+                                   bool q_known, uint32_t q_s, uint32_t *quarter)
+{
+    const Stream &s = d.s;
+    const bool flag_s = (f_s & DFL_QDIFF) != 0;
+    f_s &= ~DFL_QDIFF;
+    if (!q_known && !flag_s) { q_known = true; q_s = f_s; }
+    if (quarter) *quarter = 0;
+    if (s.n - p < DFL_MIN_MATCH) return 0;
+    uint32_t count = visit & DFL_V_COUNT;
+    const uint32_t qcount = chain >> 2;
+    if ((visit & (DFL_V_NICE | DFL_V_HEADFAR)) || count >= chain) {       // the walk ended inside y: nothing changes
+        if (quarter) *quarter = q_known ? q_s : 0;
+        return f_s | (flag_s ? DFL_QDIFF : 0u);
+    }
+    const uint32_t lx = s.lx, base = dfl_window_base(p);
+    const uint32_t maxcmp = tmin(DFL_MAX_MATCH, s.n - p);
+    const uint32_t nice_match = tmin(nice, maxcmp);
+    const uint32_t h = dfl_hash_at(s, p);
+    DflCandIter it;
+    it.d = &d; it.h = h; it.p = p; it.stage = 0;
+    it.ylo = SNACC_LDG(d.iy.bstart + h);
+    const uint32_t yhi = SNACC_LDG(d.iy.bstart + h + 1);
+    it.ycur = (p > lx && yhi > it.ylo && SNACC_LDG(d.iy.order + it.ylo) == 0) ? it.ylo + 1 : it.ylo;   // y's position 0
+    it.xlo = SNACC_LDG(d.ix.bstart + h);
+    it.xcur = SNACC_LDG(d.ix.bstart + h + 1);
+    const uint32_t limit = (p - base > DFL_MAX_DIST) ? p - DFL_MAX_DIST : base;
+    uint32_t best = (f_s >> 16) ? (f_s >> 16) : 2, bdist = f_s & 0xffff;
+    bool q_fixed = count >= qcount;                  // the quartered result was settled inside y
+    uint32_t qbest = q_fixed && q_known ? q_s : 0;
+    bool q_lost = q_fixed && !q_known;
+    uint32_t c = it.next();
+    bool stop;
+    if (count == 0) stop = c == 0xffffffffu || c <= base || p - c > DFL_MAX_DIST;   // this candidate is the chain head
+    else stop = c == 0xffffffffu || c <= limit;
+    if (!stop) {
+        const uint64_t scan = ld64(s, p);
+        // one candidate; `over` when the walk has ended
+#define DFL_VISIT(c_) do {                                                                                          \
+            const uint64_t x_ = scan ^ ld64(s, (c_));                                                               \
+            uint32_t len_ = x_ ? (uint32_t)(SNACC_FFS64(x_) - 1) >> 3                                                \
+                               : 8 + dfl_match_len(s, p + 8, (c_) + 8, maxcmp > 8 ? maxcmp - 8 : 0);                \
+            if (len_ > maxcmp) len_ = maxcmp;                                                                       \
+            if (len_ > best) {                                                                                      \
+                best = len_; bdist = p - (c_);                                                                      \
+                if (len_ >= nice_match) { ++count; over = true; break; }                                            \
+            }                                                                                                       \
+            ++count;                                                                                                \
+            if (count == qcount) qbest = best > 2 ? (best << 16) | bdist : 0;                                       \
+            if (count >= chain) over = true;                                                                        \
+        } while (0)
+        bool over = false;
+        // y's position 0 and the two straddling positions through the general iterator ...
+        while (!over && it.stage < 3) {
+            DFL_VISIT(c);
+            if (over) break;
+            c = it.next();
+            if (c == 0xffffffffu || c <= limit) { over = true; break; }
+            if (it.stage == 3) break;              // c is the first candidate out of x's bucket
+        }
+        // ... then x's bucket, most recent first, in a tight loop (the lanes of a warp walk it together)
+        if (!over) {
+            const uint32_t *ox = d.ix.order;
+            uint32_t k = it.xcur;                   // c == ox[k] has been fetched already
+            for (;;) {
+                DFL_VISIT(c);
+                if (over || k == it.xlo) break;
+                c = SNACC_LDG(ox + --k);
+                if (c <= limit) break;
+            }
+        }
+#undef DFL_VISIT
+    }
+    const uint32_t full = best > 2 ? (best << 16) | bdist : 0;
+    const uint32_t qres = count <= qcount ? full : qbest;
+    if (quarter) *quarter = qres;
+    const bool differs = count <= qcount ? false : (q_lost ? true : qbest != full);
+    return full | (differs ? DFL_QDIFF : 0u);
+}
+
 // F word of a position: the full-chain result, flagged when the quartered chain gives something else
-SNACC_HD uint32_t dfl_f_word(const DflStream &d, uint32_t p, const DflConfig &c, uint32_t hint, uint32_t *qword)
+SNACC_HD uint32_t dfl_f_word(const DflStream &d, uint32_t p, const DflConfig &c, uint32_t hint, uint32_t *qword,
+                             uint32_t *visit = nullptr)
 {
     uint32_t q;
-    const uint32_t f = dfl_longest(d, p, dfl_window_base(p), (uint32_t)c.max_chain, (uint32_t)c.nice_length, hint, &q);
+    const uint32_t f = dfl_longest(d, p, dfl_window_base(p), (uint32_t)c.max_chain, (uint32_t)c.nice_length, hint, &q, visit);
     if (qword) *qword = q;
     return q != f ? f | DFL_QDIFF : f;
 }
@@ -503,7 +599,11 @@ struct DflFView {
     // optional second tables holding the quartered-chain result of the flagged positions (level 6, where
     // prev_length >= good_length is the common case); null: recompute on demand
     const uint32_t *qx, *qy, *qj;
+    // dfl_prep_kernel: the chunk of F around the parse position, staged in shared memory (ring of 2 * DFL_PREP_CHUNK
+    // entries indexed by position); null elsewhere
+    const uint32_t *ring = nullptr;
 };
+constexpr uint32_t DFL_PREP_CHUNK = 8192;
 // The parse reads F at nearly consecutive positions (two reads per emitted match, a match is ~9 bytes on DNA) and
 // each read is a dependent DRAM round trip, so the last 32-byte sector (8 entries) is kept in registers.
 // All three tables start on 32-byte boundaries and are padded to a multiple of 8 entries.
@@ -527,6 +627,7 @@ SNACC_HD uint32_t dfl_f_cached(DflFCache &c, const uint32_t *tab, uint32_t i)
 }
 SNACC_HD uint32_t dfl_f_at(const DflFView &v, uint32_t p, DflFCache &c)
 {
+    if (v.ring) return v.ring[p & (2 * DFL_PREP_CHUNK - 1)];
     if (p < v.jx0) return dfl_f_cached(c, v.fx, p);
     if (p < v.jend) return dfl_f_cached(c, v.fj, p - v.jx0);
     return dfl_f_cached(c, v.fy, p - v.lx);
@@ -742,6 +843,9 @@ struct DflCorpus {
     const uint64_t *poff;        // per sequence: offset of its slice in `order` / F arrays
     uint32_t *order;             // all sequences
     uint32_t *bstart;            // per sequence DFL_HASH + 1 entries
+    // head of every sequence (its first DFL_JY positions), for the junction of the pair streams it ends:
+    uint16_t *head_order;        // per sequence DFL_JY entries: the indexed head positions sorted by (hash, position)
+    uint16_t *head_visit;        // per sequence and level DFL_JY entries: how longest_match went in the sequence alone
 };
 
 SNACC_HD Stream dfl_make_stream(const DflCorpus &c, int32_t x, int32_t y)
@@ -832,30 +936,249 @@ dfl_match_kernel(DflCorpus c, const int32_t *__restrict__ seqs, int32_t n_seqs, 
         for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < len; k += gridDim.x * blockDim.x) {
             if (k >= nidx) { f[k] = 0; if (fq) fq[k] = 0; continue; }       // the last two positions: no string, no search
             const uint32_t p = d.ix.order[k];
-            uint32_t q;
-            f[p] = dfl_f_word(d, p, cfg, k, &q);
+            uint32_t q, visit;
+            f[p] = dfl_f_word(d, p, cfg, k, &q, &visit);
             if (fq) fq[p] = q;
+            if (p < DFL_JY) c.head_visit[(size_t)sq * DFL_JY + p] = (uint16_t)visit;
+        }
+    }
+}
+
+// K3b': head order of the listed sequences: the first min(len - 2, DFL_JY) positions sorted by (hash, position),
+// taken bucket by bucket from the full index (a bucket's head positions are a prefix of it).  One CTA per sequence.
+__global__ void __launch_bounds__(1024)
+dfl_head_kernel(DflCorpus c, const int32_t *__restrict__ seqs, int32_t n_seqs)
+{
+    extern __shared__ uint32_t hcnt[];                   // DFL_HASH counters -> exclusive starts
+    __shared__ uint32_t wsum[32];
+    for (int32_t t = blockIdx.x; t < n_seqs; t += gridDim.x) {
+        const int32_t sq = seqs[t];
+        const uint32_t *order = c.order + c.poff[sq];
+        const uint32_t *bstart = c.bstart + (size_t)sq * (DFL_HASH + 1);
+        uint16_t *ho = c.head_order + (size_t)sq * DFL_JY;
+        __syncthreads();
+        for (uint32_t h = threadIdx.x; h < DFL_HASH; h += blockDim.x) {
+            const uint32_t lo = bstart[h], hi = bstart[h + 1];
+            hcnt[h] = lo < hi ? dfl_lower_bound(order, lo, hi, DFL_JY) - lo : 0;
+        }
+        __syncthreads();
+        // exclusive scan over DFL_HASH counters: 32 per thread
+        const uint32_t per = DFL_HASH / 1024;
+        uint32_t sum = 0;
+        for (uint32_t k = 0; k < per; ++k) sum += hcnt[threadIdx.x * per + k];
+        uint32_t inc = sum;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if ((int)(threadIdx.x & 31) >= o) inc += u; }
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const uint32_t v = wsum[threadIdx.x];
+            uint32_t w = v;
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, w, o); if ((int)threadIdx.x >= o) w += u; }
+            wsum[threadIdx.x] = w - v;
+        }
+        __syncthreads();
+        uint32_t run = wsum[threadIdx.x >> 5] + inc - sum;
+        for (uint32_t k = 0; k < per; ++k) { const uint32_t v = hcnt[threadIdx.x * per + k]; hcnt[threadIdx.x * per + k] = run; run += v; }
+        __syncthreads();
+        for (uint32_t h = threadIdx.x; h < DFL_HASH; h += blockDim.x) {
+            const uint32_t lo = bstart[h], n = (h + 1 < DFL_HASH ? hcnt[h + 1] : tmin(DFL_JY, c.len[sq] >= 3 ? c.len[sq] - 2 : 0u)) - hcnt[h];
+            for (uint32_t i = 0; i < n; ++i) ho[hcnt[h] + i] = (uint16_t)order[lo + i];
         }
     }
 }
 
 struct DflPair { int32_t x, y; };
 
-// K3c: junction F of a batch of pair streams: positions [jx0, lx + min(ly, DFL_JY))
+// K3c: junction F of a batch of pair streams: positions [jx0, lx + min(ly, DFL_JY)).  The last positions of x take
+// the general walk.  The head positions of y are handled in (hash, position) order -- the lanes of a warp then
+// walk the same bucket of x and their loads coalesce into broadcasts -- and continue the walk they had in y alone
+// (dfl_longest_cont) instead of repeating it.
 __global__ void __launch_bounds__(256)
-dfl_junction_kernel(DflCorpus c, const DflPair *__restrict__ pairs, int32_t n_pairs, int level, uint32_t *__restrict__ FJ,
-                    uint32_t *__restrict__ FJQ)
+dfl_junction_kernel(DflCorpus c, const DflPair *__restrict__ pairs, int32_t n_pairs, int level, const uint32_t *__restrict__ F,
+                    const uint32_t *__restrict__ FQ, uint32_t *__restrict__ FJ, uint32_t *__restrict__ FJQ, int only_x)
 {
     const DflConfig cfg = dfl_config(level);
     for (int32_t b = blockIdx.y; b < n_pairs; b += gridDim.y) {
-        const DflStream d = dfl_make(c, pairs[b].x, pairs[b].y);
-        const uint32_t lx = d.s.lx, jx0 = dfl_jx0(lx), jlen = dfl_jlen(lx, d.s.n - lx);
+        const int32_t y = pairs[b].y;
+        const DflStream d = dfl_make(c, pairs[b].x, y);
+        const uint32_t lx = d.s.lx, ly = d.s.n - lx, jx0 = dfl_jx0(lx), jxl = lx - jx0, jyl = tmin(ly, DFL_JY);
+        const uint32_t n_head = tmin(jyl, ly >= 3 ? ly - 2 : 0u);            // head positions that are in y's index
         uint32_t *f = FJ + (size_t)b * DFL_JSTRIDE;
         uint32_t *fq = FJQ ? FJQ + (size_t)b * DFL_JSTRIDE : nullptr;
-        for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < jlen; u += gridDim.x * blockDim.x) {
-            uint32_t q;
-            f[u] = dfl_f_word(d, jx0 + u, cfg, 0xffffffffu, &q);
-            if (fq) fq[u] = q;
+        const uint32_t *fy = F + c.poff[y];
+        const uint32_t *fqy = FQ ? FQ + c.poff[y] : nullptr;
+        const uint16_t *ho = c.head_order + (size_t)y * DFL_JY, *hv = c.head_visit + (size_t)y * DFL_JY;
+        const uint32_t u_end = only_x ? jxl : jxl + jyl;       // only_x: dfl_junction3_kernel does the head of y
+        for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < u_end; u += gridDim.x * blockDim.x) {
+            uint32_t q, w, pos;
+            if (u < jxl) {
+                pos = u;
+                w = dfl_f_word(d, jx0 + u, cfg, 0xffffffffu, &q);
+            } else if (u - jxl < n_head) {
+                const uint32_t yq = ho[u - jxl];
+                pos = jxl + yq;
+                w = dfl_longest_cont(d, lx + yq, (uint32_t)cfg.max_chain, (uint32_t)cfg.nice_length, fy[yq], hv[yq], fqy != nullptr,
+                                     fqy ? fqy[yq] : 0u, &q);
+            } else {
+                pos = u; w = 0; q = 0;                                       // the last two positions of a short y: no string
+            }
+            f[pos] = w;
+            if (fq) fq[pos] = q;
+        }
+    }
+}
+
+// K3c': the same junction tables for the head positions of y, restructured for the SM (dfl_junction_kernel keeps
+// the last positions of x and remains the reference implementation of the head walk; tests compare the two).
+//   * the bytes every walk of a pair touches -- the last 32 KiB of x and the first 32 KiB + 266 of y -- are staged
+//     once per CTA in shared memory as one contiguous string, so a candidate compare is two or three LDS;
+//   * head positions are taken in (hash, position) order, so the lanes of a warp want the same bucket of x: the
+//     warp fetches 32 candidates of that bucket with one coalesced load and hands them round by shuffle; every lane
+//     keeps its own window limit, best match, chain count and stop condition (lanes of other buckets wait
+//     their turn: __match_any-style grouping by hash);
+//   * as in dfl_longest_cont the walk continues the one the position had in y alone.
+constexpr uint32_t DFL_J3_THREADS = 512;
+constexpr uint32_t DFL_J3_TX = 32768;                 // staged bytes of x's tail (candidates are >= lx - 32505)
+constexpr uint32_t DFL_J3_TY = DFL_JY + 272;          // staged bytes of y's head (position + MAX_MATCH + over-read)
+constexpr uint32_t DFL_J3_SMEM = DFL_J3_TX + DFL_J3_TY + 16;
+
+__device__ __forceinline__ uint32_t j3_ld32(const uint32_t *w, uint32_t i)        // 4 bytes at byte offset i
+{
+    const uint32_t k = i >> 2;
+    return __funnelshift_r(w[k], w[k + 1], (i & 3) * 8);
+}
+// common prefix of buf[a..] and buf[b..], at most maxcmp
+__device__ __forceinline__ uint32_t j3_lcp(const uint32_t *w, uint32_t a, uint32_t b, uint32_t scan0, uint32_t maxcmp)
+{
+    uint32_t x = scan0 ^ j3_ld32(w, b);
+    if (x) return tmin((uint32_t)(__ffs((int)x) - 1) >> 3, maxcmp);
+    uint32_t len = 4;
+    while (len < maxcmp) {
+        x = j3_ld32(w, a + len) ^ j3_ld32(w, b + len);
+        if (x) { len += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+        len += 4;
+    }
+    return tmin(len, maxcmp);
+}
+
+__global__ void __launch_bounds__(DFL_J3_THREADS)
+dfl_junction3_kernel(DflCorpus c, const DflPair *__restrict__ pairs, int32_t n_pairs, int level, const uint32_t *__restrict__ F,
+                     const uint32_t *__restrict__ FQ, uint32_t *__restrict__ FJ, uint32_t *__restrict__ FJQ)
+{
+    extern __shared__ __align__(16) uint8_t j3_buf[];
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(j3_buf);
+    const DflConfig cfg = dfl_config(level);
+    const uint32_t chain = (uint32_t)cfg.max_chain, qcount = chain >> 2;
+    const uint32_t lane = threadIdx.x & 31;
+    for (int32_t b = blockIdx.y; b < n_pairs; b += gridDim.y) {
+        const int32_t xi = pairs[b].x, yi = pairs[b].y;
+        const uint8_t *xp = c.corpus + c.off[xi], *yp = c.corpus + c.off[yi];
+        const uint32_t lx = c.len[xi], ly = c.len[yi], n = lx + ly;
+        const uint32_t jxl = lx - dfl_jx0(lx), jyl = tmin(ly, DFL_JY);
+        const uint32_t n_head = tmin(jyl, ly >= 3 ? ly - 2 : 0u);
+        const uint32_t tx = tmin(lx, DFL_J3_TX), s0 = lx - tx;                 // buf[i] = stream byte s0 + i
+        const uint32_t ty = tmin(ly + 16, DFL_J3_TY);                          // (the corpus pads every sequence with zeros)
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < tx; i += blockDim.x) j3_buf[i] = xp[s0 + i];
+        for (uint32_t i = threadIdx.x; i < ty + 16 && tx + i < DFL_J3_SMEM; i += blockDim.x) j3_buf[tx + i] = i < ty ? yp[i] : 0;
+        __syncthreads();
+        uint32_t *f = FJ + (size_t)b * DFL_JSTRIDE;
+        uint32_t *fq = FJQ ? FJQ + (size_t)b * DFL_JSTRIDE : nullptr;
+        const uint32_t *fy = F + c.poff[yi];
+        const uint32_t *fqy = FQ ? FQ + c.poff[yi] : nullptr;
+        const uint16_t *ho = c.head_order + (size_t)yi * DFL_JY, *hv = c.head_visit + (size_t)yi * DFL_JY;
+        const uint32_t *ox = c.order + c.poff[xi], *bx = c.bstart + (size_t)xi * (DFL_HASH + 1);
+        const uint32_t *oy = c.order + c.poff[yi], *by = c.bstart + (size_t)yi * (DFL_HASH + 1);
+        for (uint32_t t0 = blockIdx.x * blockDim.x; t0 < jyl; t0 += gridDim.x * blockDim.x) {
+            const uint32_t t = t0 + threadIdx.x;
+            const bool in_index = t < n_head;
+            const uint32_t yq = in_index ? ho[t] : t;
+            const uint32_t p = lx + yq, ip = p - s0;
+            // ---- where the walk of this position stood when it ran out of y (dfl_longest_cont) ----
+            uint32_t f_s = 0, visit = 0, q_s = 0;
+            bool q_known = fqy != nullptr;
+            if (in_index) { f_s = fy[yq]; visit = hv[yq]; if (fqy) q_s = fqy[yq]; }
+            const bool flag_s = (f_s & DFL_QDIFF) != 0;
+            f_s &= ~DFL_QDIFF;
+            if (!q_known && !flag_s) { q_known = true; q_s = f_s; }
+            uint32_t count = visit & DFL_V_COUNT;
+            const bool settled = !in_index || (visit & (DFL_V_NICE | DFL_V_HEADFAR)) || count >= chain;
+            const uint32_t base = dfl_window_base(p);
+            const uint32_t maxcmp = tmin(DFL_MAX_MATCH, n - p);
+            const uint32_t nice_match = tmin((uint32_t)cfg.nice_length, maxcmp);
+            const uint32_t limit = (p - base > DFL_MAX_DIST) ? p - DFL_MAX_DIST : base;
+            uint32_t best = (f_s >> 16) ? (f_s >> 16) : 2, bdist = f_s & 0xffff;
+            const bool q_fixed = count >= qcount;
+            uint32_t qbest = q_fixed && q_known ? q_s : 0;
+            const bool q_lost = q_fixed && !q_known;
+            bool head_pending = count == 0;              // the next candidate is the chain head
+            bool no_search = false;                      // the chain head failed its test: the result is "no match"
+            bool over = settled || t >= jyl;
+            const uint32_t scan0 = over ? 0u : j3_ld32(w, ip);
+            const uint32_t h = over ? 0xffffffffu : dfl_hash3(scan0 & 0xff, (scan0 >> 8) & 0xff, (scan0 >> 16) & 0xff);
+            // one candidate c (a stream position inside the staged string); sets `over` when the walk has ended
+#define J3_VISIT(c_) do {                                                                                           \
+                const uint32_t cc_ = (c_);                                                                          \
+                if (head_pending) {                                                                                 \
+                    head_pending = false;                                                                           \
+                    if (cc_ <= base || p - cc_ > DFL_MAX_DIST) { no_search = true; over = true; break; }            \
+                } else if (cc_ <= limit) { over = true; break; }                                                    \
+                const uint32_t len_ = j3_lcp(w, ip, cc_ - s0, scan0, maxcmp);                                       \
+                if (len_ > best) {                                                                                  \
+                    best = len_; bdist = p - cc_;                                                                   \
+                    if (len_ >= nice_match) { ++count; over = true; break; }                                        \
+                }                                                                                                   \
+                ++count;                                                                                            \
+                if (count == qcount) qbest = best > 2 ? (best << 16) | bdist : 0;                                   \
+                if (count >= chain) over = true;                                                                    \
+            } while (0)
+            // ---- y's position 0 (NIL in y alone, an ordinary candidate here) and the two straddling positions ----
+            if (!over) {
+                const uint32_t ylo = by[h], yhi = by[h + 1];
+                if (yq > 0 && yhi > ylo && oy[ylo] == 0) J3_VISIT(lx);
+                if (!over && lx >= 1 && n - (lx - 1) >= 3 && lx - 1 >= s0) {
+                    const uint32_t v = j3_ld32(w, lx - 1 - s0);
+                    if (dfl_hash3(v & 0xff, (v >> 8) & 0xff, (v >> 16) & 0xff) == h) J3_VISIT(lx - 1);
+                }
+                if (!over && lx >= 2 && n - (lx - 2) >= 3 && lx - 2 >= s0) {
+                    const uint32_t v = j3_ld32(w, lx - 2 - s0);
+                    if (dfl_hash3(v & 0xff, (v >> 8) & 0xff, (v >> 16) & 0xff) == h) J3_VISIT(lx - 2);
+                }
+            }
+            // ---- x's bucket, most recent first: the lanes that share a hash walk it together ----
+            bool need = !over;
+            for (;;) {
+                const uint32_t todo = __ballot_sync(0xffffffffu, need);
+                if (!todo) break;
+                const uint32_t hl = __shfl_sync(0xffffffffu, h, __ffs((int)todo) - 1);
+                const bool mine = need && h == hl;
+                const uint32_t xlo = bx[hl];
+                uint32_t k = bx[hl + 1];
+                while (k > xlo && __any_sync(0xffffffffu, mine && !over)) {
+                    const uint32_t m = tmin(32u, k - xlo);
+                    const uint32_t cand = lane < m ? __ldg(ox + (k - 1 - lane)) : 0u;
+                    for (uint32_t i = 0; i < m; ++i) {
+                        const uint32_t cc = __shfl_sync(0xffffffffu, cand, i);
+                        if (mine && !over) J3_VISIT(cc);
+                    }
+                    k -= m;
+                }
+                if (mine) need = false;
+            }
+#undef J3_VISIT
+            if (t < jyl) {
+                uint32_t word, qres;
+                if (settled) { word = in_index ? (f_s | (flag_s ? DFL_QDIFF : 0u)) : 0u; qres = in_index && q_known ? q_s : 0u; }
+                else if (no_search) { word = 0; qres = 0; }
+                else {
+                    const uint32_t full = best > 2 ? (best << 16) | bdist : 0;
+                    qres = count <= qcount ? full : qbest;
+                    const bool differs = count <= qcount ? false : (q_lost ? true : qbest != full);
+                    word = full | (differs ? DFL_QDIFF : 0u);
+                }
+                f[jxl + yq] = word;
+                if (fq) fq[jxl + yq] = qres;
+            }
         }
     }
 }
@@ -907,43 +1230,96 @@ dfl_parse_kernel(DflCorpus c, const DflJob *__restrict__ jobs, int64_t n_jobs, i
         const long long j = (long long)atomicAdd(counter, 1ull);
         if (j >= n_jobs) break;
         const DflJob jb = jobs[j];
-        const bool pair = jb.kind != 3;
-        const DflStream d = dfl_make(c, jb.x, pair ? jb.y : -1);
+        const DflStream d = dfl_make(c, jb.x, jb.y);
         const uint32_t lx = d.s.lx;
         DflFView fv;
         fv.fx = F + c.poff[jb.x]; fv.lx = lx;
         fv.qx = FQ ? FQ + c.poff[jb.x] : nullptr; fv.qy = fv.qj = fv.qx;
+        fv.fy = F + c.poff[jb.y];
+        fv.fj = FJ + (size_t)jb.fj * DFL_JSTRIDE;
+        if (FQ) { fv.qy = FQ + c.poff[jb.y]; fv.qj = FJQ + (size_t)jb.fj * DFL_JSTRIDE; }
+        fv.jx0 = dfl_jx0(lx); fv.jend = fv.jx0 + dfl_jlen(lx, d.s.n - lx);
+        const DflCkpt &ck = ckpt[jb.x];
+        DflParseState st = ck.st;
+        dfl_resume(st, d.s.n);
+        for (int k = 0; k < DFL_L_CODES; ++k) lf[k * T] = ck.lfreq[k];
+        for (int k = 0; k < DFL_D_CODES; ++k) df[k * T] = ck.dfreq[k];
+        DflCanon cn;
+        cn.n_sym = 0;
+        if (jb.kind == 2) cn = dfl_canon_of(cp, jb.y);
+        const int how = dfl_pair_stream(d, fv, cfg, st, lf, T, df, T, tr, jb.kind == 2 ? &cn : nullptr, accA, accB);
+        out[jb.out] = how ? (int64_t)(st.bits >> 3) : -2;
+    }
+}
+
+// K3d': the parse of every listed sequence ALONE: its size, the checkpoint at its junction start (what a pair stream
+// x.* resumes from) and its canonical symbol stream.  A serial chain of ~1.1 M dependent steps for 5 Mbp, so the
+// latency of each step is what counts: one CTA per sequence, thread 0 parses, the other warps stream F through a
+// shared-memory ring one chunk ahead of it; symbol counters and tree scratch live in shared memory as well.
+constexpr int DFL_PREP_THREADS = 128;
+struct DflPrepSmem {
+    uint32_t ring[2 * DFL_PREP_CHUNK];
+    DflTrees tr;
+    uint16_t lf[DFL_L_CODES], df[DFL_D_CODES];
+    uint32_t done;
+};
+
+__global__ void __launch_bounds__(DFL_PREP_THREADS)
+dfl_prep_kernel(DflCorpus c, const int32_t *__restrict__ seqs, int32_t n_seqs, int level, const uint32_t *__restrict__ F,
+                const uint32_t *__restrict__ FQ, DflCkpt *__restrict__ ckpt, DflCanonPool cp)
+{
+    extern __shared__ __align__(16) uint8_t prep_raw[];
+    DflPrepSmem &sm = *reinterpret_cast<DflPrepSmem *>(prep_raw);
+    const DflConfig cfg = dfl_config(level);
+    const uint32_t tid = threadIdx.x, C = DFL_PREP_CHUNK;
+    for (int32_t t = blockIdx.x; t < n_seqs; t += gridDim.x) {
+        const int32_t sq = seqs[t];
+        const DflStream d = dfl_make(c, sq, -1);
+        const uint32_t n = d.s.n, n_pad = (n + 7) & ~7u, jx0 = dfl_jx0(n);
+        const uint32_t *fsrc = F + c.poff[sq];
+        DflFView fv;
         DflParseState st;
-        if (pair) {
-            fv.fy = F + c.poff[jb.y];
-            fv.fj = FJ + (size_t)jb.fj * DFL_JSTRIDE;
-            if (FQ) { fv.qy = FQ + c.poff[jb.y]; fv.qj = FJQ + (size_t)jb.fj * DFL_JSTRIDE; }
-            fv.jx0 = dfl_jx0(lx); fv.jend = fv.jx0 + dfl_jlen(lx, d.s.n - lx);
-            const DflCkpt &ck = ckpt[jb.x];
-            st = ck.st;
-            dfl_resume(st, d.s.n);
-            for (int k = 0; k < DFL_L_CODES; ++k) lf[k * T] = ck.lfreq[k];
-            for (int k = 0; k < DFL_D_CODES; ++k) df[k * T] = ck.dfreq[k];
-            DflCanon cn;
-            cn.n_sym = 0;
-            if (jb.kind == 2) cn = dfl_canon_of(cp, jb.y);
-            const int how = dfl_pair_stream(d, fv, cfg, st, lf, T, df, T, tr, jb.kind == 2 ? &cn : nullptr, accA, accB);
-            out[jb.out] = how ? (int64_t)(st.bits >> 3) : -2;
-        } else {
-            fv.fy = fv.fj = fv.fx; fv.jx0 = fv.jend = lx;     // everything from F of the sequence
-            dfl_parse_fresh(st);
-            for (int k = 0; k < DFL_L_CODES; ++k) lf[k * T] = 0;
-            for (int k = 0; k < DFL_D_CODES; ++k) df[k * T] = 0;
-            lf[256 * T] = 1;
-            DflRec rec{cp.end + cp.soff[jb.x], cp.code + cp.soff[jb.x], cp.cap[jb.x], 0};
-            int r = dfl_parse(d, fv, cfg, st, lf, T, df, T, tr, dfl_jx0(lx), &rec);
-            DflCkpt &ck = ckpt[jb.x];
-            ck.st = st;                                        // (r == 1 only for an empty sequence: never resumed)
-            for (int k = 0; k < DFL_L_CODES; ++k) ck.lfreq[k] = lf[k * T];
-            for (int k = 0; k < DFL_D_CODES; ++k) ck.dfreq[k] = df[k * T];
-            if (r == 0) dfl_parse(d, fv, cfg, st, lf, T, df, T, tr, 0xffffffffu, &rec);
-            cp.n_sym[jb.x] = rec.n == DFL_NONE ? 0u : rec.n;
-            cp.seq_size[jb.x] = (int64_t)(st.bits >> 3);
+        DflRec rec{cp.end + cp.soff[sq], cp.code + cp.soff[sq], cp.cap[sq], 0};
+        bool ck_done = false;
+        fv.fx = fv.fy = fv.fj = fsrc; fv.jx0 = fv.jend = fv.lx = n;
+        fv.qx = FQ ? FQ + c.poff[sq] : nullptr; fv.qy = fv.qj = fv.qx;
+        fv.ring = sm.ring;
+        dfl_parse_fresh(st);
+        __syncthreads();                                    // the previous sequence is done with the ring
+        for (uint32_t i = tid; i < DFL_L_CODES; i += blockDim.x) sm.lf[i] = i == 256 ? 1 : 0;
+        for (uint32_t i = tid; i < DFL_D_CODES; i += blockDim.x) sm.df[i] = 0;
+        for (uint32_t i = tid * 4; i < tmin(C, n_pad); i += blockDim.x * 4)
+            *reinterpret_cast<uint4 *>(sm.ring + i) = __ldg(reinterpret_cast<const uint4 *>(fsrc + i));
+        __syncthreads();
+        for (uint32_t lo = 0;; lo += C) {
+            const uint32_t hi = lo + C;                      // F of [lo, hi) is in the ring
+            if (tid >= 32) {                                 // next chunk into the other half
+                for (uint32_t i = hi + (tid - 32) * 4; i < tmin(hi + C, n_pad); i += (blockDim.x - 32) * 4)
+                    *reinterpret_cast<uint4 *>(sm.ring + (i & (2 * C - 1))) = __ldg(reinterpret_cast<const uint4 *>(fsrc + i));
+            } else if (tid == 0) {
+                const uint32_t stop_chunk = hi < n ? hi : 0xffffffffu;
+                bool done = false;
+                for (;;) {
+                    const uint32_t stop = ck_done ? stop_chunk : tmin(stop_chunk, jx0);
+                    if (dfl_parse(d, fv, cfg, st, sm.lf, 1, sm.df, 1, sm.tr, stop, &rec) == 1) { done = true; break; }
+                    if (!ck_done && st.strstart >= jx0) {
+                        DflCkpt &ck = ckpt[sq];
+                        ck.st = st;
+                        for (int k = 0; k < DFL_L_CODES; ++k) ck.lfreq[k] = sm.lf[k];
+                        for (int k = 0; k < DFL_D_CODES; ++k) ck.dfreq[k] = sm.df[k];
+                        ck_done = true;
+                        continue;
+                    }
+                    break;                                   // the parse stands at or beyond the end of this chunk
+                }
+                sm.done = done ? 1u : 0u;
+            }
+            __syncthreads();
+            if (sm.done) break;
+        }
+        if (tid == 0) {
+            cp.n_sym[sq] = rec.n == DFL_NONE ? 0u : rec.n;
+            cp.seq_size[sq] = (int64_t)(st.bits >> 3);
         }
     }
 }
@@ -1006,9 +1382,10 @@ struct DeflateState {
     // per-corpus
     uint64_t *d_poff = nullptr; std::vector<uint64_t> h_poff; uint64_t total = 0;
     uint32_t *d_order = nullptr, *d_bstart = nullptr;
+    uint16_t *d_head_order = nullptr, *d_head_visit[2] = {nullptr, nullptr};
     std::vector<uint8_t> indexed;                  // per sequence
     uint32_t *d_F[2] = {nullptr, nullptr};         // level 9, level 6
-    uint32_t *d_FQ = nullptr, *d_FJQ = nullptr;    // level 6 only: quartered-chain tables
+    uint32_t *d_FQ = nullptr;                      // level 6 only: quartered-chain table
     std::vector<uint8_t> have_F[2], have_prep[2];
     DflCkpt *d_ckpt[2] = {nullptr, nullptr};
     // canonical symbol streams (per level): pools + per-sequence geometry (shared by both levels)
@@ -1019,10 +1396,14 @@ struct DeflateState {
     int64_t *d_seq_size[2] = {nullptr, nullptr};
     int32_t n_seqs = 0;
     // working memory
-    DflTrees *d_scratch = nullptr; size_t scratch_n = 0;
-    uint32_t *d_FJ = nullptr; size_t fj_pairs = 0;
+    DflTrees *d_scratch2[2] = {nullptr, nullptr}; size_t scratch_n = 0;
+    uint32_t *d_FJ2[2] = {nullptr, nullptr}, *d_FJQ2[2] = {nullptr, nullptr}; size_t fj_pairs = 0;
+    DflPair *d_pairs2[2] = {nullptr, nullptr}; DflJob *d_jobs2[2] = {nullptr, nullptr};
+    cudaStream_t stream2 = nullptr; cudaEvent_t ev_j[2] = {nullptr, nullptr}, ev_p[2] = {nullptr, nullptr};
+    unsigned long long *d_counter2 = nullptr;
     double main_ms = 0.0;
     int use_canon = 1;                             // 0: every pair stream takes the full serial parse (tests)
+    int junction_impl = 3;                         // 2: dfl_junction_kernel for every junction position (tests)
     int64_t serial_jobs = 0;                       // pair jobs of the last call that fell back to it
 };
 
@@ -1031,6 +1412,8 @@ static inline void deflate_free_corpus(DeflateState &st)
     cudaFree(st.d_poff); cudaFree(st.d_order); cudaFree(st.d_bstart);
     cudaFree(st.d_FQ); st.d_FQ = nullptr;
     cudaFree(st.d_soff); cudaFree(st.d_roff); cudaFree(st.d_cap);
+    cudaFree(st.d_head_order); st.d_head_order = nullptr;
+    for (int l = 0; l < 2; ++l) { cudaFree(st.d_head_visit[l]); st.d_head_visit[l] = nullptr; }
     st.d_soff = st.d_roff = nullptr; st.d_cap = nullptr;
     for (int l = 0; l < 2; ++l) {
         cudaFree(st.d_F[l]); cudaFree(st.d_ckpt[l]); st.d_F[l] = nullptr; st.d_ckpt[l] = nullptr;
@@ -1045,8 +1428,17 @@ static inline void deflate_free_corpus(DeflateState &st)
 }
 static inline void deflate_free_work(DeflateState &st)
 {
-    cudaFree(st.d_scratch); cudaFree(st.d_FJ); cudaFree(st.d_FJQ);
-    st.d_scratch = nullptr; st.d_FJ = nullptr; st.d_FJQ = nullptr; st.scratch_n = 0; st.fj_pairs = 0;
+    st.scratch_n = 0; st.fj_pairs = 0;
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(st.d_scratch2[k]); cudaFree(st.d_FJ2[k]); cudaFree(st.d_FJQ2[k]); cudaFree(st.d_pairs2[k]); cudaFree(st.d_jobs2[k]);
+        st.d_scratch2[k] = nullptr; st.d_FJ2[k] = st.d_FJQ2[k] = nullptr; st.d_pairs2[k] = nullptr; st.d_jobs2[k] = nullptr;
+        if (st.ev_j[k]) cudaEventDestroy(st.ev_j[k]);
+        if (st.ev_p[k]) cudaEventDestroy(st.ev_p[k]);
+        st.ev_j[k] = st.ev_p[k] = nullptr;
+    }
+    if (st.stream2) cudaStreamDestroy(st.stream2);
+    st.stream2 = nullptr;
+    cudaFree(st.d_counter2); st.d_counter2 = nullptr;
 }
 static inline void deflate_invalidate(DeflateState &st)
 {
@@ -1070,7 +1462,7 @@ template <typename T> static int dfl_upload(std::string &err, cudaStream_t strea
     return 0;
 }
 
-constexpr size_t DFL_BATCH = 8192;                 // pair streams per junction batch (1.08 GB of junction F)
+constexpr size_t DFL_BATCH = 16384;                // pair streams per junction batch (2.2 GB of junction F, two buffers)
 
 // sizes of the raw deflate streams of the jobs (x alone when ys == nullptr) into d_out[0..n_jobs)
 static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, const int32_t *xs, const int32_t *ys,
@@ -1106,12 +1498,14 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
         DCK(cudaStreamSynchronize(stream));
         DCK(cudaMalloc(&st.d_order, sizeof(uint32_t) * (t + 16)));
         DCK(cudaMalloc(&st.d_bstart, sizeof(uint32_t) * (size_t)ns * (DFL_HASH + 1)));
+        DCK(cudaMalloc(&st.d_head_order, sizeof(uint16_t) * (size_t)ns * DFL_JY));
         st.indexed.assign(ns, 0);
         for (int l = 0; l < 2; ++l) { st.have_F[l].assign(ns, 0); st.have_prep[l].assign(ns, 0); }
     }
     if (!st.d_F[li]) {
         DCK(cudaMalloc(&st.d_F[li], sizeof(uint32_t) * (st.total + 16)));
         DCK(cudaMalloc(&st.d_ckpt[li], sizeof(DflCkpt) * ns));
+        DCK(cudaMalloc(&st.d_head_visit[li], sizeof(uint16_t) * (size_t)ns * DFL_JY));
         if (level != 9) DCK(cudaMalloc(&st.d_FQ, sizeof(uint32_t) * (st.total + 16)));
         DCK(cudaMalloc(&st.d_sym_end[li], sizeof(uint32_t) * (st.sym_total + 16)));
         DCK(cudaMalloc(&st.d_sym_code[li], sizeof(uint16_t) * (st.sym_total + 16)));
@@ -1121,7 +1515,7 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
         DCK(cudaMemsetAsync(st.d_nsym[li], 0, sizeof(uint32_t) * ns, stream));
     }
     uint32_t *FQ = level != 9 ? st.d_FQ : nullptr;
-    DflCorpus c{dc.d_corpus, dc.d_off, dc.d_len, st.d_poff, st.d_order, st.d_bstart};
+    DflCorpus c{dc.d_corpus, dc.d_off, dc.d_len, st.d_poff, st.d_order, st.d_bstart, st.d_head_order, st.d_head_visit[li]};
     DflCanonPool cp{st.d_sym_end[li], st.d_sym_code[li], st.d_cum[li], st.d_soff, st.d_cap, st.d_roff, st.d_nsym[li],
                     st.d_seq_size[li]};
 
@@ -1148,7 +1542,11 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
         dfl_index_kernel<<<(unsigned)std::min<size_t>(need_idx.size(), 148 * 4), 32, DFL_HASH * 4, stream>>>(
             c, d_list, (int32_t)need_idx.size(), st.d_F[li]);
         DCK(cudaGetLastError());
-        ++*launches;
+        DCK(cudaFuncSetAttribute(dfl_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DFL_HASH * 4)));
+        dfl_head_kernel<<<(unsigned)std::min<size_t>(need_idx.size(), 148), 1024, DFL_HASH * 4, stream>>>(
+            c, d_list, (int32_t)need_idx.size());
+        DCK(cudaGetLastError());
+        *launches += 2;
         DCK(cudaStreamSynchronize(stream));
         cudaFree(d_list);
     }
@@ -1165,41 +1563,27 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
     // ---- parse jobs ----
     const int parse_blocks = 148 * 4;
     if (st.scratch_n < (size_t)parse_blocks * DFL_PARSE_THREADS) {
-        cudaFree(st.d_scratch); st.d_scratch = nullptr;
+        for (int k = 0; k < 2; ++k) { cudaFree(st.d_scratch2[k]); st.d_scratch2[k] = nullptr; }
         st.scratch_n = (size_t)parse_blocks * DFL_PARSE_THREADS;
-        DCK(cudaMalloc(&st.d_scratch, sizeof(DflTrees) * st.scratch_n));
+        for (int k = 0; k < 2; ++k) DCK(cudaMalloc(&st.d_scratch2[k], sizeof(DflTrees) * st.scratch_n));
     }
-    unsigned long long *d_counter = nullptr;
-    DCK(cudaMalloc(&d_counter, sizeof(unsigned long long)));
     st.main_ms = 0.0;
     st.serial_jobs = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     DCK(cudaEventCreate(&e0)); DCK(cudaEventCreate(&e1));
-    auto run_parse = [&](const std::vector<DflJob> &jobs) -> int {
-        if (jobs.empty()) return 0;
-        DflJob *d_jobs = nullptr;
-        if (dfl_upload(err, stream, jobs, &d_jobs)) return -1;
-        DCK(cudaMemsetAsync(d_counter, 0, sizeof(unsigned long long), stream));
-        DCK(cudaEventRecord(e0, stream));
-        const int blocks = (int)std::min<size_t>((jobs.size() + DFL_PARSE_THREADS - 1) / DFL_PARSE_THREADS, parse_blocks);
-        dfl_parse_kernel<<<blocks, DFL_PARSE_THREADS, 0, stream>>>(c, d_jobs, (int64_t)jobs.size(), level, st.d_F[li], FQ, st.d_FJ,
-                                                                  FQ ? st.d_FJQ : nullptr, st.d_ckpt[li], cp, st.d_scratch,
-                                                                  d_counter, d_out);
-        DCK(cudaGetLastError());
-        DCK(cudaEventRecord(e1, stream));
-        ++*launches;
-        DCK(cudaStreamSynchronize(stream));
-        float ms = 0.f;
-        DCK(cudaEventElapsedTime(&ms, e0, e1));
-        st.main_ms += ms;                                 // the parse kernel is the dominant one
-        cudaFree(d_jobs);
-        return 0;
-    };
     int rc = 0;
     if (!need_prep.empty()) {
-        std::vector<DflJob> jobs;
-        for (int32_t i : need_prep) jobs.push_back(DflJob{i, -1, 3, 0, 0});
-        rc = run_parse(jobs);
+        {
+            int32_t *d_list = nullptr;
+            if (dfl_upload(err, stream, need_prep, &d_list)) return -1;
+            DCK(cudaFuncSetAttribute(dfl_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DflPrepSmem)));
+            dfl_prep_kernel<<<(unsigned)std::min<size_t>(need_prep.size(), 148 * 3), DFL_PREP_THREADS, sizeof(DflPrepSmem), stream>>>(
+                c, d_list, (int32_t)need_prep.size(), level, st.d_F[li], FQ, st.d_ckpt[li], cp);
+            DCK(cudaGetLastError());
+            ++*launches;
+            DCK(cudaStreamSynchronize(stream));
+            cudaFree(d_list);
+        }
         if (!rc) {
             int32_t *d_list = nullptr;
             if (dfl_upload(err, stream, need_prep, &d_list)) return -1;
@@ -1221,36 +1605,83 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
         if (cudaGetLastError() != cudaSuccess) { err = "dfl_gather_sizes_kernel launch failed"; rc = -1; }
         ++*launches;
     } else {
-        // pairs in batches: junction F of the batch, then its parses
+        // pairs in batches, double buffered: the junction tables of batch b+1 are computed on `stream` while the
+        // pair streams of batch b are parsed on st.stream2 (a latency-bound kernel with one thread per stream)
         const size_t batch = DFL_BATCH;
         if (st.fj_pairs < batch) {
-            cudaFree(st.d_FJ); st.d_FJ = nullptr;
+            for (int k = 0; k < 2; ++k) { cudaFree(st.d_FJ2[k]); cudaFree(st.d_pairs2[k]); cudaFree(st.d_jobs2[k]); }
             st.fj_pairs = batch;
-            DCK(cudaMalloc(&st.d_FJ, sizeof(uint32_t) * batch * DFL_JSTRIDE));
+            for (int k = 0; k < 2; ++k) {
+                DCK(cudaMalloc(&st.d_FJ2[k], sizeof(uint32_t) * batch * DFL_JSTRIDE));
+                DCK(cudaMalloc(&st.d_pairs2[k], sizeof(DflPair) * batch));
+                DCK(cudaMalloc(&st.d_jobs2[k], sizeof(DflJob) * batch));
+            }
         }
-        if (FQ && !st.d_FJQ) DCK(cudaMalloc(&st.d_FJQ, sizeof(uint32_t) * batch * DFL_JSTRIDE));
+        if (FQ && !st.d_FJQ2[0])
+            for (int k = 0; k < 2; ++k) DCK(cudaMalloc(&st.d_FJQ2[k], sizeof(uint32_t) * batch * DFL_JSTRIDE));
+        DCK(cudaFuncSetAttribute(dfl_junction3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DFL_J3_SMEM));
+        if (!st.stream2) {
+            DCK(cudaStreamCreateWithFlags(&st.stream2, cudaStreamNonBlocking));
+            for (int k = 0; k < 2; ++k) {
+                DCK(cudaEventCreateWithFlags(&st.ev_j[k], cudaEventDisableTiming));
+                DCK(cudaEventCreateWithFlags(&st.ev_p[k], cudaEventDisableTiming));
+            }
+            DCK(cudaMalloc(&st.d_counter2, 2 * sizeof(unsigned long long)));
+        }
         std::vector<DflJob> jobs;
+        std::vector<DflPair> pairs;
         auto run_pairs = [&](const std::vector<int64_t> *subset, int kind) -> int {
             const int64_t total = subset ? (int64_t)subset->size() : n_jobs;
-            for (int64_t b0 = 0; b0 < total; b0 += (int64_t)batch) {
+            DCK(cudaEventRecord(st.ev_j[0], stream));                  // everything queued so far (prep) precedes the parses
+            DCK(cudaStreamWaitEvent(st.stream2, st.ev_j[0], 0));
+            int64_t nbatch = 0;
+            for (int64_t b0 = 0; b0 < total; b0 += (int64_t)batch, ++nbatch) {
+                const int k2 = (int)(nbatch & 1);
                 const int64_t nb = std::min<int64_t>((int64_t)batch, total - b0);
-                std::vector<DflPair> pairs((size_t)nb);
-                jobs.assign((size_t)nb, DflJob());
+                pairs.resize((size_t)nb); jobs.resize((size_t)nb);
                 for (int64_t k = 0; k < nb; ++k) {
                     const int64_t j = subset ? (*subset)[b0 + k] : b0 + k;
                     pairs[k] = DflPair{xs[j], ys[j]};
                     jobs[k] = DflJob{xs[j], ys[j], kind, (int32_t)k, j};
                 }
-                DflPair *d_pairs = nullptr;
-                if (dfl_upload(err, stream, pairs, &d_pairs)) return -1;
-                dim3 grid((DFL_JSTRIDE + 255) / 256, (unsigned)std::min<int64_t>(nb, 4096));
-                dfl_junction_kernel<<<grid, 256, 0, stream>>>(c, d_pairs, (int32_t)nb, level, st.d_FJ, FQ ? st.d_FJQ : nullptr);
-                if (cudaGetLastError() != cudaSuccess) { err = "dfl_junction_kernel launch failed"; cudaFree(d_pairs); return -1; }
-                ++*launches;
-                const int r = run_parse(jobs);
-                cudaFree(d_pairs);
-                if (r) return r;
+                if (nbatch >= 2) DCK(cudaStreamWaitEvent(stream, st.ev_p[k2], 0));   // buffer k2 is free again
+                DCK(cudaMemcpyAsync(st.d_pairs2[k2], pairs.data(), sizeof(DflPair) * nb, cudaMemcpyHostToDevice, stream));
+                DCK(cudaMemcpyAsync(st.d_jobs2[k2], jobs.data(), sizeof(DflJob) * nb, cudaMemcpyHostToDevice, stream));
+                DCK(cudaEventRecord(e0, stream));
+                if (st.junction_impl == 3 && !getenv("SNACC_DFL_JUNCTION2")) {
+                    dim3 gx((DFL_JX + 255) / 256, (unsigned)std::min<int64_t>(nb, 4096));
+                    dfl_junction_kernel<<<gx, 256, 0, stream>>>(c, st.d_pairs2[k2], (int32_t)nb, level, st.d_F[li], FQ, st.d_FJ2[k2],
+                                                                FQ ? st.d_FJQ2[k2] : nullptr, 1);
+                    dim3 g3(DFL_JY / DFL_J3_THREADS, (unsigned)std::min<int64_t>(nb, 4096));
+                    dfl_junction3_kernel<<<g3, DFL_J3_THREADS, DFL_J3_SMEM, stream>>>(c, st.d_pairs2[k2], (int32_t)nb, level, st.d_F[li], FQ,
+                                                                                      st.d_FJ2[k2], FQ ? st.d_FJQ2[k2] : nullptr);
+                    ++*launches;
+                } else {
+                    dim3 grid((DFL_JSTRIDE + 255) / 256, (unsigned)std::min<int64_t>(nb, 4096));
+                    dfl_junction_kernel<<<grid, 256, 0, stream>>>(c, st.d_pairs2[k2], (int32_t)nb, level, st.d_F[li], FQ, st.d_FJ2[k2],
+                                                                  FQ ? st.d_FJQ2[k2] : nullptr, 0);
+                }
+                if (cudaGetLastError() != cudaSuccess) { err = "junction kernel launch failed"; return -1; }
+                DCK(cudaEventRecord(e1, stream));
+                DCK(cudaEventRecord(st.ev_j[k2], stream));
+                DCK(cudaStreamWaitEvent(st.stream2, st.ev_j[k2], 0));
+                DCK(cudaMemsetAsync(st.d_counter2 + k2, 0, sizeof(unsigned long long), st.stream2));
+                const int blocks = (int)std::min<size_t>(((size_t)nb + DFL_PARSE_THREADS - 1) / DFL_PARSE_THREADS, parse_blocks);
+                dfl_parse_kernel<<<blocks, DFL_PARSE_THREADS, 0, st.stream2>>>(c, st.d_jobs2[k2], nb, level, st.d_F[li], FQ, st.d_FJ2[k2],
+                                                                              FQ ? st.d_FJQ2[k2] : nullptr, st.d_ckpt[li], cp,
+                                                                              st.d_scratch2[k2], st.d_counter2 + k2, d_out);
+                if (cudaGetLastError() != cudaSuccess) { err = "dfl_parse_kernel launch failed"; return -1; }
+                DCK(cudaEventRecord(st.ev_p[k2], st.stream2));
+                *launches += 2;
+                // the host buffers are reused for the next batch: wait until this batch's uploads are done (the
+                // kernels of the previous batch keep the GPU busy meanwhile)
+                DCK(cudaEventSynchronize(st.ev_j[k2]));
+                float ms = 0.f;
+                DCK(cudaEventElapsedTime(&ms, e0, e1));
+                st.main_ms += ms;                                  // the junction kernel is the dominant one
             }
+            DCK(cudaStreamSynchronize(st.stream2));
+            DCK(cudaStreamSynchronize(stream));
             return 0;
         };
         rc = run_pairs(nullptr, st.use_canon ? 2 : 4);
@@ -1264,7 +1695,6 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
             if (!redo.empty()) rc = run_pairs(&redo, 4);
         }
     }
-    cudaFree(d_counter);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return rc;
 }

@@ -197,12 +197,24 @@ static EmuIndex emu_index(const uint8_t *p, uint32_t len)
     return ix;
 }
 
-static std::vector<uint32_t> emu_F_single(const DflStream &d, const DflConfig &cfg)
+// F (and, like the kernels at level 6, the quartered-chain table FQ) of a sequence alone, plus what
+// dfl_match_kernel / dfl_head_kernel keep about its head
+struct EmuSeq { std::vector<uint32_t> F, FQ; std::vector<uint16_t> head_order, head_visit; };
+static EmuSeq emu_F_single(const DflStream &d, const DflConfig &cfg, bool want_q)
 {
-    std::vector<uint32_t> F(d.s.n + 16, 0);
+    EmuSeq e;
+    e.F.assign(d.s.n + 16, 0);
+    if (want_q) e.FQ.assign(d.s.n + 16, 0);
+    e.head_visit.assign(DFL_JY, 0);
     const uint32_t nidx = d.s.n >= 3 ? d.s.n - 2 : 0;
-    for (uint32_t k = 0; k < nidx; ++k) { const uint32_t p = d.ix.order[k]; F[p] = dfl_f_word(d, p, cfg, k, nullptr); }
-    return F;
+    for (uint32_t k = 0; k < nidx; ++k) {
+        const uint32_t p = d.ix.order[k];
+        uint32_t q, visit;
+        e.F[p] = dfl_f_word(d, p, cfg, k, &q, &visit);
+        if (want_q) e.FQ[p] = q;
+        if (p < DFL_JY) { e.head_visit[p] = (uint16_t)visit; e.head_order.push_back((uint16_t)p); }   // index order = (hash, position)
+    }
+    return e;
 }
 
 // canonical symbol stream of a sequence alone, built the way dfl_parse_kernel (kind 3) + the dfl_cum kernels do
@@ -215,7 +227,7 @@ extern "C" int64_t emu_deflate_size_ex(const uint8_t *x, uint32_t lx, const uint
                                        int32_t *info)
 {
     const DflConfig cfg = dfl_config(level);
-    if (info) info[0] = info[1] = 0;
+    if (info) info[0] = info[1] = info[2] = 0;
     uint8_t *px = padded_copy(x, lx);
     uint8_t *py = ly_ >= 0 ? padded_copy(y, (uint64_t)ly_) : nullptr;
     EmuIndex ix = emu_index(px, lx), iy;
@@ -225,8 +237,11 @@ extern "C" int64_t emu_deflate_size_ex(const uint8_t *x, uint32_t lx, const uint
     // x alone
     DflStream dx; dx.s.x = px; dx.s.lx = lx; dx.s.y = px + lx; dx.s.n = lx; dx.pair = false;
     dx.ix.order = ix.order.data(); dx.ix.bstart = ix.bstart.data(); dx.iy = dx.ix;
-    std::vector<uint32_t> Fx = emu_F_single(dx, cfg);
-    DflFView fv; fv.fx = fv.fy = fv.fj = Fx.data(); fv.jx0 = fv.jend = fv.lx = lx; fv.qx = fv.qy = fv.qj = nullptr;
+    const bool want_q = level != 9;
+    EmuSeq ex = emu_F_single(dx, cfg, want_q);
+    std::vector<uint32_t> &Fx = ex.F;
+    DflFView fv; fv.fx = fv.fy = fv.fj = Fx.data(); fv.jx0 = fv.jend = fv.lx = lx;
+    fv.qx = fv.qy = fv.qj = want_q ? ex.FQ.data() : nullptr;
     DflParseState st;
     int64_t result;
     if (ly_ < 0) {
@@ -245,13 +260,15 @@ extern "C" int64_t emu_deflate_size_ex(const uint8_t *x, uint32_t lx, const uint
         // y alone
         DflStream dy; dy.s.x = py; dy.s.lx = ly; dy.s.y = py + ly; dy.s.n = ly; dy.pair = false;
         dy.ix.order = iy.order.data(); dy.ix.bstart = iy.bstart.data(); dy.iy = dy.ix;
-        std::vector<uint32_t> Fy = emu_F_single(dy, cfg);
+        EmuSeq ey = emu_F_single(dy, cfg, want_q);
+        std::vector<uint32_t> &Fy = ey.F;
         EmuCanon ec;
         if (use_canon) {
             const uint32_t cap = (ly / 4 + 1024 + DFL_CUM_G - 1) / DFL_CUM_G * DFL_CUM_G;
             ec.end.assign(cap + 16, 0); ec.code.assign(cap + 16, 0);
             DflRec rec{ec.end.data(), ec.code.data(), cap, 0};
-            DflFView fy; fy.fx = fy.fy = fy.fj = Fy.data(); fy.jx0 = fy.jend = fy.lx = ly; fy.qx = fy.qy = fy.qj = nullptr;
+            DflFView fy; fy.fx = fy.fy = fy.fj = Fy.data(); fy.jx0 = fy.jend = fy.lx = ly;
+            fy.qx = fy.qy = fy.qj = want_q ? ey.FQ.data() : nullptr;
             DflParseState sy; dfl_parse_fresh(sy);
             std::vector<uint16_t> l2(DFL_L_CODES, 0), d2(DFL_D_CODES, 0); l2[256] = 1;
             DflTrees *t2 = new DflTrees();
@@ -275,9 +292,26 @@ extern "C" int64_t emu_deflate_size_ex(const uint8_t *x, uint32_t lx, const uint
         // pair stream: junction F, then resume
         DflStream d; d.s.x = px; d.s.lx = lx; d.s.y = py; d.s.n = lx + ly; d.pair = true; d.ix = dx.ix; d.iy = dy.ix;
         const uint32_t jx0 = dfl_jx0(lx), jlen = dfl_jlen(lx, ly);
-        std::vector<uint32_t> FJ(jlen + 16, 0);
-        for (uint32_t u = 0; u < jlen; ++u) FJ[u] = dfl_f_word(d, jx0 + u, cfg, 0xffffffffu, nullptr);
+        std::vector<uint32_t> FJ(jlen + 16, 0), FJQ(jlen + 16, 0);
+        // dfl_junction_kernel: general walk for the last positions of x, continued walk for the head of y
+        const uint32_t jxl = lx - jx0, jyl = jlen - jxl, n_head = (uint32_t)ey.head_order.size();
+        int32_t mismatches = 0;
+        for (uint32_t u = 0; u < jxl; ++u) FJ[u] = dfl_f_word(d, jx0 + u, cfg, 0xffffffffu, &FJQ[u]);
+        for (uint32_t t = 0; t < jyl; ++t) {
+            if (t >= n_head) { FJ[jxl + t] = 0; FJQ[jxl + t] = 0; continue; }
+            const uint32_t yq = ey.head_order[t];
+            uint32_t q = 0;
+            const uint32_t w = dfl_longest_cont(d, lx + yq, (uint32_t)cfg.max_chain, (uint32_t)cfg.nice_length, Fy[yq], ey.head_visit[yq],
+                                                want_q, want_q ? ey.FQ[yq] : 0u, &q);
+            FJ[jxl + yq] = w; FJQ[jxl + yq] = q;
+            // self-check against the general walk over the pair stream
+            uint32_t q0 = 0;
+            const uint32_t w0 = dfl_f_word(d, lx + yq, cfg, 0xffffffffu, &q0);
+            if ((w & ~DFL_QDIFF) != (w0 & ~DFL_QDIFF) || ((w0 & DFL_QDIFF) && !(w & DFL_QDIFF)) || (want_q && q != q0)) ++mismatches;
+        }
+        if (info) info[2] = mismatches;
         fv.fx = Fx.data(); fv.fy = Fy.data(); fv.fj = FJ.data(); fv.jx0 = jx0; fv.jend = jx0 + jlen; fv.lx = lx;
+        if (want_q) { fv.qx = ex.FQ.data(); fv.qy = ey.FQ.data(); fv.qj = FJQ.data(); }
         dfl_resume(st, d.s.n);
         const DflParseState st0 = st;
         const std::vector<uint16_t> lf0 = lf, df0 = df;

@@ -194,6 +194,11 @@ def test_megabase_genomes_gzip(engine):
         assert np.array_equal(engine.tile_sizes("gzip", 0, 2, 0, 4), ref)
     finally:
         engine.set_option("deflate_canonical", 1)
+    engine.set_option("deflate_junction", 2)                                   # general junction walk instead of the smem kernel
+    try:
+        assert np.array_equal(engine.tile_sizes("gzip", 0, 2, 0, 4), ref)
+    finally:
+        engine.set_option("deflate_junction", 3)
     Sz = engine.tile_sizes("zlib", 1, 2, 0, 3)
     refz = np.array([[_ref_len(np.concatenate([g[i], g[j]]), "zlib") for j in range(3)] for i in (1, 2)])
     assert np.array_equal(Sz, refz)
