@@ -44,8 +44,9 @@ def parse_args():
     ap.add_argument("--genomes", type=int, default=N_GENOMES)
     ap.add_argument("--length", type=int, default=GENOME_LEN)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="c4", choices=["c4", "c3"],
-                    help="c4 (default, the headline): 512 x 5 Mbp; c3: 10,000 x ~11 kbp viral genomes (BASELINE.json configs[2])")
+    ap.add_argument("--config", default="c4", choices=["c4", "c3", "c5"],
+                    help="c4 (default, the headline): 512 x 5 Mbp lz4; c3: 10,000 x ~11 kbp viral genomes (BASELINE.json configs[2]); "
+                         "c5: 2,048 x 5 Mbp, gzip, the full ordered matrix C(xy) and C(yx) (BASELINE.json configs[4])")
     ap.add_argument("--band", type=int, default=0, help="rows per library call (0 = the rank's whole band, 1024 for c3)")
     return ap.parse_args()
 
@@ -143,6 +144,10 @@ def main():
     codec = args.codec
     if args.config == "c3" and args.genomes == N_GENOMES and args.length == GENOME_LEN:
         args.genomes, args.length = 10_000, 10_700
+    if args.config == "c5":
+        codec = args.codec = "gzip"
+        if args.genomes == N_GENOMES:
+            args.genomes = 2048
     n, L = args.genomes, args.length
     workload = (f"{args.config}: {n} x {L / 1e6:g} Mbp synthetic mutated-phylogeny genomes, {codec} NCD; step = the whole "
                 f"{n} x {n} ordered-pair matrix (N + N^2 compressor jobs, reference semantics cli.py:104-136) + float64 NCD")
@@ -311,8 +316,8 @@ def main():
             "algorithmic_GBps": bytes_total / wall_s / 1e9,
             "device_ms_per_step": 1e3 * timed_s / args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": ("lz4_pk_pair_kernel<linked>" if args.config == "c4" else "lz4_pk_pair_kernel<single-block>")
-                                   if codec == "lz4" else "dfl_parse_kernel",
+                         "traffic": None, "kernel": ("lz4_pk_pair_kernel<linked>" if args.config != "c3" else "lz4_pk_pair_kernel<single-block>")
+                                   if codec == "lz4" else "dfl_junction_kernel (sum over the step's batches)",
                          "peak_source": peak_src,
                          "note": "achieved = algorithmic bytes of one launch (sum of len(x)+len(y) over its pair jobs) / "
                                  "its CUDA-event duration; the path is latency/integer bound, not HBM bound"},

@@ -109,7 +109,8 @@ int snacc_get_stat(const snacc_ctx *ctx, const char *name, double *out);
  * `invalidate_caches` (any value) drops every per-sequence precomputation so the next call redoes it;
  * `lz4_packed` 0 forces the byte-wise LZ4 kernels; `deflate_canonical` 0 makes every deflate pair stream take
  * the full serial parse instead of the canonical symbol stream of y; `deflate_junction` 2 computes every junction
- * table with the general walk instead of the shared-memory kernel (all three are for tests: same results). */
+ * table without the 6-byte-index shortcut, `deflate_index6` 0 every match table from the 3-byte chain walk
+ * (all four are for tests: same results). */
 int snacc_set_option(snacc_ctx *ctx, const char *name, int64_t value);
 
 #ifdef __cplusplus

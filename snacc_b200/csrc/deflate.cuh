@@ -288,6 +288,89 @@ SNACC_HD uint32_t dfl_longest_cont(const DflStream &d, uint32_t p, uint32_t chai
     return full | (differs ? DFL_QDIFF : 0u);
 }
 
+// ---- 6-byte index of a sequence's tail -----------------------------------------------------------
+// When the walk of a head position of y leaves y with a best match of 5+ bytes -- or when x holds a candidate of
+// 6+ bytes at all -- only candidates of x that agree on 6+ bytes decide the result, and the chain visits them in
+// the same (most recent first) order whether or not the shorter ones are skipped.  Those candidates are found through a second index of the last
+// 32 KiB of every sequence, keyed by a hash of 6 bytes (a handful of entries per bucket on DNA instead of ~500
+// in the 3-byte bucket).  The shortcut is only taken when no chain limit can bind: the walk inside y visited
+// cnt candidates, x's whole 3-byte bucket holds at most U inside any window, and cnt + 3 + U stays below
+// max_chain / 4 -- then neither max_chain nor the quartered chain cuts the walk short and the visit count does
+// not matter.  Everything else takes dfl_longest_cont.
+constexpr uint32_t DFL_T6 = 32768;                    // tail positions indexed: [max(0, len - DFL_T6), len - 6]
+constexpr uint32_t DFL_H6 = 8192;                     // buckets of the 6-byte index
+SNACC_HD uint32_t dfl_hash6(uint64_t v) { return (uint32_t)(((v & 0xffffffffffffull) * 0x9E3779B97F4A7C15ull) >> 51); }
+struct DflTail6 {
+    const uint16_t *order;      // offsets from t0, sorted by (hash6, position)
+    const uint16_t *start;      // DFL_H6 + 1 bucket starts
+    uint32_t t0;                // stream position of offset 0
+};
+SNACC_HD uint32_t dfl_tail6_t0(uint32_t len) { return len > DFL_T6 ? len - DFL_T6 : 0; }
+SNACC_HD uint32_t dfl_tail6_count(uint32_t len) { return len >= 6 ? len - 5 - dfl_tail6_t0(len) : 0; }
+SNACC_HD uint32_t dfl_tail3_from(uint32_t len) { return len > DFL_MAX_DIST - 1 ? len - (DFL_MAX_DIST - 1) : 0; }  // first x position any head walk can reach
+
+// preconditions (checked by dfl_junction_word): the walk inside y started, did not stop at nice_length, and no
+// chain limit can bind; the result only stands when it is 6+ bytes long or y alone had found 5+ bytes
+SNACC_HD uint32_t dfl_longest_k6(const DflStream &d, uint32_t p, uint32_t nice, uint32_t f_s, const DflTail6 &t6)
+{
+    const Stream &s = d.s;
+    const uint32_t lx = s.lx, base = dfl_window_base(p);
+    const uint32_t maxcmp = tmin(DFL_MAX_MATCH, s.n - p);
+    const uint32_t nice_match = tmin(nice, maxcmp);
+    const uint32_t limit = (p - base > DFL_MAX_DIST) ? p - DFL_MAX_DIST : base;
+    uint32_t best = (f_s >> 16) ? (f_s >> 16) : 2, bdist = f_s & 0xffff;
+    const uint64_t scan = ld64(s, p);
+    bool over = false;
+#define DFL_K6_VISIT(c_) do {                                                                                       \
+        const uint64_t x_ = scan ^ ld64(s, (c_));                                                                   \
+        uint32_t len_ = x_ ? (uint32_t)(SNACC_FFS64(x_) - 1) >> 3                                                    \
+                           : 8 + dfl_match_len(s, p + 8, (c_) + 8, maxcmp > 8 ? maxcmp - 8 : 0);                    \
+        if (len_ > maxcmp) len_ = maxcmp;                                                                           \
+        if (len_ > best) { best = len_; bdist = p - (c_); if (len_ >= nice_match) over = true; }                    \
+    } while (0)
+    // y's position 0 (p > lx), then lx-1 .. lx-5: the positions of x whose 6 bytes run into y
+    for (uint32_t k = p > lx ? 0u : 1u; k <= 5 && !over; ++k) {
+        if (lx < k) break;
+        const uint32_t c = lx - k;
+        if (c <= limit) { over = true; break; }
+        DFL_K6_VISIT(c);
+    }
+    if (!over) {
+        const uint32_t h6 = dfl_hash6(scan);
+        const uint32_t lo = SNACC_LDG(t6.start + h6);
+        uint32_t k = SNACC_LDG(t6.start + h6 + 1);
+        while (k > lo) {
+            const uint32_t c = t6.t0 + SNACC_LDG(t6.order + --k);
+            if (c <= limit) break;
+            DFL_K6_VISIT(c);
+            if (over) break;
+        }
+    }
+#undef DFL_K6_VISIT
+    return best > 2 ? (best << 16) | bdist : 0;
+}
+
+// junction F word of head position p = lx + q of a pair stream (see dfl_longest_cont for the arguments);
+// tail_cnt: per 3-byte bucket of x, the entries at or after dfl_tail3_from(lx); t6 == null: no shortcut
+SNACC_HD uint32_t dfl_junction_word(const DflStream &d, uint32_t p, const DflConfig &cfg, uint32_t f_s, uint32_t visit, bool q_known,
+                                    uint32_t q_s, const DflTail6 *t6, const uint16_t *tail_cnt, uint32_t *quarter)
+{
+    const uint32_t cnt = visit & DFL_V_COUNT, f = f_s & ~DFL_QDIFF, chain = (uint32_t)cfg.max_chain;
+    if (t6 && !(visit & (DFL_V_NICE | DFL_V_HEADFAR)) && cnt >= 1 && d.s.n - p >= 6) {
+        const uint32_t h = dfl_hash_at(d.s, p);
+        if (cnt + 3 + SNACC_LDG(tail_cnt + h) < (chain >> 2)) {
+            // the 6-byte walk sees every candidate of 6+ bytes in chain order: when it ends with such a match, or when
+            // y alone had already found 5+ bytes, no candidate it skipped can have mattered
+            const uint32_t w = dfl_longest_k6(d, p, (uint32_t)cfg.nice_length, f, *t6);
+            if ((w >> 16) >= 6 || (f >> 16) >= 5) {
+                if (quarter) *quarter = w;
+                return w;
+            }
+        }
+    }
+    return dfl_longest_cont(d, p, chain, (uint32_t)cfg.nice_length, f_s, visit, q_known, q_s, quarter);
+}
+
 // F word of a position: the full-chain result, flagged when the quartered chain gives something else
 SNACC_HD uint32_t dfl_f_word(const DflStream &d, uint32_t p, const DflConfig &c, uint32_t hint, uint32_t *qword,
                              uint32_t *visit = nullptr)
@@ -296,6 +379,59 @@ SNACC_HD uint32_t dfl_f_word(const DflStream &d, uint32_t p, const DflConfig &c,
     const uint32_t f = dfl_longest(d, p, dfl_window_base(p), (uint32_t)c.max_chain, (uint32_t)c.nice_length, hint, &q, visit);
     if (qword) *qword = q;
     return q != f ? f | DFL_QDIFF : f;
+}
+
+// ---- 6-byte index of a whole sequence (transient: only dfl_match_kernel reads it) ---------------------
+// The same argument as for the junction gives F of a sequence alone without walking its 3-byte chain: when fewer
+// than max_chain / 4 chain members lie inside the window (one index lookup: the member max_chain / 4 places
+// back is out of reach), no limit binds, and if the candidates that share 6 bytes with p -- visited most recent
+// first -- yield a match of 6+ bytes, that match is what the full walk would have returned.  Otherwise (no such
+// candidate, head of the sequence, level 6 where the chain limit binds all the time) the full walk runs.
+SNACC_HD uint32_t dfl_hash6w(uint64_t v) { return (uint32_t)(((v & 0xffffffffffffull) * 0x9E3779B97F4A7C15ull) >> 49); }   // 15 bits
+struct DflIndex6 { const uint32_t *order6, *bstart6; };   // positions [0, len - 5) sorted by (hash6w, position)
+
+SNACC_HD uint32_t dfl_match_word(const DflStream &d, uint32_t p, const DflConfig &cfg, uint32_t k, const DflIndex6 *i6,
+                                 uint32_t *qword, uint32_t *visit)
+{
+    const Stream &s = d.s;
+    if (i6 && p >= DFL_JY && s.n - p >= 6) {
+        const uint32_t chain = (uint32_t)cfg.max_chain, qcount = chain >> 2;
+        const uint32_t h = dfl_hash_at(s, p);
+        const uint32_t lo3 = SNACC_LDG(d.ix.bstart + h);
+        const uint32_t base = dfl_window_base(p);
+        const uint32_t limit = (p - base > DFL_MAX_DIST) ? p - DFL_MAX_DIST : base;
+        // chain head (the most recent member): no search at all when it is missing, NIL or too far
+        bool fast = k > lo3;
+        if (fast) {
+            const uint32_t ch = SNACC_LDG(d.ix.order + k - 1);
+            if (ch <= base || p - ch > DFL_MAX_DIST) { if (qword) *qword = 0; if (visit) *visit = 0; return 0; }
+            fast = k - lo3 < qcount || SNACC_LDG(d.ix.order + k - qcount) <= limit;     // fewer than qcount members in reach
+        }
+        if (fast) {
+            const uint32_t maxcmp = tmin(DFL_MAX_MATCH, s.n - p);
+            const uint32_t nice_match = tmin((uint32_t)cfg.nice_length, maxcmp);
+            const uint64_t scan = ld64(s, p);
+            const uint32_t h6 = dfl_hash6w(scan);
+            const uint32_t lo6 = SNACC_LDG(i6->bstart6 + h6);
+            uint32_t j = dfl_lower_bound(i6->order6, lo6, SNACC_LDG(i6->bstart6 + h6 + 1), p);
+            uint32_t best = 2, bdist = 0;
+            while (j > lo6) {
+                const uint32_t c = SNACC_LDG(i6->order6 + --j);
+                if (c <= limit) break;
+                const uint64_t x = scan ^ ld64(s, c);
+                uint32_t len = x ? (uint32_t)(SNACC_FFS64(x) - 1) >> 3 : 8 + dfl_match_len(s, p + 8, c + 8, maxcmp > 8 ? maxcmp - 8 : 0);
+                if (len > maxcmp) len = maxcmp;
+                if (len > best) { best = len; bdist = p - c; if (len >= nice_match) break; }
+            }
+            if (best >= 6) {
+                const uint32_t w = (best << 16) | bdist;
+                if (qword) *qword = w;
+                if (visit) *visit = 0;               // only kept for p < DFL_JY, which never comes here
+                return w;
+            }
+        }
+    }
+    return dfl_f_word(d, p, cfg, k, qword, visit);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -846,6 +982,13 @@ struct DflCorpus {
     // head of every sequence (its first DFL_JY positions), for the junction of the pair streams it ends:
     uint16_t *head_order;        // per sequence DFL_JY entries: the indexed head positions sorted by (hash, position)
     uint16_t *head_visit;        // per sequence and level DFL_JY entries: how longest_match went in the sequence alone
+    // tail of every sequence, for the junction of the pair streams it starts:
+    uint16_t *tail_cnt;          // per sequence DFL_HASH entries: bucket entries at or after dfl_tail3_from(len)
+    uint16_t *tail6_order;       // per sequence DFL_T6 entries   } 6-byte index of the tail (DflTail6)
+    uint16_t *tail6_start;       // per sequence DFL_H6 + 1 entries }
+    // transient 6-byte index of whole sequences (DflIndex6): order6 is a window buffer addressed like `order`
+    uint32_t *order6;
+    uint32_t *bstart6;           // per sequence DFL_HASH + 1 entries
 };
 
 SNACC_HD Stream dfl_make_stream(const DflCorpus &c, int32_t x, int32_t y)
@@ -870,6 +1013,9 @@ __device__ __forceinline__ DflStream dfl_make(const DflCorpus &c, int32_t x, int
 
 // K3a: index of one sequence per CTA (one warp): counting sort of its positions by hash, stable.
 // tmp: per position scratch (the F slice is used) receiving the rank inside the bucket.
+// KIND 0: the 3-byte chain hash over positions [0, len - 2) -> c.order / c.bstart;
+// KIND 1: the 6-byte hash over positions [0, len - 5) -> c.order6 / c.bstart6 (DflIndex6)
+template <int KIND>
 __global__ void __launch_bounds__(32)
 dfl_index_kernel(DflCorpus c, const int32_t *__restrict__ seqs, int32_t n_seqs, uint32_t *__restrict__ tmp)
 {
@@ -879,16 +1025,17 @@ dfl_index_kernel(DflCorpus c, const int32_t *__restrict__ seqs, int32_t n_seqs, 
         const int32_t sq = seqs[t];
         const uint8_t *p = c.corpus + c.off[sq];
         const uint32_t len = c.len[sq];
-        const uint32_t nidx = len >= 3 ? len - 2 : 0;    // positions with 3 bytes left are inserted
+        const uint32_t nidx = KIND == 0 ? (len >= 3 ? len - 2 : 0) : (len >= 6 ? len - 5 : 0);   // positions with 3 (6) bytes left
         uint32_t *rank = tmp + c.poff[sq];
-        uint32_t *order = c.order + c.poff[sq];
-        uint32_t *bstart = c.bstart + (size_t)sq * (DFL_HASH + 1);
+        uint32_t *order = (KIND == 0 ? c.order : c.order6) + c.poff[sq];
+        uint32_t *bstart = (KIND == 0 ? c.bstart : c.bstart6) + (size_t)sq * (DFL_HASH + 1);
+#define DFL_IDX_HASH(i_) (KIND == 0 ? dfl_hash3(p[(i_)], p[(i_) + 1], p[(i_) + 2]) : dfl_hash6w(ldu64(p + (i_))))
         for (uint32_t i = lane; i < DFL_HASH; i += 32) cnt[i] = 0;
         __syncwarp();
         for (uint32_t base = 0; base < nidx; base += 32) {
             const uint32_t i = base + lane;
             const bool ok = i < nidx;
-            const uint32_t h = ok ? dfl_hash3(p[i], p[i + 1], p[i + 2]) : 0xffffffffu - lane;
+            const uint32_t h = ok ? DFL_IDX_HASH(i) : 0xffffffffu - lane;
             const uint32_t peers = __match_any_sync(0xffffffffu, h);
             if (ok) {
                 const uint32_t before = __popc(peers & ((1u << lane) - 1));
@@ -912,10 +1059,11 @@ dfl_index_kernel(DflCorpus c, const int32_t *__restrict__ seqs, int32_t n_seqs, 
         if (lane == 0) bstart[DFL_HASH] = carry;
         __syncwarp();
         for (uint32_t i = lane; i < nidx; i += 32) {
-            const uint32_t h = dfl_hash3(p[i], p[i + 1], p[i + 2]);
+            const uint32_t h = DFL_IDX_HASH(i);
             order[cnt[h] + rank[i]] = i;
         }
         __syncwarp();
+#undef DFL_IDX_HASH
     }
 }
 
@@ -933,11 +1081,12 @@ dfl_match_kernel(DflCorpus c, const int32_t *__restrict__ seqs, int32_t n_seqs, 
         const uint32_t nidx = len >= 3 ? len - 2 : 0;
         uint32_t *f = F + c.poff[sq];
         uint32_t *fq = FQ ? FQ + c.poff[sq] : nullptr;
+        const DflIndex6 i6{c.order6 ? c.order6 + c.poff[sq] : nullptr, c.bstart6 + (size_t)sq * (DFL_HASH + 1)};
         for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < len; k += gridDim.x * blockDim.x) {
             if (k >= nidx) { f[k] = 0; if (fq) fq[k] = 0; continue; }       // the last two positions: no string, no search
             const uint32_t p = d.ix.order[k];
             uint32_t q, visit;
-            f[p] = dfl_f_word(d, p, cfg, k, &q, &visit);
+            f[p] = dfl_match_word(d, p, cfg, k, c.order6 ? &i6 : nullptr, &q, &visit);
             if (fq) fq[p] = q;
             if (p < DFL_JY) c.head_visit[(size_t)sq * DFL_JY + p] = (uint16_t)visit;
         }
@@ -957,9 +1106,12 @@ dfl_head_kernel(DflCorpus c, const int32_t *__restrict__ seqs, int32_t n_seqs)
         const uint32_t *bstart = c.bstart + (size_t)sq * (DFL_HASH + 1);
         uint16_t *ho = c.head_order + (size_t)sq * DFL_JY;
         __syncthreads();
+        const uint32_t tail_from = dfl_tail3_from(c.len[sq]);
+        uint16_t *tc = c.tail_cnt + (size_t)sq * DFL_HASH;
         for (uint32_t h = threadIdx.x; h < DFL_HASH; h += blockDim.x) {
             const uint32_t lo = bstart[h], hi = bstart[h + 1];
             hcnt[h] = lo < hi ? dfl_lower_bound(order, lo, hi, DFL_JY) - lo : 0;
+            tc[h] = (uint16_t)(lo < hi ? hi - dfl_lower_bound(order, lo, hi, tail_from) : 0);
         }
         __syncthreads();
         // exclusive scan over DFL_HASH counters: 32 per thread
@@ -989,13 +1141,57 @@ dfl_head_kernel(DflCorpus c, const int32_t *__restrict__ seqs, int32_t n_seqs)
 
 struct DflPair { int32_t x, y; };
 
+// K3b'': 6-byte index of the tail of the listed sequences (DflTail6): stable counting sort by one warp, like
+// dfl_index_kernel.  Shared memory: DFL_H6 counters + one rank per tail position.
+__global__ void __launch_bounds__(32)
+dfl_tail6_kernel(DflCorpus c, const int32_t *__restrict__ seqs, int32_t n_seqs)
+{
+    extern __shared__ uint32_t t6_smem[];
+    uint32_t *cnt = t6_smem;                                           // DFL_H6
+    uint16_t *rank = reinterpret_cast<uint16_t *>(t6_smem + DFL_H6);   // DFL_T6
+    const uint32_t lane = threadIdx.x;
+    for (int32_t t = blockIdx.x; t < n_seqs; t += gridDim.x) {
+        const int32_t sq = seqs[t];
+        const uint32_t len = c.len[sq], t0 = dfl_tail6_t0(len), n6 = dfl_tail6_count(len);
+        const uint8_t *p = c.corpus + c.off[sq] + t0;
+        uint16_t *order = c.tail6_order + (size_t)sq * DFL_T6;
+        uint16_t *start = c.tail6_start + (size_t)sq * (DFL_H6 + 1);
+        for (uint32_t i = lane; i < DFL_H6; i += 32) cnt[i] = 0;
+        __syncwarp();
+        for (uint32_t b0 = 0; b0 < n6; b0 += 32) {
+            const uint32_t i = b0 + lane;
+            const bool ok = i < n6;
+            const uint32_t h = ok ? dfl_hash6(ldu64(p + i)) : 0xffffffffu - lane;
+            const uint32_t peers = __match_any_sync(0xffffffffu, h);
+            if (ok) rank[i] = (uint16_t)(cnt[h] + __popc(peers & ((1u << lane) - 1)));
+            __syncwarp();
+            if (ok && (peers >> lane) <= 1u) cnt[h] += __popc(peers);
+            __syncwarp();
+        }
+        uint32_t carry = 0;
+        for (uint32_t b0 = 0; b0 < DFL_H6; b0 += 32) {
+            const uint32_t v = cnt[b0 + lane];
+            uint32_t inc = v;
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if ((int)lane >= o) inc += u; }
+            const uint32_t ex = carry + inc - v;
+            start[b0 + lane] = (uint16_t)ex;
+            cnt[b0 + lane] = ex;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) start[DFL_H6] = (uint16_t)carry;
+        __syncwarp();
+        for (uint32_t i = lane; i < n6; i += 32) order[cnt[dfl_hash6(ldu64(p + i))] + rank[i]] = (uint16_t)i;
+        __syncwarp();
+    }
+}
+
 // K3c: junction F of a batch of pair streams: positions [jx0, lx + min(ly, DFL_JY)).  The last positions of x take
 // the general walk.  The head positions of y are handled in (hash, position) order -- the lanes of a warp then
 // walk the same bucket of x and their loads coalesce into broadcasts -- and continue the walk they had in y alone
 // (dfl_longest_cont) instead of repeating it.
 __global__ void __launch_bounds__(256)
 dfl_junction_kernel(DflCorpus c, const DflPair *__restrict__ pairs, int32_t n_pairs, int level, const uint32_t *__restrict__ F,
-                    const uint32_t *__restrict__ FQ, uint32_t *__restrict__ FJ, uint32_t *__restrict__ FJQ, int only_x)
+                    const uint32_t *__restrict__ FQ, uint32_t *__restrict__ FJ, uint32_t *__restrict__ FJQ, int impl)
 {
     const DflConfig cfg = dfl_config(level);
     for (int32_t b = blockIdx.y; b < n_pairs; b += gridDim.y) {
@@ -1008,7 +1204,10 @@ dfl_junction_kernel(DflCorpus c, const DflPair *__restrict__ pairs, int32_t n_pa
         const uint32_t *fy = F + c.poff[y];
         const uint32_t *fqy = FQ ? FQ + c.poff[y] : nullptr;
         const uint16_t *ho = c.head_order + (size_t)y * DFL_JY, *hv = c.head_visit + (size_t)y * DFL_JY;
-        const uint32_t u_end = only_x ? jxl : jxl + jyl;       // only_x: dfl_junction3_kernel does the head of y
+        const uint32_t u_end = jxl + jyl;
+        const int32_t xi = pairs[b].x;
+        const DflTail6 t6{c.tail6_order + (size_t)xi * DFL_T6, c.tail6_start + (size_t)xi * (DFL_H6 + 1), dfl_tail6_t0(lx)};
+        const uint16_t *tcx = c.tail_cnt + (size_t)xi * DFL_HASH;
         for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < u_end; u += gridDim.x * blockDim.x) {
             uint32_t q, w, pos;
             if (u < jxl) {
@@ -1017,168 +1216,13 @@ dfl_junction_kernel(DflCorpus c, const DflPair *__restrict__ pairs, int32_t n_pa
             } else if (u - jxl < n_head) {
                 const uint32_t yq = ho[u - jxl];
                 pos = jxl + yq;
-                w = dfl_longest_cont(d, lx + yq, (uint32_t)cfg.max_chain, (uint32_t)cfg.nice_length, fy[yq], hv[yq], fqy != nullptr,
-                                     fqy ? fqy[yq] : 0u, &q);
+                w = dfl_junction_word(d, lx + yq, cfg, fy[yq], hv[yq], fqy != nullptr, fqy ? fqy[yq] : 0u, impl == 3 ? &t6 : nullptr,
+                                      tcx, &q);
             } else {
                 pos = u; w = 0; q = 0;                                       // the last two positions of a short y: no string
             }
             f[pos] = w;
             if (fq) fq[pos] = q;
-        }
-    }
-}
-
-// K3c': the same junction tables for the head positions of y, restructured for the SM (dfl_junction_kernel keeps
-// the last positions of x and remains the reference implementation of the head walk; tests compare the two).
-//   * the bytes every walk of a pair touches -- the last 32 KiB of x and the first 32 KiB + 266 of y -- are staged
-//     once per CTA in shared memory as one contiguous string, so a candidate compare is two or three LDS;
-//   * head positions are taken in (hash, position) order, so the lanes of a warp want the same bucket of x: the
-//     warp fetches 32 candidates of that bucket with one coalesced load and hands them round by shuffle; every lane
-//     keeps its own window limit, best match, chain count and stop condition (lanes of other buckets wait
-//     their turn: __match_any-style grouping by hash);
-//   * as in dfl_longest_cont the walk continues the one the position had in y alone.
-constexpr uint32_t DFL_J3_THREADS = 512;
-constexpr uint32_t DFL_J3_TX = 32768;                 // staged bytes of x's tail (candidates are >= lx - 32505)
-constexpr uint32_t DFL_J3_TY = DFL_JY + 272;          // staged bytes of y's head (position + MAX_MATCH + over-read)
-constexpr uint32_t DFL_J3_SMEM = DFL_J3_TX + DFL_J3_TY + 16;
-
-__device__ __forceinline__ uint32_t j3_ld32(const uint32_t *w, uint32_t i)        // 4 bytes at byte offset i
-{
-    const uint32_t k = i >> 2;
-    return __funnelshift_r(w[k], w[k + 1], (i & 3) * 8);
-}
-// common prefix of buf[a..] and buf[b..], at most maxcmp
-__device__ __forceinline__ uint32_t j3_lcp(const uint32_t *w, uint32_t a, uint32_t b, uint32_t scan0, uint32_t maxcmp)
-{
-    uint32_t x = scan0 ^ j3_ld32(w, b);
-    if (x) return tmin((uint32_t)(__ffs((int)x) - 1) >> 3, maxcmp);
-    uint32_t len = 4;
-    while (len < maxcmp) {
-        x = j3_ld32(w, a + len) ^ j3_ld32(w, b + len);
-        if (x) { len += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
-        len += 4;
-    }
-    return tmin(len, maxcmp);
-}
-
-__global__ void __launch_bounds__(DFL_J3_THREADS)
-dfl_junction3_kernel(DflCorpus c, const DflPair *__restrict__ pairs, int32_t n_pairs, int level, const uint32_t *__restrict__ F,
-                     const uint32_t *__restrict__ FQ, uint32_t *__restrict__ FJ, uint32_t *__restrict__ FJQ)
-{
-    extern __shared__ __align__(16) uint8_t j3_buf[];
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(j3_buf);
-    const DflConfig cfg = dfl_config(level);
-    const uint32_t chain = (uint32_t)cfg.max_chain, qcount = chain >> 2;
-    const uint32_t lane = threadIdx.x & 31;
-    for (int32_t b = blockIdx.y; b < n_pairs; b += gridDim.y) {
-        const int32_t xi = pairs[b].x, yi = pairs[b].y;
-        const uint8_t *xp = c.corpus + c.off[xi], *yp = c.corpus + c.off[yi];
-        const uint32_t lx = c.len[xi], ly = c.len[yi], n = lx + ly;
-        const uint32_t jxl = lx - dfl_jx0(lx), jyl = tmin(ly, DFL_JY);
-        const uint32_t n_head = tmin(jyl, ly >= 3 ? ly - 2 : 0u);
-        const uint32_t tx = tmin(lx, DFL_J3_TX), s0 = lx - tx;                 // buf[i] = stream byte s0 + i
-        const uint32_t ty = tmin(ly + 16, DFL_J3_TY);                          // (the corpus pads every sequence with zeros)
-        __syncthreads();
-        for (uint32_t i = threadIdx.x; i < tx; i += blockDim.x) j3_buf[i] = xp[s0 + i];
-        for (uint32_t i = threadIdx.x; i < ty + 16 && tx + i < DFL_J3_SMEM; i += blockDim.x) j3_buf[tx + i] = i < ty ? yp[i] : 0;
-        __syncthreads();
-        uint32_t *f = FJ + (size_t)b * DFL_JSTRIDE;
-        uint32_t *fq = FJQ ? FJQ + (size_t)b * DFL_JSTRIDE : nullptr;
-        const uint32_t *fy = F + c.poff[yi];
-        const uint32_t *fqy = FQ ? FQ + c.poff[yi] : nullptr;
-        const uint16_t *ho = c.head_order + (size_t)yi * DFL_JY, *hv = c.head_visit + (size_t)yi * DFL_JY;
-        const uint32_t *ox = c.order + c.poff[xi], *bx = c.bstart + (size_t)xi * (DFL_HASH + 1);
-        const uint32_t *oy = c.order + c.poff[yi], *by = c.bstart + (size_t)yi * (DFL_HASH + 1);
-        for (uint32_t t0 = blockIdx.x * blockDim.x; t0 < jyl; t0 += gridDim.x * blockDim.x) {
-            const uint32_t t = t0 + threadIdx.x;
-            const bool in_index = t < n_head;
-            const uint32_t yq = in_index ? ho[t] : t;
-            const uint32_t p = lx + yq, ip = p - s0;
-            // ---- where the walk of this position stood when it ran out of y (dfl_longest_cont) ----
-            uint32_t f_s = 0, visit = 0, q_s = 0;
-            bool q_known = fqy != nullptr;
-            if (in_index) { f_s = fy[yq]; visit = hv[yq]; if (fqy) q_s = fqy[yq]; }
-            const bool flag_s = (f_s & DFL_QDIFF) != 0;
-            f_s &= ~DFL_QDIFF;
-            if (!q_known && !flag_s) { q_known = true; q_s = f_s; }
-            uint32_t count = visit & DFL_V_COUNT;
-            const bool settled = !in_index || (visit & (DFL_V_NICE | DFL_V_HEADFAR)) || count >= chain;
-            const uint32_t base = dfl_window_base(p);
-            const uint32_t maxcmp = tmin(DFL_MAX_MATCH, n - p);
-            const uint32_t nice_match = tmin((uint32_t)cfg.nice_length, maxcmp);
-            const uint32_t limit = (p - base > DFL_MAX_DIST) ? p - DFL_MAX_DIST : base;
-            uint32_t best = (f_s >> 16) ? (f_s >> 16) : 2, bdist = f_s & 0xffff;
-            const bool q_fixed = count >= qcount;
-            uint32_t qbest = q_fixed && q_known ? q_s : 0;
-            const bool q_lost = q_fixed && !q_known;
-            bool head_pending = count == 0;              // the next candidate is the chain head
-            bool no_search = false;                      // the chain head failed its test: the result is "no match"
-            bool over = settled || t >= jyl;
-            const uint32_t scan0 = over ? 0u : j3_ld32(w, ip);
-            const uint32_t h = over ? 0xffffffffu : dfl_hash3(scan0 & 0xff, (scan0 >> 8) & 0xff, (scan0 >> 16) & 0xff);
-            // one candidate c (a stream position inside the staged string); sets `over` when the walk has ended
-#define J3_VISIT(c_) do {                                                                                           \
-                const uint32_t cc_ = (c_);                                                                          \
-                if (head_pending) {                                                                                 \
-                    head_pending = false;                                                                           \
-                    if (cc_ <= base || p - cc_ > DFL_MAX_DIST) { no_search = true; over = true; break; }            \
-                } else if (cc_ <= limit) { over = true; break; }                                                    \
-                const uint32_t len_ = j3_lcp(w, ip, cc_ - s0, scan0, maxcmp);                                       \
-                if (len_ > best) {                                                                                  \
-                    best = len_; bdist = p - cc_;                                                                   \
-                    if (len_ >= nice_match) { ++count; over = true; break; }                                        \
-                }                                                                                                   \
-                ++count;                                                                                            \
-                if (count == qcount) qbest = best > 2 ? (best << 16) | bdist : 0;                                   \
-                if (count >= chain) over = true;                                                                    \
-            } while (0)
-            // ---- y's position 0 (NIL in y alone, an ordinary candidate here) and the two straddling positions ----
-            if (!over) {
-                const uint32_t ylo = by[h], yhi = by[h + 1];
-                if (yq > 0 && yhi > ylo && oy[ylo] == 0) J3_VISIT(lx);
-                if (!over && lx >= 1 && n - (lx - 1) >= 3 && lx - 1 >= s0) {
-                    const uint32_t v = j3_ld32(w, lx - 1 - s0);
-                    if (dfl_hash3(v & 0xff, (v >> 8) & 0xff, (v >> 16) & 0xff) == h) J3_VISIT(lx - 1);
-                }
-                if (!over && lx >= 2 && n - (lx - 2) >= 3 && lx - 2 >= s0) {
-                    const uint32_t v = j3_ld32(w, lx - 2 - s0);
-                    if (dfl_hash3(v & 0xff, (v >> 8) & 0xff, (v >> 16) & 0xff) == h) J3_VISIT(lx - 2);
-                }
-            }
-            // ---- x's bucket, most recent first: the lanes that share a hash walk it together ----
-            bool need = !over;
-            for (;;) {
-                const uint32_t todo = __ballot_sync(0xffffffffu, need);
-                if (!todo) break;
-                const uint32_t hl = __shfl_sync(0xffffffffu, h, __ffs((int)todo) - 1);
-                const bool mine = need && h == hl;
-                const uint32_t xlo = bx[hl];
-                uint32_t k = bx[hl + 1];
-                while (k > xlo && __any_sync(0xffffffffu, mine && !over)) {
-                    const uint32_t m = tmin(32u, k - xlo);
-                    const uint32_t cand = lane < m ? __ldg(ox + (k - 1 - lane)) : 0u;
-                    for (uint32_t i = 0; i < m; ++i) {
-                        const uint32_t cc = __shfl_sync(0xffffffffu, cand, i);
-                        if (mine && !over) J3_VISIT(cc);
-                    }
-                    k -= m;
-                }
-                if (mine) need = false;
-            }
-#undef J3_VISIT
-            if (t < jyl) {
-                uint32_t word, qres;
-                if (settled) { word = in_index ? (f_s | (flag_s ? DFL_QDIFF : 0u)) : 0u; qres = in_index && q_known ? q_s : 0u; }
-                else if (no_search) { word = 0; qres = 0; }
-                else {
-                    const uint32_t full = best > 2 ? (best << 16) | bdist : 0;
-                    qres = count <= qcount ? full : qbest;
-                    const bool differs = count <= qcount ? false : (q_lost ? true : qbest != full);
-                    word = full | (differs ? DFL_QDIFF : 0u);
-                }
-                f[jxl + yq] = word;
-                if (fq) fq[jxl + yq] = qres;
-            }
         }
     }
 }
@@ -1383,6 +1427,9 @@ struct DeflateState {
     uint64_t *d_poff = nullptr; std::vector<uint64_t> h_poff; uint64_t total = 0;
     uint32_t *d_order = nullptr, *d_bstart = nullptr;
     uint16_t *d_head_order = nullptr, *d_head_visit[2] = {nullptr, nullptr};
+    uint16_t *d_tail_cnt = nullptr, *d_tail6_order = nullptr, *d_tail6_start = nullptr;
+    uint32_t *d_bstart6 = nullptr, *d_order6 = nullptr; uint64_t order6_cap = 0;   // 6-byte index: starts per sequence, window buffer
+    int use_index6 = 1;                            // 0: dfl_match_kernel always walks the 3-byte chain (tests)
     std::vector<uint8_t> indexed;                  // per sequence
     uint32_t *d_F[2] = {nullptr, nullptr};         // level 9, level 6
     uint32_t *d_FQ = nullptr;                      // level 6 only: quartered-chain table
@@ -1403,7 +1450,7 @@ struct DeflateState {
     unsigned long long *d_counter2 = nullptr;
     double main_ms = 0.0;
     int use_canon = 1;                             // 0: every pair stream takes the full serial parse (tests)
-    int junction_impl = 3;                         // 2: dfl_junction_kernel for every junction position (tests)
+    int junction_impl = 3;                         // 2: no 6-byte-index shortcut in the junction walk (tests)
     int64_t serial_jobs = 0;                       // pair jobs of the last call that fell back to it
 };
 
@@ -1413,6 +1460,9 @@ static inline void deflate_free_corpus(DeflateState &st)
     cudaFree(st.d_FQ); st.d_FQ = nullptr;
     cudaFree(st.d_soff); cudaFree(st.d_roff); cudaFree(st.d_cap);
     cudaFree(st.d_head_order); st.d_head_order = nullptr;
+    cudaFree(st.d_tail_cnt); cudaFree(st.d_tail6_order); cudaFree(st.d_tail6_start);
+    st.d_tail_cnt = st.d_tail6_order = st.d_tail6_start = nullptr;
+    cudaFree(st.d_bstart6); cudaFree(st.d_order6); st.d_bstart6 = st.d_order6 = nullptr; st.order6_cap = 0;
     for (int l = 0; l < 2; ++l) { cudaFree(st.d_head_visit[l]); st.d_head_visit[l] = nullptr; }
     st.d_soff = st.d_roff = nullptr; st.d_cap = nullptr;
     for (int l = 0; l < 2; ++l) {
@@ -1462,7 +1512,10 @@ template <typename T> static int dfl_upload(std::string &err, cudaStream_t strea
     return 0;
 }
 
-constexpr size_t DFL_BATCH = 16384;                // pair streams per junction batch (2.2 GB of junction F, two buffers)
+constexpr int DFL_PARSE_BLOCKS = 148 * 5;           // 40 KiB of counters per CTA: five CTAs per SM
+constexpr size_t DFL_BATCH = (size_t)DFL_PARSE_BLOCKS * 64;   // pair streams per junction batch: one per parse thread (6.3 GB of
+                                                    // junction F per buffer, two buffers; the parse is latency-bound, so
+                                                    // its throughput is the number of streams in flight)
 
 // sizes of the raw deflate streams of the jobs (x alone when ys == nullptr) into d_out[0..n_jobs)
 static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, const int32_t *xs, const int32_t *ys,
@@ -1499,6 +1552,10 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
         DCK(cudaMalloc(&st.d_order, sizeof(uint32_t) * (t + 16)));
         DCK(cudaMalloc(&st.d_bstart, sizeof(uint32_t) * (size_t)ns * (DFL_HASH + 1)));
         DCK(cudaMalloc(&st.d_head_order, sizeof(uint16_t) * (size_t)ns * DFL_JY));
+        DCK(cudaMalloc(&st.d_tail_cnt, sizeof(uint16_t) * (size_t)ns * DFL_HASH));
+        DCK(cudaMalloc(&st.d_bstart6, sizeof(uint32_t) * (size_t)ns * (DFL_HASH + 1)));
+        DCK(cudaMalloc(&st.d_tail6_order, sizeof(uint16_t) * (size_t)ns * DFL_T6));
+        DCK(cudaMalloc(&st.d_tail6_start, sizeof(uint16_t) * (size_t)ns * (DFL_H6 + 1)));
         st.indexed.assign(ns, 0);
         for (int l = 0; l < 2; ++l) { st.have_F[l].assign(ns, 0); st.have_prep[l].assign(ns, 0); }
     }
@@ -1515,7 +1572,8 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
         DCK(cudaMemsetAsync(st.d_nsym[li], 0, sizeof(uint32_t) * ns, stream));
     }
     uint32_t *FQ = level != 9 ? st.d_FQ : nullptr;
-    DflCorpus c{dc.d_corpus, dc.d_off, dc.d_len, st.d_poff, st.d_order, st.d_bstart, st.d_head_order, st.d_head_visit[li]};
+    DflCorpus c{dc.d_corpus, dc.d_off, dc.d_len, st.d_poff, st.d_order, st.d_bstart, st.d_head_order, st.d_head_visit[li],
+                st.d_tail_cnt, st.d_tail6_order, st.d_tail6_start, nullptr, st.d_bstart6};
     DflCanonPool cp{st.d_sym_end[li], st.d_sym_code[li], st.d_cum[li], st.d_soff, st.d_cap, st.d_roff, st.d_nsym[li],
                     st.d_seq_size[li]};
 
@@ -1537,31 +1595,60 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
     if (!need_idx.empty()) {
         int32_t *d_list = nullptr;
         if (dfl_upload(err, stream, need_idx, &d_list)) return -1;
-        DCK(cudaFuncSetAttribute(dfl_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DFL_HASH * 4)));
+        DCK(cudaFuncSetAttribute(dfl_index_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DFL_HASH * 4)));
         // the F slice of this level doubles as rank scratch; it is recomputed right below
-        dfl_index_kernel<<<(unsigned)std::min<size_t>(need_idx.size(), 148 * 4), 32, DFL_HASH * 4, stream>>>(
+        dfl_index_kernel<0><<<(unsigned)std::min<size_t>(need_idx.size(), 148 * 4), 32, DFL_HASH * 4, stream>>>(
             c, d_list, (int32_t)need_idx.size(), st.d_F[li]);
         DCK(cudaGetLastError());
         DCK(cudaFuncSetAttribute(dfl_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DFL_HASH * 4)));
         dfl_head_kernel<<<(unsigned)std::min<size_t>(need_idx.size(), 148), 1024, DFL_HASH * 4, stream>>>(
             c, d_list, (int32_t)need_idx.size());
         DCK(cudaGetLastError());
-        *launches += 2;
+        const int t6_smem = (int)(DFL_H6 * 4 + DFL_T6 * 2);
+        DCK(cudaFuncSetAttribute(dfl_tail6_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, t6_smem));
+        dfl_tail6_kernel<<<(unsigned)std::min<size_t>(need_idx.size(), 148 * 2), 32, t6_smem, stream>>>(c, d_list, (int32_t)need_idx.size());
+        DCK(cudaGetLastError());
+        *launches += 3;
         DCK(cudaStreamSynchronize(stream));
         cudaFree(d_list);
     }
     if (!need_f.empty()) {
-        int32_t *d_list = nullptr;
-        if (dfl_upload(err, stream, need_f, &d_list)) return -1;
-        dim3 grid(std::max(1u, std::min((max_len + 255) / 256, 4096u)), (unsigned)std::min<size_t>(need_f.size(), 64));
-        dfl_match_kernel<<<grid, 256, 0, stream>>>(c, d_list, (int32_t)need_f.size(), level, st.d_F[li], FQ);
-        DCK(cudaGetLastError());
-        ++*launches;
-        DCK(cudaStreamSynchronize(stream));
-        cudaFree(d_list);
+        // level 9: runs of sequences whose index slices fit the window buffer get a transient 6-byte index first
+        // (dfl_match_word); level 6 always walks the chain (its limit of 128 binds everywhere on DNA)
+        const bool i6 = st.use_index6 && level == 9;
+        const uint64_t cap = 192ull << 20;                                     // entries: 768 MB
+        if (i6 && !st.d_order6) { DCK(cudaMalloc(&st.d_order6, sizeof(uint32_t) * (cap + 16))); st.order6_cap = cap; }
+        size_t a = 0;
+        while (a < need_f.size()) {
+            size_t b = a + 1;
+            const uint64_t first = st.h_poff[need_f[a]];
+            auto end_of = [&](int32_t i) { return st.h_poff[i] + (((uint64_t)dc.h_len[i] + 7) & ~7ull); };
+            while (b < need_f.size() && b - a < 64 && (!i6 || end_of(need_f[b]) - first <= cap)) ++b;
+            const bool fits = i6 && end_of(need_f[b - 1]) - first <= cap;      // (a single sequence longer than the buffer: no index)
+            std::vector<int32_t> part(need_f.begin() + a, need_f.begin() + b);
+            int32_t *d_list = nullptr;
+            if (dfl_upload(err, stream, part, &d_list)) return -1;
+            DflCorpus cm = c;
+            if (fits) {
+                cm.order6 = st.d_order6 - first;                               // addressed like `order`: + poff[sq]
+                DCK(cudaFuncSetAttribute(dfl_index_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DFL_HASH * 4)));
+                dfl_index_kernel<1><<<(unsigned)part.size(), 32, DFL_HASH * 4, stream>>>(cm, d_list, (int32_t)part.size(), st.d_F[li]);
+                DCK(cudaGetLastError());
+                ++*launches;
+            }
+            uint32_t mx = 0;
+            for (int32_t i : part) mx = std::max(mx, dc.h_len[i]);
+            dim3 grid(std::max(1u, std::min((mx + 255) / 256, 4096u)), (unsigned)part.size());
+            dfl_match_kernel<<<grid, 256, 0, stream>>>(cm, d_list, (int32_t)part.size(), level, st.d_F[li], FQ);
+            DCK(cudaGetLastError());
+            ++*launches;
+            DCK(cudaStreamSynchronize(stream));
+            cudaFree(d_list);
+            a = b;
+        }
     }
     // ---- parse jobs ----
-    const int parse_blocks = 148 * 4;
+    const int parse_blocks = DFL_PARSE_BLOCKS;
     if (st.scratch_n < (size_t)parse_blocks * DFL_PARSE_THREADS) {
         for (int k = 0; k < 2; ++k) { cudaFree(st.d_scratch2[k]); st.d_scratch2[k] = nullptr; }
         st.scratch_n = (size_t)parse_blocks * DFL_PARSE_THREADS;
@@ -1619,7 +1706,6 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
         }
         if (FQ && !st.d_FJQ2[0])
             for (int k = 0; k < 2; ++k) DCK(cudaMalloc(&st.d_FJQ2[k], sizeof(uint32_t) * batch * DFL_JSTRIDE));
-        DCK(cudaFuncSetAttribute(dfl_junction3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DFL_J3_SMEM));
         if (!st.stream2) {
             DCK(cudaStreamCreateWithFlags(&st.stream2, cudaStreamNonBlocking));
             for (int k = 0; k < 2; ++k) {
@@ -1648,18 +1734,10 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
                 DCK(cudaMemcpyAsync(st.d_pairs2[k2], pairs.data(), sizeof(DflPair) * nb, cudaMemcpyHostToDevice, stream));
                 DCK(cudaMemcpyAsync(st.d_jobs2[k2], jobs.data(), sizeof(DflJob) * nb, cudaMemcpyHostToDevice, stream));
                 DCK(cudaEventRecord(e0, stream));
-                if (st.junction_impl == 3 && !getenv("SNACC_DFL_JUNCTION2")) {
-                    dim3 gx((DFL_JX + 255) / 256, (unsigned)std::min<int64_t>(nb, 4096));
-                    dfl_junction_kernel<<<gx, 256, 0, stream>>>(c, st.d_pairs2[k2], (int32_t)nb, level, st.d_F[li], FQ, st.d_FJ2[k2],
-                                                                FQ ? st.d_FJQ2[k2] : nullptr, 1);
-                    dim3 g3(DFL_JY / DFL_J3_THREADS, (unsigned)std::min<int64_t>(nb, 4096));
-                    dfl_junction3_kernel<<<g3, DFL_J3_THREADS, DFL_J3_SMEM, stream>>>(c, st.d_pairs2[k2], (int32_t)nb, level, st.d_F[li], FQ,
-                                                                                      st.d_FJ2[k2], FQ ? st.d_FJQ2[k2] : nullptr);
-                    ++*launches;
-                } else {
+                {
                     dim3 grid((DFL_JSTRIDE + 255) / 256, (unsigned)std::min<int64_t>(nb, 4096));
                     dfl_junction_kernel<<<grid, 256, 0, stream>>>(c, st.d_pairs2[k2], (int32_t)nb, level, st.d_F[li], FQ, st.d_FJ2[k2],
-                                                                  FQ ? st.d_FJQ2[k2] : nullptr, 0);
+                                                                  FQ ? st.d_FJQ2[k2] : nullptr, st.junction_impl);
                 }
                 if (cudaGetLastError() != cudaSuccess) { err = "junction kernel launch failed"; return -1; }
                 DCK(cudaEventRecord(e1, stream));

@@ -200,9 +200,23 @@ static EmuIndex emu_index(const uint8_t *p, uint32_t len)
 // F (and, like the kernels at level 6, the quartered-chain table FQ) of a sequence alone, plus what
 // dfl_match_kernel / dfl_head_kernel keep about its head
 struct EmuSeq { std::vector<uint32_t> F, FQ; std::vector<uint16_t> head_order, head_visit; };
+static int32_t emu_match_mismatches = 0;     // dfl_match_word (6-byte index shortcut) vs dfl_f_word, over everything computed so far
 static EmuSeq emu_F_single(const DflStream &d, const DflConfig &cfg, bool want_q)
 {
     EmuSeq e;
+    // transient 6-byte index of the whole sequence (dfl_index_kernel<1>), level 9 only -- as deflate_run does
+    std::vector<uint32_t> order6, bstart6(DFL_HASH + 1, 0);
+    const bool i6on = !want_q;
+    if (i6on) {
+        const uint32_t n6 = d.s.n >= 6 ? d.s.n - 5 : 0;
+        order6.assign(n6 + 4, 0);
+        std::vector<uint32_t> cnt(DFL_HASH + 1, 0);
+        for (uint32_t i = 0; i < n6; ++i) cnt[dfl_hash6w(ldu64(d.s.x + i)) + 1]++;
+        for (uint32_t h = 0; h < DFL_HASH; ++h) cnt[h + 1] += cnt[h];
+        for (uint32_t h = 0; h <= DFL_HASH; ++h) bstart6[h] = cnt[h];
+        for (uint32_t i = 0; i < n6; ++i) order6[cnt[dfl_hash6w(ldu64(d.s.x + i))]++] = i;
+    }
+    const DflIndex6 i6{order6.data(), bstart6.data()};
     e.F.assign(d.s.n + 16, 0);
     if (want_q) e.FQ.assign(d.s.n + 16, 0);
     e.head_visit.assign(DFL_JY, 0);
@@ -210,7 +224,11 @@ static EmuSeq emu_F_single(const DflStream &d, const DflConfig &cfg, bool want_q
     for (uint32_t k = 0; k < nidx; ++k) {
         const uint32_t p = d.ix.order[k];
         uint32_t q, visit;
-        e.F[p] = dfl_f_word(d, p, cfg, k, &q, &visit);
+        e.F[p] = dfl_match_word(d, p, cfg, k, i6on ? &i6 : nullptr, &q, &visit);
+        if (i6on && p >= DFL_JY) {
+            uint32_t q0, v0;
+            if (dfl_f_word(d, p, cfg, k, &q0, &v0) != e.F[p] || q0 != q) ++emu_match_mismatches;
+        }
         if (want_q) e.FQ[p] = q;
         if (p < DFL_JY) { e.head_visit[p] = (uint16_t)visit; e.head_order.push_back((uint16_t)p); }   // index order = (hash, position)
     }
@@ -227,7 +245,7 @@ extern "C" int64_t emu_deflate_size_ex(const uint8_t *x, uint32_t lx, const uint
                                        int32_t *info)
 {
     const DflConfig cfg = dfl_config(level);
-    if (info) info[0] = info[1] = info[2] = 0;
+    if (info) info[0] = info[1] = info[2] = info[3] = 0;
     uint8_t *px = padded_copy(x, lx);
     uint8_t *py = ly_ >= 0 ? padded_copy(y, (uint64_t)ly_) : nullptr;
     EmuIndex ix = emu_index(px, lx), iy;
@@ -297,19 +315,39 @@ extern "C" int64_t emu_deflate_size_ex(const uint8_t *x, uint32_t lx, const uint
         const uint32_t jxl = lx - jx0, jyl = jlen - jxl, n_head = (uint32_t)ey.head_order.size();
         int32_t mismatches = 0;
         for (uint32_t u = 0; u < jxl; ++u) FJ[u] = dfl_f_word(d, jx0 + u, cfg, 0xffffffffu, &FJQ[u]);
+        // what dfl_head_kernel / dfl_tail6_kernel keep about the tail of x
+        std::vector<uint16_t> tail_cnt(DFL_HASH, 0), t6_order(DFL_T6, 0), t6_start(DFL_H6 + 1, 0);
+        {
+            const uint32_t from = dfl_tail3_from(lx);
+            for (uint32_t h = 0; h < DFL_HASH; ++h)
+                for (uint32_t k = ix.bstart[h]; k < ix.bstart[h + 1]; ++k) if (ix.order[k] >= from) tail_cnt[h]++;
+            const uint32_t t0 = dfl_tail6_t0(lx), n6 = dfl_tail6_count(lx);
+            std::vector<uint32_t> cnt(DFL_H6 + 1, 0);
+            for (uint32_t i = 0; i < n6; ++i) cnt[dfl_hash6(ldu64(px + t0 + i)) + 1]++;
+            for (uint32_t h = 0; h < DFL_H6; ++h) cnt[h + 1] += cnt[h];
+            for (uint32_t h = 0; h <= DFL_H6; ++h) t6_start[h] = (uint16_t)cnt[h];
+            for (uint32_t i = 0; i < n6; ++i) t6_order[cnt[dfl_hash6(ldu64(px + t0 + i))]++] = (uint16_t)i;
+        }
+        const DflTail6 t6{t6_order.data(), t6_start.data(), dfl_tail6_t0(lx)};
+        int32_t shortcuts = 0;
         for (uint32_t t = 0; t < jyl; ++t) {
             if (t >= n_head) { FJ[jxl + t] = 0; FJQ[jxl + t] = 0; continue; }
             const uint32_t yq = ey.head_order[t];
             uint32_t q = 0;
-            const uint32_t w = dfl_longest_cont(d, lx + yq, (uint32_t)cfg.max_chain, (uint32_t)cfg.nice_length, Fy[yq], ey.head_visit[yq],
-                                                want_q, want_q ? ey.FQ[yq] : 0u, &q);
+            const uint32_t w = dfl_junction_word(d, lx + yq, cfg, Fy[yq], ey.head_visit[yq], want_q, want_q ? ey.FQ[yq] : 0u, &t6,
+                                                 tail_cnt.data(), &q);
+            {   // how often the 6-byte shortcut applies (reported, not checked)
+                const uint32_t v = ey.head_visit[yq], cnt = v & DFL_V_COUNT;
+                if (!(v & (DFL_V_NICE | DFL_V_HEADFAR)) && cnt >= 1 && (((Fy[yq] & ~DFL_QDIFF) >> 16) >= 5 || (w >> 16) >= 6) && d.s.n - (lx + yq) >= 6 &&
+                    cnt + 3 + tail_cnt[dfl_hash_at(d.s, lx + yq)] < ((uint32_t)cfg.max_chain >> 2)) ++shortcuts;
+            }
             FJ[jxl + yq] = w; FJQ[jxl + yq] = q;
             // self-check against the general walk over the pair stream
             uint32_t q0 = 0;
             const uint32_t w0 = dfl_f_word(d, lx + yq, cfg, 0xffffffffu, &q0);
             if ((w & ~DFL_QDIFF) != (w0 & ~DFL_QDIFF) || ((w0 & DFL_QDIFF) && !(w & DFL_QDIFF)) || (want_q && q != q0)) ++mismatches;
         }
-        if (info) info[2] = mismatches;
+        if (info) { info[2] = mismatches + emu_match_mismatches; info[3] = shortcuts; }
         fv.fx = Fx.data(); fv.fy = Fy.data(); fv.fj = FJ.data(); fv.jx0 = jx0; fv.jend = jx0 + jlen; fv.lx = lx;
         if (want_q) { fv.qx = ex.FQ.data(); fv.qy = ey.FQ.data(); fv.qj = FJQ.data(); }
         dfl_resume(st, d.s.n);

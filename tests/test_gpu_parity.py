@@ -199,6 +199,14 @@ def test_megabase_genomes_gzip(engine):
         assert np.array_equal(engine.tile_sizes("gzip", 0, 2, 0, 4), ref)
     finally:
         engine.set_option("deflate_junction", 3)
+    engine.set_option("deflate_index6", 0)                                     # match tables from the 3-byte chain walk only
+    engine.set_option("invalidate_caches", 1)
+    try:
+        assert np.array_equal(engine.tile_sizes("gzip", 0, 2, 0, 4), ref)
+        assert np.array_equal(engine.single_sizes("gzip"), C)
+    finally:
+        engine.set_option("deflate_index6", 1)
+        engine.set_option("invalidate_caches", 1)
     Sz = engine.tile_sizes("zlib", 1, 2, 0, 3)
     refz = np.array([[_ref_len(np.concatenate([g[i], g[j]]), "zlib") for j in range(3)] for i in (1, 2)])
     assert np.array_equal(Sz, refz)
