@@ -1011,59 +1011,137 @@ __device__ __forceinline__ DflStream dfl_make(const DflCorpus &c, int32_t x, int
     return d;
 }
 
-// K3a: index of one sequence per CTA (one warp): counting sort of its positions by hash, stable.
-// tmp: per position scratch (the F slice is used) receiving the rank inside the bucket.
-// KIND 0: the 3-byte chain hash over positions [0, len - 2) -> c.order / c.bstart;
-// KIND 1: the 6-byte hash over positions [0, len - 5) -> c.order6 / c.bstart6 (DflIndex6)
-template <int KIND>
-__global__ void __launch_bounds__(32)
-dfl_index_kernel(DflCorpus c, const int32_t *__restrict__ seqs, int32_t n_seqs, uint32_t *__restrict__ tmp)
+// K3a: index of a sequence = its positions sorted by (hash, position): a stable LSD radix sort on the 15-bit hash in
+// two passes (low 8 bits, high 7 bits).  The sort key is recomputed from the bytes, only positions move.
+//   KIND 0: the 3-byte chain hash over positions [0, len - 2) -> c.order / c.bstart;
+//   KIND 1: the 6-byte hash over positions [0, len - 5) -> c.order6 / c.bstart6 (DflIndex6).
+// A tile is 8192 consecutive keys handled by one CTA of 32 warps; warp w takes keys [256 w, 256 (w + 1)) of the tile in
+// 8 rounds of 32, so (warp, round, lane) order is key order and ranks come out stable: inside a round from
+// __match_any_sync, across rounds from the warp's running digit counts, across warps from a scan of those counts,
+// across tiles from the scanned per-tile digit totals (dfl_radix_scan_kernel).
+constexpr uint32_t DFL_RX_TILE = 8192, DFL_RX_THREADS = 1024, DFL_RX_ROUNDS = DFL_RX_TILE / DFL_RX_THREADS;
+template <int KIND> SNACC_HD uint32_t dfl_index_count(uint32_t len) { return KIND == 0 ? (len >= 3 ? len - 2 : 0) : (len >= 6 ? len - 5 : 0); }
+template <int KIND> __device__ __forceinline__ uint32_t dfl_index_hash(const uint8_t *p, uint32_t i)
 {
-    extern __shared__ uint32_t cnt[];                    // DFL_HASH counters
-    const uint32_t lane = threadIdx.x;
-    for (int32_t t = blockIdx.x; t < n_seqs; t += gridDim.x) {
-        const int32_t sq = seqs[t];
-        const uint8_t *p = c.corpus + c.off[sq];
-        const uint32_t len = c.len[sq];
-        const uint32_t nidx = KIND == 0 ? (len >= 3 ? len - 2 : 0) : (len >= 6 ? len - 5 : 0);   // positions with 3 (6) bytes left
-        uint32_t *rank = tmp + c.poff[sq];
-        uint32_t *order = (KIND == 0 ? c.order : c.order6) + c.poff[sq];
-        uint32_t *bstart = (KIND == 0 ? c.bstart : c.bstart6) + (size_t)sq * (DFL_HASH + 1);
-#define DFL_IDX_HASH(i_) (KIND == 0 ? dfl_hash3(p[(i_)], p[(i_) + 1], p[(i_) + 2]) : dfl_hash6w(ldu64(p + (i_))))
-        for (uint32_t i = lane; i < DFL_HASH; i += 32) cnt[i] = 0;
+    return KIND == 0 ? dfl_hash3(p[i], p[i + 1], p[i + 2]) : dfl_hash6w(ldu64(p + i));
+}
+SNACC_HD uint32_t dfl_rx_tiles(uint32_t n) { return (n + DFL_RX_TILE - 1) / DFL_RX_TILE; }
+
+// SCATTER = false: digit totals of every tile -> hist[(seq slot * 256 + digit) * max_tiles + tile]
+// SCATTER = true : hist holds the exclusive scan of those totals; keys go to their sorted place
+template <int KIND, int PASS, bool SCATTER>
+__global__ void __launch_bounds__(DFL_RX_THREADS)
+dfl_radix_kernel(DflCorpus c, const int32_t *__restrict__ seqs, uint32_t max_tiles, uint32_t *__restrict__ hist,
+                 const uint32_t *__restrict__ src_all, uint32_t *__restrict__ dst_all)
+{
+    __shared__ uint16_t wcnt[32][256];
+    __shared__ uint32_t toff[256];
+    const int32_t slot = blockIdx.y, sq = seqs[slot];
+    const uint32_t n = dfl_index_count<KIND>(c.len[sq]);
+    const uint32_t tile = blockIdx.x;
+    if (tile * DFL_RX_TILE >= n) return;
+    const uint8_t *p = c.corpus + c.off[sq];
+    const uint32_t *src = src_all + c.poff[sq];
+    uint32_t *dst = dst_all + c.poff[sq];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (uint32_t i = threadIdx.x; i < 32 * 256; i += blockDim.x) (&wcnt[0][0])[i] = 0;
+    __syncthreads();
+    uint32_t pos[DFL_RX_ROUNDS], dg[DFL_RX_ROUNDS], lr[DFL_RX_ROUNDS];
+#pragma unroll
+    for (uint32_t r = 0; r < DFL_RX_ROUNDS; ++r) {
+        const uint32_t idx = tile * DFL_RX_TILE + w * (32 * DFL_RX_ROUNDS) + r * 32 + lane;
+        const bool ok = idx < n;
+        pos[r] = ok ? (PASS == 0 ? idx : src[idx]) : 0;
+        const uint32_t h = ok ? dfl_index_hash<KIND>(p, pos[r]) : 0;
+        dg[r] = ok ? (PASS == 0 ? (h & 255u) : (h >> 8)) : 0x10000u + lane;
+        const uint32_t peers = __match_any_sync(0xffffffffu, dg[r]);
+        lr[r] = ok ? wcnt[w][dg[r]] + __popc(peers & ((1u << lane) - 1)) : 0;
         __syncwarp();
-        for (uint32_t base = 0; base < nidx; base += 32) {
-            const uint32_t i = base + lane;
-            const bool ok = i < nidx;
-            const uint32_t h = ok ? DFL_IDX_HASH(i) : 0xffffffffu - lane;
-            const uint32_t peers = __match_any_sync(0xffffffffu, h);
-            if (ok) {
-                const uint32_t before = __popc(peers & ((1u << lane) - 1));
-                rank[i] = cnt[h] + before;
-            }
-            __syncwarp();
-            if (ok && (peers >> lane) <= 1u) cnt[h] += __popc(peers);   // highest lane of the group updates
-            __syncwarp();
-        }
-        // exclusive scan of the counters -> bucket starts
-        uint32_t carry = 0;
-        for (uint32_t b0 = 0; b0 < DFL_HASH; b0 += 32) {
-            const uint32_t v = cnt[b0 + lane];
-            uint32_t inc = v;
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o); if ((int)lane >= o) inc += u; }
-            const uint32_t ex = carry + inc - v;
-            bstart[b0 + lane] = ex;
-            cnt[b0 + lane] = ex;
-            carry += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        if (lane == 0) bstart[DFL_HASH] = carry;
+        if (ok && (peers >> lane) <= 1u) wcnt[w][dg[r]] += (uint16_t)__popc(peers);
         __syncwarp();
-        for (uint32_t i = lane; i < nidx; i += 32) {
-            const uint32_t h = DFL_IDX_HASH(i);
-            order[cnt[h] + rank[i]] = i;
-        }
-        __syncwarp();
-#undef DFL_IDX_HASH
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {                               // exclusive scan over the warps, digit by digit
+        uint32_t run = 0;
+        for (uint32_t k = 0; k < 32; ++k) { const uint32_t v = wcnt[k][threadIdx.x]; wcnt[k][threadIdx.x] = (uint16_t)run; run += v; }
+        const size_t hi = ((size_t)slot * 256 + threadIdx.x) * max_tiles + tile;
+        if (SCATTER) toff[threadIdx.x] = hist[hi]; else hist[hi] = run;
+    }
+    if (!SCATTER) return;
+    __syncthreads();
+#pragma unroll
+    for (uint32_t r = 0; r < DFL_RX_ROUNDS; ++r)
+        if (dg[r] < 256u) dst[toff[dg[r]] + wcnt[w][dg[r]] + lr[r]] = pos[r];
+}
+
+// in-place exclusive scan of the 256 * max_tiles digit totals of every sequence slot (digit-major), one CTA per slot
+__global__ void __launch_bounds__(1024)
+dfl_radix_scan_kernel(uint32_t max_tiles, uint32_t *__restrict__ hist)
+{
+    __shared__ uint32_t part[1024];
+    uint32_t *h = hist + (size_t)blockIdx.x * 256 * max_tiles;
+    const uint32_t n = 256 * max_tiles, per = (n + 1023) / 1024;
+    const uint32_t lo = tmin(n, threadIdx.x * per), hi = tmin(n, lo + per);
+    uint32_t sum = 0;
+    for (uint32_t i = lo; i < hi; ++i) sum += h[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024; o <<= 1) {              // Hillis-Steele inclusive scan
+        const uint32_t v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    uint32_t run = part[threadIdx.x] - sum;
+    for (uint32_t i = lo; i < hi; ++i) { const uint32_t v = h[i]; h[i] = run; run += v; }
+}
+
+// bucket starts from the sorted order: mark where the hash changes, then every unmarked (empty) bucket starts where the next
+// one does
+template <int KIND>
+__global__ void __launch_bounds__(256)
+dfl_index_bounds_kernel(DflCorpus c, const int32_t *__restrict__ seqs)
+{
+    const int32_t sq = seqs[blockIdx.y];
+    const uint32_t n = dfl_index_count<KIND>(c.len[sq]);
+    const uint8_t *p = c.corpus + c.off[sq];
+    const uint32_t *order = (KIND == 0 ? c.order : c.order6) + c.poff[sq];
+    uint32_t *bstart = (KIND == 0 ? c.bstart : c.bstart6) + (size_t)sq * (DFL_HASH + 1);
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t h = dfl_index_hash<KIND>(p, order[k]);
+        if (k == 0 || dfl_index_hash<KIND>(p, order[k - 1]) != h) bstart[h] = k;
+    }
+}
+template <int KIND>
+__global__ void __launch_bounds__(1024)
+dfl_index_fill_kernel(DflCorpus c, const int32_t *__restrict__ seqs, int phase)
+{
+    // phase 0: all starts unmarked; phase 1 (after dfl_index_bounds_kernel): suffix minimum
+    __shared__ uint32_t part[1024];
+    const int32_t sq = seqs[blockIdx.x];
+    const uint32_t n = dfl_index_count<KIND>(c.len[sq]);
+    uint32_t *bstart = (KIND == 0 ? c.bstart : c.bstart6) + (size_t)sq * (DFL_HASH + 1);
+    const uint32_t per = DFL_HASH / 1024;
+    if (phase == 0) {
+        for (uint32_t i = threadIdx.x; i < DFL_HASH; i += blockDim.x) bstart[i] = 0xffffffffu;
+        if (threadIdx.x == 0) bstart[DFL_HASH] = n;
+        return;
+    }
+    uint32_t m = 0xffffffffu;
+    for (uint32_t k = 0; k < per; ++k) m = tmin(m, bstart[threadIdx.x * per + k]);
+    part[threadIdx.x] = m;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024; o <<= 1) {              // inclusive suffix minimum
+        const uint32_t v = threadIdx.x + o < 1024 ? part[threadIdx.x + o] : 0xffffffffu;
+        __syncthreads();
+        part[threadIdx.x] = tmin(part[threadIdx.x], v);
+        __syncthreads();
+    }
+    uint32_t run = threadIdx.x + 1 < 1024 ? part[threadIdx.x + 1] : 0xffffffffu;
+    run = tmin(run, n);
+    for (int k = (int)per - 1; k >= 0; --k) {
+        uint32_t &v = bstart[threadIdx.x * per + k];
+        if (v == 0xffffffffu) v = run; else run = v;
     }
 }
 
@@ -1142,7 +1220,7 @@ dfl_head_kernel(DflCorpus c, const int32_t *__restrict__ seqs, int32_t n_seqs)
 struct DflPair { int32_t x, y; };
 
 // K3b'': 6-byte index of the tail of the listed sequences (DflTail6): stable counting sort by one warp, like
-// dfl_index_kernel.  Shared memory: DFL_H6 counters + one rank per tail position.
+// the first version of the full index did.  Shared memory: DFL_H6 counters + one rank per tail position.
 __global__ void __launch_bounds__(32)
 dfl_tail6_kernel(DflCorpus c, const int32_t *__restrict__ seqs, int32_t n_seqs)
 {
@@ -1428,6 +1506,7 @@ struct DeflateState {
     uint32_t *d_order = nullptr, *d_bstart = nullptr;
     uint16_t *d_head_order = nullptr, *d_head_visit[2] = {nullptr, nullptr};
     uint16_t *d_tail_cnt = nullptr, *d_tail6_order = nullptr, *d_tail6_start = nullptr;
+    uint32_t *d_rx_hist = nullptr; size_t rx_cap = 0;   // radix-sort digit totals (dfl_build_index)
     uint32_t *d_bstart6 = nullptr, *d_order6 = nullptr; uint64_t order6_cap = 0;   // 6-byte index: starts per sequence, window buffer
     int use_index6 = 1;                            // 0: dfl_match_kernel always walks the 3-byte chain (tests)
     std::vector<uint8_t> indexed;                  // per sequence
@@ -1463,6 +1542,7 @@ static inline void deflate_free_corpus(DeflateState &st)
     cudaFree(st.d_tail_cnt); cudaFree(st.d_tail6_order); cudaFree(st.d_tail6_start);
     st.d_tail_cnt = st.d_tail6_order = st.d_tail6_start = nullptr;
     cudaFree(st.d_bstart6); cudaFree(st.d_order6); st.d_bstart6 = st.d_order6 = nullptr; st.order6_cap = 0;
+    cudaFree(st.d_rx_hist); st.d_rx_hist = nullptr; st.rx_cap = 0;
     for (int l = 0; l < 2; ++l) { cudaFree(st.d_head_visit[l]); st.d_head_visit[l] = nullptr; }
     st.d_soff = st.d_roff = nullptr; st.d_cap = nullptr;
     for (int l = 0; l < 2; ++l) {
@@ -1516,6 +1596,44 @@ constexpr int DFL_PARSE_BLOCKS = 148 * 5;           // 40 KiB of counters per CT
 constexpr size_t DFL_BATCH = (size_t)DFL_PARSE_BLOCKS * 64;   // pair streams per junction batch: one per parse thread (6.3 GB of
                                                     // junction F per buffer, two buffers; the parse is latency-bound, so
                                                     // its throughput is the number of streams in flight)
+
+// build the KIND index of the listed sequences (radix sort, bucket starts); tmp: one scratch entry per position,
+// addressed like `order` (the F slices are used)
+template <int KIND>
+static int dfl_build_index(DeflateState &st, const DflCorpus &c, const std::vector<int32_t> &list, const uint32_t *h_len,
+                           uint32_t *tmp, cudaStream_t stream, int64_t *launches, std::string &err)
+{
+    if (list.empty()) return 0;
+    uint32_t mx = 0;
+    for (int32_t i : list) mx = std::max(mx, dfl_index_count<KIND>(h_len[i]));
+    const uint32_t max_tiles = std::max(1u, dfl_rx_tiles(mx));
+    const size_t need = list.size() * 256 * (size_t)max_tiles;
+    if (st.rx_cap < need) {
+        cudaFree(st.d_rx_hist); st.d_rx_hist = nullptr;
+        DCK(cudaMalloc(&st.d_rx_hist, sizeof(uint32_t) * need));
+        st.rx_cap = need;
+    }
+    int32_t *d_list = nullptr;
+    if (dfl_upload(err, stream, list, &d_list)) return -1;
+    const dim3 grid(max_tiles, (unsigned)list.size());
+    uint32_t *order = KIND == 0 ? c.order : c.order6;
+    DCK(cudaMemsetAsync(st.d_rx_hist, 0, sizeof(uint32_t) * need, stream));
+    dfl_radix_kernel<KIND, 0, false><<<grid, DFL_RX_THREADS, 0, stream>>>(c, d_list, max_tiles, st.d_rx_hist, tmp, tmp);
+    dfl_radix_scan_kernel<<<(unsigned)list.size(), 1024, 0, stream>>>(max_tiles, st.d_rx_hist);
+    dfl_radix_kernel<KIND, 0, true><<<grid, DFL_RX_THREADS, 0, stream>>>(c, d_list, max_tiles, st.d_rx_hist, tmp, tmp);
+    DCK(cudaMemsetAsync(st.d_rx_hist, 0, sizeof(uint32_t) * need, stream));
+    dfl_radix_kernel<KIND, 1, false><<<grid, DFL_RX_THREADS, 0, stream>>>(c, d_list, max_tiles, st.d_rx_hist, tmp, order);
+    dfl_radix_scan_kernel<<<(unsigned)list.size(), 1024, 0, stream>>>(max_tiles, st.d_rx_hist);
+    dfl_radix_kernel<KIND, 1, true><<<grid, DFL_RX_THREADS, 0, stream>>>(c, d_list, max_tiles, st.d_rx_hist, tmp, order);
+    dfl_index_fill_kernel<KIND><<<(unsigned)list.size(), 1024, 0, stream>>>(c, d_list, 0);
+    dfl_index_bounds_kernel<KIND><<<dim3(std::max(1u, std::min((mx + 255) / 256, 1024u)), (unsigned)list.size()), 256, 0, stream>>>(c, d_list);
+    dfl_index_fill_kernel<KIND><<<(unsigned)list.size(), 1024, 0, stream>>>(c, d_list, 1);
+    DCK(cudaGetLastError());
+    *launches += 9;
+    DCK(cudaStreamSynchronize(stream));
+    cudaFree(d_list);
+    return 0;
+}
 
 // sizes of the raw deflate streams of the jobs (x alone when ys == nullptr) into d_out[0..n_jobs)
 static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, const int32_t *xs, const int32_t *ys,
@@ -1595,11 +1713,11 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
     if (!need_idx.empty()) {
         int32_t *d_list = nullptr;
         if (dfl_upload(err, stream, need_idx, &d_list)) return -1;
-        DCK(cudaFuncSetAttribute(dfl_index_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DFL_HASH * 4)));
-        // the F slice of this level doubles as rank scratch; it is recomputed right below
-        dfl_index_kernel<0><<<(unsigned)std::min<size_t>(need_idx.size(), 148 * 4), 32, DFL_HASH * 4, stream>>>(
-            c, d_list, (int32_t)need_idx.size(), st.d_F[li]);
-        DCK(cudaGetLastError());
+        // the F slices of this level double as sort scratch; they are recomputed right below
+        for (size_t a0 = 0; a0 < need_idx.size(); a0 += 64) {
+            std::vector<int32_t> part(need_idx.begin() + a0, need_idx.begin() + std::min(need_idx.size(), a0 + 64));
+            if (dfl_build_index<0>(st, c, part, dc.h_len, st.d_F[li], stream, launches, err)) return -1;
+        }
         DCK(cudaFuncSetAttribute(dfl_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DFL_HASH * 4)));
         dfl_head_kernel<<<(unsigned)std::min<size_t>(need_idx.size(), 148), 1024, DFL_HASH * 4, stream>>>(
             c, d_list, (int32_t)need_idx.size());
@@ -1631,10 +1749,7 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
             DflCorpus cm = c;
             if (fits) {
                 cm.order6 = st.d_order6 - first;                               // addressed like `order`: + poff[sq]
-                DCK(cudaFuncSetAttribute(dfl_index_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(DFL_HASH * 4)));
-                dfl_index_kernel<1><<<(unsigned)part.size(), 32, DFL_HASH * 4, stream>>>(cm, d_list, (int32_t)part.size(), st.d_F[li]);
-                DCK(cudaGetLastError());
-                ++*launches;
+                if (dfl_build_index<1>(st, cm, part, dc.h_len, st.d_F[li], stream, launches, err)) return -1;
             }
             uint32_t mx = 0;
             for (int32_t i : part) mx = std::max(mx, dc.h_len[i]);
