@@ -648,7 +648,15 @@ static int run_lz4(snacc_ctx *ctx, const int32_t *h_x, const int32_t *h_y, int64
     if (!pairs) {
         std::vector<int32_t> seqs, want; std::vector<int64_t> idx;
         for (int64_t k = 0; k < n_jobs; ++k) {
-            if (ctx->h_packable[h_x[k]]) { seqs.push_back(h_x[k]); want.push_back(0); idx.push_back(k); }
+            if (ctx->h_packable[h_x[k]]) {
+                // the same pass leaves the prefix checkpoints a later pair call with this x would need (the extra work
+                // is a re-run of the last partial block), so that call does not have to parse the sequence again
+                const int32_t sq = h_x[k];
+                const int32_t all = 2 | (ctx->h_len[sq] < LZ4_BLOCK ? 1 : 0);
+                const int32_t missing = all & ~ctx->h_ck_have[sq];
+                ctx->h_ck_have[sq] |= (uint8_t)missing;
+                seqs.push_back(sq); want.push_back(missing); idx.push_back(k);
+            }
             else bytewise.push_back(k);
         }
         ctx->last_packed_jobs = (int64_t)seqs.size();

@@ -356,9 +356,28 @@ SNACC_HD uint32_t dfl_junction_word(const DflStream &d, uint32_t p, const DflCon
                                     uint32_t q_s, const DflTail6 *t6, const uint16_t *tail_cnt, uint32_t *quarter)
 {
     const uint32_t cnt = visit & DFL_V_COUNT, f = f_s & ~DFL_QDIFF, chain = (uint32_t)cfg.max_chain;
-    if (t6 && !(visit & (DFL_V_NICE | DFL_V_HEADFAR)) && cnt >= 1 && d.s.n - p >= 6) {
-        const uint32_t h = dfl_hash_at(d.s, p);
-        if (cnt + 3 + SNACC_LDG(tail_cnt + h) < (chain >> 2)) {
+    if (t6 && !(visit & (DFL_V_NICE | DFL_V_HEADFAR)) && d.s.n - p >= 6) {
+        const Stream &s = d.s;
+        const uint32_t h = dfl_hash_at(s, p), lx = s.lx;
+        bool ok = cnt + 3 + SNACC_LDG(tail_cnt + h) < (chain >> 2);
+        if (ok && cnt == 0) {
+            // the walk never started inside y: the first chain member met from here on is the chain head and has its
+            // own test (not NIL, at most MAX_DIST away -- one byte farther than any later candidate may be)
+            uint32_t head = 0xffffffffu;
+            if (p > lx && dfl_hash_at(s, lx) == h) head = lx;
+            else if (lx >= 1 && s.n - (lx - 1) >= 3 && dfl_hash_at(s, lx - 1) == h) head = lx - 1;
+            else if (lx >= 2 && s.n - (lx - 2) >= 3 && dfl_hash_at(s, lx - 2) == h) head = lx - 2;
+            else {
+                const uint32_t xlo = SNACC_LDG(d.ix.bstart + h), xhi = SNACC_LDG(d.ix.bstart + h + 1);
+                if (xhi > xlo) head = SNACC_LDG(d.ix.order + xhi - 1);
+            }
+            if (head == 0xffffffffu || head <= dfl_window_base(p) || p - head > DFL_MAX_DIST) {
+                if (quarter) *quarter = 0;
+                return 0;                                   // no search at all
+            }
+            ok = p - head != DFL_MAX_DIST;
+        }
+        if (ok) {
             // the 6-byte walk sees every candidate of 6+ bytes in chain order: when it ends with such a match, or when
             // y alone had already found 5+ bytes, no candidate it skipped can have mattered
             const uint32_t w = dfl_longest_k6(d, p, (uint32_t)cfg.nice_length, f, *t6);
@@ -739,7 +758,7 @@ struct DflFView {
     // entries indexed by position); null elsewhere
     const uint32_t *ring = nullptr;
 };
-constexpr uint32_t DFL_PREP_CHUNK = 8192;
+constexpr uint32_t DFL_PREP_CHUNK = 4096;
 // The parse reads F at nearly consecutive positions (two reads per emitted match, a match is ~9 bytes on DNA) and
 // each read is a dependent DRAM round trip, so the last 32-byte sector (8 entries) is kept in registers.
 // All three tables start on 32-byte boundaries and are padded to a multiple of 8 entries.
@@ -1779,7 +1798,7 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
             int32_t *d_list = nullptr;
             if (dfl_upload(err, stream, need_prep, &d_list)) return -1;
             DCK(cudaFuncSetAttribute(dfl_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DflPrepSmem)));
-            dfl_prep_kernel<<<(unsigned)std::min<size_t>(need_prep.size(), 148 * 3), DFL_PREP_THREADS, sizeof(DflPrepSmem), stream>>>(
+            dfl_prep_kernel<<<(unsigned)std::min<size_t>(need_prep.size(), 148 * 5), DFL_PREP_THREADS, sizeof(DflPrepSmem), stream>>>(
                 c, d_list, (int32_t)need_prep.size(), level, st.d_F[li], FQ, st.d_ckpt[li], cp);
             DCK(cudaGetLastError());
             ++*launches;
@@ -1822,7 +1841,11 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
         if (FQ && !st.d_FJQ2[0])
             for (int k = 0; k < 2; ++k) DCK(cudaMalloc(&st.d_FJQ2[k], sizeof(uint32_t) * batch * DFL_JSTRIDE));
         if (!st.stream2) {
-            DCK(cudaStreamCreateWithFlags(&st.stream2, cudaStreamNonBlocking));
+            // the parse kernel is a few long-running, latency-bound CTAs: give it priority over the junction kernel's
+            // many short blocks, which would otherwise keep every SM full until they are all done
+            int prio_lo = 0, prio_hi = 0;
+            DCK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            DCK(cudaStreamCreateWithPriority(&st.stream2, cudaStreamNonBlocking, prio_hi));
             for (int k = 0; k < 2; ++k) {
                 DCK(cudaEventCreateWithFlags(&st.ev_j[k], cudaEventDisableTiming));
                 DCK(cudaEventCreateWithFlags(&st.ev_p[k], cudaEventDisableTiming));

@@ -338,7 +338,7 @@ extern "C" int64_t emu_deflate_size_ex(const uint8_t *x, uint32_t lx, const uint
                                                  tail_cnt.data(), &q);
             {   // how often the 6-byte shortcut applies (reported, not checked)
                 const uint32_t v = ey.head_visit[yq], cnt = v & DFL_V_COUNT;
-                if (!(v & (DFL_V_NICE | DFL_V_HEADFAR)) && cnt >= 1 && (((Fy[yq] & ~DFL_QDIFF) >> 16) >= 5 || (w >> 16) >= 6) && d.s.n - (lx + yq) >= 6 &&
+                if (!(v & (DFL_V_NICE | DFL_V_HEADFAR)) && (((Fy[yq] & ~DFL_QDIFF) >> 16) >= 5 || (w >> 16) >= 6) && d.s.n - (lx + yq) >= 6 &&
                     cnt + 3 + tail_cnt[dfl_hash_at(d.s, lx + yq)] < ((uint32_t)cfg.max_chain >> 2)) ++shortcuts;
             }
             FJ[jxl + yq] = w; FJQ[jxl + yq] = q;
