@@ -311,7 +311,8 @@ SNACC_HD uint32_t dfl_tail3_from(uint32_t len) { return len > DFL_MAX_DIST - 1 ?
 
 // preconditions (checked by dfl_junction_word): the walk inside y started, did not stop at nice_length, and no
 // chain limit can bind; the result only stands when it is 6+ bytes long or y alone had found 5+ bytes
-SNACC_HD uint32_t dfl_longest_k6(const DflStream &d, uint32_t p, uint32_t nice, uint32_t f_s, const DflTail6 &t6)
+SNACC_HD uint32_t dfl_longest_k6(const DflStream &d, uint32_t p, uint32_t nice, uint32_t f_s, const DflTail6 &t6,
+                                 const uint64_t *edge = nullptr)   // edge[k] = ld64(s, lx - k), k = 0..5, when the caller has them
 {
     const Stream &s = d.s;
     const uint32_t lx = s.lx, base = dfl_window_base(p);
@@ -321,8 +322,9 @@ SNACC_HD uint32_t dfl_longest_k6(const DflStream &d, uint32_t p, uint32_t nice, 
     uint32_t best = (f_s >> 16) ? (f_s >> 16) : 2, bdist = f_s & 0xffff;
     const uint64_t scan = ld64(s, p);
     bool over = false;
-#define DFL_K6_VISIT(c_) do {                                                                                       \
-        const uint64_t x_ = scan ^ ld64(s, (c_));                                                                   \
+#define DFL_K6_VISIT(c_) DFL_K6_VISIT8(c_, ld64(s, (c_)))
+#define DFL_K6_VISIT8(c_, bytes_) do {                                                                              \
+        const uint64_t x_ = scan ^ (bytes_);                                                                        \
         uint32_t len_ = x_ ? (uint32_t)(SNACC_FFS64(x_) - 1) >> 3                                                    \
                            : 8 + dfl_match_len(s, p + 8, (c_) + 8, maxcmp > 8 ? maxcmp - 8 : 0);                    \
         if (len_ > maxcmp) len_ = maxcmp;                                                                           \
@@ -333,7 +335,12 @@ SNACC_HD uint32_t dfl_longest_k6(const DflStream &d, uint32_t p, uint32_t nice, 
         if (lx < k) break;
         const uint32_t c = lx - k;
         if (c <= limit) { over = true; break; }
-        DFL_K6_VISIT(c);
+        if (edge) {
+            // a candidate only counts from 6 equal bytes on: most positions are done with one register compare
+            if (((scan ^ edge[k]) & 0xffffffffffffull) == 0) DFL_K6_VISIT8(c, edge[k]);
+        } else {
+            DFL_K6_VISIT(c);
+        }
     }
     if (!over) {
         const uint32_t h6 = dfl_hash6(scan);
@@ -347,13 +354,15 @@ SNACC_HD uint32_t dfl_longest_k6(const DflStream &d, uint32_t p, uint32_t nice, 
         }
     }
 #undef DFL_K6_VISIT
+#undef DFL_K6_VISIT8
     return best > 2 ? (best << 16) | bdist : 0;
 }
 
 // junction F word of head position p = lx + q of a pair stream (see dfl_longest_cont for the arguments);
 // tail_cnt: per 3-byte bucket of x, the entries at or after dfl_tail3_from(lx); t6 == null: no shortcut
 SNACC_HD uint32_t dfl_junction_word(const DflStream &d, uint32_t p, const DflConfig &cfg, uint32_t f_s, uint32_t visit, bool q_known,
-                                    uint32_t q_s, const DflTail6 *t6, const uint16_t *tail_cnt, uint32_t *quarter)
+                                    uint32_t q_s, const DflTail6 *t6, const uint16_t *tail_cnt, uint32_t *quarter,
+                                    const uint64_t *edge = nullptr)
 {
     const uint32_t cnt = visit & DFL_V_COUNT, f = f_s & ~DFL_QDIFF, chain = (uint32_t)cfg.max_chain;
     if (t6 && !(visit & (DFL_V_NICE | DFL_V_HEADFAR)) && d.s.n - p >= 6) {
@@ -380,7 +389,7 @@ SNACC_HD uint32_t dfl_junction_word(const DflStream &d, uint32_t p, const DflCon
         if (ok) {
             // the 6-byte walk sees every candidate of 6+ bytes in chain order: when it ends with such a match, or when
             // y alone had already found 5+ bytes, no candidate it skipped can have mattered
-            const uint32_t w = dfl_longest_k6(d, p, (uint32_t)cfg.nice_length, f, *t6);
+            const uint32_t w = dfl_longest_k6(d, p, (uint32_t)cfg.nice_length, f, *t6, edge);
             if ((w >> 16) >= 6 || (f >> 16) >= 5) {
                 if (quarter) *quarter = w;
                 return w;
@@ -665,6 +674,192 @@ static __host__ __device__ void dfl_flush_block(DflTrees &t, const uint16_t *lfr
     if (last) bits = (bits + 7) & ~7ull;
 }
 
+// ---- the same block cost on compacted trees ------------------------------------------------------
+// A pair stream costs ~34 blocks and zlib's tree construction is a chain of dependent loads and stores; with the
+// scratch of one thread at 6.5 KB (DflTrees) it lives in global memory and every step is a DRAM/L2 round trip.
+// build_tree never looks at symbol numbers, only at frequencies, depths and heap positions, so it can run on the
+// NONZERO symbols alone, renumbered in order (leaves 0..L-1, internal nodes from L): same heap, same tree, same code
+// lengths.  On DNA a block uses ~25 literal/length codes and ~28 distance codes, so the scratch shrinks to under
+// 1 KB per thread and fits shared memory.  Blocks with more than DFL_C_LEAVES codes in a tree, or fewer than two
+// (zlib then invents symbols by number), take dfl_flush_block.
+constexpr int DFL_C_LEAVES = 48, DFL_C_NODES = 2 * DFL_C_LEAVES;
+struct DflCompactTrees {
+    uint16_t freq[DFL_C_NODES];
+    uint8_t dad[DFL_C_NODES], len[DFL_C_NODES], depth[DFL_C_NODES];
+    uint8_t heap[DFL_C_NODES + 4];
+    uint16_t map[DFL_C_LEAVES];                           // symbol of each leaf of the tree under construction
+    uint16_t lmap[DFL_C_LEAVES]; uint8_t llen[DFL_C_LEAVES];   // finished literal/length tree
+    uint8_t dmap[DFL_D_CODES + 2], dlen[DFL_D_CODES + 2];      // finished distance tree
+    uint16_t blfreq[DFL_BL_CODES + 1];
+    uint16_t bl_count[16];
+    uint32_t pad_[2];                                     // sizeof = 964: an odd number of words, so the scratches of the
+};                                                        // threads of a warp fall into different banks
+static_assert(sizeof(DflCompactTrees) % 8 == 4, "DflCompactTrees: odd number of 32-bit words expected");
+
+SNACC_HD bool dfl_c_smaller(const DflCompactTrees &t, int n, int m)
+{
+    return t.freq[n] < t.freq[m] || (t.freq[n] == t.freq[m] && t.depth[n] <= t.depth[m]);
+}
+SNACC_HD void dfl_c_downheap(DflCompactTrees &t, int heap_len, int k)
+{
+    const int v = t.heap[k];
+    int j = k << 1;
+    while (j <= heap_len) {
+        if (j < heap_len && dfl_c_smaller(t, t.heap[j + 1], t.heap[j])) j++;
+        if (dfl_c_smaller(t, v, t.heap[j])) break;
+        t.heap[k] = t.heap[j]; k = j;
+        j <<= 1;
+    }
+    t.heap[k] = (uint8_t)v;
+}
+// leaves 0..L-1 (freq, map) -> code lengths in len[0..L-1]; adds the tree's bits to opt_len / static_len
+static __host__ __device__ void dfl_c_build(DflCompactTrees &t, int L, int kind, int max_length, uint64_t &opt_len, uint64_t &static_len)
+{
+    const int HS = 2 * L + 1;
+    DflTreeDesc desc{nullptr, 0, kind, 0, max_length};
+    int heap_len = 0, heap_max = HS;
+    for (int n = 0; n < L; n++) { t.heap[++heap_len] = (uint8_t)n; t.depth[n] = 0; }
+    for (int n = heap_len / 2; n >= 1; n--) dfl_c_downheap(t, heap_len, n);
+    int node = L;
+    do {
+        const int n = t.heap[1];
+        t.heap[1] = t.heap[heap_len--];
+        dfl_c_downheap(t, heap_len, 1);
+        const int m = t.heap[1];
+        t.heap[--heap_max] = (uint8_t)n;
+        t.heap[--heap_max] = (uint8_t)m;
+        t.freq[node] = (uint16_t)(t.freq[n] + t.freq[m]);
+        t.depth[node] = (uint8_t)((t.depth[n] >= t.depth[m] ? t.depth[n] : t.depth[m]) + 1);
+        t.dad[n] = t.dad[m] = (uint8_t)node;
+        t.heap[1] = (uint8_t)node++;
+        dfl_c_downheap(t, heap_len, 1);
+    } while (heap_len >= 2);
+    t.heap[--heap_max] = t.heap[1];
+    // gen_bitlen
+    int h, bits, overflow = 0;
+    for (bits = 0; bits <= 15; bits++) t.bl_count[bits] = 0;
+    t.len[t.heap[heap_max]] = 0;
+    for (h = heap_max + 1; h < HS; h++) {
+        const int n = t.heap[h];
+        bits = t.len[t.dad[n]] + 1;
+        if (bits > max_length) bits = max_length, overflow++;
+        t.len[n] = (uint8_t)bits;
+        if (n >= L) continue;                            // not a leaf
+        t.bl_count[bits]++;
+        const int sym = t.map[n];
+        const int xbits = dfl_xbits(desc, sym);
+        const uint64_t f = t.freq[n];
+        opt_len += f * (unsigned)(bits + xbits);
+        if (kind != 2) static_len += f * (unsigned)(dfl_slen(desc, sym) + xbits);
+    }
+    if (overflow == 0) return;
+    do {
+        bits = max_length - 1;
+        while (t.bl_count[bits] == 0) bits--;
+        t.bl_count[bits]--;
+        t.bl_count[bits + 1] += 2;
+        t.bl_count[max_length]--;
+        overflow -= 2;
+    } while (overflow > 0);
+    for (bits = max_length; bits != 0; bits--) {
+        int n = t.bl_count[bits];
+        while (n != 0) {
+            const int m = t.heap[--h];
+            if (m >= L) continue;
+            if ((int)t.len[m] != bits) {
+                opt_len += (uint64_t)((int64_t)(bits - (int)t.len[m]) * (int64_t)t.freq[m]);
+                t.len[m] = (uint8_t)bits;
+            }
+            n--;
+        }
+    }
+}
+// scan_tree over symbols 0..max_code of a finished tree given by its leaves (map ascending) and their lengths
+template <class MapT>
+static __host__ __device__ void dfl_c_scan(DflCompactTrees &t, const MapT *map, const uint8_t *len, int L, int max_code)
+{
+    int j = 0;
+#define DFL_C_LEN(sym_) ((j < L && (int)map[j] == (sym_)) ? (int)len[j++] : 0)
+    int prevlen = -1, curlen, nextlen = DFL_C_LEN(0), count = 0, max_count = 7, min_count = 4;
+    if (nextlen == 0) max_count = 138, min_count = 3;
+    for (int n = 0; n <= max_code; n++) {
+        curlen = nextlen;
+        nextlen = n + 1 <= max_code ? DFL_C_LEN(n + 1) : 0xffff;
+        if (++count < max_count && curlen == nextlen) continue;
+        else if (count < min_count) t.blfreq[curlen] += (uint16_t)count;
+        else if (curlen != 0) {
+            if (curlen != prevlen) t.blfreq[curlen]++;
+            t.blfreq[16]++;
+        } else if (count <= 10) t.blfreq[17]++;
+        else t.blfreq[18]++;
+        count = 0; prevlen = curlen;
+        if (nextlen == 0) max_count = 138, min_count = 3;
+        else if (curlen == nextlen) max_count = 6, min_count = 3;
+        else max_count = 7, min_count = 4;
+    }
+#undef DFL_C_LEN
+}
+// dfl_flush_block on compacted trees; false (nothing changed) when the block does not qualify
+static __host__ __device__ bool dfl_flush_block_compact(DflCompactTrees &t, const uint16_t *lfreq, int lstride, const uint16_t *dfreq,
+                                                        int dstride, uint64_t stored_len, bool can_store, bool last, uint64_t &bits,
+                                                        bool *stored_cand)
+{
+    const uint8_t bl_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    uint64_t opt_len = 0, static_len = 0;
+    int L = 0;
+    for (int n = 0; n < DFL_L_CODES; n++) {
+        const uint16_t f = lfreq[n * lstride];
+        if (!f) continue;
+        if (L == DFL_C_LEAVES) return false;
+        t.freq[L] = f; t.map[L] = (uint16_t)n; L++;
+    }
+    if (L < 2) return false;
+    int D = 0;
+    for (int n = 0; n < DFL_D_CODES; n++) D += dfreq[n * dstride] != 0;
+    if (D < 2) return false;
+    const int lmax = t.map[L - 1], Ls = L;
+    dfl_c_build(t, L, 0, 15, opt_len, static_len);
+    for (int n = 0; n < L; n++) { t.lmap[n] = t.map[n]; t.llen[n] = t.len[n]; }
+    L = 0;
+    for (int n = 0; n < DFL_D_CODES; n++) {
+        const uint16_t f = dfreq[n * dstride];
+        if (f) { t.freq[L] = f; t.map[L] = (uint16_t)n; L++; }
+    }
+    const int dmax = t.map[L - 1], Ds = L;
+    dfl_c_build(t, L, 1, 15, opt_len, static_len);
+    for (int n = 0; n < L; n++) { t.dmap[n] = (uint8_t)t.map[n]; t.dlen[n] = t.len[n]; }
+    for (int n = 0; n < DFL_BL_CODES; n++) t.blfreq[n] = 0;
+    dfl_c_scan(t, t.lmap, t.llen, Ls, lmax);
+    dfl_c_scan(t, t.dmap, t.dlen, Ds, dmax);
+    L = 0;
+    for (int n = 0; n < DFL_BL_CODES; n++)
+        if (t.blfreq[n]) { t.freq[L] = t.blfreq[n]; t.map[L] = (uint16_t)n; L++; }
+    if (L < 2) return false;
+    dfl_c_build(t, L, 2, 7, opt_len, static_len);
+    // bit length of every bit-length code, by symbol (blfreq is free now)
+    for (int n = 0; n < DFL_BL_CODES; n++) t.blfreq[n] = 0;
+    for (int n = 0; n < L; n++) t.blfreq[t.map[n]] = t.len[n];
+    int max_blindex;
+    for (max_blindex = DFL_BL_CODES - 1; max_blindex >= 3; max_blindex--)
+        if (t.blfreq[bl_order[max_blindex]] != 0) break;
+    opt_len += 3 * ((uint64_t)max_blindex + 1) + 5 + 5 + 4;
+    uint64_t opt_lenb = (opt_len + 3 + 7) >> 3;
+    const uint64_t static_lenb = (static_len + 3 + 7) >> 3;
+    if (static_lenb <= opt_lenb) opt_lenb = static_lenb;
+    if (stored_cand) *stored_cand = stored_len + 4 <= opt_lenb;
+    if (stored_len + 4 <= opt_lenb && can_store) {
+        bits += 3;
+        bits = (bits + 7) & ~7ull;
+        bits += 32 + 8 * stored_len;
+    } else if (static_lenb == opt_lenb) {
+        bits += 3 + static_len;
+    } else {
+        bits += 3 + opt_len;
+    }
+    if (last) bits = (bits + 7) & ~7ull;
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------
 // canonical symbol stream of a sequence
 // ------------------------------------------------------------------------------------------------
@@ -901,6 +1096,9 @@ static __host__ __device__ int dfl_parse(const DflStream &d, const DflFView &fv,
     return done ? 1 : synced ? 2 : 0;
 }
 
+#if defined(DFL_CHECK_COMPACT)
+static int64_t dfl_compact_checked = 0, dfl_compact_mismatch = 0;     // host emulation only (tests/host_emu.cu)
+#endif
 // After dfl_parse returned 2 at canonical symbol k_sync: account every block of the pair stream that ends
 // before the tail from the cumulative histograms and leave `st` at the loop top that follows the last
 // canonical match ending at or before ly - DFL_TAIL.  Returns 1 when it advanced, 0 when there was nothing
@@ -909,7 +1107,7 @@ static __host__ __device__ int dfl_parse(const DflStream &d, const DflFView &fv,
 template <class TallyT>
 static __host__ __device__ int dfl_canon_blocks(const DflCanon &cn, uint32_t lx, uint32_t n, uint32_t k_sync, DflParseState &st,
                                                 TallyT *lfreq, int lstride, TallyT *dfreq, int dstride, DflTrees &tr,
-                                                uint32_t *accA, uint32_t *accB)
+                                                uint32_t *accA, uint32_t *accB, DflCompactTrees *ct = nullptr)
 {
     const uint32_t ly = n - lx, lim = ly - DFL_TAIL;
     uint32_t lo = 0, hi = cn.n_sym;                        // first symbol that ends beyond lim
@@ -936,7 +1134,18 @@ static __host__ __device__ int dfl_canon_blocks(const DflCanon &cn, uint32_t lx,
         if (flush) {
             const uint32_t e2 = lx + SNACC_LDG(cn.end + t2 - 1);
             bool cand = false;
-            dfl_flush_block(tr, lfreq, lstride, dfreq, dstride, e2 - st.block_start, true, false, st.bits, &cand);
+#if defined(DFL_CHECK_COMPACT) && !defined(__CUDA_ARCH__)
+            {   // host emulation: the compacted trees must give exactly what the full ones give
+                uint64_t b0 = st.bits, b1 = st.bits; bool c0 = false, c1 = false;
+                dfl_flush_block(tr, lfreq, lstride, dfreq, dstride, e2 - st.block_start, true, false, b0, &c0);
+                if (ct && dfl_flush_block_compact(*ct, lfreq, lstride, dfreq, dstride, e2 - st.block_start, true, false, b1, &c1)) {
+                    ++dfl_compact_checked;
+                    if (b0 != b1 || c0 != c1) ++dfl_compact_mismatch;
+                }
+            }
+#endif
+            if (!ct || !dfl_flush_block_compact(*ct, lfreq, lstride, dfreq, dstride, e2 - st.block_start, true, false, st.bits, &cand))
+                dfl_flush_block(tr, lfreq, lstride, dfreq, dstride, e2 - st.block_start, true, false, st.bits, &cand);
             if (cand) return -1;
             for (int k = 0; k < DFL_L_CODES; ++k) lfreq[k * lstride] = 0;
             for (int k = 0; k < DFL_D_CODES; ++k) dfreq[k * dstride] = 0;
@@ -960,7 +1169,7 @@ static __host__ __device__ int dfl_canon_blocks(const DflCanon &cn, uint32_t lx,
 template <class TallyT>
 static __host__ __device__ int dfl_pair_stream(const DflStream &d, const DflFView &fv, const DflConfig &c, DflParseState &st,
                                                 TallyT *lfreq, int lstride, TallyT *dfreq, int dstride, DflTrees &tr,
-                                                const DflCanon *cn, uint32_t *accA, uint32_t *accB)
+                                                const DflCanon *cn, uint32_t *accA, uint32_t *accB, DflCompactTrees *ct = nullptr)
 {
     const uint32_t lx = d.s.lx, n = d.s.n;
     const bool use = cn && cn->n_sym != 0 && n - lx >= DFL_CANON_MIN;
@@ -968,7 +1177,7 @@ static __host__ __device__ int dfl_pair_stream(const DflStream &d, const DflFVie
     int r = dfl_parse(d, fv, c, st, lfreq, lstride, dfreq, dstride, tr, 0xffffffffu, (DflRec *)nullptr, use ? cn : nullptr,
                       lx + DFL_JY, &k_sync);
     if (r == 2) {
-        const int b = dfl_canon_blocks(*cn, lx, n, k_sync, st, lfreq, lstride, dfreq, dstride, tr, accA, accB);
+        const int b = dfl_canon_blocks(*cn, lx, n, k_sync, st, lfreq, lstride, dfreq, dstride, tr, accA, accB, ct);
         if (b < 0) return 0;
         dfl_parse(d, fv, c, st, lfreq, lstride, dfreq, dstride, tr, 0xffffffffu);
         return b ? 2 : 1;
@@ -1305,6 +1514,10 @@ dfl_junction_kernel(DflCorpus c, const DflPair *__restrict__ pairs, int32_t n_pa
         const int32_t xi = pairs[b].x;
         const DflTail6 t6{c.tail6_order + (size_t)xi * DFL_T6, c.tail6_start + (size_t)xi * (DFL_H6 + 1), dfl_tail6_t0(lx)};
         const uint16_t *tcx = c.tail_cnt + (size_t)xi * DFL_HASH;
+        __shared__ uint64_t s_edge[6];
+        __syncthreads();
+        if (threadIdx.x < 6) s_edge[threadIdx.x] = lx >= threadIdx.x ? ld64(d.s, lx - threadIdx.x) : 0;
+        __syncthreads();
         for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < u_end; u += gridDim.x * blockDim.x) {
             uint32_t q, w, pos;
             if (u < jxl) {
@@ -1314,7 +1527,7 @@ dfl_junction_kernel(DflCorpus c, const DflPair *__restrict__ pairs, int32_t n_pa
                 const uint32_t yq = ho[u - jxl];
                 pos = jxl + yq;
                 w = dfl_junction_word(d, lx + yq, cfg, fy[yq], hv[yq], fqy != nullptr, fqy ? fqy[yq] : 0u, impl == 3 ? &t6 : nullptr,
-                                      tcx, &q);
+                                      tcx, &q, s_edge);
             } else {
                 pos = u; w = 0; q = 0;                                       // the last two positions of a short y: no string
             }
@@ -1362,9 +1575,11 @@ dfl_parse_kernel(DflCorpus c, const DflJob *__restrict__ jobs, int64_t n_jobs, i
 {
     __shared__ uint16_t s_l[DFL_L_CODES * DFL_PARSE_THREADS];
     __shared__ uint16_t s_d[DFL_D_CODES * DFL_PARSE_THREADS];
+    extern __shared__ __align__(16) uint8_t s_compact[];              // DFL_PARSE_THREADS x DflCompactTrees
     const DflConfig cfg = dfl_config(level);
     const int T = DFL_PARSE_THREADS, tid = threadIdx.x;
     uint16_t *lf = s_l + tid, *df = s_d + tid;
+    DflCompactTrees *ct = reinterpret_cast<DflCompactTrees *>(s_compact) + tid;
     DflTrees &tr = scratch[(size_t)blockIdx.x * T + tid];
     uint32_t accA[DFL_L_CODES + DFL_D_CODES], accB[DFL_L_CODES + DFL_D_CODES];
     for (;;) {
@@ -1388,7 +1603,7 @@ dfl_parse_kernel(DflCorpus c, const DflJob *__restrict__ jobs, int64_t n_jobs, i
         DflCanon cn;
         cn.n_sym = 0;
         if (jb.kind == 2) cn = dfl_canon_of(cp, jb.y);
-        const int how = dfl_pair_stream(d, fv, cfg, st, lf, T, df, T, tr, jb.kind == 2 ? &cn : nullptr, accA, accB);
+        const int how = dfl_pair_stream(d, fv, cfg, st, lf, T, df, T, tr, jb.kind == 2 ? &cn : nullptr, accA, accB, ct);
         out[jb.out] = how ? (int64_t)(st.bits >> 3) : -2;
     }
 }
@@ -1611,7 +1826,7 @@ template <typename T> static int dfl_upload(std::string &err, cudaStream_t strea
     return 0;
 }
 
-constexpr int DFL_PARSE_BLOCKS = 148 * 5;           // 40 KiB of counters per CTA: five CTAs per SM
+constexpr int DFL_PARSE_BLOCKS = 148 * 5;           // parse threads a batch is sized for (the kernel's CTAs loop over jobs)
 constexpr size_t DFL_BATCH = (size_t)DFL_PARSE_BLOCKS * 64;   // pair streams per junction batch: one per parse thread (6.3 GB of
                                                     // junction F per buffer, two buffers; the parse is latency-bound, so
                                                     // its throughput is the number of streams in flight)
@@ -1840,6 +2055,8 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
         }
         if (FQ && !st.d_FJQ2[0])
             for (int k = 0; k < 2; ++k) DCK(cudaMalloc(&st.d_FJQ2[k], sizeof(uint32_t) * batch * DFL_JSTRIDE));
+        DCK(cudaFuncSetAttribute(dfl_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(DFL_PARSE_THREADS * sizeof(DflCompactTrees))));
         if (!st.stream2) {
             // the parse kernel is a few long-running, latency-bound CTAs: give it priority over the junction kernel's
             // many short blocks, which would otherwise keep every SM full until they are all done
@@ -1883,7 +2100,7 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
                 DCK(cudaStreamWaitEvent(st.stream2, st.ev_j[k2], 0));
                 DCK(cudaMemsetAsync(st.d_counter2 + k2, 0, sizeof(unsigned long long), st.stream2));
                 const int blocks = (int)std::min<size_t>(((size_t)nb + DFL_PARSE_THREADS - 1) / DFL_PARSE_THREADS, parse_blocks);
-                dfl_parse_kernel<<<blocks, DFL_PARSE_THREADS, 0, st.stream2>>>(c, st.d_jobs2[k2], nb, level, st.d_F[li], FQ, st.d_FJ2[k2],
+                dfl_parse_kernel<<<blocks, DFL_PARSE_THREADS, DFL_PARSE_THREADS * sizeof(DflCompactTrees), st.stream2>>>(c, st.d_jobs2[k2], nb, level, st.d_F[li], FQ, st.d_FJ2[k2],
                                                                               FQ ? st.d_FJQ2[k2] : nullptr, st.d_ckpt[li], cp,
                                                                               st.d_scratch2[k2], st.d_counter2 + k2, d_out);
                 if (cudaGetLastError() != cudaSuccess) { err = "dfl_parse_kernel launch failed"; return -1; }

@@ -180,6 +180,7 @@ extern "C" int64_t emu_lz4_packed(const uint8_t *x, uint32_t lx, const uint8_t *
 // ---------------------------------------------------------------------------------------------
 // deflate path: the same index / F table / junction / checkpoint / parse logic the kernels run
 // ---------------------------------------------------------------------------------------------
+#define DFL_CHECK_COMPACT 1
 #include "../snacc_b200/csrc/deflate.cuh"
 
 struct EmuIndex { std::vector<uint32_t> order, bstart; };
@@ -347,7 +348,7 @@ extern "C" int64_t emu_deflate_size_ex(const uint8_t *x, uint32_t lx, const uint
             const uint32_t w0 = dfl_f_word(d, lx + yq, cfg, 0xffffffffu, &q0);
             if ((w & ~DFL_QDIFF) != (w0 & ~DFL_QDIFF) || ((w0 & DFL_QDIFF) && !(w & DFL_QDIFF)) || (want_q && q != q0)) ++mismatches;
         }
-        if (info) { info[2] = mismatches + emu_match_mismatches; info[3] = shortcuts; }
+        if (info) { info[2] = mismatches + emu_match_mismatches + (int32_t)dfl_compact_mismatch; info[3] = shortcuts; }
         fv.fx = Fx.data(); fv.fy = Fy.data(); fv.fj = FJ.data(); fv.jx0 = jx0; fv.jend = jx0 + jlen; fv.lx = lx;
         if (want_q) { fv.qx = ex.FQ.data(); fv.qy = ey.FQ.data(); fv.qj = FJQ.data(); }
         dfl_resume(st, d.s.n);
@@ -356,7 +357,9 @@ extern "C" int64_t emu_deflate_size_ex(const uint8_t *x, uint32_t lx, const uint
         DflCanon cn; cn.end = ec.end.data(); cn.code = ec.code.data(); cn.cum = ec.cum.data(); cn.n_sym = ec.n_sym;
         std::vector<uint32_t> accA(DFL_CUM_W), accB(DFL_CUM_W);
         const uint32_t strstart0 = st.strstart;
-        const int how = dfl_pair_stream(d, fv, cfg, st, lf.data(), 1, df.data(), 1, *tr, use_canon ? &cn : nullptr, accA.data(), accB.data());
+        DflCompactTrees *ct = new DflCompactTrees();
+        const int how = dfl_pair_stream(d, fv, cfg, st, lf.data(), 1, df.data(), 1, *tr, use_canon ? &cn : nullptr, accA.data(), accB.data(), ct);
+        delete ct;
         (void)strstart0;
         if (!how) {
             if (info) info[1] = 1;
@@ -374,4 +377,46 @@ extern "C" int64_t emu_deflate_size_ex(const uint8_t *x, uint32_t lx, const uint
 extern "C" int64_t emu_deflate_size(const uint8_t *x, uint32_t lx, const uint8_t *y, int64_t ly_, int level)
 {
     return emu_deflate_size_ex(x, lx, y, ly_, level, 1, nullptr);
+}
+
+// how many block costs the compacted trees have computed (and checked against the full ones) so far
+extern "C" int64_t emu_compact_checked() { return dfl_compact_checked; }
+
+// random symbol histograms: dfl_flush_block_compact against dfl_flush_block (bits, stored-candidate flag, last-block
+// alignment).  Returns the number of disagreements; *applied = how many cases the compact version accepted.
+extern "C" int64_t emu_flush_compact_fuzz(uint32_t seed, int32_t cases, int32_t *applied)
+{
+    uint64_t s = seed * 0x9E3779B97F4A7C15ull + 12345;
+    auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (uint32_t)(s >> 11); };
+    DflTrees *tr = new DflTrees();
+    DflCompactTrees *ct = new DflCompactTrees();
+    int64_t bad = 0; int32_t ok = 0;
+    for (int32_t c = 0; c < cases; ++c) {
+        uint16_t lf[DFL_L_CODES] = {0}, df[DFL_D_CODES] = {0};
+        const int kl = 1 + (int)(rnd() % 60), kd = (int)(rnd() % 31), shape = (int)(rnd() % 4);
+        uint32_t budget = 16383;
+        auto draw = [&]() -> uint32_t {                     // skewed frequencies: ties, powers of two, long tails
+            uint32_t f;
+            switch (shape) {
+                case 0: f = 1 + rnd() % 8; break;
+                case 1: f = 1u << (rnd() % 12); break;
+                case 2: f = 1 + rnd() % 2000; break;
+                default: f = (rnd() % 4 == 0) ? 1 + rnd() % 4000 : 1 + rnd() % 3;
+            }
+            f = f > budget ? budget : f;
+            budget -= f;
+            return f;
+        };
+        for (int k = 0; k < kl && budget; ++k) lf[shape == 3 && k < 4 ? "ACGT"[k] : rnd() % DFL_L_CODES] += (uint16_t)draw();
+        for (int k = 0; k < kd && budget; ++k) df[rnd() % DFL_D_CODES] += (uint16_t)draw();
+        lf[256] = 1;
+        const uint64_t stored = rnd() % 200000;
+        const bool last = rnd() & 1, can = rnd() & 1;
+        uint64_t b0 = rnd() % 64, b1 = b0; bool c0 = false, c1 = false;
+        dfl_flush_block(*tr, lf, 1, df, 1, stored, can, last, b0, &c0);
+        if (dfl_flush_block_compact(*ct, lf, 1, df, 1, stored, can, last, b1, &c1)) { ++ok; if (b0 != b1 || c0 != c1) ++bad; }
+    }
+    if (applied) *applied = ok;
+    delete tr; delete ct;
+    return bad;
 }

@@ -30,6 +30,8 @@ def emu():
     e.emu_lz4_packed.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int64]
     e.emu_deflate_size.restype = ctypes.c_int64
     e.emu_deflate_size.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]
+    e.emu_flush_compact_fuzz.restype = ctypes.c_int64
+    e.emu_flush_compact_fuzz.argtypes = [ctypes.c_uint32, ctypes.c_int32, ctypes.c_void_p]
     e.emu_deflate_size_ex.restype = ctypes.c_int64
     e.emu_deflate_size_ex.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_void_p]
@@ -221,3 +223,13 @@ def test_deflate_canonical_symbol_stream_shortcut(emu, level):
         if r != ref or r0 != ref or used0 or fell_back or (expect_used is not None and bool(used) != expect_used):
             bad.append((x.size, y.size, ref, r, r0, used, fell_back))
     assert not bad, bad
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_deflate_block_cost_on_compacted_trees_equals_zlib_tree_construction(emu, seed):
+    """dfl_flush_block_compact (Huffman trees built over the nonzero symbols only, the version the pair kernel keeps in
+    shared memory) against dfl_flush_block (trees.c restated, itself pinned against zlib through the size tests) on
+    random histograms: ties, power-of-two frequencies (length overflow), DNA-like shapes, stored candidates"""
+    applied = ctypes.c_int32()
+    assert emu.emu_flush_compact_fuzz(seed, 60000, ctypes.byref(applied)) == 0
+    assert applied.value > 20000
