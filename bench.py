@@ -308,6 +308,11 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     main_ms = sum(s["main_ms"] for s in stats) / len(stats)
+    traffic = None                                       # DRAM bytes per launch of the dominant kernel, from a committed ncu capture
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{codec}:{args.config}:{n}x{L}:n{world}")
+    except Exception:
+        pass
     per_launch_bytes = stats[0]["bytes"]                 # rank 0's pair-kernel launch: sum of len(x)+len(y) over its jobs
     achieved = per_launch_bytes / (main_ms * 1e-3) / 1e9
     line = {"metric": "ncd_pairs_per_s", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
@@ -316,11 +321,13 @@ def main():
             "algorithmic_GBps": bytes_total / wall_s / 1e9,
             "device_ms_per_step": 1e3 * timed_s / args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": ("lz4_pk_pair_kernel<linked>" if args.config != "c3" else "lz4_pk_pair_kernel<single-block>")
+                         "traffic": traffic, "kernel": ("lz4_pk_pair_kernel<linked>" if args.config != "c3" else "lz4_pk_pair_kernel<single-block>")
                                    if codec == "lz4" else "dfl_junction_kernel (sum over the step's batches)",
                          "peak_source": peak_src,
                          "note": "achieved = algorithmic bytes of one launch (sum of len(x)+len(y) over its pair jobs) / "
-                                 "its CUDA-event duration; the path is latency/integer bound, not HBM bound"},
+                                 "its CUDA-event duration; the path is latency/integer bound, not HBM bound; traffic (when not "
+                                 "null) = DRAM bytes of that launch measured by ncu (profiles/traffic.json): far below the "
+                                 "algorithmic bytes because y is staged once per CTA and x only enters through its checkpoint"},
             "e2e": {"value": pairs_per_step * args.steps / e2e_s, "unit": "pairs/s",
                     "h2d_bytes_per_step": int(corpus_host.numel() + so.nbytes + 4 * my_rows.size + 8 * (n * n + n)),
                     "d2h_bytes_per_step": int(8 * (stats[0]["jobs"] + my_rows.size) + 8 * n * n)},

@@ -2073,6 +2073,7 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
         std::vector<DflPair> pairs;
         auto run_pairs = [&](const std::vector<int64_t> *subset, int kind) -> int {
             const int64_t total = subset ? (int64_t)subset->size() : n_jobs;
+            cudaStream_t pstream = getenv("SNACC_DFL_NO_OVERLAP") ? stream : st.stream2;   // experiment knob
             DCK(cudaEventRecord(st.ev_j[0], stream));                  // everything queued so far (prep) precedes the parses
             DCK(cudaStreamWaitEvent(st.stream2, st.ev_j[0], 0));
             int64_t nbatch = 0;
@@ -2097,14 +2098,14 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
                 if (cudaGetLastError() != cudaSuccess) { err = "junction kernel launch failed"; return -1; }
                 DCK(cudaEventRecord(e1, stream));
                 DCK(cudaEventRecord(st.ev_j[k2], stream));
-                DCK(cudaStreamWaitEvent(st.stream2, st.ev_j[k2], 0));
-                DCK(cudaMemsetAsync(st.d_counter2 + k2, 0, sizeof(unsigned long long), st.stream2));
+                DCK(cudaStreamWaitEvent(pstream, st.ev_j[k2], 0));
+                DCK(cudaMemsetAsync(st.d_counter2 + k2, 0, sizeof(unsigned long long), pstream));
                 const int blocks = (int)std::min<size_t>(((size_t)nb + DFL_PARSE_THREADS - 1) / DFL_PARSE_THREADS, parse_blocks);
-                dfl_parse_kernel<<<blocks, DFL_PARSE_THREADS, DFL_PARSE_THREADS * sizeof(DflCompactTrees), st.stream2>>>(c, st.d_jobs2[k2], nb, level, st.d_F[li], FQ, st.d_FJ2[k2],
+                dfl_parse_kernel<<<blocks, DFL_PARSE_THREADS, DFL_PARSE_THREADS * sizeof(DflCompactTrees), pstream>>>(c, st.d_jobs2[k2], nb, level, st.d_F[li], FQ, st.d_FJ2[k2],
                                                                               FQ ? st.d_FJQ2[k2] : nullptr, st.d_ckpt[li], cp,
                                                                               st.d_scratch2[k2], st.d_counter2 + k2, d_out);
                 if (cudaGetLastError() != cudaSuccess) { err = "dfl_parse_kernel launch failed"; return -1; }
-                DCK(cudaEventRecord(st.ev_p[k2], st.stream2));
+                DCK(cudaEventRecord(st.ev_p[k2], pstream));
                 *launches += 2;
                 // the host buffers are reused for the next batch: wait until this batch's uploads are done (the
                 // kernels of the previous batch keep the GPU busy meanwhile)
