@@ -516,8 +516,6 @@ static PkGeometry pk_geometry(const snacc_ctx *ctx, bool u16)
     const size_t l_fit = (PK_SMEM_MAX - l_fixed) / l_stream;
     g.lanes = l_fit >= 104 ? 26 : 32;
     g.warps = l_fit >= 104 ? 4 : (int)std::max<size_t>(1, l_fit / 32);
-    // experiment knob: the same 104 streams as 8 warps x 13 lanes (two warps per scheduler)
-    if (l_fit >= 104 && getenv("SNACC_PK_LANES") && atoi(getenv("SNACC_PK_LANES")) == 13) { g.lanes = 13; g.warps = 8; }
     g.smem = l_fixed + (size_t)g.warps * g.lanes * l_stream;
     g.T = g.lanes * g.warps;
     return g;
@@ -560,7 +558,6 @@ static int pk_launch(snacc_ctx *ctx, bool u16, const PkGeometry &g, const std::v
     } while (0)
     if (u16) PK_GO(1, PK_S_LANES, ctx->d_alias4);
     else if (g.lanes == 26) PK_GO(2, 26, ctx->d_alias5);
-    else if (g.lanes == 13) PK_GO(2, 13, ctx->d_alias5);
     else PK_GO(2, 32, ctx->d_alias5);
 #undef PK_GO
     CK(cudaEventRecord(ctx->evm1, ctx->stream));
