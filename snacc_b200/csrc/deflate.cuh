@@ -336,7 +336,7 @@ SNACC_HD uint32_t dfl_longest_k6(const DflStream &d, uint32_t p, uint32_t nice, 
         const uint32_t c = lx - k;
         if (c <= limit) { over = true; break; }
         if (edge) {
-            // a candidate only counts from 6 equal bytes on: most positions are done with one register compare
+            // a candidate only counts from 6 equal bytes on: most positions are done with one compare
             if (((scan ^ edge[k]) & 0xffffffffffffull) == 0) DFL_K6_VISIT8(c, edge[k]);
         } else {
             DFL_K6_VISIT(c);
@@ -1511,23 +1511,31 @@ dfl_junction_kernel(DflCorpus c, const DflPair *__restrict__ pairs, int32_t n_pa
         const uint32_t *fqy = FQ ? FQ + c.poff[y] : nullptr;
         const uint16_t *ho = c.head_order + (size_t)y * DFL_JY, *hv = c.head_visit + (size_t)y * DFL_JY;
         const uint32_t u_end = jxl + jyl;
+        const bool by_hash = impl != 3 || level != 9;
         const int32_t xi = pairs[b].x;
         const DflTail6 t6{c.tail6_order + (size_t)xi * DFL_T6, c.tail6_start + (size_t)xi * (DFL_H6 + 1), dfl_tail6_t0(lx)};
         const uint16_t *tcx = c.tail_cnt + (size_t)xi * DFL_HASH;
-        __shared__ uint64_t s_edge[6];
-        __syncthreads();
-        if (threadIdx.x < 6) s_edge[threadIdx.x] = lx >= threadIdx.x ? ld64(d.s, lx - threadIdx.x) : 0;
-        __syncthreads();
+        // the 8 bytes at lx - k, k = 0..5 (dfl_longest_k6): loaded by six lanes, handed round by shuffle -- no block barrier,
+        // the warps of a block finish a pair at very different times
+        uint64_t edge[6];
+        {
+            const uint32_t ln = threadIdx.x & 31;
+            const uint64_t mine = (ln < 6 && lx >= ln) ? ld64(d.s, lx - ln) : 0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) edge[k] = __shfl_sync(0xffffffffu, mine, k);
+        }
         for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < u_end; u += gridDim.x * blockDim.x) {
             uint32_t q, w, pos;
             if (u < jxl) {
                 pos = u;
                 w = dfl_f_word(d, jx0 + u, cfg, 0xffffffffu, &q);
             } else if (u - jxl < n_head) {
-                const uint32_t yq = ho[u - jxl];
+                // with the 6-byte shortcut nearly every lane takes a handful of private candidates: position order keeps
+                // the table reads and the result writes coalesced; the chain walk wants (hash, position) order instead
+                const uint32_t yq = by_hash ? ho[u - jxl] : u - jxl;
                 pos = jxl + yq;
                 w = dfl_junction_word(d, lx + yq, cfg, fy[yq], hv[yq], fqy != nullptr, fqy ? fqy[yq] : 0u, impl == 3 ? &t6 : nullptr,
-                                      tcx, &q, s_edge);
+                                      tcx, &q, edge);
             } else {
                 pos = u; w = 0; q = 0;                                       // the last two positions of a short y: no string
             }
