@@ -40,7 +40,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="snacc_b200")
-    ap.add_argument("--codec", default="lz4", choices=["lz4", "gzip"])
+    ap.add_argument("--codec", default="lz4", choices=["lz4", "gzip", "zlib"])
     ap.add_argument("--genomes", type=int, default=N_GENOMES)
     ap.add_argument("--length", type=int, default=GENOME_LEN)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -533,16 +533,16 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, u
             raw_old = m;
             if (go) PK_TST(slot, p);
         }
-        // speculative table lookups: next probe at p+1 (miss) or p+4..p+8 (match of that length)
+        // speculative table lookups: next probe at p+1 (miss) or p+4..p+6 (match of that length)
         const uint32_t o1 = PK_OFF((Ws >> 10) & MASK), o2 = PK_OFF((Ws >> 12) & MASK), o3 = PK_OFF((Ws >> 14) & MASK);
         const uint32_t o4 = PK_OFF((Ws >> 16) & MASK), o5 = PK_OFF((Ws >> 18) & MASK), o6 = PK_OFF((Ws >> 20) & MASK);
-        const uint32_t o7 = PK_OFF((Ws >> 22) & MASK), o8 = PK_OFF(pk_fsr(Ws, Wt, 24) & MASK);
-        const uint32_t m1 = PK_TLD(tab_a + o1), m4 = PK_TLD(tab_a + o4), m5 = PK_TLD(tab_a + o5), m6 = PK_TLD(tab_a + o6),
-                       m7 = PK_TLD(tab_a + o7), m8 = PK_TLD(tab_a + o8);
-        uint32_t e1 = 0, e4 = 0, e5 = 0, e6 = 0, e7 = 0, e8 = 0;
+        // (lengths 7 and 8 are 6 % of the matches: not worth two more speculative lookups per iteration, they take the
+        // on-demand path below together with 9..11)
+        const uint32_t m1 = PK_TLD(tab_a + o1), m4 = PK_TLD(tab_a + o4), m5 = PK_TLD(tab_a + o5), m6 = PK_TLD(tab_a + o6);
+        uint32_t e1 = 0, e4 = 0, e5 = 0, e6 = 0;
         if (KIND == 2) {
             e1 = pk_lds32(PK_EWA(o1)); e4 = pk_lds32(PK_EWA(o4)); e5 = pk_lds32(PK_EWA(o5));
-            e6 = pk_lds32(PK_EWA(o6)); e7 = pk_lds32(PK_EWA(o7)); e8 = pk_lds32(PK_EWA(o8));
+            e6 = pk_lds32(PK_EWA(o6));
         }
         uint32_t Nlo, Nhi;
         PK_RING32(p - 4 - lx, Nlo, Nhi);                    // window for the next iteration
@@ -565,12 +565,12 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, u
         const uint32_t lit = pend - k;
         const uint32_t add = 3 + lit + (lit >= 15 ? (lit - 15) / 255 + 1 : 0);   // token + offset + literals
         const uint32_t pn = hit ? p + common : p + 1;
-        const bool c4 = common == 4, c5 = common == 5, c6 = common == 6, c7 = common == 7;
-        uint32_t sp = pk_sel(c4, o2, pk_sel(c5, o3, pk_sel(c6, o4, pk_sel(c7, o5, o6))));      // slot of the insert pn-2
-        uint32_t sn = pk_sel(c4, o4, pk_sel(c5, o5, pk_sel(c6, o6, pk_sel(c7, o7, o8))));      // slot of pn
-        uint32_t mn = pk_sel(c4, m4, pk_sel(c5, m5, pk_sel(c6, m6, pk_sel(c7, m7, m8))));
-        uint32_t en = KIND == 2 ? pk_sel(c4, e4, pk_sel(c5, e5, pk_sel(c6, e6, pk_sel(c7, e7, e8)))) : 0;
-        if (commit && common > 8) {                         // 9..11: not speculated, look the slots up now
+        const bool c4 = common == 4, c5 = common == 5;
+        uint32_t sp = pk_sel(c4, o2, pk_sel(c5, o3, o4));                                    // slot of the insert pn-2
+        uint32_t sn = pk_sel(c4, o4, pk_sel(c5, o5, o6));                                    // slot of pn
+        uint32_t mn = pk_sel(c4, m4, pk_sel(c5, m5, m6));
+        uint32_t en = KIND == 2 ? pk_sel(c4, e4, pk_sel(c5, e5, e6)) : 0;
+        if (commit && common > 6) {                         // 7..11: not speculated, look the slots up now
             sp = PK_OFF(pk_fsr(Ws, Wt, 2 * (common + 2)) & MASK);
             sn = PK_OFF(pk_fsr(Ws, Wt, 2 * (common + 4)) & MASK);
             mn = PK_TLD(tab_a + sn);
