@@ -5,9 +5,9 @@
 
 Workload (BASELINE.json configs[3], "c4"): 512 synthetic E. coli-sized (5 Mbp) mutated-phylogeny genomes,
 LZ4-frame NCD.  A *step* is the WHOLE job: C(i) for all 512 genomes, C(i.j) for all 512 x 512 ordered
-pairs (the reference's semantics, cli.py:104-136) and the float64 NCD matrix.  With N GPUs the rows of
-the job matrix are split into one contiguous band per rank (strong scaling; no data-path collective, the
-row bands are all-gathered at the end of the step).  Metric: NCD pairs/s, where -- as in SURVEY.md 8d -- a
+pairs (the reference's semantics, cli.py:104-136) and the float64 NCD matrix.  With N GPUs the columns of
+the job matrix are split into one contiguous band per rank -- all x against the rank's share of the y --
+(strong scaling; no data-path collective, the bands are all-gathered at the end of the step).  Metric: NCD pairs/s, where -- as in SURVEY.md 8d -- a
 pair is an unordered {i,j} entry of the finished matrix and costs two ordered compressor jobs, so
 pairs = ordered pair jobs / 2 (131072 per step).  `value` is timed with the corpus resident in HBM;
 `e2e` re-uploads the corpus from pinned host memory through the C ABI (and re-packs it) and reads the
@@ -154,8 +154,8 @@ def main():
     config = {"workload": workload, "n_genomes": n, "genome_len": L, "codec": codec,
               "seed": SEED, "pair_unit": "ordered pair jobs / 2 (an unordered {i,j} costs two ordered jobs, cli.py:120-136); N^2/2 per step",
               "l2_policy": "inputs larger than L2 (corpus %.2f GB per GPU, replicated)" % (n * L / 1e9),
-              "sharding": f"contiguous row band [r*N/{world}, (r+1)*N/{world}) of the job matrix per rank, no data-path collective; "
-                          "row bands gathered with all_gather at the end of the step"}
+              "sharding": f"contiguous column band [r*N/{world}, (r+1)*N/{world}) of the job matrix per rank (all x against the "
+                          "rank's y), no data-path collective; bands gathered with all_gather at the end of the step"}
 
     import numpy as np
 
@@ -217,40 +217,40 @@ def main():
     del corpus_dev
     torch.cuda.empty_cache()
 
-    my_rows = np.arange(rank * n // world, (rank + 1) * n // world, dtype=np.int32)   # contiguous band: a rectangle
-    step_jobs = int(my_rows.size) * n
-    step_bytes = float(n * np.sum(lengths[my_rows]) + my_rows.size * np.sum(lengths))
+    # contiguous COLUMN band per rank (all x against the rank's share of the y): a tile of the LZ4 kernel is "one y,
+    # up to 104 x", so with every row on every rank the tiles stay full for any number of ranks
+    my_cols = np.arange(rank * n // world, (rank + 1) * n // world, dtype=np.int32)
+    all_rows = np.arange(n, dtype=np.int32)
+    step_jobs = int(my_cols.size) * n
+    step_bytes = float(n * np.sum(lengths[my_cols]) + my_cols.size * np.sum(lengths))
 
     def run_step(e2e):
-        """one full pass: C(i) for the rank's rows, S(i,j) for rows x all columns, gather, NCD on rank 0"""
+        """one full pass: C(i) for every sequence, S(i,j) for all rows x the rank's columns, gather, NCD on rank 0"""
         if e2e:
             eng.upload(corpus_host.numpy(), so)          # H2D of the step's inputs from pinned memory (+ repack)
         else:
             eng.set_option("invalidate_caches", 1)       # nothing (prefix checkpoints ...) survives from the last step
-        c = eng.single_sizes(codec, my_rows)
+        c = eng.single_sizes(codec, all_rows)            # every rank: the same pass leaves the checkpoints of every x
         ms1, l1 = eng.stat("total_kernel_ms"), eng.stat("launches")
-        band = args.band or (1024 if args.config == "c3" else int(my_rows.size))
-        s = np.empty((my_rows.size, n), dtype=np.int64)
+        band = args.band or (1024 if args.config == "c3" else n)
+        s = np.empty((n, my_cols.size), dtype=np.int64)
         ms2 = l2 = main_ms = packed = 0
-        for a in range(0, my_rows.size, band):           # sizes come back to the host inside (D2H)
-            nb = min(band, my_rows.size - a)
-            s[a:a + nb] = eng.tile_sizes(codec, int(my_rows[a]), nb, 0, n)
+        for a in range(0, n, band):                      # sizes come back to the host inside (D2H)
+            nb = min(band, n - a)
+            s[a:a + nb] = eng.tile_sizes(codec, a, nb, int(my_cols[0]), int(my_cols.size))
             ms2 += eng.stat("total_kernel_ms"); l2 += eng.stat("launches"); main_ms += eng.stat("main_kernel_ms")
             packed += eng.stat("packed_jobs") if codec == "lz4" else 0
         if world > 1:
-            # gather the row bands: rank r owns rows [r*n/world, (r+1)*n/world)  (2 MiB of int64 at n = 512)
+            # gather the column bands (transposed: rank r owns columns [r*n/world, (r+1)*n/world); 2 MiB of int64 at n = 512)
             per = (n + world - 1) // world
-            cbuf = torch.zeros(per, dtype=torch.int64, device=dev); cbuf[:c.size] = torch.from_numpy(c).to(dev)
-            sbuf = torch.zeros(per * n, dtype=torch.int64, device=dev); sbuf[:s.size] = torch.from_numpy(s.ravel()).to(dev)
-            cg = [torch.empty_like(cbuf) for _ in range(world)]
+            sbuf = torch.zeros(per * n, dtype=torch.int64, device=dev)
+            sbuf[:s.size] = torch.from_numpy(np.ascontiguousarray(s.T).ravel()).to(dev)
             sg = [torch.empty_like(sbuf) for _ in range(world)]
-            dist.all_gather(cg, cbuf)
             dist.all_gather(sg, sbuf)
-            C = np.zeros(n, dtype=np.int64); S = np.zeros((n, n), dtype=np.int64)
+            C = c; S = np.zeros((n, n), dtype=np.int64)
             for r in range(world):
-                rr = np.arange(r * n // world, (r + 1) * n // world)
-                C[rr] = cg[r][:rr.size].cpu().numpy()
-                S[rr] = sg[r][:rr.size * n].cpu().numpy().reshape(rr.size, n)
+                cc = np.arange(r * n // world, (r + 1) * n // world)
+                S[:, cc] = sg[r][:cc.size * n].cpu().numpy().reshape(cc.size, n).T
         else:
             C, S = c, s.reshape(n, n)
         launches = int(l1 + l2)
@@ -329,8 +329,8 @@ def main():
                                  "null) = DRAM bytes of that launch measured by ncu (profiles/traffic.json): far below the "
                                  "algorithmic bytes because y is staged once per CTA and x only enters through its checkpoint"},
             "e2e": {"value": pairs_per_step * args.steps / e2e_s, "unit": "pairs/s",
-                    "h2d_bytes_per_step": int(corpus_host.numel() + so.nbytes + 4 * my_rows.size + 8 * (n * n + n)),
-                    "d2h_bytes_per_step": int(8 * (stats[0]["jobs"] + my_rows.size) + 8 * n * n)},
+                    "h2d_bytes_per_step": int(corpus_host.numel() + so.nbytes + 4 * n + 8 * (n * n + n)),
+                    "d2h_bytes_per_step": int(8 * (stats[0]["jobs"] + n) + 8 * n * n)},
             "packed_jobs_per_step": stats[0]["packed"],
             "gpu_launches": int(sum(s["launches"] for s in stats)),
             "clocks": clocks, "corpus_gen_s": gen_s, "checksum": stats[-1]["check"]}

@@ -92,7 +92,7 @@ def compute_distance(x, y, cxy, cyx):
 
 
 def _row_partition(n, world):
-    """rows owned by each rank: contiguous bands (see sharding.owned_rows)"""
+    """columns owned by each rank: contiguous bands (see sharding.owned_cols)"""
     return [np.arange(r * n // world, (r + 1) * n // world, dtype=np.int64) for r in range(world)]
 
 

@@ -1,9 +1,12 @@
-"""Row sharding of the ordered-pair job matrix across GPUs.
+"""Sharding of the ordered-pair job matrix across GPUs.
 
-Jobs are independent: there is no data-path collective.  The corpus is replicated (one broadcast), rank
-r owns the contiguous row band ``[r*N/W, (r+1)*N/W)`` of S (so every x prefix state is built by exactly one
-rank), and the int64 row blocks are gathered at the end.  With ``torch.distributed`` uninitialised this is the
-single-GPU path.  The same code runs under the ``gloo`` backend on CPU for the host-logic tests, with
+Jobs are independent: there is no data-path collective.  The corpus is replicated (one broadcast), rank r owns the
+contiguous COLUMN band ``[r*N/W, (r+1)*N/W)`` of S -- all x against its share of the y -- and the int64 blocks are
+gathered at the end.  Columns, not rows, because a tile of the LZ4 kernel is "one y, up to 104 x": with all N rows on
+every rank the tiles stay full however many ranks there are (row bands leave them 62 % full at 8 ranks), and the
+per-sequence work every rank then repeats (C(x) and the prefix checkpoint of every x) runs one sequence per CTA in
+parallel, so it costs the same wall time for N sequences as for N/W.  With ``torch.distributed`` uninitialised this
+is the single-GPU path.  The same code runs under the ``gloo`` backend on CPU for the host-logic tests, with
 ``size_fn`` standing in for the GPU engine.
 """
 import numpy as np
@@ -22,10 +25,13 @@ def _dist():
     return None
 
 
-def owned_rows(n, rank, world):
-    """contiguous row band of rank `rank`: a rectangle of the job matrix, which the library runs without
+def owned_cols(n, rank, world):
+    """contiguous column band of rank `rank`: a rectangle of the job matrix, which the library runs without
     per-job arrays (snacc_tile_sizes)"""
     return np.arange(rank * n // world, (rank + 1) * n // world, dtype=np.int64)
+
+
+owned_rows = owned_cols          # the bands of gather_rows (which gathers the TRANSPOSED column blocks) are the same
 
 
 def broadcast_corpus(files, dist, device=None):
@@ -51,7 +57,7 @@ def broadcast_corpus(files, dist, device=None):
 
 
 def gather_rows(local_block, n, dist):
-    """all ranks get the full n x width int64 matrix from per-rank row blocks (rows r, r+W, ...)"""
+    """all ranks get the full n x width int64 matrix from per-rank blocks of consecutive rows (owned_rows)"""
     import torch
     world = dist.get_world_size()
     width = local_block.shape[1]
@@ -84,12 +90,12 @@ def ncd_host(C, S, fast_mode=False, bias=GETSIZEOF_BIAS):
 
 
 def all_pairs(files, algorithm, reverse_complement, fast_mode, engine=None, rows_per_call=None, size_fn=None):
-    """Returns (labels, C, S, D).  ``size_fn(data, so, ro, rc, rows) -> (C_rows, S_rows)`` replaces the GPU
+    """Returns (labels, C, S, D).  ``size_fn(data, so, ro, rc, cols) -> (C_all, S[:, cols])`` replaces the GPU
     engine in CPU tests."""
     dist = _dist()
     n = len(files)
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
-    rows = owned_rows(n, rank, world)
+    cols = owned_cols(n, rank, world)
     own_engine = None
     if size_fn is None:
         from .engine import Engine
@@ -108,34 +114,39 @@ def all_pairs(files, algorithm, reverse_complement, fast_mode, engine=None, rows
         else:
             data, so, ro = fasta.load_corpus(files)
             engine.upload(data, so, ro, reverse_complement)
-        C_rows = engine.single_sizes(algorithm, rows.astype(np.int32)) if rows.size else np.zeros(0, np.int64)
-        S_rows = np.zeros((rows.size, n), dtype=np.int64)
-        step = rows_per_call or max(1, rows.size)
-        for a in range(0, rows.size, step):
-            rr = rows[a:a + step]
+        C = engine.single_sizes(algorithm)                  # every rank: all x (also leaves their prefix checkpoints)
+        S_cols = np.zeros((n, cols.size), dtype=np.int64)
+        step = rows_per_call or max(1, n)
+        for a in range(0, n, step):
+            nr = min(step, n - a)
+            if not cols.size:
+                break
             if fast_mode:
-                xs = np.concatenate([np.full(n - r, r, dtype=np.int32) for r in rr]) if rr.size else np.zeros(0, np.int32)
-                ys = np.concatenate([np.arange(r, n, dtype=np.int32) for r in rr]) if rr.size else np.zeros(0, np.int32)
-                vals = engine.pair_sizes(algorithm, xs, ys)
-                k = 0
-                for i, r in enumerate(rr):
-                    S_rows[a + i, r:] = vals[k:k + n - r]
-                    k += n - r
-            elif rr.size:
-                S_rows[a:a + rr.size] = engine.tile_sizes(algorithm, int(rr[0]), int(rr.size), 0, n)
+                # upper triangle only: rows a..a+nr-1 against the owned columns at or right of the row
+                xs, ys = [], []
+                for r in range(a, a + nr):
+                    cc = cols[cols >= r]
+                    xs.append(np.full(cc.size, r, dtype=np.int32)); ys.append(cc.astype(np.int32))
+                xs = np.concatenate(xs) if xs else np.zeros(0, np.int32)
+                ys = np.concatenate(ys) if ys else np.zeros(0, np.int32)
+                if xs.size:
+                    vals = engine.pair_sizes(algorithm, xs, ys)
+                    S_cols[xs, ys - int(cols[0])] = vals
+            else:
+                S_cols[a:a + nr] = engine.tile_sizes(algorithm, a, nr, int(cols[0]), int(cols.size))
     else:
         if dist:
             t, so, ro = broadcast_corpus(files, dist, None)
             data = t.numpy()
         else:
             data, so, ro = fasta.load_corpus(files)
-        C_rows, S_rows = size_fn(data, so, ro, reverse_complement, rows)
+        C, S_cols = size_fn(data, so, ro, reverse_complement, cols)
+    C = np.asarray(C, dtype=np.int64)
     if dist:
-        # one gather of [S rows | C] per rank; no collective on the data path before this point
-        full = gather_rows(np.concatenate([S_rows, np.asarray(C_rows, dtype=np.int64)[:, None]], axis=1), n, dist)
-        S, C = np.ascontiguousarray(full[:, :n]), np.ascontiguousarray(full[:, n])
+        # one gather of the (transposed) column blocks; no collective on the data path before this point
+        S = np.ascontiguousarray(gather_rows(np.ascontiguousarray(S_cols.T), n, dist).T)
     else:
-        S, C = S_rows, C_rows
+        S = S_cols
     if fast_mode:
         iu = np.triu_indices(n, 1)
         S = S.copy()

@@ -213,6 +213,37 @@ def test_megabase_genomes_gzip(engine):
     assert np.array_equal(engine.single_sizes("zlib"), np.array([_ref_len(s, "zlib") for s in g]))
 
 
+def test_full_size_genomes_gzip(engine):
+    """c5 shape: 5 Mbp genomes, gzip level 9 -- every shortcut of the deflate path at full size (≈ 50 blocks per stream,
+    ≈ 35 of them taken from the canonical symbol stream, several window slides inside the junction) against zlib 1.3
+    run on all host cores; and the same sizes with the shortcuts switched off"""
+    from snacc_b200 import synth
+    g = synth.phylogeny(3, 5_000_000, seed=5)
+    n = len(g)
+    engine.upload_sequences(g)
+    C = engine.single_sizes("gzip")
+    S = engine.tile_sizes("gzip", 0, n, 0, n)
+    assert engine.stat("deflate_serial_jobs") == 0
+    corpus = np.concatenate(g)
+    so = np.zeros(n + 1, dtype=np.uint64)
+    so[1:] = np.cumsum([x.size for x in g])
+    xs = np.concatenate([np.repeat(np.arange(n, dtype=np.int32), n), np.arange(n, dtype=np.int32)])
+    ys = np.concatenate([np.tile(np.arange(n, dtype=np.int32), n), np.full(n, -1, dtype=np.int32)])      # y < 0: x alone
+    threads = len(os.sched_getaffinity(0))
+    sizes = olib.ref_batch_sizes(corpus, so, xs, ys, "gzip", threads)
+    ref = sizes[:n * n].reshape(n, n)
+    assert np.array_equal(S, ref)
+    assert np.array_equal(C, sizes[n * n:])
+    for opt in ("deflate_canonical", "deflate_index6"):
+        engine.set_option(opt, 0)
+        engine.set_option("invalidate_caches", 1)
+        try:
+            assert np.array_equal(engine.tile_sizes("gzip", 0, 2, 0, n), ref[:2])
+        finally:
+            engine.set_option(opt, 1)
+    engine.set_option("invalidate_caches", 1)
+
+
 def test_lz4_stale_table_slots(engine):
     """A/T-only stretches of 66 k - 300 k bases between ACGT stretches: slots of k-mers with C/G age far beyond the
     131072 positions the 17-bit slot encoding can tell apart; the rolling sweep must have retired them"""

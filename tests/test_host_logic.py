@@ -102,7 +102,7 @@ def _free_port():
 
 
 def _oracle_size_fn(algorithm):
-    def fn(data, so, ro, rc, rows):
+    def fn(data, so, ro, rc, cols):
         from oracle import lib
         from oracle.fasta_shim import COMPLEMENT_TABLE
         raw = data.tobytes()
@@ -115,9 +115,9 @@ def _oracle_size_fn(algorithm):
                 seqs.append(b"".join(parts))
             else:
                 seqs.append(raw[so_l[i]:so_l[i + 1]])
-        C = np.array([lib.compressed_len(seqs[r], algorithm) for r in rows], dtype=np.int64)
-        S = np.array([[lib.compressed_len(seqs[r] + s, algorithm) for s in seqs] for r in rows],
-                     dtype=np.int64).reshape(len(rows), len(seqs))
+        C = np.array([lib.compressed_len(s, algorithm) for s in seqs], dtype=np.int64)
+        S = np.array([[lib.compressed_len(s + seqs[c], algorithm) for c in cols] for s in seqs],
+                     dtype=np.int64).reshape(len(seqs), len(cols))
         return C, S
     return fn
 
@@ -134,8 +134,8 @@ def _worker(rank, world, port, files, q):
         dist.destroy_process_group()
 
 
-def test_row_sharding_world_size_2_gloo(golden_dir):
-    """N > 1 path on CPU: rank 0 parses + broadcasts, rows are split round-robin, one gather at the end."""
+def test_column_sharding_world_size_2_gloo(golden_dir):
+    """N > 1 path on CPU: rank 0 parses + broadcasts, every rank takes a column band, one gather at the end."""
     import torch.multiprocessing as mp
     d = Path(golden_dir) / "fasta"
     files = [f for f in gcli.collect_files([str(d)]) if not f.name.startswith("big")]
@@ -155,8 +155,8 @@ def test_row_sharding_world_size_2_gloo(golden_dir):
         assert np.array_equal(np.array(D), snacc_oracle.ncd_from_sizes(C1, S1))
 
 
-def test_owned_rows_partition():
+def test_owned_cols_partition():
     for n in (1, 7, 8, 512):
         for w in (1, 2, 4, 8):
-            rows = np.concatenate([sharding.owned_rows(n, r, w) for r in range(w)])
-            assert sorted(rows.tolist()) == list(range(n))
+            cols = np.concatenate([sharding.owned_cols(n, r, w) for r in range(w)])
+            assert sorted(cols.tolist()) == list(range(n))

@@ -1,4 +1,4 @@
 set -x
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 3 > gpurun_out/r1d_bench_n2.json 2> gpurun_out/r1d_bench_n2.err
-tail -c 1500 gpurun_out/r1d_bench_n2.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 1 > gpurun_out/r1d_ref_n2.json 2>&1
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 > gpurun_out/r2e_lz4_n2.json 2> gpurun_out/r2e_lz4_n2.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --config c5 --genomes 1024 --steps 1 --warmup 1 > gpurun_out/r2e_gzip1024_n2.json 2> gpurun_out/r2e_gzip1024_n2.err
+tail -c 400 gpurun_out/r2e_lz4_n2.err; tail -c 400 gpurun_out/r2e_gzip1024_n2.err
