@@ -4,7 +4,7 @@ import shutil
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsnacc_b200.so")
+LIB_PATH = os.environ.get("SNACC_B200_LIB") or os.path.join(HERE, "libsnacc_b200.so")   # override: experiments only
 SOURCES = [os.path.join(HERE, "csrc", "api.cu")]
 HEADERS = [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "lz4.cuh", "deflate.cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "snacc_b200.h")]
