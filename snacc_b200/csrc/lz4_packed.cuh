@@ -850,11 +850,7 @@ __device__ void pk_single_run(PkState &st, PkTab<KIND, 1> &tab, PkView &v, PkRin
                         limit = tmin(stop, snap_bs);
                     }
                 }
-#ifdef PK_SINGLE_GENERAL
-                while (st.phase != PK_DONE && pk_next_pos(st) < limit) pk_step<KIND, 1, false>(st, tab, v, n, 0);
-#else
                 pk_run<KIND, 1>(st, tab, v, n, limit, 1u);
-#endif
             }
             s_more = (!touched && st.phase != PK_DONE && !rg.complete()) ? 1u : 0u;
         }
