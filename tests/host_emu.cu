@@ -420,3 +420,7 @@ extern "C" int64_t emu_flush_compact_fuzz(uint32_t seed, int32_t cases, int32_t 
     delete tr; delete ct;
     return bad;
 }
+
+// step counters of the packed LZ4 parse since the library was loaded: [0] general steps (pk_step), [1] steps inside the
+// speculative loop (pk_turbo)
+extern "C" void emu_lz4_step_counts(uint64_t *out) { out[0] = pk_general_steps; out[1] = pk_turbo_steps; }
