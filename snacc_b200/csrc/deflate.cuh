@@ -17,8 +17,21 @@
 //      F_x(p) holds for p <= len(x)-258, F_y(q) for q >= 32507 (window entirely inside y).  It is computed
 //      once per SEQUENCE; each pair job only recomputes the junction (<= 257 + 32768 positions);
 //   3. what remains serial per stream is the lazy-evaluation state machine over F (one table read per
-//      step) plus the Huffman cost of each 16383-symbol block (dfl_parse_kernel, one thread per job);
-//      the parse of the x part is shared through a per-x checkpoint taken at the junction start.
+//      step) plus the Huffman cost of each 16383-symbol block; the parse of the x part is shared through a
+//      per-x checkpoint taken at the junction start, and the parse of the y part -- once it has
+//      synchronised with the parse of y alone, a few symbols after the junction -- is taken from the
+//      recorded symbol stream of y (cumulative histograms give each block's symbol counts): see
+//      "canonical symbol stream" below.  A pair stream then costs its junction plus ~34 tree constructions;
+//   4. the 3-byte hash chain itself is rarely walked: a second index on a hash of 6 bytes finds the
+//      handful of candidates that can still matter (dfl_match_word, dfl_longest_k6), and the junction walk
+//      of a position continues the walk the position had in y alone (dfl_longest_cont).  Every shortcut
+//      is taken only where it is provably the same as the chain walk and has a switch for tests.
+//
+// Kernels, in the order a call runs them: dfl_radix_kernel / dfl_radix_scan_kernel / dfl_index_bounds_kernel /
+// dfl_index_fill_kernel (indexes), dfl_head_kernel, dfl_tail6_kernel (head order, tail packs),
+// dfl_match_kernel (F), dfl_prep_kernel (sequence alone: size, checkpoint, symbol stream),
+// dfl_cum_chunk_kernel / dfl_cum_scan_kernel (cumulative histograms), then per batch of pair streams
+// dfl_junction_kernel and dfl_parse_kernel.
 //
 // Rules restated from zlib 1.3 (each pinned by oracle/deflate_oracle.c against libz): hash =
 // ((b0<<10)^(b1<<5)^b2)&0x7fff; a search happens only if the chain head is within MAX_DIST (32506) and is

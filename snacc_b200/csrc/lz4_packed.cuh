@@ -443,7 +443,7 @@ SNACC_HD uint32_t pk_reduce_or(uint32_t mask, uint32_t v)
 #endif
 }
 
-template <int KIND, int STRIDE>
+template <int KIND, int STRIDE, bool LAZY>
 SNACC_HD void pk_turbo(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, uint32_t stop, uint32_t mask, bool work)
 {
     typedef PkTab<KIND, STRIDE> Tab;
@@ -538,11 +538,17 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, u
         const uint32_t o4 = PK_OFF((Ws >> 16) & MASK), o5 = PK_OFF((Ws >> 18) & MASK), o6 = PK_OFF((Ws >> 20) & MASK);
         // (lengths 7 and 8 are 6 % of the matches: not worth two more speculative lookups per iteration, they take the
         // on-demand path below together with 9..11)
-        const uint32_t m1 = PK_TLD(tab_a + o1), m4 = PK_TLD(tab_a + o4), m5 = PK_TLD(tab_a + o5), m6 = PK_TLD(tab_a + o6);
-        uint32_t e1 = 0, e4 = 0, e5 = 0, e6 = 0;
-        if (KIND == 2) {
-            e1 = pk_lds32(PK_EWA(o1)); e4 = pk_lds32(PK_EWA(o4)); e5 = pk_lds32(PK_EWA(o5));
-            e6 = pk_lds32(PK_EWA(o6));
+        // With one lane per warp (the singles pass, STRIDE 1) the loop is bound by its dependency chain and the table
+        // words of all four candidates slots are fetched ahead; with 26 or 32 lanes it is bound by instruction issue
+        // (measured: +10 % for the pair kernel, 2.2x slower singles pass) and the one slot that is needed is read
+        // once it is known.
+        uint32_t m1 = 0, m4 = 0, m5 = 0, m6 = 0, e1 = 0, e4 = 0, e5 = 0, e6 = 0;
+        if (!LAZY) {
+            m1 = PK_TLD(tab_a + o1); m4 = PK_TLD(tab_a + o4); m5 = PK_TLD(tab_a + o5); m6 = PK_TLD(tab_a + o6);
+            if (KIND == 2) {
+                e1 = pk_lds32(PK_EWA(o1)); e4 = pk_lds32(PK_EWA(o4)); e5 = pk_lds32(PK_EWA(o5));
+                e6 = pk_lds32(PK_EWA(o6));
+            }
         }
         uint32_t Nlo, Nhi;
         PK_RING32(p - 4 - lx, Nlo, Nhi);                    // window for the next iteration
@@ -568,15 +574,23 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, u
         const bool c4 = common == 4, c5 = common == 5;
         uint32_t sp = pk_sel(c4, o2, pk_sel(c5, o3, o4));                                    // slot of the insert pn-2
         uint32_t sn = pk_sel(c4, o4, pk_sel(c5, o5, o6));                                    // slot of pn
-        uint32_t mn = pk_sel(c4, m4, pk_sel(c5, m5, m6));
-        uint32_t en = KIND == 2 ? pk_sel(c4, e4, pk_sel(c5, e5, e6)) : 0;
+        uint32_t mn = LAZY ? 0u : pk_sel(c4, m4, pk_sel(c5, m5, m6));
+        uint32_t en = (LAZY || KIND != 2) ? 0u : pk_sel(c4, e4, pk_sel(c5, e5, e6));
         if (commit && common > 6) {                         // 7..11: not speculated, look the slots up now
             sp = PK_OFF(pk_fsr(Ws, Wt, 2 * (common + 2)) & MASK);
             sn = PK_OFF(pk_fsr(Ws, Wt, 2 * (common + 4)) & MASK);
+            if (!LAZY) {
+                mn = PK_TLD(tab_a + sn);
+                if (KIND == 2) en = pk_lds32(PK_EWA(sn));
+            }
+        }
+        sn = hit ? sn : o1;
+        if (LAZY) {
             mn = PK_TLD(tab_a + sn);
             if (KIND == 2) en = pk_lds32(PK_EWA(sn));
+        } else {
+            mn = hit ? mn : m1; en = hit ? en : e1;
         }
-        sn = hit ? sn : o1; mn = hit ? mn : m1; en = hit ? en : e1;
         if (commit && hit) {                                // second insert: slot of pn-2 <- pn-2
             if (KIND == 2) {
                 pk_sts16(tab_a + sp, pn - 2);
@@ -624,13 +638,15 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, u
 
 // Run the streams of the warp (lanes in `mask`, one stream each) until each one's next position reaches
 // its `stop` or it is done: turbo bursts, separated by one general pk_step for every lane.
-template <int KIND, int STRIDE>
+// LAZY: how pk_turbo fetches the table words of the next probe (see there); the kernels leave the default (many lanes:
+// yes, one lane: no), the host emulation -- where STRIDE is always 1 -- asks for the pair kernel's setting explicitly
+template <int KIND, int STRIDE, bool LAZY = (STRIDE != 1)>
 SNACC_HD void pk_run(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, uint32_t n, uint32_t stop, uint32_t mask)
 {
     for (;;) {
         bool work = st.phase != PK_DONE && pk_next_pos(st) < stop;
         if (!pk_any(mask, work)) return;
-        pk_turbo<KIND, STRIDE>(st, tab, v, stop, mask, work);
+        pk_turbo<KIND, STRIDE, LAZY>(st, tab, v, stop, mask, work);
         work = st.phase != PK_DONE && pk_next_pos(st) < stop;
         if (work) {
 #if defined(PK_COUNT_STEPS) && !defined(__CUDA_ARCH__)
