@@ -233,3 +233,33 @@ def test_deflate_block_cost_on_compacted_trees_equals_zlib_tree_construction(emu
     applied = ctypes.c_int32()
     assert emu.emu_flush_compact_fuzz(seed, 60000, ctypes.byref(applied)) == 0
     assert applied.value > 20000
+
+
+def test_deflate_shortcuts_on_repetitive_inputs(emu):
+    """long single-base runs (matches of 258: the nice_length stop), tandem repeats, a 3 kbp unit repeated (every walk ends
+    at nice_length), N runs, x == y: the junction / match-table / canonical-stream shortcuts against zlib, and every
+    shortcut word against the general chain walk (second return value)"""
+    rng = np.random.default_rng(3)
+
+    def dna(n):
+        return np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)]
+
+    unit, u2 = dna(37), dna(3000)
+    rep = np.concatenate([np.tile(u2, 15), dna(40000)])
+    cases = [
+        (np.concatenate([np.full(40000, 65, np.uint8), dna(20000)]),
+         np.concatenate([dna(5000), np.full(60000, 65, np.uint8), dna(30000)])),
+        (np.tile(unit, 2000), np.tile(unit, 2500)),
+        (np.tile(u2, 20), rep),
+        (np.concatenate([dna(30000), np.full(5000, 78, np.uint8), dna(30000)]),
+         np.concatenate([np.full(3000, 78, np.uint8), dna(60000), np.full(200, 78, np.uint8), dna(20000)])),
+        (rep, rep),
+    ]
+    bad = []
+    for x, y in cases:
+        for level in (9, 6):
+            ref = lib.ref_deflate_size(np.concatenate([x, y]), level)
+            r, _, mism = _deflate_ex(emu, x, y, level, 1)
+            if r != ref or mism:
+                bad.append((x.size, y.size, level, ref, r, mism))
+    assert not bad, bad
