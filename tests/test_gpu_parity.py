@@ -244,6 +244,30 @@ def test_full_size_genomes_gzip(engine):
     engine.set_option("invalidate_caches", 1)
 
 
+@pytest.mark.parametrize("algo", ALGOS)
+def test_repetitive_inputs(engine, algo):
+    """single-base runs of 40-60 k, a 37-base tandem repeat, a 3 kbp unit repeated, N runs: one hash bucket holds almost
+    every position (radix sort, head/tail packs, chain limits, nice_length stops, LZ4 matches of tens of kilobases)"""
+    rng = np.random.default_rng(3)
+
+    def dna(n):
+        return np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)]
+
+    unit, u2 = dna(37), dna(3000)
+    seqs = [np.concatenate([np.full(40000, 65, np.uint8), dna(20000)]),
+            np.concatenate([dna(5000), np.full(60000, 65, np.uint8), dna(30000)]),
+            np.tile(unit, 2000), np.tile(unit, 2500), np.tile(u2, 20),
+            np.concatenate([np.tile(u2, 15), dna(40000)]),
+            np.concatenate([np.full(3000, 78, np.uint8), dna(60000), np.full(200, 78, np.uint8), dna(20000)])]
+    n = len(seqs)
+    engine.upload_sequences(seqs)
+    C = engine.single_sizes(algo)
+    S = engine.tile_sizes(algo, 0, n, 0, n)
+    assert np.array_equal(C, np.array([_ref_len(s, algo) for s in seqs]))
+    ref = np.array([[_ref_len(np.concatenate([a, b]), algo) for b in seqs] for a in seqs])
+    assert np.array_equal(S, ref)
+
+
 def test_lz4_stale_table_slots(engine):
     """A/T-only stretches of 66 k - 300 k bases between ACGT stretches: slots of k-mers with C/G age far beyond the
     131072 positions the 17-bit slot encoding can tell apart; the rolling sweep must have retired them"""
