@@ -492,9 +492,9 @@ static int run_pk_single(snacc_ctx *ctx, const std::vector<int32_t> &seqs, const
     return SNACC_OK;
 }
 
-// tile geometry of lz4_pk_pair_kernel.  Linked regime: 16 lanes per warp, 16-bit slots + epoch bit plane
-// (PkTab KIND 2: 2 bytes + 1 bit per slot, as many slots as the alphabet's 5-mers reach), as many warps as
-// fit one SM's shared memory (6 for A/C/G/T: 96 streams).  Single-block regime: 12 warps x 32 lanes,
+// tile geometry of lz4_pk_pair_kernel.  Linked regime: 16-bit slots + epoch bit plane (PkTab KIND 2: 2 bytes +
+// 1 bit per slot, as many slots as the alphabet's 5-mers reach), as many streams as fit one SM's shared memory:
+// 4 warps x 26 lanes = 104 for A/C/G/T (one warp per scheduler).  Single-block regime: 12 warps x 32 lanes,
 // 512 B table per stream.
 constexpr int PK_S_LANES = 32, PK_S_WARPS = 12;
 constexpr size_t PK_SMEM_MAX = 232448 - 16;       // 227 KiB per CTA minus the kernel's static shared memory
