@@ -7,6 +7,7 @@ blanks and carriage returns inside a record are dropped, case is preserved.  Rev
 done here: record boundaries are handed to the device, which reverse-complements each record
 (snacc_upload, K0).
 """
+import re
 from pathlib import Path
 
 import numpy as np
@@ -14,9 +15,12 @@ import numpy as np
 _STRIP = bytes([9, 10, 11, 12, 13, 32])
 
 
-def read_fasta(path):
-    """-> (uint8 array of all records' residues concatenated in file order, list of record lengths)."""
-    raw = Path(path).read_bytes()
+_HEADER = re.compile(rb"^>", re.MULTILINE)
+_DROP = b" \r\n"
+
+
+def _read_fasta_lines(raw):
+    """line-by-line parser: the reference semantics spelled out (rstrip of every line, then blanks and CRs dropped)"""
     recs = []
     cur = None
     for line in raw.split(b"\n"):
@@ -28,6 +32,26 @@ def read_fasta(path):
             cur.append(line.rstrip(_STRIP).replace(b" ", b"").replace(b"\r", b""))
     if cur is not None:
         recs.append(b"".join(cur))
+    return recs
+
+
+def read_fasta(path):
+    """-> (uint8 array of all records' residues concatenated in file order, list of record lengths).
+
+    Files without tabs, vertical tabs or form feeds (all real FASTA files) take a path that never splits into lines:
+    the records are cut at the '>' line starts and each body is filtered in one ``bytes.translate`` -- rstrip of
+    every line followed by dropping blanks and CRs is then the same as deleting blanks, CRs and newlines.  c5 is
+    2 048 files of 5 MB: seconds instead of a minute of Python line handling."""
+    raw = Path(path).read_bytes()
+    if b"\t" in raw or b"\x0b" in raw or b"\x0c" in raw:
+        recs = _read_fasta_lines(raw)
+    else:
+        starts = [m.start() for m in _HEADER.finditer(raw)]
+        recs = []
+        for k, a in enumerate(starts):
+            b = starts[k + 1] if k + 1 < len(starts) else len(raw)
+            eol = raw.find(b"\n", a, b)
+            recs.append(raw[eol + 1:b].translate(None, _DROP) if eol >= 0 else b"")
     lengths = [len(r) for r in recs]
     data = np.frombuffer(b"".join(recs), dtype=np.uint8)
     return data, lengths

@@ -160,3 +160,51 @@ def test_owned_cols_partition():
         for w in (1, 2, 4, 8):
             cols = np.concatenate([sharding.owned_cols(n, r, w) for r in range(w)])
             assert sorted(cols.tolist()) == list(range(n))
+
+
+def test_fasta_fast_path_equals_the_line_parser(tmp_path):
+    """read_fasta cuts records at '>' line starts and filters each body with one translate; it must give what the
+    line-by-line parser (the reference semantics) gives: multi-record files, CRLF, blank lines, trailing blanks, text
+    before the first header, a header at EOF, empty records -- and files with tabs take the line parser"""
+    from snacc_b200 import fasta
+    rng = np.random.default_rng(2)
+    bodies = []
+    for _ in range(6):
+        seq = bytes(rng.choice(list(b"ACGTacgtNRY"), size=int(rng.integers(0, 400))).astype(np.uint8))
+        lines = [seq[i:i + 60] for i in range(0, len(seq), 60)]
+        bodies.append(lines)
+    texts = [
+        b">a desc\n" + b"\n".join(bodies[0]) + b"\n>b\n" + b"\n".join(bodies[1]) + b"\n",
+        b"junk before\n>a\r\n" + b"\r\n".join(bodies[2]) + b"\r\n\r\n>b\r\n" + b"\r\n".join(bodies[3]),
+        b">only header",
+        b">x\nAC GT  \n\n  ACGT\n>y\n\n>z\nTT\n",
+        b"no header at all\nACGT\n",
+        b">t\nAC\tGT \t\nAC\x0cGT\n",                    # tabs / form feeds: line parser
+        b"",
+    ]
+    for k, t in enumerate(texts):
+        f = tmp_path / f"f{k}.fa"
+        f.write_bytes(t)
+        data, lens = fasta.read_fasta(f)
+        recs = fasta._read_fasta_lines(t)
+        assert bytes(data) == b"".join(recs) and lens == [len(r) for r in recs], k
+
+
+def test_direct_csv_writer_is_byte_identical_to_the_pandas_route(tmp_path):
+    """write_distance_csv against the reference's own route (cli.py:138-142: DataFrame -> pivot -> to_csv) on labels that
+    sort differently as strings and as paths, labels that need quoting, and floats of every shape"""
+    import pandas as pd
+    rng = np.random.default_rng(1)
+    n = 40
+    files = [Path(f"/data/g{rng.integers(0, 3)}/sub dir/my,Genome_{i}.fasta") if i % 7 == 0 else
+             Path(f"/data/g{rng.integers(0, 3)}/Genome_{i}.fa") for i in range(n)] + [Path("/data/g1"), Path("/data/g1-x/a.fa")]
+    n = len(files)
+    D = rng.random((n, n))
+    D[0, 0], D[0, 1], D[1, 0], D[2, 2], D[3, 3] = 0.0, 1.0, 1e-5, 1.0000000000000002, -0.25
+    D[4, 4], D[5, 5], D[6, 6], D[7, 7], D[8, 8] = 1e-300, 0.1 + 0.2, 123456789.125, 1e16, 2.5e-7
+    rows = [(files[i], files[j], D[i][j]) for i in range(n) for j in range(n)]
+    ref = tmp_path / "ref.csv"
+    pd.DataFrame(rows, columns=["file", "file2", "ncd"]).pivot(index="file", columns="file2", values="ncd").to_csv(ref)
+    out = tmp_path / "out.csv"
+    gcli.write_distance_csv(files, D, out)
+    assert out.read_bytes() == ref.read_bytes()
