@@ -41,6 +41,24 @@ def test_fixture_matrix_equals_reference_golden(engine, golden_dir, ref_sizes, c
     assert np.array_equal(engine.ncd(C, S), np.array(want["D"]))
 
 
+@pytest.mark.parametrize("algo", ["lz4", "gzip"])
+def test_fast_mode_computes_the_upper_triangle_only(engine, golden_dir, ref_sizes, algo):
+    """--fast-mode True (README flag; SURVEY.md 8a divergence ledger): S(i, j) for i <= j only, mirrored, NCD from that one
+    order -- the sizes it does compute are the reference's"""
+    from snacc_b200.pairwise_ncd import ncd_matrix
+    from snacc_b200.sharding import ncd_host
+    files = [Path(golden_dir) / "fasta" / f for f in ref_sizes["files"]]
+    n = len(files)
+    labels, C, S, D = ncd_matrix(files, algo, fast_mode=True, engine=engine)
+    want = ref_sizes["cases"][algo]
+    Sref = np.array(want["S"]) - 33
+    iu = np.triu_indices(n, 1)
+    Sref[(iu[1], iu[0])] = Sref[iu]
+    assert (C + 33).tolist() == want["C"]
+    assert np.array_equal(S, Sref)
+    assert np.array_equal(D, ncd_host(C, Sref, fast_mode=True))
+
+
 @pytest.mark.parametrize("case", ["lz4", "gzip_rc"])
 def test_cli_csv_is_byte_identical_to_reference_cli(golden_dir, tmp_path, case, monkeypatch):
     from click.testing import CliRunner
