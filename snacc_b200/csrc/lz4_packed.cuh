@@ -534,14 +534,18 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, u
             if (go) PK_TST(slot, p);
         }
         // speculative table lookups: next probe at p+1 (miss) or p+4..p+6 (match of that length)
-        const uint32_t o1 = PK_OFF((Ws >> 10) & MASK), o2 = PK_OFF((Ws >> 12) & MASK), o3 = PK_OFF((Ws >> 14) & MASK);
-        const uint32_t o4 = PK_OFF((Ws >> 16) & MASK), o5 = PK_OFF((Ws >> 18) & MASK), o6 = PK_OFF((Ws >> 20) & MASK);
+        constexpr bool LLUT = LAZY;                         // many lanes: the slot addresses are resolved late as well
+        uint32_t o1 = 0, o2 = 0, o3 = 0, o4 = 0, o5 = 0, o6 = 0;
+        if (!LLUT) {
+            o1 = PK_OFF((Ws >> 10) & MASK); o2 = PK_OFF((Ws >> 12) & MASK); o3 = PK_OFF((Ws >> 14) & MASK);
+            o4 = PK_OFF((Ws >> 16) & MASK); o5 = PK_OFF((Ws >> 18) & MASK); o6 = PK_OFF((Ws >> 20) & MASK);
+        }
         // (lengths 7 and 8 are 6 % of the matches: not worth two more speculative lookups per iteration, they take the
         // on-demand path below together with 9..11)
         // With one lane per warp (the singles pass, STRIDE 1) the loop is bound by its dependency chain and the table
         // words of all four candidates slots are fetched ahead; with 26 or 32 lanes it is bound by instruction issue
-        // (measured: +10 % for the pair kernel, 2.2x slower singles pass) and the one slot that is needed is read
-        // once it is known.
+        // (measured: +10 % for the pair kernel from the table words, another +11 % from the slot addresses, and a 2.2x
+        // slower singles pass) and the one slot that is needed is resolved and read once the match length is known.
         uint32_t m1 = 0, m4 = 0, m5 = 0, m6 = 0, e1 = 0, e4 = 0, e5 = 0, e6 = 0;
         if (!LAZY) {
             m1 = PK_TLD(tab_a + o1); m4 = PK_TLD(tab_a + o4); m5 = PK_TLD(tab_a + o5); m6 = PK_TLD(tab_a + o6);
@@ -576,7 +580,11 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, u
         uint32_t sn = pk_sel(c4, o4, pk_sel(c5, o5, o6));                                    // slot of pn
         uint32_t mn = LAZY ? 0u : pk_sel(c4, m4, pk_sel(c5, m5, m6));
         uint32_t en = (LAZY || KIND != 2) ? 0u : pk_sel(c4, e4, pk_sel(c5, e5, e6));
-        if (commit && common > 6) {                         // 7..11: not speculated, look the slots up now
+        if (LLUT) {
+            const uint32_t d = hit ? common : 1u;           // the next probe is at p + d
+            sn = PK_OFF(pk_fsr(Ws, Wt, 2 * (d + 4)) & MASK);
+            sp = PK_OFF(pk_fsr(Ws, Wt, 2 * (d + 2)) & MASK);
+        } else if (commit && common > 6) {                  // 7..11: not speculated, look the slots up now
             sp = PK_OFF(pk_fsr(Ws, Wt, 2 * (common + 2)) & MASK);
             sn = PK_OFF(pk_fsr(Ws, Wt, 2 * (common + 4)) & MASK);
             if (!LAZY) {
@@ -584,7 +592,7 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, u
                 if (KIND == 2) en = pk_lds32(PK_EWA(sn));
             }
         }
-        sn = hit ? sn : o1;
+        if (!LLUT) sn = hit ? sn : o1;
         if (LAZY) {
             mn = PK_TLD(tab_a + sn);
             if (KIND == 2) en = pk_lds32(PK_EWA(sn));
