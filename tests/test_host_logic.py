@@ -129,7 +129,8 @@ def _worker(rank, world, port, files, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         labels, C, S, D = sharding.all_pairs(files, "lz4", True, False, size_fn=_oracle_size_fn("lz4"))
-        q.put((rank, C.tolist(), S.tolist(), D.tolist()))
+        _, Cf, Sf, Df = sharding.all_pairs(files, "lz4", True, True, size_fn=_oracle_size_fn("lz4"))     # fast mode
+        q.put((rank, C.tolist(), S.tolist(), D.tolist(), Sf.tolist(), Df.tolist()))
     finally:
         dist.destroy_process_group()
 
@@ -150,9 +151,13 @@ def test_column_sharding_world_size_2_gloo(golden_dir):
         p.join(timeout=60)
         assert p.exitcode == 0
     C1, S1 = snacc_oracle.size_tables(files, "lz4", True)
-    for rank, C, S, D in res:
+    iu = np.triu_indices(len(files), 1)
+    S1f = S1.copy()
+    S1f[(iu[1], iu[0])] = S1f[iu]
+    for rank, C, S, D, Sf, Df in res:
         assert np.array_equal(np.array(C), C1) and np.array_equal(np.array(S), S1)
         assert np.array_equal(np.array(D), snacc_oracle.ncd_from_sizes(C1, S1))
+        assert np.array_equal(np.array(Sf), S1f) and np.array_equal(np.array(Df), sharding.ncd_host(C1, S1f, True))
 
 
 def test_owned_cols_partition():
