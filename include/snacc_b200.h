@@ -51,6 +51,13 @@ enum snacc_formula {
 };
 
 int snacc_version(void);                                  /* 10000*major + 100*minor + patch */
+
+/* Host-side helper, no GPU involved (replaces the per-job Bio.SeqIO parse of pairwise_ncd.py:29-36, done ONCE per
+ * file): residues of every FASTA record of raw[0..n) -- records start at lines beginning with '>', sequence lines are
+ * right-stripped and lose blanks and CRs -- concatenated into out (room for n bytes); rec_len receives the length of
+ * the first max_recs records.  Returns the number of records (>= 0) or a negative snacc_status. */
+int64_t snacc_fasta_parse(const uint8_t *raw, uint64_t n, uint8_t *out, uint64_t *out_len, uint64_t *rec_len,
+                          int64_t max_recs);
 const char *snacc_last_error(const snacc_ctx *ctx);       /* NUL-terminated, owned by ctx; "" if none */
 
 /* replaces: ThreadPoolExecutor construction, cli.py:104 */

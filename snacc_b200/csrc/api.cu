@@ -138,6 +138,45 @@ __global__ void ncd_kernel(const int64_t *__restrict__ C, const int64_t *__restr
 // ---------------------------------------------------------------------------------------------
 extern "C" int snacc_version(void) { return SNACC_VERSION; }
 
+// Host-side FASTA record scan (no GPU involved): the residues of every record of `raw` with the reference's line
+// handling -- a record starts at a line that begins with '>', everything before the first one is ignored, every
+// sequence line is right-stripped of white space (9-13, 32) and loses its blanks and carriage returns
+// (pairwise_ncd.py:32-36 over Bio.SeqIO / SimpleFastaParser).  out needs room for n bytes.  Returns the number of
+// records (their lengths in rec_len[0 .. min(records, max_recs))), *out_len = residues written.
+extern "C" int64_t snacc_fasta_parse(const uint8_t *raw, uint64_t n, uint8_t *out, uint64_t *out_len, uint64_t *rec_len,
+                                     int64_t max_recs)
+{
+    if ((n && !raw) || !out || !out_len) return SNACC_ERR_ARG;
+    auto is_ws = [](uint8_t c) { return (c >= 9 && c <= 13) || c == 32; };
+    uint64_t w = 0, cur = 0;
+    int64_t recs = 0;
+    bool in_rec = false;
+    for (uint64_t a = 0; a < n;) {
+        const uint8_t *nl = (const uint8_t *)memchr(raw + a, '\n', n - a);
+        const uint64_t b = nl ? (uint64_t)(nl - raw) : n;        // line = raw[a, b)
+        if (b > a && raw[a] == '>') {
+            if (in_rec) { if (recs - 1 < max_recs && rec_len) rec_len[recs - 1] = cur; }
+            in_rec = true; ++recs; cur = 0;
+        } else if (in_rec) {
+            uint64_t e = b;
+            while (e > a && is_ws(raw[e - 1])) --e;
+            if (e > a && !memchr(raw + a, ' ', e - a) && !memchr(raw + a, '\r', e - a)) {
+                memcpy(out + w, raw + a, e - a);                 // the usual line: nothing to drop inside it
+                w += e - a; cur += e - a;
+            } else {
+                for (uint64_t i = a; i < e; ++i) {
+                    const uint8_t ch = raw[i];
+                    if (ch != ' ' && ch != '\r') { out[w++] = ch; ++cur; }
+                }
+            }
+        }
+        a = b + 1;
+    }
+    if (in_rec && recs - 1 < max_recs && rec_len) rec_len[recs - 1] = cur;
+    *out_len = w;
+    return recs;
+}
+
 extern "C" const char *snacc_last_error(const snacc_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 static void free_corpus(snacc_ctx *ctx)

@@ -49,6 +49,8 @@ def load_library():
     lib.snacc_last_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
     lib.snacc_set_option.argtypes = [vp, ctypes.c_char_p, i64]
     lib.snacc_get_stat.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]
+    lib.snacc_fasta_parse.restype = i64
+    lib.snacc_fasta_parse.argtypes = [vp, ctypes.c_uint64, vp, ctypes.POINTER(ctypes.c_uint64), vp, i64]
     _lib = lib
     return lib
 

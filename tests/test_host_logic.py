@@ -167,10 +167,11 @@ def test_owned_cols_partition():
             assert sorted(cols.tolist()) == list(range(n))
 
 
-def test_fasta_fast_path_equals_the_line_parser(tmp_path):
-    """read_fasta cuts records at '>' line starts and filters each body with one translate; it must give what the
-    line-by-line parser (the reference semantics) gives: multi-record files, CRLF, blank lines, trailing blanks, text
-    before the first header, a header at EOF, empty records -- and files with tabs take the line parser"""
+def test_native_fasta_parser_equals_the_line_parser(tmp_path):
+    """read_fasta (snacc_fasta_parse of the C ABI) must give what the line-by-line parser (the reference semantics) gives:
+    multi-record files, CRLF, blank lines, trailing blanks, text before the first header, a header at EOF, empty
+    records, tabs / form feeds inside and at the end of lines -- and a fuzz over random soups of the characters that
+    matter"""
     from snacc_b200 import fasta
     rng = np.random.default_rng(2)
     bodies = []
@@ -187,12 +188,19 @@ def test_fasta_fast_path_equals_the_line_parser(tmp_path):
         b">t\nAC\tGT \t\nAC\x0cGT\n",                    # tabs / form feeds: line parser
         b"",
     ]
+    alphabet = np.frombuffer(b"ACGTN>> \t\r\n\n\n\x0b\x0c", dtype=np.uint8)
+    for _ in range(60):
+        texts.append(bytes(alphabet[rng.integers(0, alphabet.size, int(rng.integers(0, 300)))]))
+    many = b"".join(b">r%d\nAC\n" % i for i in range(200))              # more records than the first call makes room for
+    texts.append(many)
     for k, t in enumerate(texts):
         f = tmp_path / f"f{k}.fa"
         f.write_bytes(t)
         data, lens = fasta.read_fasta(f)
+        data2, lens2 = fasta._read_fasta_native(t)
         recs = fasta._read_fasta_lines(t)
-        assert bytes(data) == b"".join(recs) and lens == [len(r) for r in recs], k
+        assert bytes(data) == b"".join(recs) and lens == [len(r) for r in recs], (k, t)
+        assert bytes(data2) == bytes(data) and lens2 == lens
 
 
 def test_direct_csv_writer_is_byte_identical_to_the_pandas_route(tmp_path):
