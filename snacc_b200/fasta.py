@@ -57,11 +57,12 @@ def _read_fasta_native(raw):
 def read_fasta(path):
     """-> (uint8 array of all records' residues concatenated in file order, list of record lengths)."""
     raw = Path(path).read_bytes()
+    from .engine import SnaccGpuError
     try:
         return _read_fasta_native(raw)
-    except Exception:                                        # library not built: the same semantics in Python
-        recs = _read_fasta_lines(raw)
-        return np.frombuffer(b"".join(recs), dtype=np.uint8), [len(r) for r in recs]
+    except (SnaccGpuError, OSError, AttributeError):         # library not built yet: the same host-side semantics in
+        recs = _read_fasta_lines(raw)                        # Python (parsing is host work either way; every
+        return np.frombuffer(b"".join(recs), dtype=np.uint8), [len(r) for r in recs]   # compressor call still needs the GPU)
 
 
 def load_corpus(files):
