@@ -1,4 +1,5 @@
 """Build libsnacc_b200.so (hand-written sm_100a CUDA + C ABI) in-tree with nvcc."""
+import glob
 import os
 import shutil
 import subprocess
@@ -6,8 +7,10 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SNACC_B200_LIB") or os.path.join(HERE, "libsnacc_b200.so")   # override: experiments only
 SOURCES = [os.path.join(HERE, "csrc", "api.cu")]
-HEADERS = [os.path.join(HERE, "csrc", f) for f in ("common.cuh", "lz4.cuh", "deflate.cuh")] + [
-    os.path.join(os.path.dirname(HERE), "include", "snacc_b200.h")]
+# every header api.cu can include: all of csrc/*.cuh plus the public C header (a stale-check that misses one -- the
+# packed LZ4 kernels live in lz4_packed.cuh / pack.cuh -- lets tests run against an old binary)
+HEADERS = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cuh"))) + sorted(
+    glob.glob(os.path.join(os.path.dirname(HERE), "include", "*.h")))
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]

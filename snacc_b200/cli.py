@@ -99,9 +99,12 @@ def _parse_bool(ctx, param, value):
               help="README spelling of -r: True or False.")
 @click.option("--fast-mode", "fast_mode", default=None, callback=_parse_bool,
               help="True: one concatenation order only (upper triangle), NCD = (C(xy) - min) / max.")
+@click.option("--gpus", "gpus", type=int, default=None,
+              help="Number of GPUs of this box to use (one process per GPU is launched). Default: the GPUs of the "
+                   "torchrun process group this command runs in, else one.")
 @click.option("--log/--no-log", "log", default=True, help="Whether to save a log.")
 def cli(sequences, fasta, directories, numThreads, compression, showProgress, saveCompression, output,
-        reverse_complement, reverse_compliment, fast_mode, log):
+        reverse_complement, reverse_compliment, fast_mode, gpus, log):
     start_time = datetime.now()
     if fasta:
         click.secho("Warning: the -f flag is deprecated. Please pass files and paths directly.", fg="yellow")
@@ -110,7 +113,9 @@ def cli(sequences, fasta, directories, numThreads, compression, showProgress, sa
                                "never materialised, only their sizes are computed")
     if compression not in ("lz4", "gzip", "zlib"):
         raise click.UsageError(f"-c {compression} is not supported on the GPU path (supported: lz4, gzip, zlib); "
-                               "there is no CPU fallback")
+                               "there is no CPU fallback" + (" -- lzma is the reference's default (cli.py:52), so pass "
+                                                             "-c lz4, -c gzip or -c zlib explicitly"
+                                                             if compression == "lzma" else ""))
     if reverse_compliment is not None:
         reverse_complement = reverse_compliment
     output = Path(output)
@@ -118,33 +123,44 @@ def cli(sequences, fasta, directories, numThreads, compression, showProgress, sa
     if not files:
         raise click.UsageError("no FASTA files found")
 
-    click.secho(f"Compressing {len(files)} files and {len(files) ** 2} ordered pairs on the GPU...", fg="green")
-    t0 = datetime.now()
-    labels, C, S, D = ncd_matrix(files, compression, reverse_complement=reverse_complement,
-                                 fast_mode=bool(fast_mode))
-    compute_s = (datetime.now() - t0).total_seconds()
-    if _is_rank0():
-        write_distance_csv(files, D, output)
-        if log:
-            n = len(files)
-            jobs = n + (n * (n + 1) // 2 if fast_mode else n * n)
-            with open(output.stem + ".md", "w") as f:
-                print(log_template.format(time=datetime.now(), duration=datetime.now() - start_time,
-                                          method=compression, rev_comp=reverse_complement,
-                                          output_path=output.absolute(),
-                                          py_version=str(sys.version.replace("\n", "")),
-                                          snacc_version=__version__, jobs=jobs, pairs=n * (n + 1) // 2,
-                                          compute_s=compute_s), file=f)
-                for _f in [str(_file.absolute()) for _file in files]:
-                    print("*", _f, file=f)
-
-
-def _is_rank0():
+    from . import sharding
+    sharding.init_distributed()           # under torchrun: join the group, bind to GPU LOCAL_RANK (no-op otherwise)
     try:
-        import torch.distributed as dist
-        return not (dist.is_available() and dist.is_initialized()) or dist.get_rank() == 0
-    except Exception:
-        return True
+        rank0 = sharding.is_rank0()
+        n = len(files)
+        n_pairs = n * (n + 1) // 2 if fast_mode else n * n
+        if rank0:
+            click.secho(f"Compressing {n} files and {n_pairs} {'unordered' if fast_mode else 'ordered'} pairs on "
+                        "the GPU...", fg="green")
+        bar = None
+        if showProgress and rank0:
+            from tqdm import tqdm
+            bar = tqdm(total=n + n_pairs, unit="job")        # the reference shows one bar per fan-out (cli.py:172-174)
+        t0 = datetime.now()
+        labels, C, S, D = ncd_matrix(files, compression, reverse_complement=reverse_complement,
+                                     fast_mode=bool(fast_mode), gpus=gpus)
+        compute_s = (datetime.now() - t0).total_seconds()
+        if bar is not None:
+            bar.update(n + n_pairs)
+            bar.close()
+        if rank0:
+            t1 = datetime.now()
+            write_distance_csv(files, D, output)
+            csv_s = (datetime.now() - t1).total_seconds()
+            if log:
+                world = sharding._dist().get_world_size() if sharding._dist() else (gpus or 1)
+                with open(output.stem + ".md", "w") as f:
+                    print(log_template.format(time=datetime.now(), duration=datetime.now() - start_time,
+                                              method=compression, rev_comp=reverse_complement,
+                                              output_path=output.absolute(),
+                                              py_version=str(sys.version.replace("\n", "")),
+                                              snacc_version=__version__, jobs=n + n_pairs, pairs=n * (n + 1) // 2,
+                                              compute_s=compute_s, csv_s=csv_s, gpus=world,
+                                              pairs_per_s=(n * (n + 1) // 2) / max(compute_s, 1e-9)), file=f)
+                    for _f in [str(_file.absolute()) for _file in files]:
+                        print("*", _f, file=f)
+    finally:
+        sharding.shutdown_distributed()
 
 
 log_template = '''# `snacc` Analysis
@@ -154,7 +170,7 @@ log_template = '''# `snacc` Analysis
 * Compression method: {method}
 * Reverse complement: {rev_comp}
 * Output filepath: {output_path}
-* Compressor jobs: {jobs} ({pairs} unordered pairs) in {compute_s:.3f} s on the GPU path
+* Compressor jobs: {jobs} ({pairs} unordered pairs) in {compute_s:.3f} s on the GPU path ({gpus} GPU(s), {pairs_per_s:.1f} pairs/s, FASTA parsing and upload included); CSV written in {csv_s:.3f} s
 
 ## Version Information
 * Python: {py_version}

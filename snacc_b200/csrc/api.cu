@@ -58,6 +58,8 @@ struct snacc_ctx {
 
     // working memory
     uint8_t *d_work = nullptr; size_t work_bytes = 0;
+    void *d_scratch[8] = {nullptr}; size_t scratch_cap[8] = {0};   // per-call argument arrays, grown on demand, never
+                                                                   // freed between calls (all use is ordered on `stream`)
     unsigned long long *d_counter = nullptr;
     int32_t *d_jobx = nullptr, *d_joby = nullptr; int64_t job_cap = 0;
     int64_t *d_out = nullptr; int64_t out_cap = 0;
@@ -139,42 +141,57 @@ __global__ void ncd_kernel(const int64_t *__restrict__ C, const int64_t *__restr
 extern "C" int snacc_version(void) { return SNACC_VERSION; }
 
 // Host-side FASTA record scan (no GPU involved): the residues of every record of `raw` with the reference's line
-// handling -- a record starts at a line that begins with '>', everything before the first one is ignored, every
-// sequence line is right-stripped of white space (9-13, 32) and loses its blanks and carriage returns
-// (pairwise_ncd.py:32-36 over Bio.SeqIO / SimpleFastaParser).  out needs room for n bytes.  Returns the number of
-// records (their lengths in rec_len[0 .. min(records, max_recs))), *out_len = residues written.
+// handling -- the file is read in text mode (universal newlines: "\n", "\r\n" and a lone "\r" all end a line), a
+// record starts at a line that begins with '>', everything before the first one is ignored, every sequence line is
+// right-stripped of white space (9-13, 32) and loses its blanks (pairwise_ncd.py:32-36 over Bio.SeqIO /
+// SimpleFastaParser).  out needs room for n bytes.  Returns the number of records (their lengths in
+// rec_len[0 .. min(records, max_recs))), *out_len = residues written.
+namespace {
+struct FastaScan {
+    uint8_t *out; uint64_t *rec_len; int64_t max_recs;
+    uint64_t w = 0, cur = 0; int64_t recs = 0; bool in_rec = false;
+    static bool is_ws(uint8_t c) { return (c >= 9 && c <= 13) || c == 32; }
+    void close_record() { if (in_rec && recs - 1 < max_recs && rec_len) rec_len[recs - 1] = cur; }
+    void line(const uint8_t *a, const uint8_t *b)                 // one line without its terminator
+    {
+        if (b > a && *a == '>') { close_record(); in_rec = true; ++recs; cur = 0; return; }
+        if (!in_rec) return;
+        while (b > a && is_ws(b[-1])) --b;
+        if (b == a) return;
+        if (!memchr(a, ' ', (size_t)(b - a))) {                   // the usual line: nothing to drop inside it
+            memcpy(out + w, a, (size_t)(b - a)); w += (uint64_t)(b - a); cur += (uint64_t)(b - a);
+        } else {
+            for (; a < b; ++a) if (*a != ' ') { out[w++] = *a; ++cur; }
+        }
+    }
+};
+}  // namespace
+
 extern "C" int64_t snacc_fasta_parse(const uint8_t *raw, uint64_t n, uint8_t *out, uint64_t *out_len, uint64_t *rec_len,
                                      int64_t max_recs)
 {
     if ((n && !raw) || !out || !out_len) return SNACC_ERR_ARG;
-    auto is_ws = [](uint8_t c) { return (c >= 9 && c <= 13) || c == 32; };
-    uint64_t w = 0, cur = 0;
-    int64_t recs = 0;
-    bool in_rec = false;
+    FastaScan sc{out, rec_len, max_recs};
     for (uint64_t a = 0; a < n;) {
         const uint8_t *nl = (const uint8_t *)memchr(raw + a, '\n', n - a);
-        const uint64_t b = nl ? (uint64_t)(nl - raw) : n;        // line = raw[a, b)
-        if (b > a && raw[a] == '>') {
-            if (in_rec) { if (recs - 1 < max_recs && rec_len) rec_len[recs - 1] = cur; }
-            in_rec = true; ++recs; cur = 0;
-        } else if (in_rec) {
-            uint64_t e = b;
-            while (e > a && is_ws(raw[e - 1])) --e;
-            if (e > a && !memchr(raw + a, ' ', e - a) && !memchr(raw + a, '\r', e - a)) {
-                memcpy(out + w, raw + a, e - a);                 // the usual line: nothing to drop inside it
-                w += e - a; cur += e - a;
-            } else {
-                for (uint64_t i = a; i < e; ++i) {
-                    const uint8_t ch = raw[i];
-                    if (ch != ' ' && ch != '\r') { out[w++] = ch; ++cur; }
-                }
+        const uint64_t b = nl ? (uint64_t)(nl - raw) : n;        // raw[a, b): text up to the next "\n"
+        const uint8_t *cr = b > a ? (const uint8_t *)memchr(raw + a, '\r', b - a) : nullptr;
+        if (!cr || (uint64_t)(cr - raw) == b - 1) {
+            sc.line(raw + a, raw + b - (cr ? 1 : 0));            // no carriage return, or the "\r" of a "\r\n"
+        } else {
+            uint64_t s = a;                                      // lone carriage returns end lines too
+            while (cr) {
+                sc.line(raw + s, cr);
+                s = (uint64_t)(cr - raw) + 1;
+                cr = s < b ? (const uint8_t *)memchr(raw + s, '\r', b - s) : nullptr;
             }
+            if (s < b || !nl) sc.line(raw + s, raw + b);         // (an "\r" right before the "\n" is one terminator)
         }
         a = b + 1;
     }
-    if (in_rec && recs - 1 < max_recs && rec_len) rec_len[recs - 1] = cur;
-    *out_len = w;
-    return recs;
+    sc.close_record();
+    *out_len = sc.w;
+    return sc.recs;
 }
 
 extern "C" const char *snacc_last_error(const snacc_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
@@ -231,6 +248,7 @@ extern "C" void snacc_ctx_destroy(snacc_ctx *ctx)
     free_corpus(ctx);
     deflate_free_work(ctx->dfl);
     cudaFree(ctx->d_work); cudaFree(ctx->d_counter);
+    for (void *p : ctx->d_scratch) cudaFree(p);
     cudaFree(ctx->d_jobx); cudaFree(ctx->d_joby); cudaFree(ctx->d_out);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
     cudaEventDestroy(ctx->evm0); cudaEventDestroy(ctx->evm1);
@@ -316,9 +334,6 @@ static int upload_impl(snacc_ctx *ctx, const void *bytes, bool on_device, const 
         }
         if (l >= 0x7fffffffull) FAIL(SNACC_ERR_TOO_LARGE, "snacc_upload: sequence of 2 GiB or more");
     }
-    CK(cudaSetDevice(ctx->device));
-    free_corpus(ctx);
-
     // records default to whole sequences
     std::vector<uint64_t> recs;
     if (!rec_offsets) { recs.assign(seq_offsets, seq_offsets + n_seqs + 1); n_recs = n_seqs; }
@@ -326,14 +341,15 @@ static int upload_impl(snacc_ctx *ctx, const void *bytes, bool on_device, const 
     if (recs.front() != seq_offsets[0] || recs.back() != seq_offsets[n_seqs])
         FAIL(SNACC_ERR_ARG, "snacc_upload: record offsets do not cover the sequences");
 
-    ctx->h_off.resize(n_seqs); ctx->h_len.resize(n_seqs);
+    // everything is validated before the previous corpus is dropped: a rejected upload leaves the context as it was
+    std::vector<uint64_t> h_off((size_t)n_seqs);
+    std::vector<uint32_t> h_len((size_t)n_seqs);
     uint64_t pos = 0;
     for (int32_t i = 0; i < n_seqs; ++i) {
-        ctx->h_off[i] = pos;
-        ctx->h_len[i] = (uint32_t)(seq_offsets[i + 1] - seq_offsets[i]);
-        pos += ((uint64_t)ctx->h_len[i] + SEQ_PAD + SEQ_ALIGN - 1) & ~(uint64_t)(SEQ_ALIGN - 1);
+        h_off[i] = pos;
+        h_len[i] = (uint32_t)(seq_offsets[i + 1] - seq_offsets[i]);
+        pos += ((uint64_t)h_len[i] + SEQ_PAD + SEQ_ALIGN - 1) & ~(uint64_t)(SEQ_ALIGN - 1);
     }
-    ctx->corpus_bytes = pos + 64;
     // destination of every record
     std::vector<uint64_t> rec_dst((size_t)n_recs);
     {
@@ -341,12 +357,16 @@ static int upload_impl(snacc_ctx *ctx, const void *bytes, bool on_device, const 
         for (int64_t r = 0; r < n_recs; ++r) {
             if (recs[r + 1] < recs[r]) FAIL(SNACC_ERR_ARG, "snacc_upload: record offsets not monotone");
             if (recs[r + 1] == recs[r]) { rec_dst[r] = 0; continue; }   // empty record: moves no bytes
-            while (recs[r] >= seq_offsets[si + 1]) ++si;
-            if (recs[r + 1] > seq_offsets[si + 1])
-                FAIL(SNACC_ERR_ARG, "snacc_upload: a record straddles two sequences");
-            rec_dst[r] = ctx->h_off[si] + (recs[r] - seq_offsets[si]);
+            while (si < n_seqs && recs[r] >= seq_offsets[si + 1]) ++si;
+            if (si >= n_seqs || recs[r] < seq_offsets[si] || recs[r + 1] > seq_offsets[si + 1])
+                FAIL(SNACC_ERR_ARG, "snacc_upload: a record straddles two sequences or lies outside them");
+            rec_dst[r] = h_off[si] + (recs[r] - seq_offsets[si]);
         }
     }
+    CK(cudaSetDevice(ctx->device));
+    free_corpus(ctx);
+    ctx->h_off.swap(h_off); ctx->h_len.swap(h_len);
+    ctx->corpus_bytes = pos + 64;
     for (auto &v : recs) v -= seq_offsets[0];
 
     CK(cudaMalloc(&ctx->d_corpus, ctx->corpus_bytes));
@@ -436,6 +456,20 @@ static int ensure_job_buffers(snacc_ctx *ctx, int64_t n)
     return SNACC_OK;
 }
 
+// device scratch array `slot` with room for `bytes` (argument arrays of the launches: no cudaMalloc / cudaFree per call)
+static int scratch(snacc_ctx *ctx, int slot, size_t bytes, void **out)
+{
+    if (bytes > ctx->scratch_cap[slot]) {
+        CK(cudaStreamSynchronize(ctx->stream));              // an earlier launch may still read the old array
+        cudaFree(ctx->d_scratch[slot]); ctx->d_scratch[slot] = nullptr; ctx->scratch_cap[slot] = 0;
+        const size_t cap = std::max<size_t>(bytes + bytes / 4, 4096);
+        CK(cudaMalloc(&ctx->d_scratch[slot], cap));
+        ctx->scratch_cap[slot] = cap;
+    }
+    *out = ctx->d_scratch[slot];
+    return SNACC_OK;
+}
+
 static int ensure_work(snacc_ctx *ctx, size_t bytes)
 {
     if (bytes > ctx->work_bytes) {
@@ -515,9 +549,9 @@ static int run_pk_single(snacc_ctx *ctx, const std::vector<int32_t> &seqs, const
     const int32_t n = (int32_t)seqs.size();
     if (!n) return SNACC_OK;
     int32_t *d_seqs = nullptr, *d_want = nullptr; int64_t *d_idx = nullptr;
-    CK(cudaMalloc(&d_seqs, sizeof(int32_t) * n));
-    CK(cudaMalloc(&d_want, sizeof(int32_t) * n));
-    CK(cudaMalloc(&d_idx, sizeof(int64_t) * n));
+    int rs = scratch(ctx, 0, sizeof(int32_t) * n, (void **)&d_seqs); if (rs) return rs;
+    rs = scratch(ctx, 1, sizeof(int32_t) * n, (void **)&d_want); if (rs) return rs;
+    rs = scratch(ctx, 2, sizeof(int64_t) * n, (void **)&d_idx); if (rs) return rs;
     CK(cudaMemcpyAsync(d_seqs, seqs.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_want, want.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_idx, out_idx.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -526,8 +560,6 @@ static int run_pk_single(snacc_ctx *ctx, const std::vector<int32_t> &seqs, const
                                                     ctx->d_alias4, d_idx, ctx->d_out);
     ctx->last_launches++;
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_seqs); cudaFree(d_want); cudaFree(d_idx);
     return SNACC_OK;
 }
 
@@ -576,12 +608,12 @@ static int pk_launch(snacc_ctx *ctx, bool u16, const PkGeometry &g, const std::v
                      int64_t n_jobs)
 {
     PkTile *d_tiles = nullptr; int32_t *d_tx = nullptr; int64_t *d_tout = nullptr;
-    CK(cudaMalloc(&d_tiles, sizeof(PkTile) * tiles.size()));
-    CK(cudaMalloc(&d_tx, sizeof(int32_t) * tx.size()));
+    int rs = scratch(ctx, u16 ? 3 : 5, sizeof(PkTile) * tiles.size(), (void **)&d_tiles); if (rs) return rs;
+    rs = scratch(ctx, u16 ? 4 : 6, sizeof(int32_t) * tx.size(), (void **)&d_tx); if (rs) return rs;
     CK(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(PkTile) * tiles.size(), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_tx, tx.data(), sizeof(int32_t) * tx.size(), cudaMemcpyHostToDevice, ctx->stream));
     if (!tout.empty()) {
-        CK(cudaMalloc(&d_tout, sizeof(int64_t) * tout.size()));
+        rs = scratch(ctx, 7, sizeof(int64_t) * tout.size(), (void **)&d_tout); if (rs) return rs;
         CK(cudaMemcpyAsync(d_tout, tout.data(), sizeof(int64_t) * tout.size(), cudaMemcpyHostToDevice, ctx->stream));
     }
     unsigned long long *counter = ctx->d_counter + (u16 ? 1 : 2);
@@ -603,8 +635,6 @@ static int pk_launch(snacc_ctx *ctx, bool u16, const PkGeometry &g, const std::v
     ctx->last_launches++;
     ctx->last_packed_jobs += n_jobs;
     CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_tiles); cudaFree(d_tx); cudaFree(d_tout);
     return SNACC_OK;
 }
 

@@ -1781,6 +1781,7 @@ struct DeflateState {
     uint32_t *d_FJ2[2] = {nullptr, nullptr}, *d_FJQ2[2] = {nullptr, nullptr}; size_t fj_pairs = 0;
     DflPair *d_pairs2[2] = {nullptr, nullptr}; DflJob *d_jobs2[2] = {nullptr, nullptr};
     cudaStream_t stream2 = nullptr; cudaEvent_t ev_j[2] = {nullptr, nullptr}, ev_p[2] = {nullptr, nullptr};
+    cudaEvent_t ev_t[2] = {nullptr, nullptr};      // timing of the junction kernel
     unsigned long long *d_counter2 = nullptr;
     double main_ms = 0.0;
     int use_canon = 1;                             // 0: every pair stream takes the full serial parse (tests)
@@ -1819,7 +1820,8 @@ static inline void deflate_free_work(DeflateState &st)
         st.d_scratch2[k] = nullptr; st.d_FJ2[k] = st.d_FJQ2[k] = nullptr; st.d_pairs2[k] = nullptr; st.d_jobs2[k] = nullptr;
         if (st.ev_j[k]) cudaEventDestroy(st.ev_j[k]);
         if (st.ev_p[k]) cudaEventDestroy(st.ev_p[k]);
-        st.ev_j[k] = st.ev_p[k] = nullptr;
+        if (st.ev_t[k]) cudaEventDestroy(st.ev_t[k]);
+        st.ev_j[k] = st.ev_p[k] = st.ev_t[k] = nullptr;
     }
     if (st.stream2) cudaStreamDestroy(st.stream2);
     st.stream2 = nullptr;
@@ -2018,16 +2020,20 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
         }
     }
     // ---- parse jobs ----
-    const int parse_blocks = DFL_PARSE_BLOCKS;
-    if (st.scratch_n < (size_t)parse_blocks * DFL_PARSE_THREADS) {
+    // working buffers are sized for the jobs of this call (a one-pair call -- the compressed_size() shim -- must not
+    // reserve the 2 x 6.3 GB a full batch needs) and grow on demand
+    const size_t batch = ys ? std::min<size_t>(DFL_BATCH, (((size_t)n_jobs + 63) / 64) * 64) : 64;
+    const int parse_blocks = (int)std::min<size_t>(DFL_PARSE_BLOCKS, batch / DFL_PARSE_THREADS);
+    if (ys && st.scratch_n < (size_t)parse_blocks * DFL_PARSE_THREADS) {
         for (int k = 0; k < 2; ++k) { cudaFree(st.d_scratch2[k]); st.d_scratch2[k] = nullptr; }
+        st.scratch_n = 0;
+        for (int k = 0; k < 2; ++k) DCK(cudaMalloc(&st.d_scratch2[k], sizeof(DflTrees) * (size_t)parse_blocks * DFL_PARSE_THREADS));
         st.scratch_n = (size_t)parse_blocks * DFL_PARSE_THREADS;
-        for (int k = 0; k < 2; ++k) DCK(cudaMalloc(&st.d_scratch2[k], sizeof(DflTrees) * st.scratch_n));
     }
     st.main_ms = 0.0;
     st.serial_jobs = 0;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    DCK(cudaEventCreate(&e0)); DCK(cudaEventCreate(&e1));
+    if (!st.ev_t[0]) { DCK(cudaEventCreate(&st.ev_t[0])); DCK(cudaEventCreate(&st.ev_t[1])); }   // owned by the state: no leak on error paths
+    cudaEvent_t e0 = st.ev_t[0], e1 = st.ev_t[1];
     int rc = 0;
     if (!need_prep.empty()) {
         {
@@ -2064,15 +2070,18 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
     } else {
         // pairs in batches, double buffered: the junction tables of batch b+1 are computed on `stream` while the
         // pair streams of batch b are parsed on st.stream2 (a latency-bound kernel with one thread per stream)
-        const size_t batch = DFL_BATCH;
         if (st.fj_pairs < batch) {
-            for (int k = 0; k < 2; ++k) { cudaFree(st.d_FJ2[k]); cudaFree(st.d_pairs2[k]); cudaFree(st.d_jobs2[k]); }
-            st.fj_pairs = batch;
+            for (int k = 0; k < 2; ++k) {
+                cudaFree(st.d_FJ2[k]); cudaFree(st.d_pairs2[k]); cudaFree(st.d_jobs2[k]); cudaFree(st.d_FJQ2[k]);
+                st.d_FJ2[k] = st.d_FJQ2[k] = nullptr; st.d_pairs2[k] = nullptr; st.d_jobs2[k] = nullptr;
+            }
+            st.fj_pairs = 0;
             for (int k = 0; k < 2; ++k) {
                 DCK(cudaMalloc(&st.d_FJ2[k], sizeof(uint32_t) * batch * DFL_JSTRIDE));
                 DCK(cudaMalloc(&st.d_pairs2[k], sizeof(DflPair) * batch));
                 DCK(cudaMalloc(&st.d_jobs2[k], sizeof(DflJob) * batch));
             }
+            st.fj_pairs = batch;
         }
         if (FQ && !st.d_FJQ2[0])
             for (int k = 0; k < 2; ++k) DCK(cudaMalloc(&st.d_FJQ2[k], sizeof(uint32_t) * batch * DFL_JSTRIDE));
@@ -2153,7 +2162,6 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
             if (!redo.empty()) rc = run_pairs(&redo, 4);
         }
     }
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     return rc;
 }
 #undef DCK

@@ -18,10 +18,12 @@ _STRIP = bytes([9, 10, 11, 12, 13, 32])
 
 
 def _read_fasta_lines(raw):
-    """line-by-line parser: the reference semantics spelled out (rstrip of every line, then blanks and CRs dropped)"""
+    """line-by-line parser: the reference semantics spelled out (text mode = universal newlines, rstrip of every
+    line, then blanks dropped)"""
+    import re
     recs = []
     cur = None
-    for line in raw.split(b"\n"):
+    for line in re.split(rb"\r\n|\r|\n", raw):
         if line.startswith(b">"):
             if cur is not None:
                 recs.append(b"".join(cur))

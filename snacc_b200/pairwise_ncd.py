@@ -91,11 +91,6 @@ def compute_distance(x, y, cxy, cyx):
     return min((cxy - lo) / hi, (cyx - lo) / hi)
 
 
-def _row_partition(n, world):
-    """columns owned by each rank: contiguous bands (see sharding.owned_cols)"""
-    return [np.arange(r * n // world, (r + 1) * n // world, dtype=np.int64) for r in range(world)]
-
-
 def ncd_matrix(files, algorithm, reverse_complement=False, fast_mode=False, gpus=None, engine=None,
                rows_per_call=None):
     """All-pairs sizes and distances for ``files`` (already de-duplicated and ordered by the caller).
@@ -104,11 +99,15 @@ def ncd_matrix(files, algorithm, reverse_complement=False, fast_mode=False, gpus
     lengths, no +33), ``D`` the float64 NCD matrix with the reference formula (both orders, +33 bias) or,
     with ``fast_mode``, the one-order formula on the upper triangle mirrored.
 
-    Multi-GPU: when ``torch.distributed`` is initialised (one process per GPU) the corpus is read by rank 0,
-    broadcast, every rank computes its rows of S, and rank 0 gathers; all ranks return the full result."""
+    Multi-GPU: inside a ``torch.distributed`` process group (one process per GPU, e.g. under ``torchrun``) every
+    rank parses and uploads its band of the files, the corpus is all-gathered over NVLink, every rank computes its
+    columns of S and all ranks return the full result.  From a plain process, ``gpus=N`` (N > 1) launches N such
+    ranks (``sharding.run_multi_gpu``) and returns rank 0's result; ``gpus`` in (None, 1) uses this process's GPU."""
     from . import sharding
     if algorithm not in CODEC_IDS:
         raise KeyError(f"compression '{algorithm}' is not supported on the GPU path (supported: lz4, gzip, zlib)")
     files = [Path(f) for f in files]
+    if gpus is not None and int(gpus) > 1 and sharding._dist() is None and engine is None:
+        return sharding.run_multi_gpu(files, algorithm, reverse_complement, fast_mode, int(gpus))
     return sharding.all_pairs(files, algorithm, reverse_complement, fast_mode, engine=engine,
                               rows_per_call=rows_per_call)

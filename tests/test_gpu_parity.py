@@ -300,3 +300,197 @@ def test_lz4_stale_table_slots(engine):
     assert engine.stat("packed_jobs") == n * n
     ref = np.array([[olib.ref_lz4f_size(np.concatenate([a, b])) for b in seqs] for a in seqs])
     assert np.array_equal(S, ref)
+
+
+# ---- the parity contract of BASELINE.md section 3 / SURVEY.md 8d at the named shapes --------------------------------------
+def _ref_jobs(seqs, xs, ys, algo):
+    """real liblz4 / zlib on all host cores: jobs (xs[k], ys[k]); ys[k] < 0 = xs[k] alone"""
+    corpus = np.concatenate(seqs)
+    so = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    so[1:] = np.cumsum([s.size for s in seqs])
+    return olib.ref_batch_sizes(corpus, so, np.asarray(xs, np.int32), np.asarray(ys, np.int32), algo,
+                                len(os.sched_getaffinity(0)))
+
+
+def _write_fasta_records(path, records, width=70):
+    with open(path, "wb") as fh:
+        for k, seq in enumerate(records):
+            fh.write(b">contig_%d some description\n" % k)
+            full = seq.size // width
+            body = np.empty((full, width + 1), dtype=np.uint8)
+            body[:, :width] = seq[:full * width].reshape(full, width)
+            body[:, width] = 10
+            body.tofile(fh)
+            if seq.size > full * width:
+                fh.write(seq[full * width:].tobytes() + b"\n")
+
+
+@pytest.fixture(scope="module")
+def mystery_genomes(tmp_path_factory):
+    """stand-ins for the reference's missing test_dataset/mysteryGenome_1..8.fasta: 8 related genomes of
+    ~4.45 Mbp (the Demo notebook's sizes); two of the files hold several records (per-record reverse complement)"""
+    from snacc_b200 import synth
+    d = tmp_path_factory.mktemp("mystery")
+    g = synth.phylogeny(8, 4_450_000, seed=1, n_indels=3)
+    files, recs = [], []
+    for i, seq in enumerate(g):
+        cuts = [0, seq.size] if i not in (2, 5) else [0, 1_000_003, 1_000_003, 3_200_000, seq.size]   # incl. an empty record
+        parts = [seq[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+        p = d / f"mysteryGenome_{i + 1}.fasta"
+        _write_fasta_records(p, parts)
+        files.append(p)
+        recs.append(parts)
+    return d, files, recs
+
+
+@pytest.mark.parametrize("case", ["c1_lz4", "c2_gzip_rc"])
+def test_config_c1_c2_cli_csv_at_the_named_shape(mystery_genomes, tmp_path, monkeypatch, case):
+    """BASELINE.json configs[0] / configs[1]: mysteryGenome_1..8 (8 x ~4.45 Mbp) through the CLI, `-c lz4` and `-c gzip
+    --reverse-compliment True`: CSV byte-identical to the reference route (cli.py:104-142 restated: real liblz4 / zlib
+    sizes -> compute_distance -> pandas pivot -> to_csv), all 8 + 64 sizes equal"""
+    from click.testing import CliRunner
+    from snacc_b200 import cli as gcli
+    from snacc_b200.pairwise_ncd import ncd_matrix
+    d, files, recs = mystery_genomes
+    algo, rc = ("lz4", False) if case == "c1_lz4" else ("gzip", True)
+    seqs = []
+    for parts in recs:
+        if rc:
+            parts = [np.frombuffer(p.tobytes().translate(COMPLEMENT_TABLE)[::-1], dtype=np.uint8) for p in parts]
+        seqs.append(np.concatenate(parts))
+    n = len(seqs)
+    xs = np.concatenate([np.repeat(np.arange(n), n), np.arange(n)])
+    ys = np.concatenate([np.tile(np.arange(n), n), np.full(n, -1)])
+    ref = _ref_jobs(seqs, xs, ys, algo)
+    Sref, Cref = ref[:n * n].reshape(n, n), ref[n * n:]
+    out = tmp_path / "dist.csv"
+    monkeypatch.chdir(tmp_path)
+    args = [str(d), "-o", str(out), "-c", algo, "--no-show-progress"] + (["--reverse-compliment", "True"] if rc else [])
+    r = CliRunner().invoke(gcli.cli, args)
+    assert r.exit_code == 0, r.output
+    want = tmp_path / "want.csv"
+    order = snacc_oracle.sorted_files([d])
+    assert [p.name for p in order] == [f"mysteryGenome_{i}.fasta" for i in range(1, 9)]
+    snacc_oracle.write_csv(order, snacc_oracle.ncd_from_sizes(Cref, Sref), want)
+    assert out.read_bytes() == want.read_bytes()
+    log = (tmp_path / "dist.md").read_text()
+    assert f"* Compression method: {algo}" in log and f"* Reverse complement: {rc}" in log
+    assert all(f"* {p}" in log for p in order)
+    labels, C, S, D = ncd_matrix(order, algo, reverse_complement=rc)
+    assert np.array_equal(C, Cref) and np.array_equal(S, Sref)
+
+
+def test_config_c3_sample_of_ten_thousand_jobs(engine):
+    """c3 shape (BASELINE.json configs[2]): dengue-sized genomes, single-block LZ4 regime, rectangle mode; >= 10^4 of the
+    pair jobs and all singles against the real liblz4"""
+    from snacc_b200 import synth
+    g = synth.phylogeny(160, 10700, seed=3)
+    n = len(g)
+    engine.upload_sequences(g)
+    C = engine.single_sizes("lz4")
+    S = engine.tile_sizes("lz4", 0, n, 0, n)
+    assert engine.stat("packed_jobs") == n * n
+    rng = np.random.default_rng(3)
+    k = rng.choice(n * n, size=12000, replace=False)
+    xs, ys = k // n, k % n
+    ref = _ref_jobs(g, np.concatenate([xs, np.arange(n)]), np.concatenate([ys, np.full(n, -1)]), "lz4")
+    assert np.array_equal(S[xs, ys], ref[:k.size])
+    assert np.array_equal(C, ref[k.size:])
+
+
+def test_config_c4_sample_of_256_jobs(engine):
+    """c4 shape: 5 Mbp genomes, linked LZ4 regime; >= 256 sampled ordered pair jobs + all singles against the real liblz4"""
+    from snacc_b200 import synth
+    g = synth.phylogeny(20, 5_000_000, seed=4, n_indels=2)
+    n = len(g)
+    engine.upload_sequences(g)
+    C = engine.single_sizes("lz4")
+    S = engine.tile_sizes("lz4", 0, n, 0, n)
+    assert engine.stat("packed_jobs") == n * n and engine.stat("bytewise_jobs") == 0
+    rng = np.random.default_rng(4)
+    k = rng.choice(n * n, size=300, replace=False)
+    xs, ys = k // n, k % n
+    ref = _ref_jobs(g, np.concatenate([xs, np.arange(n)]), np.concatenate([ys, np.full(n, -1)]), "lz4")
+    assert np.array_equal(S[xs, ys], ref[:k.size])
+    assert np.array_equal(C, ref[k.size:])
+
+
+def test_config_c5_sample_of_64_gzip_jobs(engine):
+    """c5 shape: 5 Mbp genomes, gzip level 9, both orders; >= 64 sampled ordered pair jobs + singles against zlib 1.3"""
+    from snacc_b200 import synth
+    g = synth.phylogeny(10, 5_000_000, seed=5)
+    n = len(g)
+    engine.upload_sequences(g)
+    C = engine.single_sizes("gzip")
+    S = engine.tile_sizes("gzip", 0, n, 0, n)
+    assert engine.stat("deflate_serial_jobs") == 0
+    rng = np.random.default_rng(5)
+    k = rng.choice(n * n, size=66, replace=False)
+    xs, ys = k // n, k % n
+    ref = _ref_jobs(g, np.concatenate([xs, np.arange(4)]), np.concatenate([ys, np.full(4, -1)]), "gzip")
+    assert np.array_equal(S[xs, ys], ref[:k.size])
+    assert np.array_equal(C[:4], ref[k.size:])
+    assert np.array_equal(S, S.T) is False or n == 1          # both orders are really computed (asymmetric sizes)
+
+
+# ---- the product's multi-GPU path on hardware (needs 2 GPUs: gpurun --gpus 2) ----------------------------------------
+def _n_gpus():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("launcher", ["torchrun", "gpus_flag"])
+def test_two_rank_cli_over_nccl(golden_dir, tmp_path, launcher):
+    """`python -m torch.distributed.run --nproc-per-node 2 -m snacc_b200.cli ...` and `snacc --gpus 2`: every rank parses
+    its band of the files, NCCL all-gather of the corpus, column bands, one writer; CSV byte-identical to the reference
+    CLI's, for the reference semantics and for --fast-mode"""
+    import subprocess
+    import sys
+    if _n_gpus() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    d = Path(golden_dir) / "fasta"
+    files = [str(f) for f in sorted(d.iterdir()) if not f.name.startswith("big")]
+    root = str(Path(__file__).resolve().parents[1])
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    for fast in (False, True):
+        out = tmp_path / f"dist_{launcher}_{int(fast)}.csv"
+        tail = files + ["-o", str(out), "-c", "lz4", "--no-show-progress"] + (["--fast-mode", "True"] if fast else [])
+        if launcher == "torchrun":
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--standalone",
+                   "--local-addr", "127.0.0.1", "-m", "snacc_b200.cli"] + tail
+        else:
+            cmd = [sys.executable, "-m", "snacc_b200.cli", "--gpus", "2"] + tail
+        r = subprocess.run(cmd, cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-3000:]
+        got = out.read_text().replace(str(d.absolute()) + "/", "")
+        if not fast:
+            assert got == (Path(golden_dir) / "reference_cli_lz4.csv").read_text()
+        else:
+            from snacc_b200.pairwise_ncd import ncd_matrix
+            from snacc_b200 import cli as gcli
+            labels, C, S, D = ncd_matrix([Path(f) for f in files], "lz4", fast_mode=True)
+            want = tmp_path / "want_fast.csv"
+            gcli.write_distance_csv([Path(f) for f in files], D, want)
+            assert out.read_text() == want.read_text()
+        assert (tmp_path / (out.stem + ".md")).exists()
+
+
+def test_two_rank_matrix_at_scale_over_nccl(tmp_path):
+    """2 ranks, 12 x 1.5 Mbp genomes: sharded corpus load + NCCL all-gather + column bands == the single-GPU result,
+    lz4 and gzip"""
+    import subprocess
+    import sys
+    if _n_gpus() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    from snacc_b200 import synth
+    from snacc_b200.pairwise_ncd import ncd_matrix
+    g = synth.phylogeny(12, 1_500_000, seed=8)
+    files = []
+    for i, s in enumerate(g):
+        p = tmp_path / f"g{i:02d}.fa"
+        _write_fasta_records(p, [s])
+        files.append(p)
+    for algo in ("lz4", "gzip"):
+        _, C1, S1, D1 = ncd_matrix(files, algo, reverse_complement=True)
+        _, C2, S2, D2 = ncd_matrix(files, algo, reverse_complement=True, gpus=2)
+        assert np.array_equal(C1, C2) and np.array_equal(S1, S2) and np.array_equal(D1, D2)

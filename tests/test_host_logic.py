@@ -128,15 +128,16 @@ def _worker(rank, world, port, files, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        labels, C, S, D = sharding.all_pairs(files, "lz4", True, False, size_fn=_oracle_size_fn("lz4"))
-        _, Cf, Sf, Df = sharding.all_pairs(files, "lz4", True, True, size_fn=_oracle_size_fn("lz4"))     # fast mode
+        labels, C, S, D = sharding.all_pairs(files, "lz4", True, False, _size_fn=_oracle_size_fn("lz4"))
+        _, Cf, Sf, Df = sharding.all_pairs(files, "lz4", True, True, _size_fn=_oracle_size_fn("lz4"))     # fast mode
         q.put((rank, C.tolist(), S.tolist(), D.tolist(), Sf.tolist(), Df.tolist()))
     finally:
         dist.destroy_process_group()
 
 
 def test_column_sharding_world_size_2_gloo(golden_dir):
-    """N > 1 path on CPU: rank 0 parses + broadcasts, every rank takes a column band, one gather at the end."""
+    """N > 1 path on CPU: every rank parses its band of the files, the bands are all-gathered, every rank takes a
+    column band (or, in fast mode, its share of the upper-triangle columns), one gather at the end."""
     import torch.multiprocessing as mp
     d = Path(golden_dir) / "fasta"
     files = [f for f in gcli.collect_files([str(d)]) if not f.name.startswith("big")]
@@ -161,10 +162,67 @@ def test_column_sharding_world_size_2_gloo(golden_dir):
 
 
 def test_owned_cols_partition():
+    rng = np.random.default_rng(0)
     for n in (1, 7, 8, 512):
         for w in (1, 2, 4, 8):
-            cols = np.concatenate([sharding.owned_cols(n, r, w) for r in range(w)])
-            assert sorted(cols.tolist()) == list(range(n))
+            for lengths in (None, rng.integers(1000, 6_000_000, n)):
+                bands = [sharding.owned_cols(n, r, w, lengths) for r in range(w)]
+                assert np.concatenate(bands).tolist() == list(range(n))                 # contiguous, ordered, complete
+                if n >= w:
+                    assert all(b.size for b in bands)
+    # bands cut by bytes: 8 long genomes followed by 504 short ones must not put all the work on rank 0
+    lengths = np.array([5_000_000] * 8 + [10_000] * 504)
+    b = sharding.band_bounds(lengths, 4)
+    w = [lengths[b[r]:b[r + 1]].sum() for r in range(4)]
+    assert max(w) <= 15_040_000 and min(w) >= 10_000_000      # (the best contiguous cut of this input has max 15.0 M)
+
+
+def test_fast_mode_shares_are_balanced_and_complete():
+    """--fast-mode: the upper triangle is dealt by whole columns, heaviest first; every (i <= j) job exactly once and
+    no rank more than a few percent above the mean (north_star: 'a balanced set of upper-triangle tiles')"""
+    rng = np.random.default_rng(1)
+    for n, w in ((512, 8), (512, 2), (37, 4), (3, 8)):
+        lengths = rng.integers(4_900_000, 5_100_000, n)
+        shares = sharding.fast_mode_cols(lengths, w)
+        assert sorted(np.concatenate(shares).tolist()) == list(range(n))
+        seen = np.zeros((n, n), dtype=np.int32)
+        loads = []
+        for cols in shares:
+            xs, ys = sharding.triangle_jobs(cols)
+            assert np.all(xs <= ys)
+            seen[xs, ys] += 1
+            loads.append(float(lengths[xs].sum() + lengths[ys].sum()))
+        assert np.array_equal(seen, np.triu(np.ones((n, n), dtype=np.int32)))
+        if n >= 8 * w:
+            assert max(loads) <= 1.03 * (sum(loads) / w), (n, w, loads)
+
+
+def test_lone_carriage_returns_end_lines_like_text_mode(tmp_path):
+    """the reference opens FASTA files in text mode (universal newlines): a lone CR ends a line, also a header line"""
+    from snacc_b200 import fasta
+    cases = [b">a\rACGT\rTTGA\r>b\rGG\r", b">a desc\rAC GT\r\nTT\r\r\nGA\n>b\r\nCC", b"x\r>a\rAC\r\n\rGT\r",
+             b">a\nAC\rGT\nTT\r", b">h\r\r\rA\r"]
+    for k, t in enumerate(cases):
+        f = tmp_path / f"cr{k}.fa"
+        f.write_bytes(t)
+        want = snacc_oracle.extract_sequences(f, False)
+        data, lens = fasta.read_fasta(f)
+        assert data.tobytes().decode() == want, (k, t)
+        recs = fasta._read_fasta_lines(t)
+        assert b"".join(recs).decode() == want and lens == [len(r) for r in recs]
+
+
+def test_run_log_contents(tmp_path, monkeypatch):
+    """A9 (cli.py:147-160): the markdown log names the method, the reverse-complement flag, the output path, the
+    versions and every analysed file"""
+    import datetime
+    files = [tmp_path / "b.fa", tmp_path / "a.fa"]
+    txt = gcli.log_template.format(time=datetime.datetime.now(), duration=datetime.timedelta(seconds=3), method="gzip",
+                                   rev_comp=True, output_path=tmp_path / "o.csv", py_version="3.12", snacc_version="0.1.0",
+                                   jobs=6, pairs=3, compute_s=1.5, csv_s=0.01, gpus=1, pairs_per_s=2.0)
+    for needle in ("# `snacc` Analysis", "* Compression method: gzip", "* Reverse complement: True", str(tmp_path / "o.csv"),
+                   "## Version Information", "## Analyzed Files", "6 (3 unordered pairs)"):
+        assert needle in txt, needle
 
 
 def test_native_fasta_parser_equals_the_line_parser(tmp_path):
