@@ -569,7 +569,7 @@ static int run_pk_single(snacc_ctx *ctx, const std::vector<int32_t> &seqs, const
 // 512 B table per stream.
 constexpr int PK_S_LANES = 32, PK_S_WARPS = 12;
 constexpr size_t PK_SMEM_MAX = 232448 - 16;       // 227 KiB per CTA minus the kernel's static shared memory
-constexpr size_t PK_S_SMEM = PK_RING_WORDS * 8 + 256 * 2 + (size_t)PK_S_WARPS * 256 * PK_S_LANES * 2;
+constexpr size_t PK_S_SMEM = PK_RING_BYTES + 256 * 2 + (size_t)PK_S_WARPS * 256 * PK_S_LANES * 2;
 
 struct PkJob { int32_t y, x; int64_t j; };
 
@@ -583,7 +583,7 @@ static PkGeometry pk_geometry(const snacc_ctx *ctx, bool u16)
     // -> 104 streams = 4 warps x 26 lanes; a full 1024-slot alphabet: 90 -> 2 warps x 32 lanes)
     g.nslot = (ctx->nslot5 + 1) & ~1u;
     const size_t l_stream = (size_t)g.nslot * 2 + ((g.nslot + 31) / 32) * 4;        // bytes of table per linked stream
-    const size_t l_fixed = PK_RING_WORDS * 8 + 1024 * 2;
+    const size_t l_fixed = PK_RING_BYTES + 1024 * 2;
     const size_t l_fit = (PK_SMEM_MAX - l_fixed) / l_stream;
     g.lanes = l_fit >= 104 ? 26 : 32;
     g.warps = l_fit >= 104 ? 4 : (int)std::max<size_t>(1, l_fit / 32);

@@ -30,6 +30,7 @@ namespace snacc {
 
 constexpr uint32_t PK_RING_WORDS = 4096;                 // 32 KiB: 131072 bases
 constexpr uint32_t PK_RING_BASES = PK_RING_WORDS * 32;
+constexpr uint32_t PK_RING_BYTES = PK_RING_WORDS * 8 + 16;   // + mirror of the first two words (pk_turbo_lean reads up to 3 x u32 from one masked address)
 constexpr uint32_t PK_CHUNK_BASES = 32768;               // refill granularity (keeps >= 96 Ki bases behind)
 constexpr uint32_t PK_GUARD = 128;                       // streams stop this far before the ring's end
 constexpr uint32_t PK_ABORT = 0xffffffffu;
@@ -98,16 +99,16 @@ SNACC_HD uint64_t pk_get32(const PkView &v, uint32_t p)
 // the library's while holding at most 1024 (256) live entries.  Three storage kinds:
 //   KIND 0  linked regime, 32-bit positions                                  (4 B per slot)
 //   KIND 1  single-block regime, 16-bit positions (streams <= 64 KiB)         (2 B per slot)
-//   KIND 2  linked regime, 17 bits per slot: the low 16 bits of the position plus an epoch bit
-//           (bit 16 of the position) kept in a separate bit plane            (2 B + 1 bit per slot)
-// KIND 2 is what lets twice as many streams stay resident per SM.  It is exact because a candidate only
-// counts when it is at most 65535 behind the probe: with p = probe position, d' = (p - low16) mod 65536 and
-// m' = p - d', the slot holds a usable candidate iff d' != 0 and bit 16 of m' equals the stored epoch bit --
-// PROVIDED no slot is ever 131072 or more positions old.  That is guaranteed by a rolling sweep: slots are
-// visited round-robin, at least one per ~40 positions of progress (one per vote in the turbo loop, 1 + adv/40
-// per general step, everything after a match longer than 4096), and a visited slot that is out of reach is
-// rewritten to "current position - 65536".  A full cycle therefore takes at most ~40 K positions, so a slot
-// is never older than 65536 + 40 K + 4 K < 131072 when it is read.
+//   KIND 2  linked regime, 17 bits per slot: the low 16 bits of the position plus one bit in a separate bit plane
+//           that says "written during the current 64 Ki epoch"              (2 B + 1 bit per slot)
+// KIND 2 is what lets twice as many streams stay resident per SM.  An epoch is one LZ4 block: blocks start at
+// multiples of 65536 of the stream position, so all positions probed between two block starts share their upper
+// bits.  A slot with its bit set was written at (epoch base | low16) <= the probe: always within reach.  A slot
+// with its bit clear was written during the PREVIOUS epoch at (epoch base - 65536 + low16), which is within 65535
+// of a probe at p iff low16 > (p & 0xffff).  At every block start (new_epoch) the slots whose bit is still clear
+// -- not written for a whole epoch, so at least 65536 behind every later probe -- are retired to low16 = 0, which the
+// rule above never accepts, and all bits are cleared.  Inserts only ever SET a bit (one shared-memory atomic OR, no
+// read-modify-write), and nothing has to be swept in the inner loop.
 template <int KIND, int STRIDE> struct PkTab {
     static constexpr bool U16 = KIND == 1;
     typedef typename std::conditional<KIND == 0, uint32_t, uint16_t>::type T;
@@ -116,68 +117,51 @@ template <int KIND, int STRIDE> struct PkTab {
     static constexpr uint32_t ENTRIES = MASK + 1;
     static constexpr uint32_t ESZ = STRIDE * sizeof(T);   // bytes between two slots of one lane
     T *t;
-    uint32_t *ep;                                         // KIND 2: epoch bit plane, word w of this lane at ep[w * STRIDE]
+    uint32_t *ep;                                         // KIND 2: bit plane, word w of this lane at ep[w * STRIDE]
     uint32_t nslot;                                       // KIND 2: slots actually stored
-    uint32_t cur, last_pos;                               // KIND 2: rolling-sweep cursor and the position it was last advanced at
-    const uint16_t *lut;                                  // code -> BYTE offset of the slot (slot index * ESZ)
-    SNACC_HD uint32_t slot(uint32_t c) const { return (uint32_t)lut[c] / (uint32_t)sizeof(T); }
+    uint32_t epoch_base;                                  // KIND 2: start of the epoch the bits refer to (a block start)
+    const uint16_t *lut;                                  // code -> slot index
+    SNACC_HD uint32_t slot(uint32_t c) const { return lut[c]; }
     // candidate of code c for a probe at position ip; false: nothing within reach
     SNACC_HD bool lookup(uint32_t c, uint32_t ip, uint32_t &m) const
     {
-        const uint32_t sl = slot(c);
-        if (KIND == 0) { m = t[sl]; return m + LZ4_MAX_DISTANCE >= ip; }
-        if (KIND == 1) { m = t[sl]; return true; }
-        const uint32_t idx = sl / STRIDE;
-        const uint32_t e = (ep[(idx >> 5) * STRIDE] >> (idx & 31)) & 1;
-        const uint32_t d = (ip - t[sl]) & 0xffffu;
-        m = ip - d;
-        return d != 0 && (((m >> 16) ^ e) & 1) == 0;
+        const uint32_t idx = slot(c);
+        if (KIND == 0) { m = t[idx * STRIDE]; return m + LZ4_MAX_DISTANCE >= ip; }
+        if (KIND == 1) { m = t[idx * STRIDE]; return true; }
+        const uint32_t v = t[idx * STRIDE];
+        const uint32_t cur = (ep[(idx >> 5) * STRIDE] >> (idx & 31)) & 1;
+        m = ip - ((ip - v) & 0xffffu);
+        return cur ? m != ip : v > (ip & 0xffffu);
     }
     SNACC_HD void put(uint32_t c, uint32_t pos)
     {
-        const uint32_t sl = slot(c);
-        t[sl] = (T)pos;
-        if (KIND == 2) {
-            const uint32_t idx = sl / STRIDE;
-            uint32_t &w = ep[(idx >> 5) * STRIDE];
-            w = (w & ~(1u << (idx & 31))) | (((pos >> 16) & 1) << (idx & 31));
+        const uint32_t idx = slot(c);
+        t[idx * STRIDE] = (T)pos;
+        if (KIND == 2) ep[(idx >> 5) * STRIDE] |= 1u << (idx & 31);
+    }
+    // KIND 2, at a block start: retire what was not written during the epoch that ends, clear the bits
+    SNACC_HD void new_epoch(uint32_t base)
+    {
+        if constexpr (KIND == 2) {
+            for (uint32_t w = 0; w * 32 < nslot; ++w) {
+                uint32_t z = ~ep[w * STRIDE];
+                if (nslot - w * 32 < 32) z &= (1u << (nslot - w * 32)) - 1;
+                for (; z; z &= z - 1) t[(w * 32 + (uint32_t)SNACC_FFS32(z) - 1) * STRIDE] = 0;
+                ep[w * STRIDE] = 0;
+            }
+            epoch_base = base;
         }
     }
-    // KIND 2 rolling sweep: retire slot `cur` if it is out of reach of a probe at ip, then move on
-    SNACC_HD void sweep_one(uint32_t ip)
-    {
-        if (KIND != 2) return;
-        const uint32_t idx = cur;
-        cur = cur + 1 == nslot ? 0 : cur + 1;
-        uint32_t &w = ep[(idx >> 5) * STRIDE];
-        const uint32_t e = (w >> (idx & 31)) & 1;
-        const uint32_t d = (ip - t[idx * STRIDE]) & 0xffffu;
-        const uint32_t m = ip - d;
-        if (!(d != 0 && (((m >> 16) ^ e) & 1) == 0)) {
-            t[idx * STRIDE] = (T)ip;                                                  // low 16 bits of ip - 65536
-            w = (w & ~(1u << (idx & 31))) | ((((ip >> 16) & 1) ^ 1) << (idx & 31));
-        }
-    }
-    // as many slots as the progress since the last call asks for
-    SNACC_HD void sweep_progress(uint32_t ip)
-    {
-        if (KIND != 2) return;
-        const uint32_t adv = ip - last_pos;
-        last_pos = ip;
-        uint32_t k = adv > 4096 ? nslot : 1 + adv / 40;
-        if (ip < 65536u) return;                           // nothing can be out of reach yet (and "0" means position 0)
-        for (; k; --k) sweep_one(ip);
-    }
-    // KIND 2: store an absolute position coming from a 32-bit checkpoint table, for a stream whose open
-    // block starts at bs
+    // KIND 2: store an absolute position coming from a 32-bit checkpoint table, for a stream whose open block
+    // (= current epoch) starts at bs.  (The epoch word of a slot is shared by 32 slots: callers import a whole word
+    // from one thread, or clear the words first.)
     SNACC_HD void import_slot(uint32_t idx, uint32_t pos, uint32_t bs)
     {
         if (KIND != 2) { t[idx * STRIDE] = (T)pos; return; }
-        const bool live = pos + LZ4_MAX_DISTANCE >= bs;
-        const uint32_t store = live ? pos : bs - 65536u;
-        t[idx * STRIDE] = (T)store;
+        const bool cur = pos >= bs, prev = !cur && pos + 65536u >= bs;
+        t[idx * STRIDE] = (T)((cur || prev) ? pos : 0u);
         uint32_t &w = ep[(idx >> 5) * STRIDE];
-        w = (w & ~(1u << (idx & 31))) | (((store >> 16) & 1) << (idx & 31));
+        w = (w & ~(1u << (idx & 31))) | ((cur ? 1u : 0u) << (idx & 31));
     }
 };
 
@@ -217,9 +201,11 @@ template <int KIND, int STRIDE, bool DETECT>
 SNACC_HD bool pk_step(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, uint32_t n, uint32_t xend)
 {
     constexpr uint32_t K = PkTab<KIND, STRIDE>::K, MASK = PkTab<KIND, STRIDE>::MASK;
-    tab.sweep_progress(pk_next_pos(st));
     if (st.phase == PK_BLOCK_START) {
         if (st.bs >= n) { st.phase = PK_DONE; return false; }
+        // KIND 2: a block start is an epoch boundary of the table (the pair kernel has usually done this already,
+        // cooperatively -- pk_run -- and then epoch_base == bs)
+        if (KIND == 2 && tab.epoch_base != st.bs) tab.new_epoch(st.bs);
         const uint32_t be = (n - st.bs > LZ4_BLOCK) ? st.bs + LZ4_BLOCK : n;
         const uint32_t blen = be - st.bs;
         if (DETECT && st.bs + K > xend) return true;
@@ -443,10 +429,12 @@ SNACC_HD uint32_t pk_reduce_or(uint32_t mask, uint32_t v)
 #endif
 }
 
-template <int KIND, int STRIDE, bool LAZY>
-SNACC_HD void pk_turbo(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, uint32_t stop, uint32_t mask, bool work)
+template <int KIND, int STRIDE>
+SNACC_HD void pk_turbo_spec(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, uint32_t stop, uint32_t mask, bool work)
 {
     typedef PkTab<KIND, STRIDE> Tab;
+    static_assert(KIND != 2, "the speculative loop keeps 32-bit / 16-bit tables only (singles pass); KIND 2 runs pk_turbo_lean");
+    constexpr bool LAZY = false;
     constexpr bool U16 = Tab::U16;
     constexpr uint32_t MASK = Tab::MASK;
     constexpr uint32_t ESZ = Tab::ESZ;                      // bytes between two slots of one lane
@@ -467,7 +455,7 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, u
                   tab_a = pk_opaque(pk_sptr_of(tab.t)), ep_a = KIND == 2 ? pk_opaque(pk_sptr_of(tab.ep)) : 0;
 #define PK_TLD(addr) (KIND == 0 ? pk_lds32(addr) : pk_lds16(addr))
 #define PK_TST(addr, val) do { if (KIND == 0) pk_sts32(addr, val); else pk_sts16(addr, val); } while (0)
-#define PK_OFF(code) pk_lds16(lut_a + 2 * (code))            /* slot handle: byte offset of the slot */
+#define PK_OFF(code) (pk_lds16(lut_a + 2 * (code)) * ESZ)    /* slot handle: byte offset of the slot */
 #define PK_EWA(off) (ep_a + (((off) / ESZ) >> 5) * EWB)      /* address of the epoch word of a slot */
 #define PK_EBIT(off) ((((off) / ESZ)) & 31)
     // 32 bases starting at y offset q, as two 32-bit halves (three consecutive ring words)
@@ -476,12 +464,12 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, u
                        c_ = pk_lds32(ring_a + ((j_ + 8) & RMASK));                                             \
         lo = pk_fsr(a_, b_, s_); hi = pk_fsr(b_, c_, s_); } while (0)
     uint32_t Wlo = 0, Whi = 0;                              // bases [pw-4, pw+28)
-    uint32_t pw = p, soff = 0, m = 0, scur = tab.cur;
+    uint32_t pw = p, soff = 0, m = 0;
     bool near = false;                                      // the slot of p holds a candidate within reach
     if (!fin) {
         PK_RING32(p - 4 - lx, Wlo, Whi);
         const uint32_t c0 = (Wlo >> 8) & MASK;
-        soff = tab.lut[c0];
+        soff = tab.lut[c0] * ESZ;
         near = tab.lookup(c0, p, m);
     }
     bool blocked = false;
@@ -498,18 +486,6 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, u
             // warp vote every 4th iteration: leave when a live lane is stuck or nobody runs any more
             // (a stuck lane simply idles for up to 3 iterations)
             if (pk_reduce_or(mask, (go ? 2u : 0u) | ((live && !ok) ? 1u : 0u)) != 2u) break;
-            if (KIND == 2 && p >= 65536u) {                 // rolling sweep: one slot per vote (PkTab comment)
-                const uint32_t so = scur * ESZ;
-                scur = scur + 1 == tab.nslot ? 0 : scur + 1;
-                const uint32_t rv = pk_lds16(tab_a + so), ew = pk_lds32(PK_EWA(so));
-                const uint32_t d = (p - rv) & 0xffffu;
-                const bool reach = d != 0 && ((((p - d) >> 16) ^ (ew >> PK_EBIT(so))) & 1) == 0;
-                // never touch the slot of the pending probe: its candidate is already in registers
-                if (!reach && so != soff) {
-                    pk_sts16(tab_a + so, p);
-                    pk_sts32(PK_EWA(so), (ew & ~(1u << PK_EBIT(so))) | ((((p >> 16) & 1) ^ 1) << PK_EBIT(so)));
-                }
-            }
         }
         // ---- straight-line body; loads are harmless for any lane, stores and commits are predicated
         // candidate: 16 bases from m-4
@@ -640,22 +616,208 @@ SNACC_HD void pk_turbo(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, u
         if (p != anchor) { st.phase = PK_SEARCH; st.fip = p; st.step = 1; st.nb = nb; }
         else             { st.phase = PK_RETEST; st.ip = p; }
         st.anchor = anchor; st.op = op;
-        if (KIND == 2 && it) { tab.cur = scur; tab.last_pos = p; }
     }
 }
 
+// ---- lean inner loop (many-lane tiles) ---------------------------------------------------------------------------
+// With 26 or 32 streams per warp and one warp per scheduler the pair kernel is bound by the number of instructions a
+// warp iteration issues, not by the dependency chain, so this version does nothing ahead of time: per probe it reads the
+// candidate's 16 bases, compares, and only then resolves the two slots it needs (the insert at pn-2 and the next probe
+// pn).  What keeps it short:
+//   * KIND 2 inserts are a 16-bit store plus one shared-memory atomic OR on the epoch bit plane (PkTab): nothing to read
+//     back, nothing to undo -- both inserts are issued after the compare, predicated on the iteration being committed;
+//   * the ring carries a 16-byte mirror of its first words behind its end, so a 2- or 3-word read needs one masked address;
+//   * the conditions that can only change slowly (output budget, skip counter, pending literals) are evaluated at the
+//     warp vote, every 4th iteration, with the slack 4 iterations can use up; per iteration only the block limit and
+//     the candidate's residence in the ring are tested;
+//   * stores are predicated PTX (no branches inside the body).
+// Same contract as pk_turbo_spec: warp-uniform, every lane of `mask` executes every iteration, a lane that meets
+// anything unusual leaves its state untouched and the burst ends at the next vote.
+#ifdef __CUDA_ARCH__
+__device__ __forceinline__ void pk_sor32_if(bool c, pk_sptr a, uint32_t v)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q red.shared.or.b32 [%0], %1;\n\t}" :: "r"(a), "r"(v), "r"((uint32_t)c) : "memory");
+}
+__device__ __forceinline__ void pk_sts16_if(bool c, pk_sptr a, uint32_t v)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.u16 [%0], %1;\n\t}" :: "r"(a), "h"((uint16_t)v), "r"((uint32_t)c) : "memory");
+}
+__device__ __forceinline__ void pk_sts32_if(bool c, pk_sptr a, uint32_t v)
+{
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %2, 0;\n\t@q st.shared.u32 [%0], %1;\n\t}" :: "r"(a), "r"(v), "r"((uint32_t)c) : "memory");
+}
+#else
+inline void pk_sor32_if(bool c, pk_sptr a, uint32_t v) { if (c) *reinterpret_cast<uint32_t *>(a) |= v; }
+inline void pk_sts16_if(bool c, pk_sptr a, uint32_t v) { if (c) *reinterpret_cast<uint16_t *>(a) = (uint16_t)v; }
+inline void pk_sts32_if(bool c, pk_sptr a, uint32_t v) { if (c) *reinterpret_cast<uint32_t *>(a) = v; }
+#endif
+
+template <int KIND, int STRIDE>
+SNACC_HD void pk_turbo_lean(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, uint32_t stop, uint32_t mask, bool work)
+{
+    typedef PkTab<KIND, STRIDE> Tab;
+    constexpr uint32_t MASK = Tab::MASK;
+    constexpr uint32_t ESZ = Tab::ESZ;                      // bytes between two slots of one lane
+    constexpr uint32_t EWB = STRIDE * 4;                    // KIND 2: bytes between two epoch words of one lane
+    constexpr uint32_t RMASK = (2 * PK_RING_WORDS - 1) * 4; // byte-offset mask of the ring seen as u32 words
+    const uint32_t lx = v.lx, rlo = v.rlo, rspan = v.rspan;
+    uint32_t p = st.phase == PK_SEARCH ? st.fip : st.ip;
+    uint32_t anchor = st.anchor, nb = st.nb, op = st.op;
+    const uint32_t lim = tmin(stop, st.mfl1 > 16 ? st.mfl1 - 16 : 0u);
+    // output budget: 4 iterations add at most 4 x (token + offset + length byte) + the literals pending at the vote + 44
+    const uint32_t op_lim = st.budget > 160 ? st.budget - 160 : 0u;
+    const bool fin = !work || p >= stop;
+    const bool ok0 = fin || (st.phase <= PK_RETEST && !(st.phase == PK_SEARCH && st.step != 1) &&
+                             (uint32_t)(p - 4 - lx - rlo) <= rspan);
+    if (!pk_all(mask, ok0) || pk_all(mask, fin)) return;
+    const pk_sptr ring_a = pk_opaque(pk_sptr_of(v.ring)), lut_a = pk_opaque(pk_sptr_of(tab.lut)),
+                  tab_a = pk_opaque(pk_sptr_of(tab.t)), ep_a = KIND == 2 ? pk_opaque(pk_sptr_of(tab.ep)) : 0;
+#define PK_TLD(addr) (KIND == 0 ? pk_lds32(addr) : pk_lds16(addr))
+#define PK_TST_IF(c, addr, val) do { if (KIND == 0) pk_sts32_if(c, addr, val); else pk_sts16_if(c, addr, val); } while (0)
+    // 32 bases starting at y offset q, as two 32-bit halves (three consecutive ring words; the mirror behind the ring's
+    // end makes +4 / +8 safe without a second mask)
+#define PK_RING32(q, lo, hi) do { const uint32_t j_ = ((q) >> 2) & RMASK, s_ = (q) * 2;                          \
+        const uint32_t a_ = pk_lds32(ring_a + j_), b_ = pk_lds32(ring_a + j_ + 4), c_ = pk_lds32(ring_a + j_ + 8); \
+        lo = pk_fsr(a_, b_, s_); hi = pk_fsr(b_, c_, s_); } while (0)
+    uint32_t Wlo = 0, Whi = 0, sh = 0;                      // bases [p-4-sh/2, ...): the window was loaded one iteration ago
+    pk_sptr sa = tab_a, ea = ep_a;                          // slot / epoch word of the pending probe p
+    uint32_t eb = 0, m = 0;                                 // its slot index (bit position) and candidate
+    bool near = false;                                      // the slot of p holds a candidate within reach
+    if (!fin) {
+        PK_RING32(p - 4 - lx, Wlo, Whi);
+        const uint32_t c0 = (Wlo >> 8) & MASK;
+        eb = tab.lut[c0];
+        sa = tab_a + eb * ESZ; ea = ep_a + (eb >> 5) * EWB;
+        near = tab.lookup(c0, p, m);
+    }
+    bool blocked = false, run = false;
+    for (uint32_t it = 0;; ++it) {
+        if ((it & 3) == 0) {
+            // warp vote every 4th iteration: leave when a live lane is stuck or nobody runs any more
+            const uint32_t pend0 = p - anchor;
+            const bool live = !fin && p < stop;
+            run = live && !blocked && op + pend0 <= op_lim && nb <= 116 && pend0 <= 200;
+            const bool can = run && p < lim;
+            if (pk_reduce_or(mask, (can ? 2u : 0u) | ((live && !can) ? 1u : 0u)) != 2u) break;
+        }
+        const bool go = run && p < lim;
+        // ---- straight-line body; loads are harmless for any lane, stores and commits are predicated
+        const uint32_t pend = p - anchor;                   // pending literals; search mode iff != 0
+        const uint32_t qm4 = m - 4 - lx;
+        uint32_t xm;                                        // candidate: 16 bases from m-4
+        {
+            const uint32_t j = (qm4 >> 2) & RMASK;
+            xm = pk_fsr(pk_lds32(ring_a + j), pk_lds32(ring_a + j + 4), qm4 * 2);
+        }
+        const uint32_t Ws = pk_fsr(Wlo, Whi, sh), Wt = Whi >> sh;   // bases [p-4, p+12) and the 16 after them
+        const uint32_t x = Ws ^ xm;
+        const uint32_t fwd = x >> 8, back = x << 24;        // bases p.. ; base p-1 in the two top bits
+        uint32_t common = fwd ? (pk_ctz32(fwd) >> 1) : 12;
+        common = near ? common : 0;
+        uint32_t k = back ? (pk_clz32(back) >> 1) : 4;
+        k = pend ? k : 0;
+        const uint32_t kmax = tmin(pend, m);
+        const bool hit = common >= 4;
+        const bool inring = (uint32_t)(qm4 - rlo) <= rspan + 32;
+        // candidate outside the ring / long match / long catch-up: not for this loop
+        const bool bail = go && ((near && !inring) || common > 11 || (hit && k == 4 && kmax > 4));
+        blocked = blocked || bail;
+        run = run && !bail;
+        const bool commit = go && !bail;
+        k = tmin(k, kmax);
+        const uint32_t lit = pend - k;
+        const uint32_t add = 3 + lit + (lit >= 15 ? 1u : 0u);   // token + offset + literals (lit <= 200: one length byte at most)
+        const uint32_t d = hit ? common : 1u;               // the next probe is at p + d
+        const uint32_t pn = p + d;
+        // first insert: slot of p <- p
+        PK_TST_IF(commit, sa, p);
+        if (KIND == 2) pk_sor32_if(commit, ea, 1u << (eb & 31));
+        // slots of pn-2 (second insert) and pn (next probe), from the register window
+        const uint32_t in = pk_lds16(lut_a + 2 * (pk_fsr(Ws, Wt, 2 * d + 8) & MASK));
+        const uint32_t i2 = pk_lds16(lut_a + 2 * (pk_fsr(Ws, Wt, 2 * d + 4) & MASK));
+        const bool ch = commit && hit;                      // second insert (after a match only): slot of pn-2 <- pn-2
+        PK_TST_IF(ch, tab_a + i2 * ESZ, pn - 2);
+        if (KIND == 2) pk_sor32_if(ch, ep_a + (i2 >> 5) * EWB, 1u << (i2 & 31));
+        // candidate of the next probe (program order after both inserts: it sees them)
+        const pk_sptr san = tab_a + in * ESZ, ean = ep_a + (in >> 5) * EWB;
+        const uint32_t vn = PK_TLD(san);
+        uint32_t mn; bool nn;
+        if (KIND == 2) {
+            const uint32_t cur = (pk_lds32(ean) >> (in & 31)) & 1;
+            mn = pn - ((pn - vn) & 0xffffu);
+            nn = cur ? mn != pn : vn > (pn & 0xffffu);
+        } else {
+            mn = vn;
+            nn = KIND == 1 || (pn - vn <= LZ4_MAX_DISTANCE);
+        }
+        uint32_t Nlo, Nhi;
+        PK_RING32(p - 4 - lx, Nlo, Nhi);                    // window for the next iteration
+        if (commit) {
+#if defined(PK_COUNT_STEPS) && !defined(__CUDA_ARCH__)
+            ++pk_turbo_steps;
+#endif
+            op += hit ? add : 0;
+            nb = hit ? nb : (pend ? nb + 1 : 64);
+            anchor = hit ? pn : anchor;
+            m = mn; near = nn; sa = san; ea = ean; eb = in;
+            Wlo = Nlo; Whi = Nhi; sh = 2 * d; p = pn;
+        }
+    }
+#undef PK_TLD
+#undef PK_TST_IF
+#undef PK_RING32
+    if (work && st.phase <= PK_RETEST) {
+        if (p != anchor) { st.phase = PK_SEARCH; st.fip = p; st.step = 1; st.nb = nb; }
+        else             { st.phase = PK_RETEST; st.ip = p; }
+        st.anchor = anchor; st.op = op;
+    }
+}
+
+#ifdef __CUDA_ARCH__
+// KIND 2 epoch boundary (PkTab::new_epoch) done by the whole warp for every lane that stands at a block start: 32
+// slots per lane and step instead of one lane walking its ~900 slots while the others wait
+template <int STRIDE>
+__device__ __forceinline__ void pk_epoch_coop(const PkState &st, PkTab<2, STRIDE> &tab, uint32_t n, uint32_t mask, bool work)
+{
+    const bool need = work && st.phase == PK_BLOCK_START && st.bs < n && tab.epoch_base != st.bs;
+    uint32_t todo = __ballot_sync(mask, need);
+    if (!todo) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t rank = __popc(mask & ((1u << lane) - 1)), nact = __popc(mask);
+    const uint32_t nw = (tab.nslot + 31) >> 5;
+    while (todo) {
+        const int L = __ffs(todo) - 1;
+        todo &= todo - 1;
+        uint16_t *tL = tab.t + (L - (int)lane);
+        uint32_t *eL = tab.ep + (L - (int)lane);
+        for (uint32_t w = rank; w < nw; w += nact) {
+            uint32_t z = ~eL[w * STRIDE];
+            if (tab.nslot - w * 32 < 32) z &= (1u << (tab.nslot - w * 32)) - 1;
+            for (; z; z &= z - 1) tL[(w * 32 + __ffs(z) - 1) * STRIDE] = 0;
+            eL[w * STRIDE] = 0;
+        }
+    }
+    __syncwarp(mask);
+    if (need) tab.epoch_base = st.bs;
+}
+#endif
+
 // Run the streams of the warp (lanes in `mask`, one stream each) until each one's next position reaches
 // its `stop` or it is done: turbo bursts, separated by one general pk_step for every lane.
-// LAZY: how pk_turbo fetches the table words of the next probe (see there); the kernels leave the default (many lanes:
-// yes, one lane: no), the host emulation -- where STRIDE is always 1 -- asks for the pair kernel's setting explicitly
+// LAZY: which inner loop (many lanes: the lean one, one lane: the speculative one); the kernels leave the default, the
+// host emulation -- where STRIDE is always 1 -- asks for the pair kernel's setting explicitly
 template <int KIND, int STRIDE, bool LAZY = (STRIDE != 1)>
 SNACC_HD void pk_run(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, uint32_t n, uint32_t stop, uint32_t mask)
 {
     for (;;) {
         bool work = st.phase != PK_DONE && pk_next_pos(st) < stop;
         if (!pk_any(mask, work)) return;
-        pk_turbo<KIND, STRIDE, LAZY>(st, tab, v, stop, mask, work);
+        if constexpr (LAZY) pk_turbo_lean<KIND, STRIDE>(st, tab, v, stop, mask, work);
+        else pk_turbo_spec<KIND, STRIDE>(st, tab, v, stop, mask, work);
         work = st.phase != PK_DONE && pk_next_pos(st) < stop;
+#ifdef __CUDA_ARCH__
+        if constexpr (KIND == 2 && STRIDE != 1) pk_epoch_coop<STRIDE>(st, tab, n, mask, work);
+#endif
         if (work) {
 #if defined(PK_COUNT_STEPS) && !defined(__CUDA_ARCH__)
             ++pk_general_steps;
@@ -728,8 +890,11 @@ __device__ __forceinline__ void pk_ring_fill(uint64_t *ring, const uint64_t *yw,
 {
     const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(yw);
     ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(ring);
-    for (uint32_t i = (w0 >> 1) + threadIdx.x; i < (w1 >> 1); i += blockDim.x)
-        dst[i & (PK_RING_WORDS / 2 - 1)] = __ldg(src + i);
+    for (uint32_t i = (w0 >> 1) + threadIdx.x; i < (w1 >> 1); i += blockDim.x) {
+        const ulonglong2 q = __ldg(src + i);
+        dst[i & (PK_RING_WORDS / 2 - 1)] = q;
+        if ((i & (PK_RING_WORDS / 2 - 1)) == 0) dst[PK_RING_WORDS / 2] = q;   // mirror of the first 16 bytes behind the end
+    }
 }
 
 // ---- pair tiles: one stream per thread, LANES active lanes per warp, tables in shared memory --------
@@ -748,8 +913,8 @@ lz4_pk_pair_kernel(PkCorpus pc, const PkTile *__restrict__ tiles, int32_t n_tile
     constexpr bool U16 = Tab::U16;
     extern __shared__ __align__(16) uint8_t smem[];
     uint64_t *ring = reinterpret_cast<uint64_t *>(smem);
-    uint16_t *lut = reinterpret_cast<uint16_t *>(smem + PK_RING_WORDS * 8);
-    typename Tab::T *tabs = reinterpret_cast<typename Tab::T *>(smem + PK_RING_WORDS * 8 + Tab::ENTRIES * 2);
+    uint16_t *lut = reinterpret_cast<uint16_t *>(smem + PK_RING_BYTES);
+    typename Tab::T *tabs = reinterpret_cast<typename Tab::T *>(smem + PK_RING_BYTES + Tab::ENTRIES * 2);
     const uint32_t n_warps = blockDim.x >> 5;
     if (KIND != 2) nslot = Tab::ENTRIES;
     const uint32_t nw = (nslot + 31) >> 5;                 // epoch words per stream
@@ -758,7 +923,7 @@ lz4_pk_pair_kernel(PkCorpus pc, const PkTile *__restrict__ tiles, int32_t n_tile
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t slot = warp * LANES + lane;
-    for (uint32_t i = threadIdx.x; i < Tab::ENTRIES; i += blockDim.x) lut[i] = (uint16_t)(lut_g[i] * Tab::ESZ);
+    for (uint32_t i = threadIdx.x; i < Tab::ENTRIES; i += blockDim.x) lut[i] = lut_g[i];
     Tab tab;
     tab.t = tabs + (size_t)warp * (nslot * LANES) + lane;
     tab.ep = eps + (size_t)warp * (nw * LANES) + lane;
@@ -813,7 +978,7 @@ lz4_pk_pair_kernel(PkCorpus pc, const PkTile *__restrict__ tiles, int32_t n_tile
             n = v.lx + ly;
             bail = !pk_resume(st, n);
             if (bail) st.phase = PK_DONE;
-            tab.cur = 0; tab.last_pos = pk_next_pos(st);
+            tab.epoch_base = st.bs;                // the imported bits refer to the checkpoint's open block
         }
         for (;;) {
             __syncthreads();                       // ring (and on the first pass the tables) visible
@@ -892,13 +1057,13 @@ lz4_pk_single_kernel(PkCorpus pc, const int32_t *__restrict__ seqs, const int32_
                      const uint16_t *__restrict__ lut4_g, const int64_t *__restrict__ out_idx,
                      int64_t *__restrict__ out)
 {
-    __shared__ __align__(16) uint64_t ring[PK_RING_WORDS];
+    __shared__ __align__(16) uint64_t ring[PK_RING_WORDS + 2];
     __shared__ uint32_t s_tab[1024];
     __shared__ uint32_t s_snap[1024];
     __shared__ uint16_t s_lut5[1024];
     __shared__ uint16_t s_lut4[256];
-    for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) s_lut5[i] = (uint16_t)(lut5_g[i] * 4);   // byte offsets
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_lut4[i] = (uint16_t)(lut4_g[i] * 2);
+    for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) s_lut5[i] = lut5_g[i];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) s_lut4[i] = lut4_g[i];
     for (int32_t t = blockIdx.x; t < n_seqs; t += gridDim.x) {
         const int32_t s = seqs[t];
         const int32_t wn = want[t];
@@ -908,8 +1073,8 @@ lz4_pk_single_kernel(PkCorpus pc, const int32_t *__restrict__ seqs, const int32_
         v.ring = ring; v.yw = yw; v.xw = yw; v.lx = 0;
         PkRing rg;
         PkState st, snap;
-        PkTab<0, 1> tl; tl.t = s_tab; tl.lut = s_lut5; tl.ep = nullptr; tl.nslot = 1024; tl.cur = tl.last_pos = 0;
-        PkTab<1, 1> ts; ts.t = reinterpret_cast<uint16_t *>(s_tab); ts.lut = s_lut4; ts.ep = nullptr; ts.nslot = 256; ts.cur = ts.last_pos = 0;
+        PkTab<0, 1> tl; tl.t = s_tab; tl.lut = s_lut5; tl.ep = nullptr; tl.nslot = 1024; tl.epoch_base = 0;
+        PkTab<1, 1> ts; ts.t = reinterpret_cast<uint16_t *>(s_tab); ts.lut = s_lut4; ts.ep = nullptr; ts.nslot = 256; ts.epoch_base = 0;
         const bool linked_single = len > LZ4_BLOCK;
         const uint32_t last_bs = (len / LZ4_BLOCK) * LZ4_BLOCK;
 

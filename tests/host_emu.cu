@@ -58,7 +58,10 @@ static std::vector<uint64_t> pack_host(const PkAlphabet &a, const uint8_t *p, ui
 
 static void ring_fill_host(std::vector<uint64_t> &ring, const std::vector<uint64_t> &yw, uint32_t w0, uint32_t w1)
 {
-    for (uint32_t i = w0; i < w1; ++i) ring[i & (PK_RING_WORDS - 1)] = yw[i];
+    for (uint32_t i = w0; i < w1; ++i) {
+        ring[i & (PK_RING_WORDS - 1)] = yw[i];
+        if ((i & (PK_RING_WORDS - 1)) < 2) ring[PK_RING_WORDS + (i & 1)] = yw[i];      // the mirror pk_ring_fill keeps
+    }
 }
 
 struct EmuCkpt { PkState st; std::vector<uint32_t> tab; };
@@ -93,12 +96,10 @@ static bool emu_run(PkState &st, PkTab<KIND, 1> &tab, std::vector<uint32_t> *tab
     }
 }
 
-// the kernels keep BYTE offsets in the shared-memory code->slot map
+// the shared-memory code->slot map of the kernels: slot indices
 template <int KIND> static std::vector<uint16_t> emu_lut(const uint16_t *raw)
 {
-    std::vector<uint16_t> l(PkTab<KIND, 1>::ENTRIES);
-    for (size_t i = 0; i < l.size(); ++i) l[i] = (uint16_t)(raw[i] * PkTab<KIND, 1>::ESZ);
-    return l;
+    return std::vector<uint16_t>(raw, raw + PkTab<KIND, 1>::ENTRIES);
 }
 
 // returns the size, -1 when the packed pair path bails out, -2 when the input is not packable
@@ -116,10 +117,10 @@ extern "C" int64_t emu_lz4_packed(const uint8_t *x, uint32_t lx, const uint8_t *
     const uint32_t nslot5 = pk_slot_lut(a, false, raw5);
     pk_slot_lut(a, true, raw4);
     const std::vector<uint16_t> lut32 = emu_lut<0>(raw5), lut16 = emu_lut<1>(raw4), lut17 = emu_lut<2>(raw5);
-    std::vector<uint64_t> ring(PK_RING_WORDS, 0);
+    std::vector<uint64_t> ring(PK_RING_WORDS + 2, 0);
     std::vector<uint32_t> tab(1024, 0);
-    PkTab<0, 1> t32; t32.t = tab.data(); t32.ep = nullptr; t32.nslot = 1024; t32.cur = t32.last_pos = 0; t32.lut = lut32.data();
-    PkTab<1, 1> t16; t16.t = reinterpret_cast<uint16_t *>(tab.data()); t16.ep = nullptr; t16.nslot = 256; t16.cur = t16.last_pos = 0; t16.lut = lut16.data();
+    PkTab<0, 1> t32; t32.t = tab.data(); t32.ep = nullptr; t32.nslot = 1024; t32.epoch_base = 0; t32.lut = lut32.data();
+    PkTab<1, 1> t16; t16.t = reinterpret_cast<uint16_t *>(tab.data()); t16.ep = nullptr; t16.nslot = 256; t16.epoch_base = 0; t16.lut = lut16.data();
     PkView v; PkRing rg; PkState st; uint32_t w0, w1;
 
     // ---- the sequence x on its own (kernel lz4_pk_single_kernel, step 1) ----
@@ -171,7 +172,7 @@ extern "C" int64_t emu_lz4_packed(const uint8_t *x, uint32_t lx, const uint8_t *
         const uint32_t nslot = (nslot5 + 1) & ~1u;
         std::vector<uint16_t> lo(nslot, 0);
         std::vector<uint32_t> ep((nslot + 31) / 32, 0);
-        PkTab<2, 1> t17; t17.t = lo.data(); t17.ep = ep.data(); t17.nslot = nslot; t17.cur = 0; t17.last_pos = pk_next_pos(st); t17.lut = lut17.data();
+        PkTab<2, 1> t17; t17.t = lo.data(); t17.ep = ep.data(); t17.nslot = nslot; t17.epoch_base = ck.st.bs; t17.lut = lut17.data();
         for (uint32_t e = 0; e < nslot; ++e) t17.import_slot(e, ck.tab[e], ck.st.bs);
         emu_run<2, false, true>(st, t17, nullptr, v, rg, ring, yw, n, 0, 0, nullptr);
     }
