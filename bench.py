@@ -64,6 +64,7 @@ def parse_args():
     ap.add_argument("--config", default="c4", choices=["c4", "c3", "c5"],
                     help="c4 (default, the headline): 512 x 5 Mbp lz4; c3: 10,000 x ~11 kbp viral genomes (BASELINE.json configs[2]); "
                          "c5: 2,048 x 5 Mbp, gzip, the full ordered matrix C(xy) and C(yx) (BASELINE.json configs[4])")
+    ap.add_argument("--opt", action="append", default=[], help="library tunable name=value (snacc_set_option), repeatable")
     ap.add_argument("--band", type=int, default=0, help="rows per library call (0 = the rank's whole band, 1024 for c3)")
     return ap.parse_args()
 
@@ -315,6 +316,9 @@ def main():
     gen_s = time.perf_counter() - t0
 
     eng = Engine(local_rank)
+    for kv in args.opt:
+        name, val = kv.split("=")
+        eng.set_option(name, int(val))
     eng.upload_device(corpus_dev.data_ptr(), so)
     del corpus_dev
     torch.cuda.empty_cache()

@@ -99,6 +99,18 @@ int snacc_pair_sizes(snacc_ctx *ctx, int codec, const int32_t *xs, const int32_t
 int snacc_tile_sizes(snacc_ctx *ctx, int codec, int32_t row0, int32_t n_rows, int32_t col0, int32_t n_cols,
                      int64_t *out);
 
+/*
+ * Multi-GPU (one context per GPU, one process per GPU): for the deflate codecs the per-sequence preparation is the
+ * part of a run that does not shrink when the pair jobs are split over ranks, so ranks prepare disjoint bands of the
+ * sequences -- snacc_single_sizes on the band does it -- and exchange what a pair stream x.* needs of x (its parse
+ * checkpoint and the size of x alone) as opaque fixed-size records: export on the rank that owns x, all-gather (NCCL),
+ * import on the others.  A rank then only needs the full preparation of the sequences it uses as y.  The reference
+ * has no counterpart (single process, cli.py:104); record_bytes == 0 means the codec has nothing to exchange (LZ4).
+ */
+int64_t snacc_prefix_record_bytes(const snacc_ctx *ctx, int codec);
+int snacc_export_prefix(snacc_ctx *ctx, int codec, const int32_t *seqs, int64_t n, void *out /* n records */);
+int snacc_import_prefix(snacc_ctx *ctx, int codec, const int32_t *seqs, int64_t n, const void *in /* n records */);
+
 /* replaces compute_distance (pairwise_ncd.py:93-111) + the loop cli.py:131-136, in float64:
  * D[i*n+j] from C[n], S[n*n] (raw lengths) with `bias` added to every size (33 = sys.getsizeof(b"")). */
 int snacc_ncd(snacc_ctx *ctx, const int64_t *C, const int64_t *S, int32_t n, int formula, int32_t bias,

@@ -47,6 +47,8 @@ struct snacc_ctx {
 
     // 2-bit packed copy + packed-path prefix checkpoints (lz4_packed.cuh)
     int use_packed = 1;                    // option "lz4_packed": 0 forces the byte-wise kernels
+    int pk_lanes = 26;                     // option "lz4_lanes": 13 = 8 warps x 13 lanes instead of 4 x 26 (experiment)
+    int singles_lean = 0;                  // option "lz4_singles_lean": which inner loop the one-lane singles pass runs
     int sm_count = 148;
     uint64_t *d_pk_words = nullptr, *d_pk_woff = nullptr;
     uint16_t *d_alias5 = nullptr, *d_alias4 = nullptr;
@@ -262,6 +264,7 @@ extern "C" void snacc_ctx_destroy(snacc_ctx *ctx)
 // ---------------------------------------------------------------------------------------------
 static int pack_corpus(snacc_ctx *ctx)
 {
+    NvtxRange nvtx_("snacc_b200: alphabet + 2-bit pack");
     const int32_t n = ctx->n_seqs;
     unsigned long long *d_hist = nullptr;
     CK(cudaMalloc(&d_hist, 256 * sizeof(unsigned long long)));
@@ -318,6 +321,7 @@ static int pack_corpus(snacc_ctx *ctx)
 static int upload_impl(snacc_ctx *ctx, const void *bytes, bool on_device, const uint64_t *seq_offsets,
                        int32_t n_seqs, const uint64_t *rec_offsets, int64_t n_recs, int rc)
 {
+    NvtxRange nvtx_("snacc_b200: upload (scatter records, reverse complement)");
     if (!ctx) return SNACC_ERR_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);
     ctx->err.clear();
@@ -508,6 +512,7 @@ static int lz4_prepare_prefixes(snacc_ctx *ctx, const int32_t *xs, int64_t n)
 static int run_lz4_bytewise(snacc_ctx *ctx, const int32_t *h_x, const std::vector<int64_t> *sel, int64_t n_jobs,
                             bool pairs)
 {
+    NvtxRange nvtx_("snacc_b200: lz4 byte-wise streams");
     const int64_t n = sel ? (int64_t)sel->size() : n_jobs;
     if (n == 0) return SNACC_OK;
     std::vector<int32_t> xs((size_t)n);
@@ -546,6 +551,7 @@ static int run_lz4_bytewise(snacc_ctx *ctx, const int32_t *h_x, const std::vecto
 static int run_pk_single(snacc_ctx *ctx, const std::vector<int32_t> &seqs, const std::vector<int32_t> &want,
                          const std::vector<int64_t> &out_idx)
 {
+    NvtxRange nvtx_("snacc_b200: lz4 singles + prefix checkpoints");
     const int32_t n = (int32_t)seqs.size();
     if (!n) return SNACC_OK;
     int32_t *d_seqs = nullptr, *d_want = nullptr; int64_t *d_idx = nullptr;
@@ -556,8 +562,12 @@ static int run_pk_single(snacc_ctx *ctx, const std::vector<int32_t> &seqs, const
     CK(cudaMemcpyAsync(d_want, want.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_idx, out_idx.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
     const PkCorpus pc{ctx->d_pk_words, ctx->d_pk_woff, ctx->d_len};
-    lz4_pk_single_kernel<<<n, 64, 0, ctx->stream>>>(pc, d_seqs, d_want, n, ctx->d_ck_tab, ctx->d_ck_state, ctx->d_alias5,
-                                                    ctx->d_alias4, d_idx, ctx->d_out);
+    if (ctx->singles_lean)
+        lz4_pk_single_kernel<true><<<n, 64, 0, ctx->stream>>>(pc, d_seqs, d_want, n, ctx->d_ck_tab, ctx->d_ck_state, ctx->d_alias5,
+                                                              ctx->d_alias4, d_idx, ctx->d_out);
+    else
+        lz4_pk_single_kernel<false><<<n, 64, 0, ctx->stream>>>(pc, d_seqs, d_want, n, ctx->d_ck_tab, ctx->d_ck_state, ctx->d_alias5,
+                                                               ctx->d_alias4, d_idx, ctx->d_out);
     ctx->last_launches++;
     CK(cudaGetLastError());
     return SNACC_OK;
@@ -587,6 +597,7 @@ static PkGeometry pk_geometry(const snacc_ctx *ctx, bool u16)
     const size_t l_fit = (PK_SMEM_MAX - l_fixed) / l_stream;
     g.lanes = l_fit >= 104 ? 26 : 32;
     g.warps = l_fit >= 104 ? 4 : (int)std::max<size_t>(1, l_fit / 32);
+    if (l_fit >= 104 && ctx->pk_lanes == 13) { g.lanes = 13; g.warps = 8; }     // experiment: two warps per scheduler
     g.smem = l_fixed + (size_t)g.warps * g.lanes * l_stream;
     g.T = g.lanes * g.warps;
     return g;
@@ -607,6 +618,7 @@ static int pk_launch(snacc_ctx *ctx, bool u16, const PkGeometry &g, const std::v
                      const std::vector<int32_t> &tx, const std::vector<int64_t> &tout, int64_t out_stride, int32_t col0,
                      int64_t n_jobs)
 {
+    NvtxRange nvtx_("snacc_b200: lz4 pair tiles");
     PkTile *d_tiles = nullptr; int32_t *d_tx = nullptr; int64_t *d_tout = nullptr;
     int rs = scratch(ctx, u16 ? 3 : 5, sizeof(PkTile) * tiles.size(), (void **)&d_tiles); if (rs) return rs;
     rs = scratch(ctx, u16 ? 4 : 6, sizeof(int32_t) * tx.size(), (void **)&d_tx); if (rs) return rs;
@@ -629,6 +641,7 @@ static int pk_launch(snacc_ctx *ctx, bool u16, const PkGeometry &g, const std::v
     } while (0)
     if (u16) PK_GO(1, PK_S_LANES, ctx->d_alias4);
     else if (g.lanes == 26) PK_GO(2, 26, ctx->d_alias5);
+    else if (g.lanes == 13) PK_GO(2, 13, ctx->d_alias5);
     else PK_GO(2, 32, ctx->d_alias5);
 #undef PK_GO
     CK(cudaEventRecord(ctx->evm1, ctx->stream));
@@ -886,9 +899,45 @@ extern "C" int snacc_tile_sizes(snacc_ctx *ctx, int codec, int32_t row0, int32_t
     return sizes_impl(ctx, codec, xs.data(), ys.data(), n, out);
 }
 
+// ---- multi-GPU: exchange of per-sequence prefix state between ranks that prepared different sequences ----
+extern "C" int64_t snacc_prefix_record_bytes(const snacc_ctx *ctx, int codec)
+{
+    if (!ctx) return SNACC_ERR_ARG;
+    // LZ4: every rank parses every x itself (one sequence per CTA: the pass costs the latency of ONE sequence however
+    // many a rank owns, so there is nothing to gain from sharing); deflate: checkpoint + size of the sequence alone
+    return (codec == SNACC_GZIP9 || codec == SNACC_ZLIB6) ? (int64_t)sizeof(DflPrefixRecord) : 0;
+}
+
+static int prefix_xfer(snacc_ctx *ctx, int codec, const int32_t *seqs, int64_t n, void *buf, bool do_export)
+{
+    if (!ctx) return SNACC_ERR_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->err.clear();
+    if (!ctx->n_seqs) FAIL(SNACC_ERR_STATE, "nothing uploaded");
+    if (codec != SNACC_GZIP9 && codec != SNACC_ZLIB6) FAIL(SNACC_ERR_CODEC, "this codec has no prefix records to exchange");
+    if (n < 0 || (n && (!seqs || !buf))) FAIL(SNACC_ERR_ARG, "bad sequence list");
+    CK(cudaSetDevice(ctx->device));
+    DeflateCorpus dc{ctx->d_corpus, ctx->d_off, ctx->d_len, ctx->h_off.data(), ctx->h_len.data(), ctx->n_seqs};
+    const int level = codec == SNACC_GZIP9 ? 9 : 6;
+    const int r = do_export ? deflate_export_prefix(ctx->dfl, dc, level, seqs, n, (DflPrefixRecord *)buf, ctx->stream, ctx->err)
+                            : deflate_import_prefix(ctx->dfl, dc, level, seqs, n, (const DflPrefixRecord *)buf, ctx->stream, ctx->err);
+    return r ? SNACC_ERR_CUDA : SNACC_OK;
+}
+
+extern "C" int snacc_export_prefix(snacc_ctx *ctx, int codec, const int32_t *seqs, int64_t n, void *out)
+{
+    return prefix_xfer(ctx, codec, seqs, n, out, true);
+}
+
+extern "C" int snacc_import_prefix(snacc_ctx *ctx, int codec, const int32_t *seqs, int64_t n, const void *in)
+{
+    return prefix_xfer(ctx, codec, seqs, n, const_cast<void *>(in), false);
+}
+
 extern "C" int snacc_ncd(snacc_ctx *ctx, const int64_t *C, const int64_t *S, int32_t n, int formula, int32_t bias,
                          double *D)
 {
+    NvtxRange nvtx_("snacc_b200: ncd epilogue");
     if (!ctx) return SNACC_ERR_ARG;
     std::lock_guard<std::mutex> lock(ctx->mu);
     ctx->err.clear();
@@ -938,6 +987,8 @@ extern "C" int snacc_set_option(snacc_ctx *ctx, const char *name, int64_t value)
     std::lock_guard<std::mutex> lock(ctx->mu);
     if (!strcmp(name, "streams_in_flight")) { ctx->streams_in_flight = value; return SNACC_OK; }
     if (!strcmp(name, "lz4_packed")) { ctx->use_packed = value ? 1 : 0; return SNACC_OK; }
+    if (!strcmp(name, "lz4_lanes")) { ctx->pk_lanes = value == 13 ? 13 : 26; return SNACC_OK; }
+    if (!strcmp(name, "lz4_singles_lean")) { ctx->singles_lean = value ? 1 : 0; return SNACC_OK; }
     if (!strcmp(name, "deflate_canonical")) { ctx->dfl.use_canon = value ? 1 : 0; return SNACC_OK; }
     if (!strcmp(name, "deflate_index6")) { ctx->dfl.use_index6 = value ? 1 : 0; return SNACC_OK; }
     if (!strcmp(name, "deflate_junction")) { ctx->dfl.junction_impl = value == 2 ? 2 : 3; return SNACC_OK; }

@@ -16,6 +16,16 @@
 #define SNACC_FFS64(x) __builtin_ffsll((long long)(x))
 #endif
 
+// NVTX ranges around the phases of a call (upload / pack / singles / pair tiles / deflate stages / epilogue): visible to
+// `ncu --nvtx` and any NVTX-aware tool; header-only NVTX3, a no-op when no tool is attached.  Host builds of the
+// device headers (tests/host_emu.cu) do not need it.
+#if defined(__CUDACC__) && !defined(SNACC_NO_NVTX) && __has_include(<nvtx3/nvToolsExt.h>)
+#include <nvtx3/nvToolsExt.h>
+namespace snacc { struct NvtxRange { explicit NvtxRange(const char *name) { nvtxRangePushA(name); } ~NvtxRange() { nvtxRangePop(); } }; }
+#else
+namespace snacc { struct NvtxRange { explicit NvtxRange(const char *) {} }; }
+#endif
+
 namespace snacc {
 
 template <typename T> SNACC_HD T tmin(T a, T b) { return a < b ? a : b; }

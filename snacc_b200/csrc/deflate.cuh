@@ -1768,6 +1768,8 @@ struct DeflateState {
     uint32_t *d_F[2] = {nullptr, nullptr};         // level 9, level 6
     uint32_t *d_FQ = nullptr;                      // level 6 only: quartered-chain table
     std::vector<uint8_t> have_F[2], have_prep[2];
+    std::vector<uint8_t> have_ckpt[2];             // x-side product present (own parse or imported from another rank): the
+                                                   // checkpoint a pair stream x.* resumes from and the size of x alone
     DflCkpt *d_ckpt[2] = {nullptr, nullptr};
     // canonical symbol streams (per level): pools + per-sequence geometry (shared by both levels)
     uint64_t *d_soff = nullptr, *d_roff = nullptr; uint32_t *d_cap = nullptr;
@@ -1807,7 +1809,7 @@ static inline void deflate_free_corpus(DeflateState &st)
         cudaFree(st.d_seq_size[l]);
         st.d_sym_end[l] = nullptr; st.d_sym_code[l] = nullptr; st.d_cum[l] = nullptr; st.d_nsym[l] = nullptr;
         st.d_seq_size[l] = nullptr;
-        st.have_F[l].clear(); st.have_prep[l].clear();
+        st.have_F[l].clear(); st.have_prep[l].clear(); st.have_ckpt[l].clear();
     }
     st.d_poff = nullptr; st.d_order = nullptr; st.d_bstart = nullptr; st.indexed.clear(); st.h_poff.clear();
     st.n_seqs = 0; st.total = 0;
@@ -1833,6 +1835,7 @@ static inline void deflate_invalidate(DeflateState &st)
     for (int l = 0; l < 2; ++l) {
         std::fill(st.have_F[l].begin(), st.have_F[l].end(), 0);
         std::fill(st.have_prep[l].begin(), st.have_prep[l].end(), 0);
+        std::fill(st.have_ckpt[l].begin(), st.have_ckpt[l].end(), 0);
     }
 }
 
@@ -1893,9 +1896,8 @@ static int dfl_build_index(DeflateState &st, const DflCorpus &c, const std::vect
 }
 
 // sizes of the raw deflate streams of the jobs (x alone when ys == nullptr) into d_out[0..n_jobs)
-static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, const int32_t *xs, const int32_t *ys,
-                       const int32_t *d_xs, const int32_t *, int64_t n_jobs, int64_t *d_out, cudaStream_t stream,
-                       int64_t, int64_t *launches, std::string &err)
+// per-corpus and per-level device state (allocated on first use)
+static int deflate_ensure_alloc(DeflateState &st, const DeflateCorpus &dc, int level, cudaStream_t stream, std::string &err)
 {
     const int li = level == 9 ? 0 : 1;
     const int32_t ns = dc.n_seqs;
@@ -1932,7 +1934,7 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
         DCK(cudaMalloc(&st.d_tail6_order, sizeof(uint16_t) * (size_t)ns * DFL_T6));
         DCK(cudaMalloc(&st.d_tail6_start, sizeof(uint16_t) * (size_t)ns * (DFL_H6 + 1)));
         st.indexed.assign(ns, 0);
-        for (int l = 0; l < 2; ++l) { st.have_F[l].assign(ns, 0); st.have_prep[l].assign(ns, 0); }
+        for (int l = 0; l < 2; ++l) { st.have_F[l].assign(ns, 0); st.have_prep[l].assign(ns, 0); st.have_ckpt[l].assign(ns, 0); }
     }
     if (!st.d_F[li]) {
         DCK(cudaMalloc(&st.d_F[li], sizeof(uint32_t) * (st.total + 16)));
@@ -1946,6 +1948,53 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
         DCK(cudaMalloc(&st.d_seq_size[li], sizeof(int64_t) * ns));
         DCK(cudaMemsetAsync(st.d_nsym[li], 0, sizeof(uint32_t) * ns, stream));
     }
+    return 0;
+}
+
+// The x-side product of a sequence -- what every pair stream x.* needs of x: the parse checkpoint at its junction
+// start and the size of x alone -- as a flat record, so that ranks which prepared different sequences can exchange
+// them (sharding.py: each rank parses its own band of sequences, one all-gather of these records).
+struct DflPrefixRecord { DflCkpt ck; int64_t size; };
+
+static int deflate_export_prefix(DeflateState &st, const DeflateCorpus &dc, int level, const int32_t *seqs, int64_t n,
+                                 DflPrefixRecord *out, cudaStream_t stream, std::string &err)
+{
+    const int li = level == 9 ? 0 : 1;
+    if (!st.d_ckpt[li] || st.n_seqs != dc.n_seqs) { err = "deflate_export_prefix: nothing prepared"; return -1; }
+    for (int64_t k = 0; k < n; ++k) {
+        const int32_t i = seqs[k];
+        if (i < 0 || i >= dc.n_seqs || !st.have_ckpt[li][i]) { err = "deflate_export_prefix: sequence not prepared"; return -1; }
+        DCK(cudaMemcpyAsync(&out[k].ck, st.d_ckpt[li] + i, sizeof(DflCkpt), cudaMemcpyDeviceToHost, stream));
+        DCK(cudaMemcpyAsync(&out[k].size, st.d_seq_size[li] + i, sizeof(int64_t), cudaMemcpyDeviceToHost, stream));
+    }
+    DCK(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+static int deflate_import_prefix(DeflateState &st, const DeflateCorpus &dc, int level, const int32_t *seqs, int64_t n,
+                                 const DflPrefixRecord *in, cudaStream_t stream, std::string &err)
+{
+    const int li = level == 9 ? 0 : 1;
+    if (deflate_ensure_alloc(st, dc, level, stream, err)) return -1;
+    for (int64_t k = 0; k < n; ++k) {
+        const int32_t i = seqs[k];
+        if (i < 0 || i >= dc.n_seqs) { err = "deflate_import_prefix: sequence index out of range"; return -1; }
+        if (st.have_ckpt[li][i]) continue;                      // this rank parsed it itself
+        DCK(cudaMemcpyAsync(st.d_ckpt[li] + i, &in[k].ck, sizeof(DflCkpt), cudaMemcpyHostToDevice, stream));
+        DCK(cudaMemcpyAsync(st.d_seq_size[li] + i, &in[k].size, sizeof(int64_t), cudaMemcpyHostToDevice, stream));
+        st.have_ckpt[li][i] = 1;
+    }
+    DCK(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, const int32_t *xs, const int32_t *ys,
+                       const int32_t *d_xs, const int32_t *, int64_t n_jobs, int64_t *d_out, cudaStream_t stream,
+                       int64_t, int64_t *launches, std::string &err)
+{
+    const int li = level == 9 ? 0 : 1;
+    const int32_t ns = dc.n_seqs;
+    if (deflate_ensure_alloc(st, dc, level, stream, err)) return -1;
     uint32_t *FQ = level != 9 ? st.d_FQ : nullptr;
     DflCorpus c{dc.d_corpus, dc.d_off, dc.d_len, st.d_poff, st.d_order, st.d_bstart, st.d_head_order, st.d_head_visit[li],
                 st.d_tail_cnt, st.d_tail6_order, st.d_tail6_start, nullptr, st.d_bstart6};
@@ -1956,18 +2005,25 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
     //      (size, checkpoint, canonical symbol stream) ----
     std::vector<int32_t> need_idx, need_f, need_prep;
     {
+        // role of every sequence in this call: bit 0 = x of a pair stream or a single (needs its index -- the junction
+        // walk reads x's buckets -- and its x-side product, own or imported), bit 1 = y of a pair stream (needs its
+        // index, match table and the parse of the sequence alone: canonical stream, head visits)
         std::vector<uint8_t> used(ns, 0);
-        for (int64_t k = 0; k < n_jobs; ++k) { used[xs[k]] = 1; if (ys) used[ys[k]] = 1; }
+        for (int64_t k = 0; k < n_jobs; ++k) { used[xs[k]] |= 1; if (ys) used[ys[k]] |= 2; }
         for (int32_t i = 0; i < ns; ++i) {
             if (!used[i]) continue;
+            const bool full = (used[i] & 2) || !st.have_ckpt[li][i];
+            if (ys && !st.indexed[i]) { need_idx.push_back(i); st.indexed[i] = 1; st.have_F[0][i] = st.have_F[1][i] = 0; }
+            if (!full) continue;
             if (!st.indexed[i]) { need_idx.push_back(i); st.indexed[i] = 1; st.have_F[0][i] = st.have_F[1][i] = 0; }
             if (!st.have_F[li][i]) { need_f.push_back(i); st.have_F[li][i] = 1; st.have_prep[li][i] = 0; }
-            if (!st.have_prep[li][i]) { need_prep.push_back(i); st.have_prep[li][i] = 1; }
+            if (!st.have_prep[li][i]) { need_prep.push_back(i); st.have_prep[li][i] = 1; st.have_ckpt[li][i] = 1; }
         }
     }
     uint32_t max_len = 0;
     for (int32_t i : need_f) max_len = std::max(max_len, dc.h_len[i]);
     if (!need_idx.empty()) {
+        NvtxRange nvtx_("snacc_b200: deflate index (radix sort, head/tail packs)");
         int32_t *d_list = nullptr;
         if (dfl_upload(err, stream, need_idx, &d_list)) return -1;
         // the F slices of this level double as sort scratch; they are recomputed right below
@@ -1988,6 +2044,7 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
         cudaFree(d_list);
     }
     if (!need_f.empty()) {
+        NvtxRange nvtx_("snacc_b200: deflate match tables");
         // level 9: runs of sequences whose index slices fit the window buffer get a transient 6-byte index first
         // (dfl_match_word); level 6 always walks the chain (its limit of 128 binds everywhere on DNA)
         const bool i6 = st.use_index6 && level == 9;
@@ -2036,6 +2093,7 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
     cudaEvent_t e0 = st.ev_t[0], e1 = st.ev_t[1];
     int rc = 0;
     if (!need_prep.empty()) {
+        NvtxRange nvtx_("snacc_b200: deflate sequence parses (sizes, checkpoints, canonical streams)");
         {
             int32_t *d_list = nullptr;
             if (dfl_upload(err, stream, need_prep, &d_list)) return -1;
@@ -2102,6 +2160,7 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
         std::vector<DflJob> jobs;
         std::vector<DflPair> pairs;
         auto run_pairs = [&](const std::vector<int64_t> *subset, int kind) -> int {
+            NvtxRange nvtx_("snacc_b200: deflate pair batches (junction tables + pair parses)");
             const int64_t total = subset ? (int64_t)subset->size() : n_jobs;
             // measured: the junction kernel and the parse kernel running side by side (st.stream2) take 10 % longer
             // than one after the other -- each fills the SMs on its own (registers / shared memory) -- so the second

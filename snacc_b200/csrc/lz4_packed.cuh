@@ -633,6 +633,9 @@ SNACC_HD void pk_turbo_spec(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView 
 //   * stores are predicated PTX (no branches inside the body).
 // Same contract as pk_turbo_spec: warp-uniform, every lane of `mask` executes every iteration, a lane that meets
 // anything unusual leaves its state untouched and the burst ends at the next vote.
+#ifndef PK_EPOCH_ATOMIC
+#define PK_EPOCH_ATOMIC 0        // 1: epoch bits set with red.shared.or (measured: the shared-memory atomics stall the in-order LSU)
+#endif
 #ifdef __CUDA_ARCH__
 __device__ __forceinline__ void pk_sor32_if(bool c, pk_sptr a, uint32_t v)
 {
@@ -660,6 +663,7 @@ SNACC_HD void pk_turbo_lean(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView 
     constexpr uint32_t ESZ = Tab::ESZ;                      // bytes between two slots of one lane
     constexpr uint32_t EWB = STRIDE * 4;                    // KIND 2: bytes between two epoch words of one lane
     constexpr uint32_t RMASK = (2 * PK_RING_WORDS - 1) * 4; // byte-offset mask of the ring seen as u32 words
+    constexpr uint32_t VMASK = KIND == 0 ? 0xffffffffu : 0xffffu;   // what a slot keeps of a position
     const uint32_t lx = v.lx, rlo = v.rlo, rspan = v.rspan;
     uint32_t p = st.phase == PK_SEARCH ? st.fip : st.ip;
     uint32_t anchor = st.anchor, nb = st.nb, op = st.op;
@@ -674,98 +678,102 @@ SNACC_HD void pk_turbo_lean(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView 
                   tab_a = pk_opaque(pk_sptr_of(tab.t)), ep_a = KIND == 2 ? pk_opaque(pk_sptr_of(tab.ep)) : 0;
 #define PK_TLD(addr) (KIND == 0 ? pk_lds32(addr) : pk_lds16(addr))
 #define PK_TST_IF(c, addr, val) do { if (KIND == 0) pk_sts32_if(c, addr, val); else pk_sts16_if(c, addr, val); } while (0)
-    // 32 bases starting at y offset q, as two 32-bit halves (three consecutive ring words; the mirror behind the ring's
-    // end makes +4 / +8 safe without a second mask)
-#define PK_RING32(q, lo, hi) do { const uint32_t j_ = ((q) >> 2) & RMASK, s_ = (q) * 2;                          \
-        const uint32_t a_ = pk_lds32(ring_a + j_), b_ = pk_lds32(ring_a + j_ + 4), c_ = pk_lds32(ring_a + j_ + 8); \
-        lo = pk_fsr(a_, b_, s_); hi = pk_fsr(b_, c_, s_); } while (0)
-    uint32_t Wlo = 0, Whi = 0, sh = 0;                      // bases [p-4-sh/2, ...): the window was loaded one iteration ago
-    pk_sptr sa = tab_a, ea = ep_a;                          // slot / epoch word of the pending probe p
-    uint32_t eb = 0, m = 0;                                 // its slot index (bit position) and candidate
+    // state of the pending probe p: slot / epoch-word address, slot index (bit position), candidate, epoch word as last read
+    pk_sptr sa = tab_a, ea = ep_a;
+    uint32_t eb = 0, m = 0, ew = 0;
     bool near = false;                                      // the slot of p holds a candidate within reach
     if (!fin) {
-        PK_RING32(p - 4 - lx, Wlo, Whi);
-        const uint32_t c0 = (Wlo >> 8) & MASK;
+        const uint32_t c0 = (uint32_t)(pk_ring_read(v.ring, p - lx)) & MASK;
         eb = tab.lut[c0];
         sa = tab_a + eb * ESZ; ea = ep_a + (eb >> 5) * EWB;
         near = tab.lookup(c0, p, m);
+        if (KIND == 2) ew = pk_lds32(ea);
     }
-    bool blocked = false, run = false;
-    for (uint32_t it = 0;; ++it) {
-        if ((it & 3) == 0) {
-            // warp vote every 4th iteration: leave when a live lane is stuck or nobody runs any more
-            const uint32_t pend0 = p - anchor;
-            const bool live = !fin && p < stop;
-            run = live && !blocked && op + pend0 <= op_lim && nb <= 116 && pend0 <= 200;
-            const bool can = run && p < lim;
-            if (pk_reduce_or(mask, (can ? 2u : 0u) | ((live && !can) ? 1u : 0u)) != 2u) break;
-        }
-        const bool go = run && p < lim;
-        // ---- straight-line body; loads are harmless for any lane, stores and commits are predicated
-        const uint32_t pend = p - anchor;                   // pending literals; search mode iff != 0
-        const uint32_t qm4 = m - 4 - lx;
-        uint32_t xm;                                        // candidate: 16 bases from m-4
-        {
-            const uint32_t j = (qm4 >> 2) & RMASK;
-            xm = pk_fsr(pk_lds32(ring_a + j), pk_lds32(ring_a + j + 4), qm4 * 2);
-        }
-        const uint32_t Ws = pk_fsr(Wlo, Whi, sh), Wt = Whi >> sh;   // bases [p-4, p+12) and the 16 after them
-        const uint32_t x = Ws ^ xm;
-        const uint32_t fwd = x >> 8, back = x << 24;        // bases p.. ; base p-1 in the two top bits
-        uint32_t common = fwd ? (pk_ctz32(fwd) >> 1) : 12;
-        common = near ? common : 0;
-        uint32_t k = back ? (pk_clz32(back) >> 1) : 4;
-        k = pend ? k : 0;
-        const uint32_t kmax = tmin(pend, m);
-        const bool hit = common >= 4;
-        const bool inring = (uint32_t)(qm4 - rlo) <= rspan + 32;
-        // candidate outside the ring / long match / long catch-up: not for this loop
-        const bool bail = go && ((near && !inring) || common > 11 || (hit && k == 4 && kmax > 4));
-        blocked = blocked || bail;
-        run = run && !bail;
-        const bool commit = go && !bail;
-        k = tmin(k, kmax);
-        const uint32_t lit = pend - k;
-        const uint32_t add = 3 + lit + (lit >= 15 ? 1u : 0u);   // token + offset + literals (lit <= 200: one length byte at most)
-        const uint32_t d = hit ? common : 1u;               // the next probe is at p + d
-        const uint32_t pn = p + d;
-        // first insert: slot of p <- p
-        PK_TST_IF(commit, sa, p);
-        if (KIND == 2) pk_sor32_if(commit, ea, 1u << (eb & 31));
-        // slots of pn-2 (second insert) and pn (next probe), from the register window
-        const uint32_t in = pk_lds16(lut_a + 2 * (pk_fsr(Ws, Wt, 2 * d + 8) & MASK));
-        const uint32_t i2 = pk_lds16(lut_a + 2 * (pk_fsr(Ws, Wt, 2 * d + 4) & MASK));
-        const bool ch = commit && hit;                      // second insert (after a match only): slot of pn-2 <- pn-2
-        PK_TST_IF(ch, tab_a + i2 * ESZ, pn - 2);
-        if (KIND == 2) pk_sor32_if(ch, ep_a + (i2 >> 5) * EWB, 1u << (i2 & 31));
-        // candidate of the next probe (program order after both inserts: it sees them)
-        const pk_sptr san = tab_a + in * ESZ, ean = ep_a + (in >> 5) * EWB;
-        const uint32_t vn = PK_TLD(san);
-        uint32_t mn; bool nn;
-        if (KIND == 2) {
-            const uint32_t cur = (pk_lds32(ean) >> (in & 31)) & 1;
-            mn = pn - ((pn - vn) & 0xffffu);
-            nn = cur ? mn != pn : vn > (pn & 0xffffu);
-        } else {
-            mn = vn;
-            nn = KIND == 1 || (pn - vn <= LZ4_MAX_DISTANCE);
-        }
-        uint32_t Nlo, Nhi;
-        PK_RING32(p - 4 - lx, Nlo, Nhi);                    // window for the next iteration
-        if (commit) {
+    bool blocked = false;
+    for (;;) {
+        // warp vote every 4 iterations: leave when a live lane cannot go on or nobody runs any more.  What can only
+        // change slowly is tested here, with the slack 4 iterations can use up.
+        const uint32_t pend0 = p - anchor;
+        const bool live = !fin && p < stop;
+        bool run = live && !blocked && op + pend0 <= op_lim && nb <= 116 && pend0 <= 200;
+        const bool can = run && p < lim;
+        if (pk_any(mask, live && !can) || !pk_any(mask, can)) break;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            // ---- straight-line, branch-free body: every lane executes everything, stores are predicated, and a lane
+            // that does not commit looks its own probe up again (d = 0), which leaves its state as it was
+            const bool go = run & (p < lim);
+            const uint32_t pend = p - anchor;               // pending literals; search mode iff != 0
+            const uint32_t qm4 = m - 4 - lx, qp4 = p - 4 - lx;
+            const uint32_t jm = (qm4 >> 2) & RMASK, jp = (qp4 >> 2) & RMASK;
+            // candidate: 16 bases from m-4; window: bases [p-4, p+12) and the 16 after them (the mirror behind the
+            // ring's end makes +4 / +8 safe without a second mask)
+            const uint32_t ca = pk_lds32(ring_a + jm), cb = pk_lds32(ring_a + jm + 4);
+            const uint32_t wa = pk_lds32(ring_a + jp), wb = pk_lds32(ring_a + jp + 4), wc = pk_lds32(ring_a + jp + 8);
+            const uint32_t xm = pk_fsr(ca, cb, qm4 * 2);
+            const uint32_t Ws = pk_fsr(wa, wb, qp4 * 2), Wt = pk_fsr(wb, wc, qp4 * 2);
+            const uint32_t x = Ws ^ xm;
+            // equal bases forwards from p (a sentinel bit caps the count at 12) and backwards from p-1 (at 4)
+            uint32_t common = pk_ctz32((x >> 8) | 0x01000000u) >> 1;
+            common = near ? common : 0;
+            uint32_t k = pk_clz32((x << 24) | 0x00800000u) >> 1;
+            const uint32_t kmax = tmin(pend, m);
+            const bool hit = common >= 4;
+            const bool inring = (uint32_t)(qm4 - rlo) <= rspan + 32;
+            // candidate outside the ring / long match / long catch-up: not for this loop
+            // (bitwise on purpose: no short-circuit branches in the body)
+            const bool bail = go & ((near & !inring) | (common > 11) | (hit & (k == 4) & (kmax > 4)));
+            blocked = blocked | bail;
+            run = run & !bail;
+            const bool commit = go & !bail, ch = commit & hit;
+            k = tmin(k, kmax);
+            const uint32_t lit = pend - k;
+            const uint32_t add = 3 + lit + (lit >= 15 ? 1u : 0u);   // token + offset + literals (lit <= 200: one length byte at most)
+            const uint32_t d = commit ? (hit ? common : 1u) : 0u;   // the next probe is at p + d
+            const uint32_t pn = p + d;
+            // first insert: slot of p <- p.  KIND 2: the lookup of p read the epoch word last and nothing has been
+            // written to the lane's plane since, so the bit is set from the register copy -- only when it is not set
+            // yet (one write per slot and epoch in the steady state)
+            PK_TST_IF(commit, sa, p);
+            if (KIND == 2) {
+                const uint32_t b1 = 1u << (eb & 31);
+                pk_sts32_if(commit & ((ew & b1) == 0), ea, ew | b1);
+            }
+            // slots of pn-2 (second insert) and pn (next probe), from the register window
+            const uint32_t in = pk_lds16(lut_a + 2 * (pk_fsr(Ws, Wt, 2 * d + 8) & MASK));
+            const uint32_t i2 = pk_lds16(lut_a + 2 * (pk_fsr(Ws, Wt, 2 * d + 4) & MASK));
+            const pk_sptr san = tab_a + in * ESZ, ean = ep_a + (in >> 5) * EWB;
+            const pk_sptr s2 = tab_a + i2 * ESZ, e2 = ep_a + (i2 >> 5) * EWB;
+            // all loads first (the candidate of the next probe must not wait for the second insert's read-modify-write) ...
+            uint32_t vn = PK_TLD(san), ewn = 0, w2 = 0;
+            if (KIND == 2) { ewn = pk_lds32(ean); w2 = pk_lds32(e2); }
+            // ... then the second insert (after a match only): slot of pn-2 <- pn-2 ...
+            PK_TST_IF(ch, s2, pn - 2);
+            const uint32_t b2 = 1u << (i2 & 31);
+            if (KIND == 2) pk_sts32_if(ch & ((w2 & b2) == 0), e2, w2 | b2);
+            // ... and what it changes in the values just loaded
+            vn = (ch & (i2 == in)) ? ((pn - 2) & VMASK) : vn;
+            if (KIND == 2) ewn = (ch & ((i2 >> 5) == (in >> 5))) ? (ewn | b2) : ewn;
+            // candidate of the next probe
+            uint32_t mn; bool nn;
+            if (KIND == 2) {
+                mn = pn - ((pn - vn) & 0xffffu);
+                nn = ((ewn >> (in & 31)) & 1) ? mn != pn : vn > (pn & 0xffffu);
+            } else {
+                mn = vn;
+                nn = KIND == 1 || (pn - vn <= LZ4_MAX_DISTANCE);
+            }
 #if defined(PK_COUNT_STEPS) && !defined(__CUDA_ARCH__)
-            ++pk_turbo_steps;
+            if (commit) ++pk_turbo_steps;
 #endif
-            op += hit ? add : 0;
-            nb = hit ? nb : (pend ? nb + 1 : 64);
-            anchor = hit ? pn : anchor;
-            m = mn; near = nn; sa = san; ea = ean; eb = in;
-            Wlo = Nlo; Whi = Nhi; sh = 2 * d; p = pn;
+            op += ch ? add : 0u;
+            nb = commit ? (hit ? nb : (pend ? nb + 1 : 64u)) : nb;
+            anchor = ch ? pn : anchor;
+            m = mn; near = nn; sa = san; ea = ean; eb = in; ew = ewn; p = pn;
         }
     }
 #undef PK_TLD
 #undef PK_TST_IF
-#undef PK_RING32
     if (work && st.phase <= PK_RETEST) {
         if (p != anchor) { st.phase = PK_SEARCH; st.fip = p; st.step = 1; st.nb = nb; }
         else             { st.phase = PK_RETEST; st.ip = p; }
@@ -783,13 +791,14 @@ __device__ __forceinline__ void pk_epoch_coop(const PkState &st, PkTab<2, STRIDE
     uint32_t todo = __ballot_sync(mask, need);
     if (!todo) return;
     const uint32_t lane = threadIdx.x & 31;
+    const int mine = (int)tmin(lane, (uint32_t)STRIDE - 1);   // lanes beyond the tile's streams point at the last stream's table
     const uint32_t rank = __popc(mask & ((1u << lane) - 1)), nact = __popc(mask);
     const uint32_t nw = (tab.nslot + 31) >> 5;
     while (todo) {
         const int L = __ffs(todo) - 1;
         todo &= todo - 1;
-        uint16_t *tL = tab.t + (L - (int)lane);
-        uint32_t *eL = tab.ep + (L - (int)lane);
+        uint16_t *tL = tab.t + (L - mine);
+        uint32_t *eL = tab.ep + (L - mine);
         for (uint32_t w = rank; w < nw; w += nact) {
             uint32_t z = ~eL[w * STRIDE];
             if (tab.nslot - w * 32 < 32) z &= (1u << (tab.nslot - w * 32)) - 1;
@@ -924,9 +933,13 @@ lz4_pk_pair_kernel(PkCorpus pc, const PkTile *__restrict__ tiles, int32_t n_tile
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t slot = warp * LANES + lane;
     for (uint32_t i = threadIdx.x; i < Tab::ENTRIES; i += blockDim.x) lut[i] = lut_g[i];
+    // all 32 lanes of a warp run the stream loop (full-mask votes, no partial-warp synchronisation); the lanes beyond
+    // the tile's LANES streams never have work and point at the last stream's table (they only ever load from it)
+    const uint32_t tl = lane < LANES ? lane : LANES - 1;
     Tab tab;
-    tab.t = tabs + (size_t)warp * (nslot * LANES) + lane;
-    tab.ep = eps + (size_t)warp * (nw * LANES) + lane;
+    tab.t = tabs + (size_t)warp * (nslot * LANES) + tl;
+    tab.ep = eps + (size_t)warp * (nw * LANES) + tl;
+    tab.epoch_base = 0;
     tab.nslot = nslot;
     tab.lut = lut;
 
@@ -945,7 +958,7 @@ lz4_pk_pair_kernel(PkCorpus pc, const PkTile *__restrict__ tiles, int32_t n_tile
         pk_ring_fill(ring, yw, w0, w1);
 
         const bool has = lane < LANES && (int32_t)slot < td.count;
-        PkState st;
+        PkState st = PkState();
         PkView v;
         v.ring = ring; v.yw = yw; v.xw = yw; v.lx = 0;
         uint32_t n = 0;
@@ -985,10 +998,7 @@ lz4_pk_pair_kernel(PkCorpus pc, const PkTile *__restrict__ tiles, int32_t n_tile
             rg.view(v);
             const uint32_t stop_q = rg.stop_q();
             const uint32_t stop = stop_q == 0xffffffffu ? 0xffffffffu : v.lx + stop_q;
-            const uint32_t lanes = __ballot_sync(0xffffffffu, has);
-            if (has) {
-                pk_run<KIND, LANES>(st, tab, v, n, stop, lanes);
-            }
+            pk_run<KIND, LANES>(st, tab, v, n, stop, 0xffffffffu);
             if (rg.complete()) break;
             __syncthreads();                       // everyone is done reading the slots about to be replaced
             rg.advance(w0, w1);
@@ -1011,7 +1021,7 @@ struct PkSingleSmem {
     uint32_t snap[1024];
 };
 
-template <int KIND, bool DETECT>
+template <int KIND, bool DETECT, bool LEAN>
 __device__ void pk_single_run(PkState &st, PkTab<KIND, 1> &tab, PkView &v, PkRing &rg, const uint64_t *yw, uint64_t *ring,
                               uint32_t n, uint32_t xend, uint32_t snap_bs, PkState *snap_st, uint32_t *snap_tab)
 {
@@ -1039,7 +1049,7 @@ __device__ void pk_single_run(PkState &st, PkTab<KIND, 1> &tab, PkView &v, PkRin
                         limit = tmin(stop, snap_bs);
                     }
                 }
-                pk_run<KIND, 1>(st, tab, v, n, limit, 1u);
+                pk_run<KIND, 1, LEAN>(st, tab, v, n, limit, 1u);
             }
             s_more = (!touched && st.phase != PK_DONE && !rg.complete()) ? 1u : 0u;
         }
@@ -1051,6 +1061,7 @@ __device__ void pk_single_run(PkState &st, PkTab<KIND, 1> &tab, PkView &v, PkRin
     }
 }
 
+template <bool LEAN>
 __global__ void __launch_bounds__(64)
 lz4_pk_single_kernel(PkCorpus pc, const int32_t *__restrict__ seqs, const int32_t *__restrict__ want, int32_t n_seqs,
                      uint32_t *__restrict__ ck_tab, PkState *__restrict__ ck_state, const uint16_t *__restrict__ lut5_g,
@@ -1085,8 +1096,8 @@ lz4_pk_single_kernel(PkCorpus pc, const int32_t *__restrict__ seqs, const int32_
         rg.start(len, w0, w1);
         pk_ring_fill(ring, yw, w0, w1);
         pk_fresh(st); pk_fresh(snap);
-        if (linked_single) pk_single_run<0, false>(st, tl, v, rg, yw, ring, len, 0, last_bs, &snap, s_snap);
-        else               pk_single_run<1, false>(st, ts, v, rg, yw, ring, len, 0, 0, nullptr, nullptr);
+        if (linked_single) pk_single_run<0, false, LEAN>(st, tl, v, rg, yw, ring, len, 0, last_bs, &snap, s_snap);
+        else               pk_single_run<1, false, LEAN>(st, ts, v, rg, yw, ring, len, 0, 0, nullptr, nullptr);
         if (threadIdx.x == 0 && out_idx[t] >= 0) out[out_idx[t]] = (int64_t)(st.total + lz4_frame_overhead(len));
 
         // (2) linked-regime checkpoint: from the snapshot at the last block start (or from scratch)
@@ -1104,7 +1115,7 @@ lz4_pk_single_kernel(PkCorpus pc, const int32_t *__restrict__ seqs, const int32_
                 rg.start(len, w0, w1);
                 pk_ring_fill(ring, yw, w0, w1);
             }
-            pk_single_run<0, true>(st, tl, v, rg, yw, ring, 0xffffffffu, len, 0, nullptr, nullptr);
+            pk_single_run<0, true, LEAN>(st, tl, v, rg, yw, ring, 0xffffffffu, len, 0, nullptr, nullptr);
             __syncthreads();
             uint32_t *dst = ck_tab + (size_t)(2 * s + 1) * PK_CKPT_TAB;
             for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) dst[i] = s_tab[i];
@@ -1117,7 +1128,7 @@ lz4_pk_single_kernel(PkCorpus pc, const int32_t *__restrict__ seqs, const int32_
             pk_fresh(st);
             rg.start(len, w0, w1);
             pk_ring_fill(ring, yw, w0, w1);
-            pk_single_run<1, true>(st, ts, v, rg, yw, ring, 0xffffffffu, len, 0, nullptr, nullptr);
+            pk_single_run<1, true, LEAN>(st, ts, v, rg, yw, ring, 0xffffffffu, len, 0, nullptr, nullptr);
             __syncthreads();
             uint32_t *dst = ck_tab + (size_t)(2 * s) * PK_CKPT_TAB;
             const uint16_t *t16 = reinterpret_cast<const uint16_t *>(s_tab);

@@ -49,6 +49,10 @@ def load_library():
     lib.snacc_last_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
     lib.snacc_set_option.argtypes = [vp, ctypes.c_char_p, i64]
     lib.snacc_get_stat.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]
+    lib.snacc_prefix_record_bytes.restype = i64
+    lib.snacc_prefix_record_bytes.argtypes = [vp, ctypes.c_int]
+    lib.snacc_export_prefix.argtypes = [vp, ctypes.c_int, vp, i64, vp]
+    lib.snacc_import_prefix.argtypes = [vp, ctypes.c_int, vp, i64, vp]
     lib.snacc_fasta_parse.restype = i64
     lib.snacc_fasta_parse.argtypes = [vp, ctypes.c_uint64, vp, ctypes.POINTER(ctypes.c_uint64), vp, i64]
     _lib = lib
@@ -162,6 +166,23 @@ class Engine:
         out = np.zeros((n_rows, n_cols), dtype=np.int64)
         self._check(self._lib.snacc_tile_sizes(self._h, _codec(algorithm), row0, n_rows, col0, n_cols, out.ctypes.data))
         return out
+
+    # ---- multi-GPU: per-sequence prefix state (see include/snacc_b200.h) ----
+    def prefix_record_bytes(self, algorithm):
+        return int(self._lib.snacc_prefix_record_bytes(self._h, _codec(algorithm)))
+
+    def export_prefix(self, algorithm, seqs):
+        seqs = np.ascontiguousarray(seqs, dtype=np.int32)
+        out = np.zeros((seqs.size, self.prefix_record_bytes(algorithm)), dtype=np.uint8)
+        self._check(self._lib.snacc_export_prefix(self._h, _codec(algorithm), seqs.ctypes.data, seqs.size, out.ctypes.data))
+        return out
+
+    def import_prefix(self, algorithm, seqs, records):
+        seqs = np.ascontiguousarray(seqs, dtype=np.int32)
+        records = np.ascontiguousarray(records, dtype=np.uint8)
+        if records.size != seqs.size * self.prefix_record_bytes(algorithm):
+            raise ValueError("prefix records do not match the sequence list")
+        self._check(self._lib.snacc_import_prefix(self._h, _codec(algorithm), seqs.ctypes.data, seqs.size, records.ctypes.data))
 
     def ncd(self, C, S, formula=0, bias=GETSIZEOF_BIAS):
         C = np.ascontiguousarray(C, dtype=np.int64)

@@ -25,6 +25,26 @@ from .engine import GETSIZEOF_BIAS
 _OWN_GROUP = False
 
 
+class _nvtx:
+    """NVTX range around the collectives (no-op without CUDA)"""
+    def __init__(self, name):
+        self.name, self.on = name, False
+
+    def __enter__(self):
+        try:
+            import torch
+            if torch.cuda.is_available():
+                torch.cuda.nvtx.range_push(self.name)
+                self.on = True
+        except Exception:
+            pass
+
+    def __exit__(self, *exc):
+        if self.on:
+            import torch
+            torch.cuda.nvtx.range_pop()
+
+
 def _dist():
     try:
         import torch.distributed as dist
@@ -143,7 +163,8 @@ def exchange_corpus(local_data, local_seq_lens, local_rec_lens, dist, device=Non
     buf = torch.empty(cap, dtype=torch.uint8, device=device if device is not None else "cpu")
     buf[:t.numel()].copy_(t, non_blocking=True)           # the H2D copy of this rank's band
     allb = torch.empty(world * cap, dtype=torch.uint8, device=buf.device)
-    dist.all_gather_into_tensor(allb, buf)
+    with _nvtx("snacc_b200: corpus all-gather"):
+        dist.all_gather_into_tensor(allb, buf)
     if all(b == cap for b in nbytes):
         full = allb
     else:
@@ -196,7 +217,8 @@ def _all_gather_padded(local, dist, device=None):
     if device is not None:
         t = t.to(device)
     out = torch.empty(world * cap, dtype=torch.int64, device=t.device)
-    dist.all_gather_into_tensor(out, t)
+    with _nvtx("snacc_b200: result / record all-gather"):
+        dist.all_gather_into_tensor(out, t)
     out = out.cpu().numpy()
     return [out[r * cap:r * cap + sizes[r]] for r in range(world)]
 
@@ -251,11 +273,26 @@ def sizes_matrix(engine, algorithm, fast_mode=False, rows_per_call=None, stats=N
                 stats["packed_jobs"] = stats.get("packed_jobs", 0) + int(engine.stat("packed_jobs"))
                 stats["bytewise_jobs"] = stats.get("bytewise_jobs", 0) + int(engine.stat("bytewise_jobs"))
 
-    # every rank: all x (the same pass leaves the prefix checkpoint every pair stream x.y resumes from)
+    bounds = band_bounds(lengths, world)
+    shares = fast_mode_cols(lengths, world) if fast_mode else [np.arange(bounds[r], bounds[r + 1]) for r in range(world)]
+    if dist and engine.prefix_record_bytes(algorithm):
+        # deflate codecs: the per-sequence preparation (index, match table, parse of the sequence alone) is what does
+        # not shrink with the number of ranks, so each rank prepares only the sequences it owns as y -- its columns --
+        # and the x-side products (checkpoint + size of x alone, a 680-byte record) are all-gathered
+        mine = np.asarray(shares[rank], dtype=np.int32)
+        if mine.size:
+            engine.single_sizes(algorithm, mine)
+            note(main=False)
+        recs = engine.export_prefix(algorithm, mine)
+        parts = _all_gather_padded(recs.view(np.int64).ravel() if recs.size else np.zeros(0, np.int64), dist, dev)
+        for r, part in enumerate(parts):
+            if r != rank and part.size:
+                engine.import_prefix(algorithm, np.asarray(shares[r], dtype=np.int32), part.view(np.uint8))
+    # every rank: all x (LZ4: the same pass leaves the prefix checkpoint every pair stream x.y resumes from; deflate
+    # under a process group: served from the records just exchanged)
     C = engine.single_sizes(algorithm)
     note(main=False)
     if not fast_mode:
-        bounds = band_bounds(lengths, world)
         a, b = int(bounds[rank]), int(bounds[rank + 1])
         S_cols = np.zeros((n, b - a), dtype=np.int64)
         step = rows_per_call or max(1, n)
@@ -269,7 +306,6 @@ def sizes_matrix(engine, algorithm, fast_mode=False, rows_per_call=None, stats=N
             stats["bytes"] = float(n * lengths[a:b].sum() + (b - a) * lengths.sum())
         S = gather_cols(S_cols, bounds, n, dist, dev) if dist else S_cols
     else:
-        shares = fast_mode_cols(lengths, world)
         xs, ys = triangle_jobs(shares[rank])
         vals = np.zeros(xs.size, dtype=np.int64)
         for k in range(0, xs.size, MAX_JOBS_PER_CALL):

@@ -102,6 +102,9 @@ template <int KIND> static std::vector<uint16_t> emu_lut(const uint16_t *raw)
     return std::vector<uint16_t>(raw, raw + PkTab<KIND, 1>::ENTRIES);
 }
 
+static int g_singles_lean = 0;       // which inner loop the singles pass of the emulation runs (kernel option lz4_singles_lean)
+extern "C" void emu_set_singles_lean(int v) { g_singles_lean = v; }
+
 // returns the size, -1 when the packed pair path bails out, -2 when the input is not packable
 extern "C" int64_t emu_lz4_packed(const uint8_t *x, uint32_t lx, const uint8_t *y, int64_t ly_)
 {
@@ -130,8 +133,13 @@ extern "C" int64_t emu_lz4_packed(const uint8_t *x, uint32_t lx, const uint8_t *
     v.ring = ring.data(); v.yw = xw.data(); v.xw = xw.data(); v.lx = 0;
     rg.start(lx, w0, w1); ring_fill_host(ring, xw, w0, w1);
     pk_fresh(st);
-    if (linked_single) emu_run<0, false>(st, t32, &tab, v, rg, ring, xw, lx, 0, last_bs, &snap);
-    else               emu_run<1, false>(st, t16, &tab, v, rg, ring, xw, lx, 0, 0, nullptr);
+    if (g_singles_lean) {
+        if (linked_single) emu_run<0, false, true>(st, t32, &tab, v, rg, ring, xw, lx, 0, last_bs, &snap);
+        else               emu_run<1, false, true>(st, t16, &tab, v, rg, ring, xw, lx, 0, 0, nullptr);
+    } else {
+        if (linked_single) emu_run<0, false>(st, t32, &tab, v, rg, ring, xw, lx, 0, last_bs, &snap);
+        else               emu_run<1, false>(st, t16, &tab, v, rg, ring, xw, lx, 0, 0, nullptr);
+    }
     const int64_t single = (int64_t)(st.total + lz4_frame_overhead(lx));
     if (ly_ < 0) return single;
 

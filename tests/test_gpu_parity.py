@@ -494,3 +494,27 @@ def test_two_rank_matrix_at_scale_over_nccl(tmp_path):
         _, C1, S1, D1 = ncd_matrix(files, algo, reverse_complement=True)
         _, C2, S2, D2 = ncd_matrix(files, algo, reverse_complement=True, gpus=2)
         assert np.array_equal(C1, C2) and np.array_equal(S1, S2) and np.array_equal(D1, D2)
+
+
+@pytest.mark.parametrize("algo", ["gzip", "zlib"])
+def test_deflate_prefix_records_exchange(engine, algo):
+    """what the multi-GPU path does for the deflate codecs, on one GPU: sequences prepared 'elsewhere' enter only as
+    imported prefix records (checkpoint + size); pair streams x.y with such an x, and the singles, equal zlib's"""
+    from snacc_b200 import synth
+    g = synth.phylogeny(6, 400_000, seed=11) + [synth_vector("dna", 70000, 3), synth_vector("dna", 200, 4)]
+    n = len(g)
+    engine.upload_sequences(g)
+    assert engine.prefix_record_bytes(algo) > 0 and engine.prefix_record_bytes("lz4") == 0
+    theirs = np.array([0, 2, 4, 6, 7], dtype=np.int32)            # "prepared by another rank"
+    mine = np.array([1, 3, 5], dtype=np.int32)
+    engine.single_sizes(algo, theirs)
+    recs = engine.export_prefix(algo, theirs)
+    engine.set_option("invalidate_caches", 1)
+    engine.import_prefix(algo, theirs, recs)
+    C = engine.single_sizes(algo)                                  # theirs: from the records; mine: parsed here
+    assert np.array_equal(C, np.array([_ref_len(s, algo) for s in g]))
+    xs, ys = np.repeat(np.arange(n), mine.size), np.tile(mine, n)  # all x against my y
+    S = engine.pair_sizes(algo, xs, ys)
+    ref = np.array([_ref_len(np.concatenate([g[a], g[b]]), algo) for a, b in zip(xs, ys)])
+    assert np.array_equal(S, ref)
+    engine.set_option("invalidate_caches", 1)
