@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--length", type=int, default=GENOME_LEN)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gzip-leg", action="store_true", help="skip the gzip sub-leg of the default run")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the c3 / c5 sub-legs of the default run")
     ap.add_argument("--no-host-stages", action="store_true", help="skip the FASTA-parse / CSV-write timings")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     ap.add_argument("--fast-mode", action="store_true", help="upper triangle only (README --fast-mode True)")
@@ -253,53 +254,31 @@ def inject_exceptions(corpus_dev, rate, seed):
     return torch.where(m, pick, corpus_dev)
 
 
-def main():
-    args = parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    codec = args.codec
-    if args.config == "c3" and args.genomes == N_GENOMES and args.length == GENOME_LEN:
-        args.genomes, args.length = 10_000, 10_700
-    if args.config == "c5":
-        codec = args.codec = "gzip"
-        if args.genomes == N_GENOMES:
-            args.genomes = 2048
-    n, L = args.genomes, args.length
-    mode = "upper triangle only (--fast-mode: N + N(N+1)/2 jobs)" if args.fast_mode else \
+def describe(cfg_name, n, L, codec, world, fast_mode, seed):
+    mode = "upper triangle only (--fast-mode: N + N(N+1)/2 jobs)" if fast_mode else \
         "ordered-pair matrix (N + N^2 compressor jobs, reference semantics cli.py:104-136)"
-    workload = (f"{args.config}: {n} x {L / 1e6:g} Mbp synthetic mutated-phylogeny genomes, {codec} NCD; step = the whole "
+    workload = (f"{cfg_name}: {n} x {L / 1e6:g} Mbp synthetic mutated-phylogeny genomes, {codec} NCD; step = the whole "
                 f"{n} x {n} {mode} + float64 NCD")
-    config = {"workload": workload, "n_genomes": n, "genome_len": L, "codec": codec,
-              "seed": SEED, "pair_unit": "ordered pair jobs / 2 (an unordered {i,j} costs two ordered jobs, cli.py:120-136); N^2/2 per step",
-              "l2_policy": "inputs larger than L2 (corpus %.2f GB per GPU, replicated)" % (n * L / 1e9),
-              "sharding": f"product path snacc_b200/sharding.py: contiguous column bands of the job matrix cut by bytes, one per rank "
-                          f"({world} rank(s): all x against the rank's y), no data-path collective; bands all-gathered at the end "
-                          "of the step; e2e: each rank uploads 1/N of the corpus, NCCL all-gather over NVLink"}
-    if args.exceptions:
-        config["exceptions"] = f"{args.exceptions:g} of the bases replaced by N / IUPAC / lower-case bytes"
+    return {"workload": workload, "n_genomes": n, "genome_len": L, "codec": codec,
+            "seed": seed, "pair_unit": "ordered pair jobs / 2 (an unordered {i,j} costs two ordered jobs, cli.py:120-136); N^2/2 per step",
+            "l2_policy": "inputs larger than L2 (corpus %.2f GB per GPU, replicated)" % (n * L / 1e9),
+            "sharding": f"product path snacc_b200/sharding.py: contiguous column bands of the job matrix cut by bytes, one per rank "
+                        f"({world} rank(s): all x against the rank's y), no data-path collective; bands all-gathered at the end "
+                        "of the step; deflate codecs: per-sequence preparation sharded, 680-byte prefix records all-gathered; "
+                        "e2e: each rank uploads 1/N of the corpus, NCCL all-gather over NVLink"}
 
+
+def run_workload(args, cfg_name, n, L, seed, legs, env, want_host_stages):
+    """One synthetic corpus of the named shape on the GPU(s); `legs` = [(codec, steps, warmup, with_cpu)] timed one after
+    the other on it.  Returns (reports per codec -- rank 0 only --, corpus generation seconds, host stage timings,
+    parity failures)."""
     import numpy as np
-
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        return reference_arm(args, config, codec, n, L)
-
     import torch
-    import torch.distributed as dist
     from snacc_b200 import sharding, synth
     from snacc_b200.engine import Engine
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"                # keep NCCL's version banner off stdout: ONE JSON line
-    sharding.init_distributed()                          # the product's own entry: NCCL group + GPU LOCAL_RANK
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    ddist = sharding._dist()
-
+    rank, local_rank, world, dev, ddist = env["rank"], env["local_rank"], env["world"], env["dev"], env["ddist"]
+    peak, peak_src, traffic_tab = env["peak"], env["peak_src"], env["traffic_tab"]
+    SEED = seed
     # ---- synthetic corpus: generated on the device (same seed on every rank), then mirrored to pinned host ----
     t0 = time.perf_counter()
     genomes = synth.phylogeny_torch(n, L, SEED, dev)
@@ -348,7 +327,7 @@ def main():
         else:
             eng.set_option("invalidate_caches", 1)       # nothing (prefix checkpoints ...) survives from the last step
         st = {}
-        band = args.band or (1024 if args.config == "c3" else None)
+        band = args.band or (1024 if cfg_name == "c3" else None)
         C, S = sharding.sizes_matrix(eng, cdc, args.fast_mode, band, st)
         D = eng.ncd(C, S, formula=1 if args.fast_mode else 0)           # K4: float64 epilogue kernel, result read back
         st["launches"] = st.get("launches", 0) + 1
@@ -384,16 +363,6 @@ def main():
             ddist.all_reduce(t, op=ddist.ReduceOp.MAX)
         dev_s, wall_s, e2e_s = [float(v) for v in t.tolist()]
         return stats, clocks, dev_s, wall_s, (e2e_s if with_e2e else None)
-
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    try:
-        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-    except Exception:
-        traffic_tab = {}
 
     host_np = corpus_host.numpy()
     parity_failed = []
@@ -463,31 +432,103 @@ def main():
                                              "`reference_verbatim` leg of --impl reference), one thread per core"}
         return rep
 
-    with_cpu = (not args.no_cpu_baseline) and world == 1
-    main_rep = leg_report(codec, args.steps, args.warmup, with_cpu, args.config)
-    gz_rep = None
-    if codec == "lz4" and args.config == "c4" and not args.no_gzip_leg and not args.fast_mode:
-        gz_rep = leg_report("gzip", max(1, min(args.steps, 5)), min(args.warmup, 3), with_cpu, "c4")
-
+    reports = {}
+    for cdc, steps, warmup, with_cpu in legs:
+        reports[cdc] = leg_report(cdc, steps, warmup, with_cpu, cfg_name)
     host_s = None
-    if rank == 0 and world == 1 and not args.no_host_stages:
-        host_s = host_stages(host_np, so, n, main_rep)
+    if want_host_stages and rank == 0:
+        host_s = host_stages(host_np, so, n, None)
+    eng.close()
+    del corpus_host, band_bytes, host_np
+    torch.cuda.empty_cache()
+    return reports, gen_s, host_s, parity_failed
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    codec = args.codec
+    if args.config == "c3" and args.genomes == N_GENOMES and args.length == GENOME_LEN:
+        args.genomes, args.length = 10_000, 10_700
+    if args.config == "c5":
+        codec = args.codec = "gzip"
+        if args.genomes == N_GENOMES:
+            args.genomes = 2048
+    n, L = args.genomes, args.length
+    config = describe(args.config, n, L, codec, world, args.fast_mode, SEED)
+    if args.exceptions:
+        config["exceptions"] = f"{args.exceptions:g} of the bases replaced by N / IUPAC / lower-case bytes"
+
+    import numpy as np
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        return reference_arm(args, config, codec, n, L)
+
+    import torch
+    import torch.distributed as dist
+    from snacc_b200 import sharding, synth
+    from snacc_b200.engine import Engine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"                # keep NCCL's version banner off stdout: ONE JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", os.path.join(tempfile.gettempdir(), "snacc_bench_nccl.%h.%p.log"))
+    sharding.init_distributed()                          # the product's own entry: NCCL group + GPU LOCAL_RANK
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ddist = sharding._dist()
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        traffic_tab = {}
+    env = {"rank": rank, "local_rank": local_rank, "world": world, "dev": dev, "ddist": ddist, "peak": peak,
+           "peak_src": peak_src, "traffic_tab": traffic_tab}
+
+    with_cpu = (not args.no_cpu_baseline) and world == 1
+    default_run = codec == "lz4" and args.config == "c4" and not args.fast_mode and n == N_GENOMES and L == GENOME_LEN
+    legs = [(codec, args.steps, args.warmup, with_cpu)]
+    if codec == "lz4" and args.config == "c4" and not args.no_gzip_leg and not args.fast_mode:
+        legs.append(("gzip", max(1, min(args.steps, 5)), min(args.warmup, 3), with_cpu))
+    reports, gen_s, host_s, failed = run_workload(args, args.config, n, L, SEED, legs, env,
+                                                  world == 1 and not args.no_host_stages)
+    extra = {}
+    if default_run and not args.no_extra_legs:
+        # the other configurations the metric is quoted on (BASELINE.json configs[2] and configs[4]), a few steps each
+        r3, g3, _, f3 = run_workload(args, "c3", 10_000, 10_700, 3, [("lz4", max(1, min(args.steps, 3)), 1, with_cpu)], env, False)
+        r5, g5, _, f5 = run_workload(args, "c5", 2048, GENOME_LEN, 5, [("gzip", 1, 1, False)], env, False)
+        failed = failed + f3 + f5
+        if rank == 0:
+            r3["lz4"]["config"] = describe("c3", 10_000, 10_700, "lz4", world, False, 3)
+            r5["gzip"]["config"] = describe("c5", 2048, GENOME_LEN, "gzip", world, False, 5)
+            extra = {"c3": r3["lz4"], "c5": r5["gzip"]}
     if rank != 0:
         sharding.shutdown_distributed()
         return 0
     line = {"metric": "ncd_pairs_per_s", "n_gpus": world, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic", "config": config, "corpus_gen_s": gen_s}
-    line.update(main_rep)
-    if gz_rep is not None:
-        gz_rep["config"] = {"workload": workload.replace(f"{codec} NCD", "gzip NCD"), "codec": "gzip",
-                            "note": "same corpus, same step definition, deflate level 9 kernels (gzip.compress, pairwise_ncd.py:74)"}
-        line["gzip"] = gz_rep
+    line.update(reports[codec])
+    if "gzip" in reports and codec != "gzip":
+        reports["gzip"]["config"] = {"workload": config["workload"].replace(f"{codec} NCD", "gzip NCD"), "codec": "gzip",
+                                     "note": "same corpus, same step definition, deflate level 9 kernels (gzip.compress, pairwise_ncd.py:74)"}
+        line["gzip"] = reports["gzip"]
+    line.update(extra)
     if host_s is not None:
         line["host_s"] = host_s
     print(json.dumps(line))
     sharding.shutdown_distributed()
-    if parity_failed:
-        print(f"PARITY FAILURE: {parity_failed}", file=sys.stderr)
+    if failed:
+        print(f"PARITY FAILURE: {failed}", file=sys.stderr)
         return 3
     return 0
 

@@ -123,9 +123,10 @@ template <int KIND, int STRIDE> struct PkTab {
     const uint16_t *lut;                                  // code -> slot index
     SNACC_HD uint32_t slot(uint32_t c) const { return lut[c]; }
     // candidate of code c for a probe at position ip; false: nothing within reach
-    SNACC_HD bool lookup(uint32_t c, uint32_t ip, uint32_t &m) const
+    SNACC_HD bool lookup(uint32_t c, uint32_t ip, uint32_t &m) const { return lookup_idx(slot(c), ip, m); }
+    SNACC_HD void put(uint32_t c, uint32_t pos) { put_idx(slot(c), pos); }
+    SNACC_HD bool lookup_idx(uint32_t idx, uint32_t ip, uint32_t &m) const
     {
-        const uint32_t idx = slot(c);
         if (KIND == 0) { m = t[idx * STRIDE]; return m + LZ4_MAX_DISTANCE >= ip; }
         if (KIND == 1) { m = t[idx * STRIDE]; return true; }
         const uint32_t v = t[idx * STRIDE];
@@ -133,9 +134,8 @@ template <int KIND, int STRIDE> struct PkTab {
         m = ip - ((ip - v) & 0xffffu);
         return cur ? m != ip : v > (ip & 0xffffu);
     }
-    SNACC_HD void put(uint32_t c, uint32_t pos)
+    SNACC_HD void put_idx(uint32_t idx, uint32_t pos)
     {
-        const uint32_t idx = slot(c);
         t[idx * STRIDE] = (T)pos;
         if (KIND == 2) ep[(idx >> 5) * STRIDE] |= 1u << (idx & 31);
     }
@@ -298,6 +298,130 @@ SNACC_HD bool pk_step(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, ui
     return false;
 }
 
+// ---- byte-exact step: sequences with bytes outside the 4-symbol alphabet ------------------------------------------
+// A packed sequence may hold a few bytes outside the corpus alphabet (N, IUPAC codes, soft-masked lower case): in the
+// 2-bit text they carry a filler code and are flagged in a one-bit-per-base mask.  The fast loop never runs with such a
+// base inside its window (the streams stop ahead of it) and treats one inside a candidate's window as a mismatch
+// (pk_turbo_lean, EXC); everything else -- the probes around such a base -- takes this step, which works on the TRUE
+// bytes of the stream (the ASCII corpus in global memory): LZ4's hash of the five real bytes selects the bucket; a
+// bucket that some alphabet k-mer reaches is that k-mer's slot of the shared-memory table (so the two kinds of k-mers
+// collide exactly as in the library's table), any other bucket lives in a per-stream overflow table in global memory.
+// Same state machine, same DETECT contract as pk_step.
+struct PkExact {
+    Stream s;                 // the true bytes: x then y
+    const uint16_t *b2s;      // LZ4 hash bucket (12 bits) -> slot index, 0xffff: no alphabet k-mer reaches this bucket
+    uint32_t *ovf;            // this stream's table for those buckets: 4096 absolute positions (0 = position 0, as in the library)
+};
+constexpr uint32_t PK_OVF_ENTRIES = 4096;
+
+SNACC_HD uint32_t pkx_bucket(const PkExact &xv, uint32_t p)
+{
+    return (uint32_t)(((ld64(xv.s, p) << 24) * 889523592379ull) >> (64 - 12));      // LZ4_hash5 on little-endian 64-bit
+}
+template <int KIND, int STRIDE>
+SNACC_HD bool pkx_lookup(const PkTab<KIND, STRIDE> &tab, const PkExact &xv, uint32_t bucket, uint32_t ip, uint32_t &m)
+{
+    const uint32_t idx = SNACC_LDG(xv.b2s + bucket);
+    if (idx != 0xffffu) return tab.lookup_idx(idx, ip, m);
+    m = xv.ovf[bucket];
+    return m + LZ4_MAX_DISTANCE >= ip;
+}
+template <int KIND, int STRIDE>
+SNACC_HD void pkx_put(PkTab<KIND, STRIDE> &tab, const PkExact &xv, uint32_t bucket, uint32_t pos)
+{
+    const uint32_t idx = SNACC_LDG(xv.b2s + bucket);
+    if (idx != 0xffffu) tab.put_idx(idx, pos);
+    else xv.ovf[bucket] = pos;
+}
+// equal bytes from stream positions a and b forwards, at most max
+SNACC_HD uint32_t pkx_common(const PkExact &xv, uint32_t a, uint32_t b, uint32_t max)
+{
+    uint32_t l = 0;
+    while (l < max) {
+        const uint64_t d = ld64(xv.s, a + l) ^ ld64(xv.s, b + l);
+        if (d) { l += (uint32_t)(SNACC_FFS64(d) - 1) >> 3; break; }
+        l += 8;
+    }
+    return tmin(l, max);
+}
+
+template <int KIND, int STRIDE, bool DETECT>
+SNACC_HD bool pk_step_exact(PkState &st, PkTab<KIND, STRIDE> &tab, const PkExact &xv, uint32_t n, uint32_t xend)
+{
+    static_assert(KIND != 1, "the byte-exact step covers the linked regime (5-byte hash) only");
+    constexpr uint32_t K = 5;
+    if (st.phase == PK_BLOCK_START) {
+        if (st.bs >= n) { st.phase = PK_DONE; return false; }
+        if (KIND == 2 && tab.epoch_base != st.bs) tab.new_epoch(st.bs);
+        const uint32_t be = (n - st.bs > LZ4_BLOCK) ? st.bs + LZ4_BLOCK : n;
+        const uint32_t blen = be - st.bs;
+        if (DETECT && st.bs + K > xend) return true;
+        st.be = be; st.budget = blen - 1; st.anchor = st.bs; st.op = 0; st.max_lhs = 0;
+        if (blen >= LZ4_MINLENGTH) {
+            st.mfl1 = be - LZ4_MFLIMIT + 1; st.mlim = be - LZ4_LASTLITERALS;
+            pkx_put(tab, xv, pkx_bucket(xv, st.bs), st.bs);
+            st.ip = st.bs; st.fip = st.bs + 1; st.step = 1; st.nb = 64;
+            st.phase = PK_SEARCH;
+        } else {
+            pk_end_block(st);
+        }
+        return false;
+    }
+    const bool searching = st.phase == PK_SEARCH;
+    PkState pre;
+    if (DETECT) pre = st;
+    uint32_t ip;
+    if (searching) {
+        ip = st.fip; st.fip += st.step; st.step = (st.nb++ >> 6);
+        if (DETECT && st.fip > xend) { st = pre; return true; }
+        if (st.fip > st.mfl1) { pk_end_block(st); return false; }
+    } else {
+        ip = st.ip;
+    }
+    if (DETECT && ip + K > xend) { st = pre; return true; }
+    const uint32_t b = pkx_bucket(xv, ip);
+    uint32_t m;
+    bool hit = pkx_lookup(tab, xv, b, ip, m);
+    const uint32_t old_m = m;
+    pkx_put(tab, xv, b, ip);
+    if (hit) hit = (uint32_t)ld64(xv.s, ip) == (uint32_t)ld64(xv.s, m);        // LZ4_read32(match) == LZ4_read32(ip)
+    if (hit) {
+        uint32_t op = st.op;
+        if (searching) {
+            while (ip > st.anchor && m > 0 && ld8(xv.s, ip - 1) == ld8(xv.s, m - 1)) { --ip; --m; }
+            const uint32_t lit = ip - st.anchor;
+            op += 1;
+            const uint32_t lhs = op + lit + 8 + lit / 255;
+            st.max_lhs = tmax(st.max_lhs, lhs);
+            if (lhs > st.budget) { st.op = PK_ABORT; pk_end_block(st); return false; }
+            if (lit >= 15) op += (lit - 15) / 255 + 1;
+            op += lit;
+        } else {
+            op += 1;                               // token with zero literals
+        }
+        op += 2;                                   // offset
+        uint32_t lim = st.mlim;
+        if (DETECT) lim = tmin(lim, xend);
+        const uint32_t mlen = pkx_common(xv, ip, m, lim - ip);
+        const uint32_t ip2 = ip + mlen;
+        if (DETECT && (ip2 >= xend || (ip2 < st.mfl1 && ip2 + K - 2 > xend))) {
+            pkx_put(tab, xv, b, old_m); st = pre; return true;
+        }
+        const uint32_t mcode = mlen - 4;
+        const uint32_t lhs2 = op + 6 + (mcode + 240) / 255;
+        st.max_lhs = tmax(st.max_lhs, lhs2);
+        if (lhs2 > st.budget) { st.op = PK_ABORT; pk_end_block(st); return false; }
+        if (mcode >= 15) op += (mcode - 15) / 255 + 1;
+        st.op = op; st.anchor = ip2; st.ip = ip2;
+        if (ip2 >= st.mfl1) { pk_end_block(st); return false; }
+        pkx_put(tab, xv, pkx_bucket(xv, ip2 - 2), ip2 - 2);
+        st.phase = PK_RETEST;                      // immediate re-test at ip2
+    } else if (!searching) {
+        st.phase = PK_SEARCH; st.fip = ip + 1; st.step = 1; st.nb = 64;
+    }
+    return false;
+}
+
 #if defined(PK_COUNT_STEPS)
 static uint64_t pk_general_steps = 0, pk_lean_steps = 0, pk_turbo_steps = 0;
 #endif
@@ -369,30 +493,20 @@ static __host__ __device__ __noinline__ void pk_step_general(PkState &st, PkTab<
     pk_step<KIND, STRIDE, false>(st, tab, v, n, 0);
 }
 
-// ---- speculative inner loop ("turbo") ----------------------------------------------------------
+// ---- inner loop ("turbo") ------------------------------------------------------------------------
 // One thread is one serial dependency chain: probe position -> table slot -> candidate -> compare ->
-// next probe position.  With a handful of warps per SM the issue slots are mostly idle, so this loop
-// spends instructions to shorten the chain: while the candidate of the current probe is being fetched
-// and compared, the table lookups for every likely NEXT probe position (p+1 after a miss, p+4 .. p+6
-// after a match of that length) are already in flight, taken from a 32-base register window; when the
-// match length arrives the right one is selected, patched if this iteration's second insert (p2-2) hit
-// the same slot, and the next compare starts at once.  The window also carries the 4 bases before p, so
-// catch-up over pending literals is a count-leading-zeros on the same XOR.
-//
-// The lanes of a warp run different streams, so the loop is kept WARP-UNIFORM: every lane of `mask`
-// executes every iteration (lanes that have reached `stop` idle), and the burst ends for all of them as
-// soon as one lane meets something the loop does not cover (end of block, candidate outside the ring,
+// next probe position.  The lanes of a warp run different streams, so the loop is kept WARP-UNIFORM: every
+// lane executes every iteration (lanes that have reached `stop` idle), and the burst ends for all of them
+// as soon as one lane meets something the loop does not cover (end of block, candidate outside the ring,
 // match of 12+ bases, catch-up of 4+ bases, tight output budget, skip step > 1).  pk_run then gives every
 // lane one general pk_step -- in lock-step again -- and starts the next burst.  Without this the lanes
 // drift apart and the warp executes them one by one (measured: 4.3 of 16 lanes active per instruction).
 //
-// Exactness: the table sees precisely the library's sequence of reads and writes (speculative reads are
-// issued after the insert of p and corrected for the insert of p2-2); an iteration that cannot be
-// completed restores the one table entry it wrote and leaves the rest of the state untouched.
-// Shared-memory accessors of the turbo loop.  On the device they are explicit ld.shared / st.shared on
-// 32-bit shared-window addresses (the compiler otherwise re-derives the generic->shared base inside the
-// loop) and `selp` selects (it otherwise turns the 5-way selects into divergent branches); on the host --
-// the emulation used by the tests -- they are plain pointer accesses.
+// Exactness: the table sees precisely the library's sequence of reads and writes; an iteration that cannot
+// be completed writes nothing and leaves the state untouched.
+// Shared-memory accessors of the loop.  On the device they are explicit ld.shared / st.shared on 32-bit
+// shared-window addresses (the compiler otherwise re-derives the generic->shared base inside the loop); on the
+// host -- the emulation used by the tests -- they are plain pointer accesses.
 #ifdef __CUDA_ARCH__
 typedef uint32_t pk_sptr;
 __device__ __forceinline__ pk_sptr pk_sptr_of(const void *p) { return (pk_sptr)__cvta_generic_to_shared(p); }
@@ -429,199 +543,10 @@ SNACC_HD uint32_t pk_reduce_or(uint32_t mask, uint32_t v)
 #endif
 }
 
-template <int KIND, int STRIDE>
-SNACC_HD void pk_turbo_spec(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, uint32_t stop, uint32_t mask, bool work)
-{
-    typedef PkTab<KIND, STRIDE> Tab;
-    static_assert(KIND != 2, "the speculative loop keeps 32-bit / 16-bit tables only (singles pass); KIND 2 runs pk_turbo_lean");
-    constexpr bool LAZY = false;
-    constexpr bool U16 = Tab::U16;
-    constexpr uint32_t MASK = Tab::MASK;
-    constexpr uint32_t ESZ = Tab::ESZ;                      // bytes between two slots of one lane
-    constexpr uint32_t EWB = STRIDE * 4;                    // KIND 2: bytes between two epoch words of one lane
-    constexpr uint32_t RMASK = (2 * PK_RING_WORDS - 1) * 4; // byte-offset mask of the ring seen as u32 words
-    const uint32_t lx = v.lx, rlo = v.rlo, rspan = v.rspan;
-    uint32_t p = st.phase == PK_SEARCH ? st.fip : st.ip;
-    uint32_t anchor = st.anchor, nb = st.nb, op = st.op;
-    const uint32_t lim = tmin(stop, st.mfl1 > 16 ? st.mfl1 - 16 : 0u);
-    const uint32_t op_lim = st.budget > 80 ? st.budget - 80 : 0u;
-    const bool fin = !work || p >= stop;
-    const bool ok0 = fin || (st.phase <= PK_RETEST && !(st.phase == PK_SEARCH && st.step != 1) &&
-                             (uint32_t)(p - 4 - lx - rlo) <= rspan);
-    if (!pk_all(mask, ok0) || pk_all(mask, fin)) return;
-    // (pk_opaque: keep the base addresses in registers -- the compiler otherwise re-derives them from
-    // SR_CgaCtaId inside the loop)
-    const pk_sptr ring_a = pk_opaque(pk_sptr_of(v.ring)), lut_a = pk_opaque(pk_sptr_of(tab.lut)),
-                  tab_a = pk_opaque(pk_sptr_of(tab.t)), ep_a = KIND == 2 ? pk_opaque(pk_sptr_of(tab.ep)) : 0;
-#define PK_TLD(addr) (KIND == 0 ? pk_lds32(addr) : pk_lds16(addr))
-#define PK_TST(addr, val) do { if (KIND == 0) pk_sts32(addr, val); else pk_sts16(addr, val); } while (0)
-#define PK_OFF(code) (pk_lds16(lut_a + 2 * (code)) * ESZ)    /* slot handle: byte offset of the slot */
-#define PK_EWA(off) (ep_a + (((off) / ESZ) >> 5) * EWB)      /* address of the epoch word of a slot */
-#define PK_EBIT(off) ((((off) / ESZ)) & 31)
-    // 32 bases starting at y offset q, as two 32-bit halves (three consecutive ring words)
-#define PK_RING32(q, lo, hi) do { const uint32_t j_ = ((q) >> 4) * 4, s_ = ((q) & 15) * 2;                      \
-        const uint32_t a_ = pk_lds32(ring_a + (j_ & RMASK)), b_ = pk_lds32(ring_a + ((j_ + 4) & RMASK)),       \
-                       c_ = pk_lds32(ring_a + ((j_ + 8) & RMASK));                                             \
-        lo = pk_fsr(a_, b_, s_); hi = pk_fsr(b_, c_, s_); } while (0)
-    uint32_t Wlo = 0, Whi = 0;                              // bases [pw-4, pw+28)
-    uint32_t pw = p, soff = 0, m = 0;
-    bool near = false;                                      // the slot of p holds a candidate within reach
-    if (!fin) {
-        PK_RING32(p - 4 - lx, Wlo, Whi);
-        const uint32_t c0 = (Wlo >> 8) & MASK;
-        soff = tab.lut[c0] * ESZ;
-        near = tab.lookup(c0, p, m);
-    }
-    bool blocked = false;
-    uint32_t it = 0;
-    for (;; ++it) {
-        // ---- may this lane take one more iteration?  (evaluated by every lane, every iteration)
-        const uint32_t pend = p - anchor;                   // pending literals; search mode iff != 0
-        const uint32_t qm4 = m - 4 - lx;
-        const bool live = !fin && p < stop;
-        const bool ok = !blocked && p < lim && op + pend + (pend >> 7) <= op_lim && nb <= 120 &&
-                        (!near || (uint32_t)(qm4 - rlo) <= rspan + 32);
-        const bool go = live && ok;
-        if ((it & 3) == 0) {
-            // warp vote every 4th iteration: leave when a live lane is stuck or nobody runs any more
-            // (a stuck lane simply idles for up to 3 iterations)
-            if (pk_reduce_or(mask, (go ? 2u : 0u) | ((live && !ok) ? 1u : 0u)) != 2u) break;
-        }
-        // ---- straight-line body; loads are harmless for any lane, stores and commits are predicated
-        // candidate: 16 bases from m-4
-        uint32_t xm;
-        {
-            const uint32_t j = (qm4 >> 4) * 4;
-            xm = pk_fsr(pk_lds32(ring_a + (j & RMASK)), pk_lds32(ring_a + ((j + 4) & RMASK)), (qm4 & 15) * 2);
-        }
-        const uint32_t sh = 2 * (p - pw);
-        const uint32_t Ws = pk_fsr(Wlo, Whi, sh), Wt = Whi >> sh;   // bases [p-4, p+12) and the 16 after them
-        // first insert: slot of p <- p (remember what it held, an unfinished iteration puts it back)
-        const pk_sptr slot = tab_a + soff;
-        uint32_t raw_old = 0, ew_old = 0;
-        if (KIND == 2) {
-            raw_old = pk_lds16(slot); ew_old = pk_lds32(PK_EWA(soff));
-            if (go) {
-                pk_sts16(slot, p);
-                pk_sts32(PK_EWA(soff), (ew_old & ~(1u << PK_EBIT(soff))) | (((p >> 16) & 1) << PK_EBIT(soff)));
-            }
-        } else {
-            raw_old = m;
-            if (go) PK_TST(slot, p);
-        }
-        // speculative table lookups: next probe at p+1 (miss) or p+4..p+6 (match of that length)
-        constexpr bool LLUT = LAZY;                         // many lanes: the slot addresses are resolved late as well
-        uint32_t o1 = 0, o2 = 0, o3 = 0, o4 = 0, o5 = 0, o6 = 0;
-        if (!LLUT) {
-            o1 = PK_OFF((Ws >> 10) & MASK); o2 = PK_OFF((Ws >> 12) & MASK); o3 = PK_OFF((Ws >> 14) & MASK);
-            o4 = PK_OFF((Ws >> 16) & MASK); o5 = PK_OFF((Ws >> 18) & MASK); o6 = PK_OFF((Ws >> 20) & MASK);
-        }
-        // (lengths 7 and 8 are 6 % of the matches: not worth two more speculative lookups per iteration, they take the
-        // on-demand path below together with 9..11)
-        // With one lane per warp (the singles pass, STRIDE 1) the loop is bound by its dependency chain and the table
-        // words of all four candidates slots are fetched ahead; with 26 or 32 lanes it is bound by instruction issue
-        // (measured: +10 % for the pair kernel from the table words, another +11 % from the slot addresses, and a 2.2x
-        // slower singles pass) and the one slot that is needed is resolved and read once the match length is known.
-        uint32_t m1 = 0, m4 = 0, m5 = 0, m6 = 0, e1 = 0, e4 = 0, e5 = 0, e6 = 0;
-        if (!LAZY) {
-            m1 = PK_TLD(tab_a + o1); m4 = PK_TLD(tab_a + o4); m5 = PK_TLD(tab_a + o5); m6 = PK_TLD(tab_a + o6);
-            if (KIND == 2) {
-                e1 = pk_lds32(PK_EWA(o1)); e4 = pk_lds32(PK_EWA(o4)); e5 = pk_lds32(PK_EWA(o5));
-                e6 = pk_lds32(PK_EWA(o6));
-            }
-        }
-        uint32_t Nlo, Nhi;
-        PK_RING32(p - 4 - lx, Nlo, Nhi);                    // window for the next iteration
-        const uint32_t x = Ws ^ xm;
-        const uint32_t fwd = x >> 8, back = x << 24;        // bases p.. ; base p-1 in the two top bits
-        uint32_t common = fwd ? (pk_ctz32(fwd) >> 1) : 12;
-        common = near ? common : 0;
-        uint32_t k = back ? (pk_clz32(back) >> 1) : 4;
-        k = pend ? k : 0;
-        const uint32_t kmax = tmin(pend, m);
-        const bool hit = common >= 4;
-        const bool bail = go && (common > 11 || (hit && k == 4 && kmax > 4));   // long match / long catch-up
-        if (bail) {
-            if (KIND == 2) { pk_sts16(slot, raw_old); pk_sts32(PK_EWA(soff), ew_old); }
-            else PK_TST(slot, raw_old);
-            blocked = true;
-        }
-        const bool commit = go && !bail;
-        k = tmin(k, kmax);
-        const uint32_t lit = pend - k;
-        const uint32_t add = 3 + lit + (lit >= 15 ? (lit - 15) / 255 + 1 : 0);   // token + offset + literals
-        const uint32_t pn = hit ? p + common : p + 1;
-        const bool c4 = common == 4, c5 = common == 5;
-        uint32_t sp = pk_sel(c4, o2, pk_sel(c5, o3, o4));                                    // slot of the insert pn-2
-        uint32_t sn = pk_sel(c4, o4, pk_sel(c5, o5, o6));                                    // slot of pn
-        uint32_t mn = LAZY ? 0u : pk_sel(c4, m4, pk_sel(c5, m5, m6));
-        uint32_t en = (LAZY || KIND != 2) ? 0u : pk_sel(c4, e4, pk_sel(c5, e5, e6));
-        if (LLUT) {
-            const uint32_t d = hit ? common : 1u;           // the next probe is at p + d
-            sn = PK_OFF(pk_fsr(Ws, Wt, 2 * (d + 4)) & MASK);
-            sp = PK_OFF(pk_fsr(Ws, Wt, 2 * (d + 2)) & MASK);
-        } else if (commit && common > 6) {                  // 7..11: not speculated, look the slots up now
-            sp = PK_OFF(pk_fsr(Ws, Wt, 2 * (common + 2)) & MASK);
-            sn = PK_OFF(pk_fsr(Ws, Wt, 2 * (common + 4)) & MASK);
-            if (!LAZY) {
-                mn = PK_TLD(tab_a + sn);
-                if (KIND == 2) en = pk_lds32(PK_EWA(sn));
-            }
-        }
-        if (!LLUT) sn = hit ? sn : o1;
-        if (LAZY) {
-            mn = PK_TLD(tab_a + sn);
-            if (KIND == 2) en = pk_lds32(PK_EWA(sn));
-        } else {
-            mn = hit ? mn : m1; en = hit ? en : e1;
-        }
-        if (commit && hit) {                                // second insert: slot of pn-2 <- pn-2
-            if (KIND == 2) {
-                pk_sts16(tab_a + sp, pn - 2);
-                const uint32_t w2 = pk_lds32(PK_EWA(sp));
-                pk_sts32(PK_EWA(sp), (w2 & ~(1u << PK_EBIT(sp))) | ((((pn - 2) >> 16) & 1) << PK_EBIT(sp)));
-            } else {
-                PK_TST(tab_a + sp, pn - 2);
-            }
-        }
-        // candidate of the next probe: the speculative read, unless the second insert just overwrote that slot
-        uint32_t mnext; bool nnext;
-        if (KIND == 2) {
-            const uint32_t d = (pn - mn) & 0xffffu;
-            mnext = pn - d;
-            nnext = d != 0 && ((((mnext >> 16) ^ (en >> PK_EBIT(sn))) & 1) == 0);
-        } else {
-            mnext = mn;
-            nnext = U16 || (pn - mn <= LZ4_MAX_DISTANCE);
-        }
-        if (hit && sn == sp) { mnext = pn - 2; nnext = true; }
-        if (commit) {
-#if defined(PK_COUNT_STEPS) && !defined(__CUDA_ARCH__)
-            ++pk_turbo_steps;
-#endif
-            op += hit ? add : 0;
-            nb = hit ? nb : (pend ? nb + 1 : 64);
-            anchor = hit ? pn : anchor;
-            m = mnext; near = nnext; soff = sn;
-            Wlo = Nlo; Whi = Nhi; pw = p; p = pn;
-        }
-    }
-#undef PK_TLD
-#undef PK_TST
-#undef PK_OFF
-#undef PK_EWA
-#undef PK_EBIT
-#undef PK_RING32
-    if (work && st.phase <= PK_RETEST) {
-        if (p != anchor) { st.phase = PK_SEARCH; st.fip = p; st.step = 1; st.nb = nb; }
-        else             { st.phase = PK_RETEST; st.ip = p; }
-        st.anchor = anchor; st.op = op;
-    }
-}
-
-// ---- lean inner loop (many-lane tiles) ---------------------------------------------------------------------------
-// With 26 or 32 streams per warp and one warp per scheduler the pair kernel is bound by the number of instructions a
-// warp iteration issues, not by the dependency chain, so this version does nothing ahead of time: per probe it reads the
+// ---- the loop ----------------------------------------------------------------------------------------------------
+// With one warp per scheduler (26 or 32 streams per warp in the pair tiles, a single stream per warp in the singles
+// pass) a warp iteration costs what its instructions and their dependency stalls cost, so the loop does nothing ahead
+// of time: per probe it reads the
 // candidate's 16 bases, compares, and only then resolves the two slots it needs (the insert at pn-2 and the next probe
 // pn).  What keeps it short:
 //   * KIND 2 inserts are a 16-bit store plus one shared-memory atomic OR on the epoch bit plane (PkTab): nothing to read
@@ -631,8 +556,11 @@ SNACC_HD void pk_turbo_spec(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView 
 //     warp vote, every 4th iteration, with the slack 4 iterations can use up; per iteration only the block limit and
 //     the candidate's residence in the ring are tested;
 //   * stores are predicated PTX (no branches inside the body).
-// Same contract as pk_turbo_spec: warp-uniform, every lane of `mask` executes every iteration, a lane that meets
-// anything unusual leaves its state untouched and the burst ends at the next vote.
+// (An earlier version looked the table up speculatively for every likely next probe to shorten the dependency chain;
+// measured on B200 the lean loop is 1.8x faster even with a single lane per warp -- profiles/README.md.)
+#ifndef PK_UNROLL
+#define PK_UNROLL 8              // iterations between two warp votes (the body is unrolled that many times)
+#endif
 #ifndef PK_EPOCH_ATOMIC
 #define PK_EPOCH_ATOMIC 0        // 1: epoch bits set with red.shared.or (measured: the shared-memory atomics stall the in-order LSU)
 #endif
@@ -668,8 +596,10 @@ SNACC_HD void pk_turbo_lean(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView 
     uint32_t p = st.phase == PK_SEARCH ? st.fip : st.ip;
     uint32_t anchor = st.anchor, nb = st.nb, op = st.op;
     const uint32_t lim = tmin(stop, st.mfl1 > 16 ? st.mfl1 - 16 : 0u);
-    // output budget: 4 iterations add at most 4 x (token + offset + length byte) + the literals pending at the vote + 44
-    const uint32_t op_lim = st.budget > 160 ? st.budget - 160 : 0u;
+    // output budget: PK_UNROLL iterations add at most that many x (token + offset + length byte) + the literals pending
+    // at the vote + 11 bases each
+    constexpr uint32_t OP_SLACK = 80 + 15 * PK_UNROLL;
+    const uint32_t op_lim = st.budget > OP_SLACK ? st.budget - OP_SLACK : 0u;
     const bool fin = !work || p >= stop;
     const bool ok0 = fin || (st.phase <= PK_RETEST && !(st.phase == PK_SEARCH && st.step != 1) &&
                              (uint32_t)(p - 4 - lx - rlo) <= rspan);
@@ -691,15 +621,15 @@ SNACC_HD void pk_turbo_lean(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView 
     }
     bool blocked = false;
     for (;;) {
-        // warp vote every 4 iterations: leave when a live lane cannot go on or nobody runs any more.  What can only
-        // change slowly is tested here, with the slack 4 iterations can use up.
+        // warp vote every PK_UNROLL iterations: leave when a live lane cannot go on or nobody runs any more.  What can
+        // only change slowly is tested here, with the slack that many iterations can use up.
         const uint32_t pend0 = p - anchor;
         const bool live = !fin && p < stop;
-        bool run = live && !blocked && op + pend0 <= op_lim && nb <= 116 && pend0 <= 200;
+        bool run = live && !blocked && op + pend0 <= op_lim && nb <= 120 - PK_UNROLL && pend0 <= 200;
         const bool can = run && p < lim;
         if (pk_any(mask, live && !can) || !pk_any(mask, can)) break;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < (int)PK_UNROLL; ++u) {
             // ---- straight-line, branch-free body: every lane executes everything, stores are predicated, and a lane
             // that does not commit looks its own probe up again (d = 0), which leaves its state as it was
             const bool go = run & (p < lim);
@@ -813,16 +743,13 @@ __device__ __forceinline__ void pk_epoch_coop(const PkState &st, PkTab<2, STRIDE
 
 // Run the streams of the warp (lanes in `mask`, one stream each) until each one's next position reaches
 // its `stop` or it is done: turbo bursts, separated by one general pk_step for every lane.
-// LAZY: which inner loop (many lanes: the lean one, one lane: the speculative one); the kernels leave the default, the
-// host emulation -- where STRIDE is always 1 -- asks for the pair kernel's setting explicitly
-template <int KIND, int STRIDE, bool LAZY = (STRIDE != 1)>
+template <int KIND, int STRIDE>
 SNACC_HD void pk_run(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, uint32_t n, uint32_t stop, uint32_t mask)
 {
     for (;;) {
         bool work = st.phase != PK_DONE && pk_next_pos(st) < stop;
         if (!pk_any(mask, work)) return;
-        if constexpr (LAZY) pk_turbo_lean<KIND, STRIDE>(st, tab, v, stop, mask, work);
-        else pk_turbo_spec<KIND, STRIDE>(st, tab, v, stop, mask, work);
+        pk_turbo_lean<KIND, STRIDE>(st, tab, v, stop, mask, work);
         work = st.phase != PK_DONE && pk_next_pos(st) < stop;
 #ifdef __CUDA_ARCH__
         if constexpr (KIND == 2 && STRIDE != 1) pk_epoch_coop<STRIDE>(st, tab, n, mask, work);
@@ -1021,7 +948,7 @@ struct PkSingleSmem {
     uint32_t snap[1024];
 };
 
-template <int KIND, bool DETECT, bool LEAN>
+template <int KIND, bool DETECT>
 __device__ void pk_single_run(PkState &st, PkTab<KIND, 1> &tab, PkView &v, PkRing &rg, const uint64_t *yw, uint64_t *ring,
                               uint32_t n, uint32_t xend, uint32_t snap_bs, PkState *snap_st, uint32_t *snap_tab)
 {
@@ -1049,7 +976,7 @@ __device__ void pk_single_run(PkState &st, PkTab<KIND, 1> &tab, PkView &v, PkRin
                         limit = tmin(stop, snap_bs);
                     }
                 }
-                pk_run<KIND, 1, LEAN>(st, tab, v, n, limit, 1u);
+                pk_run<KIND, 1>(st, tab, v, n, limit, 1u);
             }
             s_more = (!touched && st.phase != PK_DONE && !rg.complete()) ? 1u : 0u;
         }
@@ -1061,7 +988,6 @@ __device__ void pk_single_run(PkState &st, PkTab<KIND, 1> &tab, PkView &v, PkRin
     }
 }
 
-template <bool LEAN>
 __global__ void __launch_bounds__(64)
 lz4_pk_single_kernel(PkCorpus pc, const int32_t *__restrict__ seqs, const int32_t *__restrict__ want, int32_t n_seqs,
                      uint32_t *__restrict__ ck_tab, PkState *__restrict__ ck_state, const uint16_t *__restrict__ lut5_g,
@@ -1096,8 +1022,8 @@ lz4_pk_single_kernel(PkCorpus pc, const int32_t *__restrict__ seqs, const int32_
         rg.start(len, w0, w1);
         pk_ring_fill(ring, yw, w0, w1);
         pk_fresh(st); pk_fresh(snap);
-        if (linked_single) pk_single_run<0, false, LEAN>(st, tl, v, rg, yw, ring, len, 0, last_bs, &snap, s_snap);
-        else               pk_single_run<1, false, LEAN>(st, ts, v, rg, yw, ring, len, 0, 0, nullptr, nullptr);
+        if (linked_single) pk_single_run<0, false>(st, tl, v, rg, yw, ring, len, 0, last_bs, &snap, s_snap);
+        else               pk_single_run<1, false>(st, ts, v, rg, yw, ring, len, 0, 0, nullptr, nullptr);
         if (threadIdx.x == 0 && out_idx[t] >= 0) out[out_idx[t]] = (int64_t)(st.total + lz4_frame_overhead(len));
 
         // (2) linked-regime checkpoint: from the snapshot at the last block start (or from scratch)
@@ -1115,7 +1041,7 @@ lz4_pk_single_kernel(PkCorpus pc, const int32_t *__restrict__ seqs, const int32_
                 rg.start(len, w0, w1);
                 pk_ring_fill(ring, yw, w0, w1);
             }
-            pk_single_run<0, true, LEAN>(st, tl, v, rg, yw, ring, 0xffffffffu, len, 0, nullptr, nullptr);
+            pk_single_run<0, true>(st, tl, v, rg, yw, ring, 0xffffffffu, len, 0, nullptr, nullptr);
             __syncthreads();
             uint32_t *dst = ck_tab + (size_t)(2 * s + 1) * PK_CKPT_TAB;
             for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) dst[i] = s_tab[i];
@@ -1128,7 +1054,7 @@ lz4_pk_single_kernel(PkCorpus pc, const int32_t *__restrict__ seqs, const int32_
             pk_fresh(st);
             rg.start(len, w0, w1);
             pk_ring_fill(ring, yw, w0, w1);
-            pk_single_run<1, true, LEAN>(st, ts, v, rg, yw, ring, 0xffffffffu, len, 0, nullptr, nullptr);
+            pk_single_run<1, true>(st, ts, v, rg, yw, ring, 0xffffffffu, len, 0, nullptr, nullptr);
             __syncthreads();
             uint32_t *dst = ck_tab + (size_t)(2 * s) * PK_CKPT_TAB;
             const uint16_t *t16 = reinterpret_cast<const uint16_t *>(s_tab);

@@ -67,8 +67,7 @@ static void ring_fill_host(std::vector<uint64_t> &ring, const std::vector<uint64
 struct EmuCkpt { PkState st; std::vector<uint32_t> tab; };
 
 // run a stream until DONE (or until DETECT touches); mirrors pk_single_run / the pair kernel loop
-// LAZY: the table-lookup flavour of pk_turbo (false: singles pass, true: pair kernel)
-template <int KIND, bool DETECT, bool LAZY = false>
+template <int KIND, bool DETECT>
 static bool emu_run(PkState &st, PkTab<KIND, 1> &tab, std::vector<uint32_t> *tab32, PkView &v, PkRing &rg,
                     std::vector<uint64_t> &ring, const std::vector<uint64_t> &yw, uint32_t n, uint32_t xend,
                     uint32_t snap_bs, EmuCkpt *snap)
@@ -87,7 +86,7 @@ static bool emu_run(PkState &st, PkTab<KIND, 1> &tab, std::vector<uint32_t> *tab
                 if (st.phase == PK_BLOCK_START && st.bs == snap_bs) { snap->st = st; snap->tab = *tab32; snap = nullptr; }
                 else limit = tmin(stop, snap_bs);
             }
-            pk_run<KIND, 1, LAZY>(st, tab, v, n, limit, 1u);
+            pk_run<KIND, 1>(st, tab, v, n, limit, 1u);
         }
         if (st.phase == PK_DONE || rg.complete()) return false;
         uint32_t w0, w1;
@@ -101,9 +100,6 @@ template <int KIND> static std::vector<uint16_t> emu_lut(const uint16_t *raw)
 {
     return std::vector<uint16_t>(raw, raw + PkTab<KIND, 1>::ENTRIES);
 }
-
-static int g_singles_lean = 0;       // which inner loop the singles pass of the emulation runs (kernel option lz4_singles_lean)
-extern "C" void emu_set_singles_lean(int v) { g_singles_lean = v; }
 
 // returns the size, -1 when the packed pair path bails out, -2 when the input is not packable
 extern "C" int64_t emu_lz4_packed(const uint8_t *x, uint32_t lx, const uint8_t *y, int64_t ly_)
@@ -133,13 +129,8 @@ extern "C" int64_t emu_lz4_packed(const uint8_t *x, uint32_t lx, const uint8_t *
     v.ring = ring.data(); v.yw = xw.data(); v.xw = xw.data(); v.lx = 0;
     rg.start(lx, w0, w1); ring_fill_host(ring, xw, w0, w1);
     pk_fresh(st);
-    if (g_singles_lean) {
-        if (linked_single) emu_run<0, false, true>(st, t32, &tab, v, rg, ring, xw, lx, 0, last_bs, &snap);
-        else               emu_run<1, false, true>(st, t16, &tab, v, rg, ring, xw, lx, 0, 0, nullptr);
-    } else {
-        if (linked_single) emu_run<0, false>(st, t32, &tab, v, rg, ring, xw, lx, 0, last_bs, &snap);
-        else               emu_run<1, false>(st, t16, &tab, v, rg, ring, xw, lx, 0, 0, nullptr);
-    }
+    if (linked_single) emu_run<0, false>(st, t32, &tab, v, rg, ring, xw, lx, 0, last_bs, &snap);
+    else               emu_run<1, false>(st, t16, &tab, v, rg, ring, xw, lx, 0, 0, nullptr);
     const int64_t single = (int64_t)(st.total + lz4_frame_overhead(lx));
     if (ly_ < 0) return single;
 
@@ -174,7 +165,7 @@ extern "C" int64_t emu_lz4_packed(const uint8_t *x, uint32_t lx, const uint8_t *
         uint16_t *p16 = reinterpret_cast<uint16_t *>(t.data());
         for (int i = 0; i < 256; ++i) p16[i] = (uint16_t)ck.tab[i];
         t16.t = p16;
-        emu_run<1, false, true>(st, t16, &t, v, rg, ring, yw, n, 0, 0, nullptr);
+        emu_run<1, false>(st, t16, &t, v, rg, ring, yw, n, 0, 0, nullptr);
     } else {
         // linked regime: 16-bit slots + epoch bit plane (PkTab KIND 2), imported from the 32-bit checkpoint
         const uint32_t nslot = (nslot5 + 1) & ~1u;
@@ -182,7 +173,7 @@ extern "C" int64_t emu_lz4_packed(const uint8_t *x, uint32_t lx, const uint8_t *
         std::vector<uint32_t> ep((nslot + 31) / 32, 0);
         PkTab<2, 1> t17; t17.t = lo.data(); t17.ep = ep.data(); t17.nslot = nslot; t17.epoch_base = ck.st.bs; t17.lut = lut17.data();
         for (uint32_t e = 0; e < nslot; ++e) t17.import_slot(e, ck.tab[e], ck.st.bs);
-        emu_run<2, false, true>(st, t17, nullptr, v, rg, ring, yw, n, 0, 0, nullptr);
+        emu_run<2, false>(st, t17, nullptr, v, rg, ring, yw, n, 0, 0, nullptr);
     }
     return (int64_t)(st.total + lz4_frame_overhead(n));
 }

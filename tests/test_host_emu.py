@@ -97,9 +97,7 @@ def _four_symbol_vector(kind, n, seed):
     return _dna(n, seed)
 
 
-@pytest.mark.parametrize("singles_lean", [0, 1])
-def test_lz4_packed_logic_regime_boundaries(emu, singles_lean):
-    emu.emu_set_singles_lean(singles_lean)
+def test_lz4_packed_logic_regime_boundaries(emu):
     bad = []
     for lx in [1, 5, 12, 13, 20, 700, 11000, 40000, 65519, 65520, 65535, 65536, 65537, 65540, 70000, 131071, 131072, 131073,
                150000, 300000]:
@@ -110,14 +108,11 @@ def test_lz4_packed_logic_regime_boundaries(emu, singles_lean):
             y = _dna(ly, ly + 3)
             if _call2(emu.emu_lz4_packed, x, y) != lib.ref_lz4f_size(np.concatenate([x, y])):
                 bad.append(("pair", lx, ly))
-    emu.emu_set_singles_lean(0)
     assert not bad, bad[:10]
 
 
-@pytest.mark.parametrize("singles_lean", [0, 1])
 @pytest.mark.parametrize("kind", ["run", "period", "two", "skew", "lower", "repeat", "longrep"])
-def test_lz4_packed_logic_adversarial_four_symbol_inputs(emu, kind, singles_lean):
-    emu.emu_set_singles_lean(singles_lean)
+def test_lz4_packed_logic_adversarial_four_symbol_inputs(emu, kind):
     bad = []
     for lx in [1, 13, 300, 11000, 65535, 65536, 65537, 100000, 140000]:
         x = _four_symbol_vector(kind, lx, lx)
@@ -134,7 +129,6 @@ def test_lz4_packed_logic_adversarial_four_symbol_inputs(emu, kind, singles_lean
         got = _call2(emu.emu_lz4_packed, x, x)
         if got != lib.ref_lz4f_size(np.concatenate([x, x])) and not (lx < 16 and got == -1):
             bad.append(("self", lx))
-    emu.emu_set_singles_lean(0)
     assert not bad, bad[:10]
 
 
