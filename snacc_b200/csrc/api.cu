@@ -51,7 +51,14 @@ struct snacc_ctx {
     uint64_t *d_pk_words = nullptr, *d_pk_woff = nullptr;
     uint16_t *d_alias5 = nullptr, *d_alias4 = nullptr;
     uint32_t *d_ck_tab = nullptr; PkState *d_ck_state = nullptr;
-    std::vector<uint8_t> h_packable, h_ck_have;   // per sequence; h_ck_have bit0: single-block regime, bit1: linked
+    std::vector<uint8_t> h_packable, h_ck_have;   // per sequence; h_packable 0: no 2-bit copy usable, 1: clean, 2: a few bytes
+                                                  // outside the alphabet (flagged in the per-base mask); h_ck_have bit0:
+                                                  // single-block regime, bit1: linked
+    // sequences with a few bytes outside the alphabet (EXC kernels; allocated only for corpora that have any)
+    int corpus_dirty = 0;
+    uint32_t *d_pk_mask = nullptr; uint64_t *d_pk_moff = nullptr; uint64_t mask_words = 0;
+    uint16_t *d_b2s = nullptr;
+    uint32_t *d_ck_ovf = nullptr, *d_ovf_work = nullptr; size_t ovf_work_tabs = 0;
     PkAlphabet alphabet;
     uint32_t nslot5 = 1024;                // distinct hash buckets the 1024 5-mers of the alphabet reach
     int64_t last_packed_jobs = 0, last_bytewise_jobs = 0;
@@ -210,6 +217,11 @@ static void free_corpus(snacc_ctx *ctx)
     cudaFree(ctx->d_alias4); ctx->d_alias4 = nullptr;
     cudaFree(ctx->d_ck_tab); ctx->d_ck_tab = nullptr;
     cudaFree(ctx->d_ck_state); ctx->d_ck_state = nullptr;
+    cudaFree(ctx->d_pk_mask); ctx->d_pk_mask = nullptr; ctx->mask_words = 0;
+    cudaFree(ctx->d_pk_moff); ctx->d_pk_moff = nullptr;
+    cudaFree(ctx->d_b2s); ctx->d_b2s = nullptr;
+    cudaFree(ctx->d_ck_ovf); ctx->d_ck_ovf = nullptr;
+    ctx->corpus_dirty = 0;
     ctx->h_packable.clear(); ctx->h_ck_have.clear();
     ctx->n_seqs = 0; ctx->n_slots = 0;
     deflate_free_corpus(ctx->dfl);
@@ -247,7 +259,7 @@ extern "C" void snacc_ctx_destroy(snacc_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     free_corpus(ctx);
     deflate_free_work(ctx->dfl);
-    cudaFree(ctx->d_work); cudaFree(ctx->d_counter);
+    cudaFree(ctx->d_work); cudaFree(ctx->d_counter); cudaFree(ctx->d_ovf_work);
     for (void *p : ctx->d_scratch) cudaFree(p);
     cudaFree(ctx->d_jobx); cudaFree(ctx->d_joby); cudaFree(ctx->d_out);
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
@@ -289,29 +301,54 @@ static int pack_corpus(snacc_ctx *ctx)
 
     PkCodes codes;
     memcpy(codes.c, ctx->alphabet.code_of, 256);
-    std::vector<uint64_t> woff((size_t)n);
-    uint64_t w = 0;
-    for (int32_t i = 0; i < n; ++i) { woff[i] = w; w += pk_words(ctx->h_len[i]); }
-    int32_t *d_bad = nullptr;
+    std::vector<uint64_t> woff((size_t)n), moff((size_t)n);
+    uint64_t w = 0, mw = 0;
+    for (int32_t i = 0; i < n; ++i) { woff[i] = w; w += pk_words(ctx->h_len[i]); moff[i] = mw; mw += pk_mask_words(ctx->h_len[i]); }
+    // bytes outside the alphabet anywhere in the corpus?  Then the packed copy carries a per-base mask of them and the
+    // EXC kernels run (lz4_packed.cuh: pk_step_exact)
+    unsigned long long outside = 0;
+    for (int i = 0; i < 256; ++i) if (ctx->alphabet.code_of[i] > 3) outside += hist[i];
+    ctx->corpus_dirty = outside ? 1 : 0;
+    int32_t *d_nexc = nullptr;
     if (!ctx->d_pk_words) CK(cudaMalloc(&ctx->d_pk_words, w * sizeof(uint64_t)));
     if (!ctx->d_pk_woff) CK(cudaMalloc(&ctx->d_pk_woff, sizeof(uint64_t) * n));
-    CK(cudaMalloc(&d_bad, sizeof(int32_t) * n));
-    CK(cudaMemsetAsync(d_bad, 0, sizeof(int32_t) * n, ctx->stream));
+    CK(cudaMalloc(&d_nexc, sizeof(int32_t) * n));
+    CK(cudaMemsetAsync(d_nexc, 0, sizeof(int32_t) * n, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_pk_woff, woff.data(), sizeof(uint64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->corpus_dirty) {
+        if (ctx->d_pk_mask && ctx->mask_words < mw) { cudaFree(ctx->d_pk_mask); ctx->d_pk_mask = nullptr; }
+        if (!ctx->d_pk_mask) { CK(cudaMalloc(&ctx->d_pk_mask, (mw + 64) * sizeof(uint32_t))); ctx->mask_words = mw; }
+        if (!ctx->d_pk_moff) CK(cudaMalloc(&ctx->d_pk_moff, sizeof(uint64_t) * n));
+        if (!ctx->d_b2s) CK(cudaMalloc(&ctx->d_b2s, sizeof(uint16_t) * PK_OVF_ENTRIES));
+        if (!ctx->d_ck_ovf) CK(cudaMalloc(&ctx->d_ck_ovf, sizeof(uint32_t) * PK_OVF_ENTRIES * (size_t)n));
+        CK(cudaMemsetAsync(ctx->d_pk_mask, 0, (mw + 64) * sizeof(uint32_t), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_ck_ovf, 0, sizeof(uint32_t) * PK_OVF_ENTRIES * (size_t)n, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_pk_moff, moff.data(), sizeof(uint64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+        uint16_t b2s[PK_OVF_ENTRIES];
+        for (uint32_t i = 0; i < PK_OVF_ENTRIES; ++i) b2s[i] = 0xffff;
+        for (uint32_t c = 0; c < 1024; ++c) b2s[pk_bucket(ctx->alphabet, c, false)] = a5[c];
+        CK(cudaMemcpyAsync(ctx->d_b2s, b2s, sizeof b2s, cudaMemcpyHostToDevice, ctx->stream));
+    }
     {
         dim3 grid(std::min<uint32_t>((pk_words(max_len) + 255) / 256, 256), (unsigned)std::min<int32_t>(n, 4096));
         pk_pack_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->d_corpus, ctx->d_off, ctx->d_len, ctx->d_pk_woff, n,
-                                                      ctx->d_pk_words, d_bad, codes);
+                                                      ctx->d_pk_words, d_nexc, ctx->corpus_dirty ? ctx->d_pk_mask : nullptr,
+                                                      ctx->d_pk_moff, codes);
         CK(cudaGetLastError());
     }
-    std::vector<int32_t> bad((size_t)n);
-    CK(cudaMemcpyAsync(bad.data(), d_bad, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<int32_t> nexc((size_t)n);
+    CK(cudaMemcpyAsync(nexc.data(), d_nexc, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
     if (!ctx->d_ck_tab) CK(cudaMalloc(&ctx->d_ck_tab, (size_t)n * 2 * PK_CKPT_TAB * sizeof(uint32_t)));
     if (!ctx->d_ck_state) CK(cudaMalloc(&ctx->d_ck_state, (size_t)n * 2 * sizeof(PkState)));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_bad);
+    cudaFree(d_nexc);
+    // a sequence keeps to the tile kernels while its flagged bases are sparse: an isolated one costs every stream that
+    // meets it a handful of byte-exact steps (about what 450 ordinary probes cost a warp), so the tile kernels stay
+    // ahead of the byte-wise ones up to roughly one flagged base in 64; denser sequences -- proteins, heavily
+    // soft-masked assemblies -- take the byte-wise kernels
     ctx->h_packable.assign(n, 0);
-    for (int32_t i = 0; i < n; ++i) ctx->h_packable[i] = bad[i] ? 0 : 1;
+    for (int32_t i = 0; i < n; ++i)
+        ctx->h_packable[i] = nexc[i] == 0 ? 1 : ((uint64_t)nexc[i] <= (uint64_t)ctx->h_len[i] / 64 + 8 ? 2 : 0);
     ctx->h_ck_have.assign(n, 0);
     return SNACC_OK;
 }
@@ -558,6 +595,19 @@ static int run_lz4_bytewise(snacc_ctx *ctx, const int32_t *h_x, const std::vecto
     return SNACC_OK;
 }
 
+// what the EXC kernels take on top of the packed corpus; `tabs` overflow tables of working memory are made available
+static int pk_exc_corpus(snacc_ctx *ctx, size_t tabs, PkExcCorpus *xc)
+{
+    if (tabs > ctx->ovf_work_tabs) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->d_ovf_work); ctx->d_ovf_work = nullptr; ctx->ovf_work_tabs = 0;
+        CK(cudaMalloc(&ctx->d_ovf_work, tabs * PK_OVF_ENTRIES * sizeof(uint32_t)));
+        ctx->ovf_work_tabs = tabs;
+    }
+    *xc = PkExcCorpus{ctx->d_pk_mask, ctx->d_pk_moff, ctx->d_corpus, ctx->d_off, ctx->d_b2s, ctx->d_ovf_work, ctx->d_ck_ovf};
+    return SNACC_OK;
+}
+
 // packed path, step 1: singles and/or prefix checkpoints of the listed sequences (lz4_pk_single_kernel)
 static int run_pk_single(snacc_ctx *ctx, const std::vector<int32_t> &seqs, const std::vector<int32_t> &want,
                          const std::vector<int64_t> &out_idx)
@@ -573,8 +623,15 @@ static int run_pk_single(snacc_ctx *ctx, const std::vector<int32_t> &seqs, const
     CK(cudaMemcpyAsync(d_want, want.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(d_idx, out_idx.data(), sizeof(int64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
     const PkCorpus pc{ctx->d_pk_words, ctx->d_pk_woff, ctx->d_len};
-    lz4_pk_single_kernel<<<n, 64, 0, ctx->stream>>>(pc, d_seqs, d_want, n, ctx->d_ck_tab, ctx->d_ck_state, ctx->d_alias5,
-                                                    ctx->d_alias4, d_idx, ctx->d_out);
+    PkExcCorpus xc{};
+    if (ctx->corpus_dirty) {
+        rs = pk_exc_corpus(ctx, (size_t)n, &xc); if (rs) return rs;
+        lz4_pk_single_kernel<true><<<n, 64, 0, ctx->stream>>>(pc, xc, d_seqs, d_want, n, ctx->d_ck_tab, ctx->d_ck_state,
+                                                              ctx->d_alias5, ctx->d_alias4, d_idx, ctx->d_out);
+    } else {
+        lz4_pk_single_kernel<false><<<n, 64, 0, ctx->stream>>>(pc, xc, d_seqs, d_want, n, ctx->d_ck_tab, ctx->d_ck_state,
+                                                               ctx->d_alias5, ctx->d_alias4, d_idx, ctx->d_out);
+    }
     ctx->last_launches++;
     CK(cudaGetLastError());
     return SNACC_OK;
@@ -590,20 +647,23 @@ constexpr size_t PK_S_SMEM = PK_RING_BYTES + 256 * 2 + (size_t)PK_S_WARPS * 256 
 
 struct PkJob { int32_t y, x; int64_t j; };
 
-struct PkGeometry { uint32_t nslot; int lanes, warps; size_t smem; int T; };
+struct PkGeometry { uint32_t nslot; int lanes, warps; size_t smem; int T; bool exc; };
 
 static PkGeometry pk_geometry(const snacc_ctx *ctx, bool u16)
 {
     PkGeometry g;
+    g.exc = false;
     if (u16) { g.nslot = 256; g.lanes = PK_S_LANES; g.warps = PK_S_WARPS; g.smem = PK_S_SMEM; g.T = PK_S_LANES * PK_S_WARPS; return g; }
     // linked regime: as many streams as one SM's shared memory holds (A/C/G/T: 894 slots -> 1900 B per stream
     // -> 104 streams = 4 warps x 26 lanes; a full 1024-slot alphabet: 90 -> 2 warps x 32 lanes)
     g.nslot = (ctx->nslot5 + 1) & ~1u;
     const size_t l_stream = (size_t)g.nslot * 2 + ((g.nslot + 31) / 32) * 4;        // bytes of table per linked stream
+    // a corpus with flagged bases runs the EXC kernel (same geometry: its dirty ring lives inside the ring)
+    g.exc = ctx->corpus_dirty != 0;
     const size_t l_fixed = PK_RING_BYTES + 1024 * 2;
     const size_t l_fit = (PK_SMEM_MAX - l_fixed) / l_stream;
-    g.lanes = l_fit >= 104 ? 26 : 32;
-    g.warps = l_fit >= 104 ? 4 : (int)std::max<size_t>(1, l_fit / 32);
+    g.lanes = l_fit >= 104 ? 26 : l_fit >= 100 ? 25 : 32;
+    g.warps = l_fit >= 100 ? 4 : (int)std::max<size_t>(1, l_fit / 32);
     g.smem = l_fixed + (size_t)g.warps * g.lanes * l_stream;
     g.T = g.lanes * g.warps;
     return g;
@@ -640,14 +700,20 @@ static int pk_launch(snacc_ctx *ctx, bool u16, const PkGeometry &g, const std::v
     const int grid = (int)std::min<size_t>(tiles.size(), (size_t)ctx->sm_count);
     const int32_t nt = (int32_t)tiles.size();
     CK(cudaEventRecord(ctx->evm0, ctx->stream));
-#define PK_GO(KIND_, LANES_, lut_) do {                                                                              \
-        CK(cudaFuncSetAttribute(lz4_pk_pair_kernel<KIND_, LANES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem)); \
-        lz4_pk_pair_kernel<KIND_, LANES_><<<grid, g.warps * 32, g.smem, ctx->stream>>>(                                \
-            pc, d_tiles, nt, d_tx, d_tout, ctx->d_ck_tab, ctx->d_ck_state, lut_, g.nslot, out_stride, col0, counter, ctx->d_out); \
+    PkExcCorpus xc{};
+    if (g.exc) { rs = pk_exc_corpus(ctx, (size_t)grid * g.T, &xc); if (rs) return rs; }
+#define PK_GO(KIND_, LANES_, EXC_, lut_) do {                                                                        \
+        CK(cudaFuncSetAttribute(lz4_pk_pair_kernel<KIND_, LANES_, EXC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem)); \
+        lz4_pk_pair_kernel<KIND_, LANES_, EXC_><<<grid, g.warps * 32, g.smem, ctx->stream>>>(                          \
+            pc, xc, d_tiles, nt, d_tx, d_tout, ctx->d_ck_tab, ctx->d_ck_state, lut_, g.nslot, out_stride, col0, counter, ctx->d_out); \
     } while (0)
-    if (u16) PK_GO(1, PK_S_LANES, ctx->d_alias4);
-    else if (g.lanes == 26) PK_GO(2, 26, ctx->d_alias5);
-    else PK_GO(2, 32, ctx->d_alias5);
+    if (u16) PK_GO(1, PK_S_LANES, false, ctx->d_alias4);
+    else if (g.exc && g.lanes == 26) PK_GO(2, 26, true, ctx->d_alias5);
+    else if (g.exc && g.lanes == 25) PK_GO(2, 25, true, ctx->d_alias5);
+    else if (g.exc) PK_GO(2, 32, true, ctx->d_alias5);
+    else if (g.lanes == 26) PK_GO(2, 26, false, ctx->d_alias5);
+    else if (g.lanes == 25) PK_GO(2, 25, false, ctx->d_alias5);
+    else PK_GO(2, 32, false, ctx->d_alias5);
 #undef PK_GO
     CK(cudaEventRecord(ctx->evm1, ctx->stream));
     ctx->last_launches++;
@@ -695,17 +761,21 @@ static int pk_ensure_ckpts(snacc_ctx *ctx, const std::vector<int32_t> &need)
 static int run_pk_rect(snacc_ctx *ctx, int32_t row0, int32_t n_rows, int32_t col0, int32_t n_cols)
 {
     uint32_t min_x = 0xffffffffu, max_x = 0, min_y = 0xffffffffu, max_y = 0;
+    bool any_flagged = false;
     for (int32_t r = row0; r < row0 + n_rows; ++r) {
         if (!ctx->h_packable[r]) return 1;
+        any_flagged |= ctx->h_packable[r] == 2;
         min_x = std::min(min_x, ctx->h_len[r]); max_x = std::max(max_x, ctx->h_len[r]);
     }
     for (int32_t c = col0; c < col0 + n_cols; ++c) {
         if (!ctx->h_packable[c]) return 1;
+        any_flagged |= ctx->h_packable[c] == 2;
         min_y = std::min(min_y, ctx->h_len[c]); max_y = std::max(max_y, ctx->h_len[c]);
     }
     if (min_y < 16) return 1;
     const bool all_small = (uint64_t)max_x + max_y <= LZ4_BLOCK, all_linked = (uint64_t)min_x + min_y > LZ4_BLOCK;
     if (!all_small && !all_linked) return 1;
+    if (all_small && any_flagged) return 1;            // flagged bases: linked regime only (per-job path sorts it out)
     const bool u16 = all_small;
     std::vector<int32_t> need((size_t)ctx->n_seqs, 0);
     for (int32_t r = row0; r < row0 + n_rows; ++r) need[r] = u16 ? 1 : 2;
@@ -732,7 +802,8 @@ static int run_lz4(snacc_ctx *ctx, const int32_t *h_x, const int32_t *h_y, int64
     if (!pairs) {
         std::vector<int32_t> seqs, want; std::vector<int64_t> idx;
         for (int64_t k = 0; k < n_jobs; ++k) {
-            if (ctx->h_packable[h_x[k]]) {
+            // (a sequence with flagged bases that is a single-block stream has no byte-exact step: byte-wise kernel)
+            if (ctx->h_packable[h_x[k]] == 1 || (ctx->h_packable[h_x[k]] == 2 && ctx->h_len[h_x[k]] > LZ4_BLOCK)) {
                 // the same pass leaves the prefix checkpoints a later pair call with this x would need (the extra work
                 // is a re-run of the last partial block), so that call does not have to parse the sequence again
                 const int32_t sq = h_x[k];
@@ -755,6 +826,7 @@ static int run_lz4(snacc_ctx *ctx, const int32_t *h_x, const int32_t *h_y, int64
             const int32_t x = h_x[k], y = h_y[k];
             if (!ctx->h_packable[x] || !ctx->h_packable[y] || ctx->h_len[y] < 16) { bytewise.push_back(k); continue; }
             const bool u16 = (uint64_t)ctx->h_len[x] + ctx->h_len[y] <= LZ4_BLOCK;
+            if (u16 && (ctx->h_packable[x] == 2 || ctx->h_packable[y] == 2)) { bytewise.push_back(k); continue; }
             (u16 ? small : linked).push_back(PkJob{y, x, k});
             need[x] |= u16 ? 1 : 2;
         }

@@ -53,7 +53,13 @@ struct PkView {
     uint32_t rlo, rspan;             // fast path iff (q - rlo) <= rspan (unsigned), q = p - lx
     const uint64_t *xw, *yw;         // packed x / y in global memory (zero padded)
     uint32_t lx;
+    // sequences with bytes outside the alphabet (EXC variants only; see pk_step_exact):
+    const uint32_t *dring;           // dirty ring: bit g & 31 of word (g >> 5) & (PK_DRING_WORDS - 1) is set when one of the 16
+                                     // bases of y granule g (y offsets [16 g, 16 g + 16)) is flagged; word PK_DRING_WORDS mirrors word 0
+    const uint32_t *ymask;           // one bit per base of y (global memory): the base is outside the alphabet
 };
+constexpr uint32_t PK_DRING_WORDS = PK_RING_WORDS * 32 / 16 / 32;      // 256 words: one bit per 16 bases of the ring
+constexpr uint32_t PK_NONE = 0xffffffffu;
 
 SNACC_HD uint32_t pk_ctz64(uint64_t d)
 {
@@ -492,6 +498,44 @@ static __host__ __device__ __noinline__ void pk_step_general(PkState &st, PkTab<
 {
     pk_step<KIND, STRIDE, false>(st, tab, v, n, 0);
 }
+template <int KIND, int STRIDE>
+static __host__ __device__ __noinline__ void pk_step_exact_general(PkState &st, PkTab<KIND, STRIDE> &tab, const PkExact &xv, uint32_t n)
+{
+    if constexpr (KIND != 1) pk_step_exact<KIND, STRIDE, false>(st, tab, xv, n, 0);
+}
+
+// ---- flagged bases and the fast loop ---------------------------------------------------------------------------------
+// words of the per-base mask of a sequence (one u32 per 32 bases, like the packed words, plus zero padding)
+SNACC_HD uint32_t pk_mask_words(uint32_t len) { return pk_words(len) + 32; }
+
+// one word of the dirty ring from 16 words of the per-base mask (512 bases = 32 granules)
+SNACC_HD uint32_t pk_dirty_word(const uint32_t *mask16)
+{
+    uint32_t d = 0;
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t w = SNACC_LDG(mask16 + i);
+        d |= ((w & 0xffffu) ? 1u : 0u) << (2 * i) | ((w >> 16) ? 1u : 0u) << (2 * i + 1);
+    }
+    return d;
+}
+
+// first flagged granule at or after y offset q inside the ring's coverage [rlo, hi): its start offset (PK_NONE: none)
+// and, in *end, the end of the run of flagged granules it starts (at most hi)
+SNACC_HD uint32_t pk_next_dirty(const PkView &v, uint32_t q, uint32_t hi, uint32_t *end)
+{
+    uint32_t g = tmax(q, v.rlo) >> 4;
+    const uint32_t gh = hi >> 4;
+    while (g < gh) {
+        const uint32_t w = v.dring[(g >> 5) & (PK_DRING_WORDS - 1)] >> (g & 31);
+        if (w) { g += (uint32_t)SNACC_FFS32(w) - 1; break; }
+        g = (g | 31) + 1;
+    }
+    if (g >= gh) return PK_NONE;
+    uint32_t e = g + 1;
+    while (e < gh && ((v.dring[(e >> 5) & (PK_DRING_WORDS - 1)] >> (e & 31)) & 1)) ++e;
+    *end = e << 4;
+    return g << 4;
+}
 
 // ---- inner loop ("turbo") ------------------------------------------------------------------------
 // One thread is one serial dependency chain: probe position -> table slot -> candidate -> compare ->
@@ -583,7 +627,7 @@ inline void pk_sts16_if(bool c, pk_sptr a, uint32_t v) { if (c) *reinterpret_cas
 inline void pk_sts32_if(bool c, pk_sptr a, uint32_t v) { if (c) *reinterpret_cast<uint32_t *>(a) = v; }
 #endif
 
-template <int KIND, int STRIDE>
+template <int KIND, int STRIDE, bool EXC>
 SNACC_HD void pk_turbo_lean(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, uint32_t stop, uint32_t mask, bool work)
 {
     typedef PkTab<KIND, STRIDE> Tab;
@@ -605,7 +649,8 @@ SNACC_HD void pk_turbo_lean(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView 
                              (uint32_t)(p - 4 - lx - rlo) <= rspan);
     if (!pk_all(mask, ok0) || pk_all(mask, fin)) return;
     const pk_sptr ring_a = pk_opaque(pk_sptr_of(v.ring)), lut_a = pk_opaque(pk_sptr_of(tab.lut)),
-                  tab_a = pk_opaque(pk_sptr_of(tab.t)), ep_a = KIND == 2 ? pk_opaque(pk_sptr_of(tab.ep)) : 0;
+                  tab_a = pk_opaque(pk_sptr_of(tab.t)), ep_a = KIND == 2 ? pk_opaque(pk_sptr_of(tab.ep)) : 0,
+                  dr_a = EXC ? pk_opaque(pk_sptr_of(v.dring)) : 0;
 #define PK_TLD(addr) (KIND == 0 ? pk_lds32(addr) : pk_lds16(addr))
 #define PK_TST_IF(c, addr, val) do { if (KIND == 0) pk_sts32_if(c, addr, val); else pk_sts16_if(c, addr, val); } while (0)
     // state of the pending probe p: slot / epoch-word address, slot index (bit position), candidate, epoch word as last read
@@ -642,14 +687,30 @@ SNACC_HD void pk_turbo_lean(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView 
             const uint32_t wa = pk_lds32(ring_a + jp), wb = pk_lds32(ring_a + jp + 4), wc = pk_lds32(ring_a + jp + 8);
             const uint32_t xm = pk_fsr(ca, cb, qm4 * 2);
             const uint32_t Ws = pk_fsr(wa, wb, qp4 * 2), Wt = pk_fsr(wb, wc, qp4 * 2);
-            const uint32_t x = Ws ^ xm;
+            uint32_t x = Ws ^ xm;
+            const bool inring = (uint32_t)(qm4 - rlo) <= rspan + 32;
+            if (EXC) {
+                // a flagged base inside the candidate's 16 bases [m-4, m+12) (two granules at most) never equals the
+                // clean base it is compared with: force a mismatch there.  Only a candidate that matches 4+ bases in the
+                // 2-bit text can change (a shorter match stays a miss), and only if its window is flagged: rare -- the
+                // lane that meets one fetches the per-base mask from global memory while the others wait.
+                const uint32_t g0 = qm4 >> 4;
+                const pk_sptr da = dr_a + ((g0 >> 5) & (PK_DRING_WORDS - 1)) * 4;
+                const uint32_t dirty = pk_fsr(pk_lds32(da), pk_lds32(da + 4), g0) & 3;
+                if (dirty && near && inring && ((x >> 8) & 0xffu) == 0) {
+                    const uint32_t *mw = v.ymask + (qm4 >> 5);
+                    uint32_t em = pk_fsr(SNACC_LDG(mw), SNACC_LDG(mw + 1), qm4) & 0xffffu;
+                    em = (em | (em << 8)) & 0x00ff00ffu; em = (em | (em << 4)) & 0x0f0f0f0fu;
+                    em = (em | (em << 2)) & 0x33333333u; em = (em | (em << 1)) & 0x55555555u;
+                    x |= em;
+                }
+            }
             // equal bases forwards from p (a sentinel bit caps the count at 12) and backwards from p-1 (at 4)
             uint32_t common = pk_ctz32((x >> 8) | 0x01000000u) >> 1;
             common = near ? common : 0;
             uint32_t k = pk_clz32((x << 24) | 0x00800000u) >> 1;
             const uint32_t kmax = tmin(pend, m);
             const bool hit = common >= 4;
-            const bool inring = (uint32_t)(qm4 - rlo) <= rspan + 32;
             // candidate outside the ring / long match / long catch-up: not for this loop
             // (bitwise on purpose: no short-circuit branches in the body)
             const bool bail = go & ((near & !inring) | (common > 11) | (hit & (k == 4) & (kmax > 4)));
@@ -743,13 +804,13 @@ __device__ __forceinline__ void pk_epoch_coop(const PkState &st, PkTab<2, STRIDE
 
 // Run the streams of the warp (lanes in `mask`, one stream each) until each one's next position reaches
 // its `stop` or it is done: turbo bursts, separated by one general pk_step for every lane.
-template <int KIND, int STRIDE>
-SNACC_HD void pk_run(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, uint32_t n, uint32_t stop, uint32_t mask)
+template <int KIND, int STRIDE, bool EXC = false>
+SNACC_HD void pk_run(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, const PkExact *xv, uint32_t n, uint32_t stop, uint32_t mask)
 {
     for (;;) {
         bool work = st.phase != PK_DONE && pk_next_pos(st) < stop;
         if (!pk_any(mask, work)) return;
-        pk_turbo_lean<KIND, STRIDE>(st, tab, v, stop, mask, work);
+        pk_turbo_lean<KIND, STRIDE, EXC>(st, tab, v, stop, mask, work);
         work = st.phase != PK_DONE && pk_next_pos(st) < stop;
 #ifdef __CUDA_ARCH__
         if constexpr (KIND == 2 && STRIDE != 1) pk_epoch_coop<STRIDE>(st, tab, n, mask, work);
@@ -758,7 +819,48 @@ SNACC_HD void pk_run(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, uin
 #if defined(PK_COUNT_STEPS) && !defined(__CUDA_ARCH__)
             ++pk_general_steps;
 #endif
-            pk_step_general<KIND, STRIDE>(st, tab, v, n);
+            if constexpr (EXC) pk_step_exact_general<KIND, STRIDE>(st, tab, *xv, n);
+            else pk_step_general<KIND, STRIDE>(st, tab, v, n);
+        }
+    }
+}
+
+// The same for sequences that may hold flagged bases (EXC): every lane runs the fast loop up to 20 bases ahead of the
+// next flagged granule of y (its window [p-4, p+16) then holds clean bases only), waits there for the other lanes --
+// they share y, so they arrive within a few iterations of each other -- and all of them cross the flagged stretch with
+// byte-exact steps in lock-step.  `hi`: end of the ring's coverage (y offset).
+template <int KIND, int STRIDE>
+SNACC_HD void pk_run_exc(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, const PkExact &xv, uint32_t n, uint32_t stop,
+                         uint32_t hi, uint32_t mask)
+{
+    for (;;) {
+        uint32_t np = pk_next_pos(st);
+        const bool active = st.phase != PK_DONE && np < stop;
+        uint32_t lane_stop = stop, until = 0;
+        if (active) {
+            uint32_t e_end = 0;
+            const uint32_t q = np > v.lx + 4 ? np - v.lx - 4 : 0;
+            const uint32_t e = pk_next_dirty(v, q, hi, &e_end);
+            if (e != PK_NONE) {
+                lane_stop = tmin(stop, v.lx + e > 20 ? v.lx + e - 20 : 0u);
+                until = v.lx + e_end + 4;
+            }
+        }
+        pk_run<KIND, STRIDE, true>(st, tab, v, &xv, n, lane_stop, mask);
+        const bool cross = active && lane_stop < stop;       // stopped by a flagged granule, not by the ring
+        if (!pk_any(mask, cross && st.phase != PK_DONE && pk_next_pos(st) < stop)) return;
+        for (;;) {
+            const bool c = cross && st.phase != PK_DONE && pk_next_pos(st) < tmin(until, stop);
+            if (!pk_any(mask, c)) break;
+#ifdef __CUDA_ARCH__
+            if constexpr (KIND == 2 && STRIDE != 1) pk_epoch_coop<STRIDE>(st, tab, n, mask, c);
+#endif
+            if (c) {
+#if defined(PK_COUNT_STEPS) && !defined(__CUDA_ARCH__)
+                ++pk_general_steps;
+#endif
+                pk_step_exact_general<KIND, STRIDE>(st, tab, xv, n);
+            }
         }
     }
 }
@@ -780,10 +882,14 @@ SNACC_HD bool pk_resume(PkState &st, uint32_t n)
 struct PkRing {
     uint32_t yw_total;     // words of y that may be loaded (incl. zero padding)
     uint32_t hi_w;         // words [.., hi_w) loaded so far
-    SNACC_HD void start(uint32_t ly, uint32_t &w0, uint32_t &w1)
+    uint32_t cover;        // words behind hi_w that count as resident: PK_RING_WORDS, or PK_RING_COVER_EXC when the words
+                           // the next refill replaces host the dirty ring (EXC kernels)
+    SNACC_HD void start(uint32_t ly, uint32_t &w0, uint32_t &w1, uint32_t cover_ = PK_RING_WORDS)
     {
+        cover = cover_;
         yw_total = pk_words(ly);
-        hi_w = tmin(yw_total, PK_RING_WORDS);
+        // EXC: the first fill leaves the ring's tail free for the dirty ring
+        hi_w = tmin(yw_total, first_fill());
         w0 = 0; w1 = hi_w;
     }
     SNACC_HD bool complete() const { return hi_w >= yw_total; }
@@ -793,15 +899,36 @@ struct PkRing {
         hi_w = tmin(yw_total, hi_w + PK_CHUNK_BASES / 32);
         w1 = hi_w;
     }
+    SNACC_HD uint32_t first_fill() const { return cover == PK_RING_WORDS ? PK_RING_WORDS : PK_RING_WORDS - 160; }
+    // until the ring wraps every word loaded so far is resident
+    SNACC_HD uint32_t lo_w() const { return hi_w <= first_fill() ? 0 : hi_w - cover; }
     SNACC_HD void view(PkView &v) const
     {
-        const uint32_t lo_w = hi_w > PK_RING_WORDS ? hi_w - PK_RING_WORDS : 0;
-        v.rlo = lo_w * 32;
-        v.rspan = (hi_w - lo_w) * 32 - 64;       // hi_w - lo_w >= 6 words always (padding)
+        v.rlo = lo_w() * 32;
+        v.rspan = (hi_w - lo_w()) * 32 - 64;     // hi_w - lo_w >= 6 words always (padding)
     }
     // streams may run while their next position is below this y offset
     SNACC_HD uint32_t stop_q() const { return complete() ? 0xffffffffu : hi_w * 32 - PK_GUARD; }
+    // EXC: where the dirty ring (PK_DRING_WORDS + 1 u32 = 129 ring words) lives inside the ring: in the words that are
+    // no longer resident -- the ones the next refill replaces, or the never-filled tail of a short y
+    SNACC_HD uint32_t dring_word() const
+    {
+        const uint32_t b = hi_w & (PK_RING_WORDS - 1);
+        return hi_w < PK_RING_WORDS ? hi_w : (b + 129 <= PK_RING_WORDS ? b : 0);
+    }
 };
+// EXC: 992 ring words (31 Ki bases) are given up: the window (64 Ki) + one refill chunk (32 Ki) + the guard still fit
+constexpr uint32_t PK_RING_COVER_EXC = PK_RING_WORDS - 992;
+
+// entry k of the dirty ring for the ring's current coverage (the one dirty word j with j mod PK_DRING_WORDS == k that
+// overlaps the resident packed words; 0 if none), from y's per-base mask
+SNACC_HD uint32_t pk_dring_entry(const PkRing &rg, const uint32_t *ymask, uint32_t k)
+{
+    const uint32_t j0 = rg.lo_w() >> 4, j1 = (rg.hi_w + 15) >> 4;
+    uint32_t j = (j0 & ~(PK_DRING_WORDS - 1)) + k;
+    if (j < j0) j += PK_DRING_WORDS;
+    return j < j1 ? pk_dirty_word(ymask + 16 * j) : 0u;
+}
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------------------------------------
@@ -816,6 +943,18 @@ struct PkCorpus {
 struct PkTile {                  // up to T pair jobs sharing y
     int32_t y, count;
     int64_t first;               // index of the tile's first job in tile_x / tile_out
+};
+
+// what the EXC kernels need on top of PkCorpus (corpora with bytes outside the alphabet): the per-base masks, the true
+// bytes, the bucket -> slot map and the overflow tables of pk_step_exact
+struct PkExcCorpus {
+    const uint32_t *mask;        // per-base masks of all sequences
+    const uint64_t *moff;        // word offset of sequence i in mask
+    const uint8_t *bytes;        // the padded ASCII corpus
+    const uint64_t *boff;        // byte offset of sequence i
+    const uint16_t *b2s;         // LZ4 bucket -> slot index (0xffff: overflow table)
+    uint32_t *ovf_work;          // one overflow table (PK_OVF_ENTRIES words) per resident stream
+    uint32_t *ck_ovf;            // overflow table of every sequence's prefix checkpoint
 };
 
 // checkpoint storage: slot = seq * 2 + (linked ? 1 : 0); table stored as u32[1024] in both regimes
@@ -833,14 +972,27 @@ __device__ __forceinline__ void pk_ring_fill(uint64_t *ring, const uint64_t *yw,
     }
 }
 
+// (re)build the dirty ring for the ring's current coverage, inside the ring words that are not resident (PkRing::dring_word)
+__device__ __forceinline__ void pk_dring_build(uint64_t *ring, const PkRing &rg, const uint32_t *ymask)
+{
+    uint32_t *dr = reinterpret_cast<uint32_t *>(ring + rg.dring_word());
+    for (uint32_t k = threadIdx.x; k < PK_DRING_WORDS; k += blockDim.x) {
+        const uint32_t d = pk_dring_entry(rg, ymask, k);
+        dr[k] = d;
+        if (k == 0) dr[PK_DRING_WORDS] = d;
+    }
+}
+
 // ---- pair tiles: one stream per thread, LANES active lanes per warp, tables in shared memory --------
 // KIND: table storage (PkTab).  nslot: slots per stream (KIND 2: what pk_slot_lut needs, rounded up to 2).
 // tile_out == nullptr: rectangle mode -- the tile's jobs are rows first .. first+count-1 of tile_x against
 // column y, and results go to out[(first + k) * out_stride + (y - col0)] (no per-job arrays on the host).
 // shared memory: ring | code->slot map | position tables (warp-major, lane-interleaved) | epoch planes
-template <int KIND, int LANES>
+// (EXC: the dirty ring lives inside the ring, in the words that are not resident -- PkRing::dring_word)
+// EXC: the corpus holds sequences with bytes outside the alphabet (pk_run_exc, pk_step_exact); xc is unused otherwise.
+template <int KIND, int LANES, bool EXC>
 __global__ void __launch_bounds__(384, 1)
-lz4_pk_pair_kernel(PkCorpus pc, const PkTile *__restrict__ tiles, int32_t n_tiles, const int32_t *__restrict__ tile_x,
+lz4_pk_pair_kernel(PkCorpus pc, PkExcCorpus xc, const PkTile *__restrict__ tiles, int32_t n_tiles, const int32_t *__restrict__ tile_x,
                    const int64_t *__restrict__ tile_out, const uint32_t *__restrict__ ck_tab,
                    const PkState *__restrict__ ck_state, const uint16_t *__restrict__ lut_g, uint32_t nslot,
                    int64_t out_stride, int32_t col0, unsigned long long *__restrict__ counter, int64_t *__restrict__ out)
@@ -881,13 +1033,17 @@ lz4_pk_pair_kernel(PkCorpus pc, const PkTile *__restrict__ tiles, int32_t n_tile
         const uint64_t *yw = pc.words + pc.woff[td.y];
         PkRing rg;
         uint32_t w0, w1;
-        rg.start(ly, w0, w1);
+        rg.start(ly, w0, w1, EXC ? PK_RING_COVER_EXC : PK_RING_WORDS);
         pk_ring_fill(ring, yw, w0, w1);
+        const uint32_t *ymask = EXC ? xc.mask + xc.moff[td.y] : nullptr;
+        if (EXC) pk_dring_build(ring, rg, ymask);
 
         const bool has = lane < LANES && (int32_t)slot < td.count;
         PkState st = PkState();
         PkView v;
-        v.ring = ring; v.yw = yw; v.xw = yw; v.lx = 0;
+        v.ring = ring; v.yw = yw; v.xw = yw; v.lx = 0; v.dring = nullptr; v.ymask = ymask;
+        PkExact xv;
+        xv.b2s = xc.b2s; xv.ovf = nullptr; xv.s.x = xv.s.y = nullptr; xv.s.lx = xv.s.n = 0;
         uint32_t n = 0;
         bool bail = false;
         st.phase = PK_DONE; st.total = 0;
@@ -909,6 +1065,11 @@ lz4_pk_pair_kernel(PkCorpus pc, const PkTile *__restrict__ tiles, int32_t n_tile
             } else {
                 for (uint32_t e = lane; e < nslot; e += 32) tk.import_slot(e, src[e], bs);
             }
+            if (EXC) {                                         // the stream's overflow table starts as its x's
+                const uint4 *so = reinterpret_cast<const uint4 *>(xc.ck_ovf + (size_t)x * PK_OVF_ENTRIES);
+                uint4 *dd = reinterpret_cast<uint4 *>(xc.ovf_work + ((size_t)blockIdx.x * (n_warps * LANES) + sl) * PK_OVF_ENTRIES);
+                for (uint32_t e = lane; e < PK_OVF_ENTRIES / 4; e += 32) dd[e] = so[e];
+            }
         }
         if (has) {
             const int32_t x = tile_x[td.first + slot];
@@ -916,6 +1077,10 @@ lz4_pk_pair_kernel(PkCorpus pc, const PkTile *__restrict__ tiles, int32_t n_tile
             v.lx = pc.len[x];
             v.xw = pc.words + pc.woff[x];
             n = v.lx + ly;
+            if (EXC) {
+                xv.s.x = xc.bytes + xc.boff[x]; xv.s.y = xc.bytes + xc.boff[td.y]; xv.s.lx = v.lx; xv.s.n = n;
+                xv.ovf = xc.ovf_work + ((size_t)blockIdx.x * (n_warps * LANES) + slot) * PK_OVF_ENTRIES;
+            }
             bail = !pk_resume(st, n);
             if (bail) st.phase = PK_DONE;
             tab.epoch_base = st.bs;                // the imported bits refer to the checkpoint's open block
@@ -923,13 +1088,16 @@ lz4_pk_pair_kernel(PkCorpus pc, const PkTile *__restrict__ tiles, int32_t n_tile
         for (;;) {
             __syncthreads();                       // ring (and on the first pass the tables) visible
             rg.view(v);
+            if (EXC) v.dring = reinterpret_cast<const uint32_t *>(ring + rg.dring_word());
             const uint32_t stop_q = rg.stop_q();
             const uint32_t stop = stop_q == 0xffffffffu ? 0xffffffffu : v.lx + stop_q;
-            pk_run<KIND, LANES>(st, tab, v, n, stop, 0xffffffffu);
+            if constexpr (EXC) pk_run_exc<KIND, LANES>(st, tab, v, xv, n, stop, rg.hi_w * 32, 0xffffffffu);
+            else pk_run<KIND, LANES>(st, tab, v, nullptr, n, stop, 0xffffffffu);
             if (rg.complete()) break;
             __syncthreads();                       // everyone is done reading the slots about to be replaced
             rg.advance(w0, w1);
             pk_ring_fill(ring, yw, w0, w1);
+            if (EXC) pk_dring_build(ring, rg, ymask);
         }
         if (has) {
             // explicit output index per job, or (rectangle mode) row-major position of (x, y) in the rectangle
@@ -948,21 +1116,26 @@ struct PkSingleSmem {
     uint32_t snap[1024];
 };
 
-template <int KIND, bool DETECT>
+template <int KIND, bool DETECT, bool EXC>
 __device__ void pk_single_run(PkState &st, PkTab<KIND, 1> &tab, PkView &v, PkRing &rg, const uint64_t *yw, uint64_t *ring,
-                              uint32_t n, uint32_t xend, uint32_t snap_bs, PkState *snap_st, uint32_t *snap_tab)
+                              uint32_t n, uint32_t xend, uint32_t snap_bs, PkState *snap_st, uint32_t *snap_tab,
+                              PkExact *xv, uint32_t *snap_ovf)
 {
     // CTA-uniform control flow: thread 0 parses, all threads take part in ring refills
     __shared__ uint32_t s_more;
     for (;;) {
         __syncthreads();
         rg.view(v);
+        if (EXC) v.dring = reinterpret_cast<const uint32_t *>(ring + rg.dring_word());
         const uint32_t stop = rg.stop_q();
         if (threadIdx.x == 0) {
             bool touched = false;
             while (st.phase != PK_DONE && pk_next_pos(st) < stop) {
                 if (DETECT) {
-                    if (pk_step<KIND, 1, true>(st, tab, v, n, xend)) { touched = true; break; }
+                    bool t;
+                    if constexpr (EXC && KIND != 1) t = pk_step_exact<KIND, 1, true>(st, tab, *xv, n, xend);
+                    else t = pk_step<KIND, 1, true>(st, tab, v, n, xend);
+                    if (t) { touched = true; break; }
                     continue;
                 }
                 uint32_t limit = stop;
@@ -971,12 +1144,14 @@ __device__ void pk_single_run(PkState &st, PkTab<KIND, 1> &tab, PkView &v, PkRin
                     if (st.phase == PK_BLOCK_START && st.bs == snap_bs) {
                         *snap_st = st;
                         for (uint32_t e = 0; e < PkTab<KIND, 1>::ENTRIES; ++e) snap_tab[e] = tab.t[e];
+                        if (EXC && snap_ovf) for (uint32_t e = 0; e < PK_OVF_ENTRIES; ++e) snap_ovf[e] = xv->ovf[e];
                         snap_st = nullptr;
                     } else {
                         limit = tmin(stop, snap_bs);
                     }
                 }
-                pk_run<KIND, 1>(st, tab, v, n, limit, 1u);
+                if constexpr (EXC && KIND != 1) pk_run_exc<KIND, 1>(st, tab, v, *xv, n, limit, rg.hi_w * 32, 1u);
+                else pk_run<KIND, 1>(st, tab, v, nullptr, n, limit, 1u);
             }
             s_more = (!touched && st.phase != PK_DONE && !rg.complete()) ? 1u : 0u;
         }
@@ -985,11 +1160,16 @@ __device__ void pk_single_run(PkState &st, PkTab<KIND, 1> &tab, PkView &v, PkRin
         uint32_t w0, w1;
         rg.advance(w0, w1);
         pk_ring_fill(ring, yw, w0, w1);
+        if (EXC) pk_dring_build(ring, rg, v.ymask);
     }
 }
 
+// EXC: the corpus holds sequences with bytes outside the alphabet.  Such a sequence is handled here when it is a
+// linked-regime stream (> 64 KiB) or the x of one; the single-block regime (16-bit table, 4-byte hash) has no byte-exact
+// step -- the host sends those jobs to the byte-wise kernels.
+template <bool EXC>
 __global__ void __launch_bounds__(64)
-lz4_pk_single_kernel(PkCorpus pc, const int32_t *__restrict__ seqs, const int32_t *__restrict__ want, int32_t n_seqs,
+lz4_pk_single_kernel(PkCorpus pc, PkExcCorpus xc, const int32_t *__restrict__ seqs, const int32_t *__restrict__ want, int32_t n_seqs,
                      uint32_t *__restrict__ ck_tab, PkState *__restrict__ ck_state, const uint16_t *__restrict__ lut5_g,
                      const uint16_t *__restrict__ lut4_g, const int64_t *__restrict__ out_idx,
                      int64_t *__restrict__ out)
@@ -1007,7 +1187,15 @@ lz4_pk_single_kernel(PkCorpus pc, const int32_t *__restrict__ seqs, const int32_
         const uint32_t len = pc.len[s];
         const uint64_t *yw = pc.words + pc.woff[s];
         PkView v;
-        v.ring = ring; v.yw = yw; v.xw = yw; v.lx = 0;
+        v.ring = ring; v.yw = yw; v.xw = yw; v.lx = 0; v.dring = nullptr; v.ymask = EXC ? xc.mask + xc.moff[s] : nullptr;
+        PkExact xv;
+        uint32_t *ovf_w = nullptr, *ovf_ck = nullptr;
+        if (EXC) {
+            ovf_w = xc.ovf_work + (size_t)blockIdx.x * PK_OVF_ENTRIES;
+            ovf_ck = xc.ck_ovf + (size_t)s * PK_OVF_ENTRIES;
+            xv.b2s = xc.b2s; xv.ovf = ovf_w;
+            xv.s.x = xc.bytes + xc.boff[s]; xv.s.y = xv.s.x + len; xv.s.lx = len; xv.s.n = len;
+        }
         PkRing rg;
         PkState st, snap;
         PkTab<0, 1> tl; tl.t = s_tab; tl.lut = s_lut5; tl.ep = nullptr; tl.nslot = 1024; tl.epoch_base = 0;
@@ -1018,12 +1206,15 @@ lz4_pk_single_kernel(PkCorpus pc, const int32_t *__restrict__ seqs, const int32_
         // (1) the sequence on its own
         __syncthreads();
         for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) s_tab[i] = 0;
+        if (EXC) for (uint32_t i = threadIdx.x; i < PK_OVF_ENTRIES; i += blockDim.x) ovf_w[i] = 0;
         uint32_t w0, w1;
-        rg.start(len, w0, w1);
+        const uint32_t cover = EXC ? PK_RING_COVER_EXC : PK_RING_WORDS;
+        rg.start(len, w0, w1, cover);
         pk_ring_fill(ring, yw, w0, w1);
+        if (EXC) pk_dring_build(ring, rg, v.ymask);
         pk_fresh(st); pk_fresh(snap);
-        if (linked_single) pk_single_run<0, false>(st, tl, v, rg, yw, ring, len, 0, last_bs, &snap, s_snap);
-        else               pk_single_run<1, false>(st, ts, v, rg, yw, ring, len, 0, 0, nullptr, nullptr);
+        if (linked_single) pk_single_run<0, false, EXC>(st, tl, v, rg, yw, ring, len, 0, last_bs, &snap, s_snap, &xv, ovf_ck);
+        else               pk_single_run<1, false, EXC>(st, ts, v, rg, yw, ring, len, 0, 0, nullptr, nullptr, &xv, nullptr);
         if (threadIdx.x == 0 && out_idx[t] >= 0) out[out_idx[t]] = (int64_t)(st.total + lz4_frame_overhead(len));
 
         // (2) linked-regime checkpoint: from the snapshot at the last block start (or from scratch)
@@ -1037,11 +1228,14 @@ lz4_pk_single_kernel(PkCorpus pc, const int32_t *__restrict__ seqs, const int32_
                 st = snap;
             } else {
                 for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) s_tab[i] = 0;
+                if (EXC) for (uint32_t i = threadIdx.x; i < PK_OVF_ENTRIES; i += blockDim.x) ovf_ck[i] = 0;
                 pk_fresh(st);
-                rg.start(len, w0, w1);
+                rg.start(len, w0, w1, cover);
                 pk_ring_fill(ring, yw, w0, w1);
+                if (EXC) pk_dring_build(ring, rg, v.ymask);
             }
-            pk_single_run<0, true>(st, tl, v, rg, yw, ring, 0xffffffffu, len, 0, nullptr, nullptr);
+            if (EXC) xv.ovf = ovf_ck;                       // the checkpoint's overflow table is updated in place
+            pk_single_run<0, true, EXC>(st, tl, v, rg, yw, ring, 0xffffffffu, len, 0, nullptr, nullptr, &xv, nullptr);
             __syncthreads();
             uint32_t *dst = ck_tab + (size_t)(2 * s + 1) * PK_CKPT_TAB;
             for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) dst[i] = s_tab[i];
@@ -1054,7 +1248,7 @@ lz4_pk_single_kernel(PkCorpus pc, const int32_t *__restrict__ seqs, const int32_
             pk_fresh(st);
             rg.start(len, w0, w1);
             pk_ring_fill(ring, yw, w0, w1);
-            pk_single_run<1, true>(st, ts, v, rg, yw, ring, 0xffffffffu, len, 0, nullptr, nullptr);
+            pk_single_run<1, true, false>(st, ts, v, rg, yw, ring, 0xffffffffu, len, 0, nullptr, nullptr, nullptr, nullptr);
             __syncthreads();
             uint32_t *dst = ck_tab + (size_t)(2 * s) * PK_CKPT_TAB;
             const uint16_t *t16 = reinterpret_cast<const uint16_t *>(s_tab);

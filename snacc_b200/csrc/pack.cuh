@@ -87,20 +87,23 @@ __global__ void pk_hist_kernel(const uint8_t *__restrict__ corpus, const uint64_
 
 struct PkCodes { uint8_t c[256]; };   // byte -> code (0xff: outside the alphabet), passed by value
 
-// one thread per packed word; bad[s] is raised when sequence s holds a byte outside the alphabet
+// one thread per packed word; nexc[s] counts the bytes of sequence s outside the alphabet.  Such a byte gets the filler
+// code 0 and -- when `mask` is given (corpora that have any) -- its bit in the per-base mask (word j of a sequence's
+// mask covers the same 32 bases as its packed word j; the mask is zeroed beforehand).
 __global__ void pk_pack_kernel(const uint8_t *__restrict__ corpus, const uint64_t *__restrict__ off,
                                const uint32_t *__restrict__ len, const uint64_t *__restrict__ woff, int32_t n_seqs,
-                               uint64_t *__restrict__ words, int32_t *__restrict__ bad,
-                               const PkCodes codes)
+                               uint64_t *__restrict__ words, int32_t *__restrict__ nexc,
+                               uint32_t *__restrict__ mask, const uint64_t *__restrict__ moff, const PkCodes codes)
 {
     for (int32_t s = blockIdx.y; s < n_seqs; s += gridDim.y) {
         const uint8_t *p = corpus + off[s];
         const uint32_t l = len[s];
         const uint32_t nw = pk_words(l);
         uint64_t *dst = words + woff[s];
-        bool any_bad = false;
+        int32_t n_bad = 0;
         for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nw; j += gridDim.x * blockDim.x) {
             uint64_t w = 0;
+            uint32_t mw = 0;
             const uint32_t b0 = j * 32;
             if (b0 < l) {
                 const uint4 q0 = __ldg(reinterpret_cast<const uint4 *>(p + b0));
@@ -109,13 +112,17 @@ __global__ void pk_pack_kernel(const uint8_t *__restrict__ corpus, const uint64_
                 const uint32_t cnt = tmin(32u, l - b0);
                 for (uint32_t b = 0; b < cnt; ++b) {
                     const uint32_t code = codes.c[(v[b >> 2] >> (8 * (b & 3))) & 0xff];
-                    any_bad |= code > 3;
-                    w |= (uint64_t)(code & 3) << (2 * b);
+                    if (code > 3) mw |= 1u << b;
+                    else w |= (uint64_t)code << (2 * b);
                 }
             }
             dst[j] = w;
+            if (mw) {
+                n_bad += __popc(mw);
+                if (mask) mask[moff[s] + j] = mw;
+            }
         }
-        if (any_bad) bad[s] = 1;
+        if (n_bad) atomicAdd(&nexc[s], n_bad);
     }
 }
 #endif

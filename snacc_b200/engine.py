@@ -162,8 +162,13 @@ class Engine:
                                                out.ctypes.data))
         return out.reshape(xs.shape)
 
-    def tile_sizes(self, algorithm, row0, n_rows, col0, n_cols):
-        out = np.zeros((n_rows, n_cols), dtype=np.int64)
+    def tile_sizes(self, algorithm, row0, n_rows, col0, n_cols, out=None):
+        """rows [row0, row0+n_rows) x cols [col0, col0+n_cols) of the ordered-pair matrix; ``out``: a C-contiguous
+        int64 (n_rows, n_cols) array to fill in place (e.g. a slice of a pinned buffer), else a new array"""
+        if out is None:
+            out = np.empty((n_rows, n_cols), dtype=np.int64)
+        elif out.dtype != np.int64 or out.shape != (n_rows, n_cols) or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous int64 array of shape (n_rows, n_cols)")
         self._check(self._lib.snacc_tile_sizes(self._h, _codec(algorithm), row0, n_rows, col0, n_cols, out.ctypes.data))
         return out
 

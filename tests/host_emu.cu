@@ -86,7 +86,7 @@ static bool emu_run(PkState &st, PkTab<KIND, 1> &tab, std::vector<uint32_t> *tab
                 if (st.phase == PK_BLOCK_START && st.bs == snap_bs) { snap->st = st; snap->tab = *tab32; snap = nullptr; }
                 else limit = tmin(stop, snap_bs);
             }
-            pk_run<KIND, 1>(st, tab, v, n, limit, 1u);
+            pk_run<KIND, 1>(st, tab, v, nullptr, n, limit, 1u);
         }
         if (st.phase == PK_DONE || rg.complete()) return false;
         uint32_t w0, w1;
@@ -176,6 +176,172 @@ extern "C" int64_t emu_lz4_packed(const uint8_t *x, uint32_t lx, const uint8_t *
         emu_run<2, false>(st, t17, nullptr, v, rg, ring, yw, n, 0, 0, nullptr);
     }
     return (int64_t)(st.total + lz4_frame_overhead(n));
+}
+
+// ---------------------------------------------------------------------------------------------
+// byte-exact LZ4 step (pk_step_exact) on its own: every step of the stream through the true-byte path -- any byte
+// values, the alphabet's buckets in the slot table, all other buckets in the overflow table -- singles and pairs
+// (prefix checkpoint by the DETECT variant, resume on the 17-bit table).  Linked regime only: returns -5 otherwise.
+// ---------------------------------------------------------------------------------------------
+static std::vector<uint16_t> emu_b2s(const PkAlphabet &a, const uint16_t *raw5)
+{
+    std::vector<uint16_t> b2s(PK_OVF_ENTRIES, 0xffff);
+    for (uint32_t c = 0; c < 1024; ++c) b2s[pk_bucket(a, c, false)] = raw5[c];
+    return b2s;
+}
+
+extern "C" int64_t emu_lz4_exact(const uint8_t *x, uint32_t lx, const uint8_t *y, int64_t ly_)
+{
+    unsigned long long hist[256] = {0};
+    for (uint32_t i = 0; i < lx; ++i) hist[x[i]]++;
+    for (int64_t i = 0; i < ly_; ++i) hist[y[i]]++;
+    const PkAlphabet a = pk_choose_alphabet(hist);
+    uint16_t raw5[1024];
+    const uint32_t nslot5 = pk_slot_lut(a, false, raw5);
+    const std::vector<uint16_t> b2s = emu_b2s(a, raw5);
+    uint8_t *px = padded_copy(x, lx);
+    uint8_t *py = ly_ >= 0 ? padded_copy(y, (uint64_t)ly_) : nullptr;
+    std::vector<uint32_t> tab(1024, 0), ovf(PK_OVF_ENTRIES, 0);
+    PkTab<0, 1> t32; t32.t = tab.data(); t32.ep = nullptr; t32.nslot = 1024; t32.epoch_base = 0; t32.lut = raw5;
+    PkExact xv; xv.b2s = b2s.data(); xv.ovf = ovf.data();
+    PkState st;
+    int64_t result = -5;
+    if (ly_ < 0) {
+        if (lx > LZ4_BLOCK) {
+            xv.s.x = px; xv.s.y = px + lx; xv.s.lx = lx; xv.s.n = lx;
+            pk_fresh(st);
+            while (st.phase != PK_DONE) pk_step_exact<0, 1, false>(st, t32, xv, lx, 0);
+            result = (int64_t)(st.total + lz4_frame_overhead(lx));
+        }
+    } else if ((uint64_t)lx + (uint64_t)ly_ > LZ4_BLOCK) {
+        const uint32_t n = lx + (uint32_t)ly_;
+        // prefix checkpoint of x: the state right before the first iteration that looks at a byte of y
+        xv.s.x = px; xv.s.y = px + lx; xv.s.lx = lx; xv.s.n = lx;
+        pk_fresh(st);
+        bool touched = false;
+        while (st.phase != PK_DONE && !(touched = pk_step_exact<0, 1, true>(st, t32, xv, 0xffffffffu, lx))) {}
+        if (touched && pk_resume(st, n)) {
+            const uint32_t nslot = (nslot5 + 1) & ~1u;
+            std::vector<uint16_t> lo(nslot, 0);
+            std::vector<uint32_t> ep((nslot + 31) / 32, 0);
+            PkTab<2, 1> t17; t17.t = lo.data(); t17.ep = ep.data(); t17.nslot = nslot; t17.epoch_base = st.bs; t17.lut = raw5;
+            for (uint32_t e = 0; e < nslot; ++e) t17.import_slot(e, tab[e], st.bs);
+            xv.s.y = py; xv.s.n = n;
+            while (st.phase != PK_DONE) pk_step_exact<2, 1, false>(st, t17, xv, n, 0);
+            result = (int64_t)(st.total + lz4_frame_overhead(n));
+        } else {
+            result = -1;
+        }
+    }
+    free(px); free(py);
+    return result;
+}
+
+// ---------------------------------------------------------------------------------------------
+// packed path for sequences with a few bytes outside the alphabet (the EXC kernels): filler code + per-base mask,
+// dirty ring, fast loop up to the flagged granules (pk_run_exc), byte-exact steps across them and for every general
+// step, overflow table, prefix checkpoint by the byte-exact DETECT step.  Linked regime only (-5 otherwise).
+// ---------------------------------------------------------------------------------------------
+struct EmuSeqX { std::vector<uint64_t> words; std::vector<uint32_t> mask; uint8_t *bytes; uint32_t len; };
+
+static EmuSeqX emu_pack_x(const PkAlphabet &a, const uint8_t *p, uint32_t n)
+{
+    EmuSeqX q;
+    q.len = n;
+    q.words.assign(pk_words(n) + 2, 0);
+    q.mask.assign(pk_mask_words(n) + 64, 0);
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint8_t c = a.code_of[p[i]];
+        if (c > 3) q.mask[i >> 5] |= 1u << (i & 31);
+        else q.words[i >> 5] |= (uint64_t)c << (2 * (i & 31));
+    }
+    q.bytes = padded_copy(p, n);
+    return q;
+}
+
+// what the EXC kernels do at every ring (re)fill: packed words [w0, w1), then the dirty ring rebuilt inside the ring
+static void ring_fill_x(std::vector<uint64_t> &ring, const PkRing &rg, const EmuSeqX &y, uint32_t w0, uint32_t w1)
+{
+    ring_fill_host(ring, y.words, w0, w1);
+    uint32_t *dr = reinterpret_cast<uint32_t *>(ring.data() + rg.dring_word());
+    for (uint32_t k = 0; k < PK_DRING_WORDS; ++k) dr[k] = pk_dring_entry(rg, y.mask.data(), k);
+    dr[PK_DRING_WORDS] = dr[0];
+}
+
+// one stream through pk_run_exc with ring refills (the loop of lz4_pk_pair_kernel<.., EXC> / the singles kernel)
+template <int KIND>
+static void emu_run_x(PkState &st, PkTab<KIND, 1> &tab, PkView &v, const PkExact &xv, const EmuSeqX &y, uint32_t n,
+                      std::vector<uint64_t> &ring, uint32_t limit)
+{
+    PkRing rg; uint32_t w0, w1;
+    rg.start(y.len, w0, w1, PK_RING_COVER_EXC); ring_fill_x(ring, rg, y, w0, w1);
+    for (;;) {
+        rg.view(v);
+        v.dring = reinterpret_cast<const uint32_t *>(ring.data() + rg.dring_word());
+        const uint32_t sq = rg.stop_q();
+        const uint32_t stop = tmin(limit, sq == 0xffffffffu ? sq : v.lx + sq);
+        pk_run_exc<KIND, 1>(st, tab, v, xv, n, stop, rg.hi_w * 32, 1u);
+        if (st.phase == PK_DONE || rg.complete() || pk_next_pos(st) >= limit) return;
+        rg.advance(w0, w1);
+        ring_fill_x(ring, rg, y, w0, w1);
+    }
+}
+
+extern "C" int64_t emu_lz4_packed_exc(const uint8_t *x, uint32_t lx, const uint8_t *y, int64_t ly_)
+{
+    unsigned long long hist[256] = {0};
+    for (uint32_t i = 0; i < lx; ++i) hist[x[i]]++;
+    for (int64_t i = 0; i < ly_; ++i) hist[y[i]]++;
+    const PkAlphabet a = pk_choose_alphabet(hist);
+    uint16_t raw5[1024];
+    const uint32_t nslot5 = pk_slot_lut(a, false, raw5);
+    const std::vector<uint16_t> b2s = emu_b2s(a, raw5);
+    EmuSeqX sx = emu_pack_x(a, x, lx), sy;
+    if (ly_ >= 0) sy = emu_pack_x(a, y, (uint32_t)ly_); else sy.bytes = nullptr;
+    std::vector<uint64_t> ring(PK_RING_WORDS + 2, 0);
+    std::vector<uint32_t> tab(1024, 0), ovf(PK_OVF_ENTRIES, 0);
+    PkTab<0, 1> t32; t32.t = tab.data(); t32.ep = nullptr; t32.nslot = 1024; t32.epoch_base = 0; t32.lut = raw5;
+    PkExact xv; xv.b2s = b2s.data(); xv.ovf = ovf.data();
+    PkView v; v.ring = ring.data(); v.dring = nullptr;
+    PkState st;
+    int64_t result = -5;
+    const uint32_t last_bs = (lx / LZ4_BLOCK) * LZ4_BLOCK;
+    if (lx > LZ4_BLOCK || (ly_ >= 16 && (uint64_t)lx + (uint64_t)ly_ > LZ4_BLOCK)) {
+        // ---- x on its own (singles kernel): size when it is a linked-regime stream; the state at its last block start ----
+        v.yw = sx.words.data(); v.xw = sx.words.data(); v.lx = 0; v.ymask = sx.mask.data();
+        xv.s.x = sx.bytes; xv.s.y = sx.bytes + lx; xv.s.lx = lx; xv.s.n = lx;
+        pk_fresh(st);
+        if (lx > LZ4_BLOCK) {
+            // up to the last block start with the fast loop, snapshot, then on to the end for the size of x alone
+            emu_run_x<0>(st, t32, v, xv, sx, lx, ring, last_bs);
+            while (!(st.phase == PK_BLOCK_START && st.bs == last_bs) && st.phase != PK_DONE) pk_step_exact<0, 1, false>(st, t32, xv, lx, 0);
+            const PkState snap = st; const std::vector<uint32_t> stab = tab, sovf = ovf;
+            emu_run_x<0>(st, t32, v, xv, sx, lx, ring, 0xffffffffu);
+            result = (int64_t)(st.total + lz4_frame_overhead(lx));
+            st = snap; tab = stab; ovf = sovf;
+        }
+        if (ly_ >= 0) {
+            // ---- prefix checkpoint: byte-exact DETECT steps over the last partial block of x ----
+            const uint32_t n = lx + (uint32_t)ly_;
+            bool touched = false;
+            while (st.phase != PK_DONE && !(touched = pk_step_exact<0, 1, true>(st, t32, xv, 0xffffffffu, lx))) {}
+            result = -1;
+            if (touched && pk_resume(st, n)) {
+                // ---- the pair stream (pair kernel, EXC) ----
+                const uint32_t nslot = (nslot5 + 1) & ~1u;
+                std::vector<uint16_t> lo(nslot, 0);
+                std::vector<uint32_t> ep((nslot + 31) / 32, 0);
+                PkTab<2, 1> t17; t17.t = lo.data(); t17.ep = ep.data(); t17.nslot = nslot; t17.epoch_base = st.bs; t17.lut = raw5;
+                for (uint32_t e = 0; e < nslot; ++e) t17.import_slot(e, tab[e], st.bs);
+                v.yw = sy.words.data(); v.xw = sx.words.data(); v.lx = lx; v.ymask = sy.mask.data();
+                xv.s.y = sy.bytes; xv.s.n = n;
+                emu_run_x<2>(st, t17, v, xv, sy, n, ring, 0xffffffffu);
+                result = (int64_t)(st.total + lz4_frame_overhead(n));
+            }
+        }
+    }
+    free(sx.bytes); free(sy.bytes);
+    return result;
 }
 
 // ---------------------------------------------------------------------------------------------

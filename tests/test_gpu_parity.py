@@ -518,3 +518,56 @@ def test_deflate_prefix_records_exchange(engine, algo):
     ref = np.array([_ref_len(np.concatenate([g[a], g[b]]), algo) for a, b in zip(xs, ys)])
     assert np.array_equal(S, ref)
     engine.set_option("invalidate_caches", 1)
+
+
+def _sprinkle(seq, rate, seed, alt=b"NNNNRYKMSWacgtn", runs=3):
+    """what real assemblies contain: a fraction `rate` of the bases replaced by N / IUPAC / lower-case bytes, a few N runs"""
+    rng = np.random.default_rng(seed)
+    s = np.array(seq, dtype=np.uint8, copy=True)
+    m = rng.random(s.size) < rate
+    s[m] = np.frombuffer(alt, dtype=np.uint8)[rng.integers(0, len(alt), int(m.sum()))]
+    for _ in range(runs):
+        a = int(rng.integers(0, max(1, s.size - 1)))
+        s[a:a + int(rng.integers(1, 400))] = ord("N")
+    return s
+
+
+def test_lz4_sequences_with_sparse_non_alphabet_bytes_stay_on_the_tile_kernels(engine):
+    """VERDICT r1 'cliff': an N / IUPAC code / soft-masked base no longer sends a genome to the byte-wise kernel.  Flagged
+    bases are crossed with byte-exact steps (pk_step_exact), candidates whose window holds one get a forced mismatch, k-mers
+    with such bytes live in the overflow table: sizes equal liblz4's for every pair, and the jobs stay 'packed'"""
+    from snacc_b200 import synth
+    g = synth.phylogeny(8, 150000, seed=9)
+    seqs = [_sprinkle(s, r, 40 + i) for i, (s, r) in enumerate(zip(g, [1e-4, 1e-4, 1e-3, 0, 3e-3, 1e-5, 0, 1e-4]))]
+    seqs[1][-2:] = ord("N"); seqs[2][:3] = ord("n"); seqs[4][65530:65541] = ord("N"); seqs[5][131071] = ord("R")
+    seqs += [_sprinkle(synth.phylogeny(1, 30000, seed=3)[0], 1e-3, 77),       # flagged and shorter than a block
+             synth_vector("nrun", 90000, 5)]                                  # 10 % N: too dense, byte-wise
+    n = len(seqs)
+    engine.upload_sequences(seqs)
+    C = engine.single_sizes("lz4")
+    assert np.array_equal(C, np.array([olib.ref_lz4f_size(s) for s in seqs]))
+    S = engine.tile_sizes("lz4", 0, n, 0, n)
+    ref = _ref_jobs(seqs, np.repeat(np.arange(n), n), np.tile(np.arange(n), n), "lz4").reshape(n, n)
+    assert np.array_equal(S, ref), np.argwhere(S != ref)[:10].tolist()
+    # only the jobs touching the dense sequence (and the single-block pair of the short one with itself) are byte-wise
+    assert engine.stat("bytewise_jobs") <= 2 * n + 1 and engine.stat("packed_jobs") >= (n - 1) * (n - 1) - 1
+    engine.set_option("lz4_packed", 0)
+    try:
+        assert np.array_equal(engine.tile_sizes("lz4", 0, n, 0, n), ref)
+    finally:
+        engine.set_option("lz4_packed", 1)
+
+
+def test_lz4_full_size_genomes_with_flagged_bases(engine):
+    """c4 shape with 1e-4 of the bases outside the alphabet: every job on the tile kernels, sizes == liblz4"""
+    from snacc_b200 import synth
+    g = [_sprinkle(s, 1e-4, 60 + i, runs=6) for i, s in enumerate(synth.phylogeny(5, 5_000_000, seed=4, n_indels=2))]
+    n = len(g)
+    engine.upload_sequences(g)
+    C = engine.single_sizes("lz4")
+    S = engine.tile_sizes("lz4", 0, n, 0, n)
+    assert engine.stat("packed_jobs") == n * n and engine.stat("bytewise_jobs") == 0
+    ref = _ref_jobs(g, np.concatenate([np.repeat(np.arange(n), n), np.arange(n)]),
+                    np.concatenate([np.tile(np.arange(n), n), np.full(n, -1)]), "lz4")
+    assert np.array_equal(S, ref[:n * n].reshape(n, n))
+    assert np.array_equal(C, ref[n * n:])

@@ -28,6 +28,10 @@ def emu():
     e.emu_lz4_size.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int64]
     e.emu_lz4_packed.restype = ctypes.c_int64
     e.emu_lz4_packed.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int64]
+    e.emu_lz4_exact.restype = ctypes.c_int64
+    e.emu_lz4_exact.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int64]
+    e.emu_lz4_packed_exc.restype = ctypes.c_int64
+    e.emu_lz4_packed_exc.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int64]
     e.emu_deflate_size.restype = ctypes.c_int64
     e.emu_deflate_size.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int]
     e.emu_flush_compact_fuzz.restype = ctypes.c_int64
@@ -138,6 +142,59 @@ def test_lz4_packed_related_genomes(emu):
     for a in g:
         for b in g:
             assert _call2(emu.emu_lz4_packed, a, b) == lib.ref_lz4f_size(np.concatenate([a, b]))
+
+
+@pytest.mark.parametrize("kind", VECTOR_KINDS)
+def test_lz4_byte_exact_step_on_any_bytes(emu, kind):
+    """pk_step_exact alone (the path probes near non-alphabet bytes take): true-byte hash, alphabet buckets in the slot
+    table, the rest in the overflow table, DETECT checkpoint + resume on the 17-bit table -- against liblz4"""
+    rng = np.random.default_rng(7)
+    bad = []
+    for lx in [13, 700, 40000, 65536, 65537, 70000, 140000]:
+        x = synth_vector(kind, lx, lx + 1)
+        if lx > 65536 and _call2(emu.emu_lz4_exact, x, None) != lib.ref_lz4f_size(x):
+            bad.append(("single", lx))
+        for ly in [16, 17, 9000, 65536, 80000, 150000]:       # (y < 16: host-side eligibility rule of the packed pair path)
+            if lx + ly <= 65536:
+                continue
+            y = synth_vector(kind if rng.random() < 0.6 else "dna", ly, ly + 7)
+            got = _call2(emu.emu_lz4_exact, x, y)
+            if got != lib.ref_lz4f_size(np.concatenate([x, y])) and got != -1:
+                bad.append(("pair", lx, ly, got))
+    assert not bad, bad[:10]
+
+
+def _sprinkle(seq, rate, seed, alt=b"NNNNRYKMSWacgtn"):
+    """genome-like input: a fraction `rate` of the bases replaced by N / IUPAC / lower-case bytes, plus a few runs of N"""
+    rng = np.random.default_rng(seed)
+    s = np.array(seq, dtype=np.uint8, copy=True)
+    m = rng.random(s.size) < rate
+    s[m] = np.frombuffer(alt, dtype=np.uint8)[rng.integers(0, len(alt), int(m.sum()))]
+    for _ in range(int(rng.integers(0, 4))):
+        a = int(rng.integers(0, max(1, s.size - 1)))
+        s[a:a + int(rng.integers(1, 700))] = ord("N")
+    return s
+
+
+@pytest.mark.parametrize("rate", [1e-4, 1e-3, 2e-2])
+def test_lz4_packed_path_with_flagged_bases(emu, rate):
+    """the EXC kernels' logic: fast loop up to the flagged granules, byte-exact crossings, forced mismatches inside
+    candidate windows, overflow table, N runs, exceptions at the x|y junction and at block / ring-refill boundaries"""
+    from snacc_b200 import synth
+    bad = []
+    g = synth.phylogeny(3, 180000, seed=21) + [_dna(70000, 5), _dna(300000, 6)]
+    seqs = [_sprinkle(s, rate, 30 + i) for i, s in enumerate(g)]
+    seqs[1][-3:] = ord("N"); seqs[2][:2] = ord("n"); seqs[3][65534:65540] = ord("N"); seqs[4][131070:131075] = ord("R")
+    for i, x in enumerate(seqs):
+        if x.size > 65536 and _call2(emu.emu_lz4_packed_exc, x, None) != lib.ref_lz4f_size(x):
+            bad.append(("single", i))
+        for j, y in enumerate(seqs):
+            got = _call2(emu.emu_lz4_packed_exc, x, y)
+            if got != lib.ref_lz4f_size(np.concatenate([x, y])):
+                bad.append(("pair", i, j, got))
+    # clean inputs take the same path unchanged
+    assert _call2(emu.emu_lz4_packed_exc, g[0], g[1]) == lib.ref_lz4f_size(np.concatenate([g[0], g[1]]))
+    assert not bad, bad[:10]
 
 
 def test_lz4_packed_refuses_more_than_four_symbols(emu):
