@@ -627,8 +627,9 @@ inline void pk_sts16_if(bool c, pk_sptr a, uint32_t v) { if (c) *reinterpret_cas
 inline void pk_sts32_if(bool c, pk_sptr a, uint32_t v) { if (c) *reinterpret_cast<uint32_t *>(a) = v; }
 #endif
 
+// Returns whether THIS lane is the reason the burst ended (it needs a general step); the other lanes just re-enter.
 template <int KIND, int STRIDE, bool EXC>
-SNACC_HD void pk_turbo_lean(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, uint32_t stop, uint32_t mask, bool work)
+SNACC_HD bool pk_turbo_lean(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, uint32_t stop, uint32_t mask, bool work)
 {
     typedef PkTab<KIND, STRIDE> Tab;
     constexpr uint32_t MASK = Tab::MASK;
@@ -642,12 +643,13 @@ SNACC_HD void pk_turbo_lean(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView 
     const uint32_t lim = tmin(stop, st.mfl1 > 16 ? st.mfl1 - 16 : 0u);
     // output budget: PK_UNROLL iterations add at most that many x (token + offset + length byte) + the literals pending
     // at the vote + 11 bases each
-    constexpr uint32_t OP_SLACK = 80 + 15 * PK_UNROLL;
+    constexpr uint32_t UNROLL = EXC ? PK_UNROLL / 2 : PK_UNROLL;   // (the EXC body is longer: keep the loop inside the instruction cache)
+    constexpr uint32_t OP_SLACK = 80 + 15 * UNROLL;
     const uint32_t op_lim = st.budget > OP_SLACK ? st.budget - OP_SLACK : 0u;
     const bool fin = !work || p >= stop;
     const bool ok0 = fin || (st.phase <= PK_RETEST && !(st.phase == PK_SEARCH && st.step != 1) &&
                              (uint32_t)(p - 4 - lx - rlo) <= rspan);
-    if (!pk_all(mask, ok0) || pk_all(mask, fin)) return;
+    if (!pk_all(mask, ok0) || pk_all(mask, fin)) return !ok0;
     const pk_sptr ring_a = pk_opaque(pk_sptr_of(v.ring)), lut_a = pk_opaque(pk_sptr_of(tab.lut)),
                   tab_a = pk_opaque(pk_sptr_of(tab.t)), ep_a = KIND == 2 ? pk_opaque(pk_sptr_of(tab.ep)) : 0,
                   dr_a = EXC ? pk_opaque(pk_sptr_of(v.dring)) : 0;
@@ -664,17 +666,18 @@ SNACC_HD void pk_turbo_lean(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView 
         near = tab.lookup(c0, p, m);
         if (KIND == 2) ew = pk_lds32(ea);
     }
-    bool blocked = false;
+    bool blocked = false, stuck = false;
     for (;;) {
         // warp vote every PK_UNROLL iterations: leave when a live lane cannot go on or nobody runs any more.  What can
         // only change slowly is tested here, with the slack that many iterations can use up.
         const uint32_t pend0 = p - anchor;
         const bool live = !fin && p < stop;
-        bool run = live && !blocked && op + pend0 <= op_lim && nb <= 120 - PK_UNROLL && pend0 <= 200;
+        bool run = live && !blocked && op + pend0 <= op_lim && nb <= 120 - UNROLL && pend0 <= 200;
         const bool can = run && p < lim;
-        if (pk_any(mask, live && !can) || !pk_any(mask, can)) break;
+        stuck = live && !can;
+        if (pk_any(mask, stuck) || !pk_any(mask, can)) break;
 #pragma unroll
-        for (int u = 0; u < (int)PK_UNROLL; ++u) {
+        for (int u = 0; u < (int)UNROLL; ++u) {
             // ---- straight-line, branch-free body: every lane executes everything, stores are predicated, and a lane
             // that does not commit looks its own probe up again (d = 0), which leaves its state as it was
             const bool go = run & (p < lim);
@@ -770,6 +773,7 @@ SNACC_HD void pk_turbo_lean(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView 
         else             { st.phase = PK_RETEST; st.ip = p; }
         st.anchor = anchor; st.op = op;
     }
+    return stuck;
 }
 
 #ifdef __CUDA_ARCH__
@@ -803,15 +807,18 @@ __device__ __forceinline__ void pk_epoch_coop(const PkState &st, PkTab<2, STRIDE
 #endif
 
 // Run the streams of the warp (lanes in `mask`, one stream each) until each one's next position reaches
-// its `stop` or it is done: turbo bursts, separated by one general pk_step for every lane.
+// its `stop` or it is done: turbo bursts, separated by one general pk_step for the lanes that ended the burst.
 template <int KIND, int STRIDE, bool EXC = false>
 SNACC_HD void pk_run(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, const PkExact *xv, uint32_t n, uint32_t stop, uint32_t mask)
 {
     for (;;) {
         bool work = st.phase != PK_DONE && pk_next_pos(st) < stop;
         if (!pk_any(mask, work)) return;
-        pk_turbo_lean<KIND, STRIDE, EXC>(st, tab, v, stop, mask, work);
-        work = st.phase != PK_DONE && pk_next_pos(st) < stop;
+        // only the lanes that ended the burst take a general step: a round then costs one lane's path, not the divergent
+        // paths of all 26 (measured: the general steps were 13 % of the pair kernel's time, mostly block ends, which the
+        // lanes reach at unrelated times)
+        const bool stuck = pk_turbo_lean<KIND, STRIDE, EXC>(st, tab, v, stop, mask, work);
+        work = stuck && st.phase != PK_DONE && pk_next_pos(st) < stop;
 #ifdef __CUDA_ARCH__
         if constexpr (KIND == 2 && STRIDE != 1) pk_epoch_coop<STRIDE>(st, tab, n, mask, work);
 #endif
