@@ -116,6 +116,11 @@ int snacc_import_prefix(snacc_ctx *ctx, int codec, const int32_t *seqs, int64_t 
 int snacc_ncd(snacc_ctx *ctx, const int64_t *C, const int64_t *S, int32_t n, int formula, int32_t bias,
               double *D);
 
+/* Downstream of the matrix: metrify -- 0.5 (D + D^T), zero diagonal, snacc/misc.py:20-25 -- when
+ * `metrify` is non-zero, then UPGMA, i.e. scipy.cluster.hierarchy.linkage(squareform(D_sym), method='average') of
+ * snacc/distmatrix_to_tree.py:9-15.  Z receives scipy's linkage matrix, (n-1) rows of (id_a < id_b, height, leaves). */
+int snacc_upgma(snacc_ctx *ctx, const double *D, int32_t n, int metrify, double *Z);
+
 /* ---- instrumentation used by bench.py ---- */
 /* device milliseconds (CUDA events on the library's stream) spent in codec kernels during the last
  * sizes call, and the number of kernel launches it made */

@@ -16,6 +16,7 @@
 #include "pack.cuh"
 #include "lz4_packed.cuh"
 #include "deflate.cuh"
+#include "upgma.cuh"
 
 using namespace snacc;
 
@@ -65,7 +66,7 @@ struct snacc_ctx {
 
     // working memory
     uint8_t *d_work = nullptr; size_t work_bytes = 0;
-    void *d_scratch[9] = {nullptr}; size_t scratch_cap[9] = {0};   // per-call argument arrays, grown on demand, never
+    void *d_scratch[12] = {nullptr}; size_t scratch_cap[12] = {0};   // per-call argument arrays, grown on demand, never
                                                                    // freed between calls (all use is ordered on `stream`)
     unsigned long long *d_counter = nullptr;
     int32_t *d_jobx = nullptr, *d_joby = nullptr; int64_t job_cap = 0;
@@ -1023,9 +1024,9 @@ extern "C" int snacc_ncd(snacc_ctx *ctx, const int64_t *C, const int64_t *S, int
     CK(cudaSetDevice(ctx->device));
     int64_t *dC = nullptr, *dS = nullptr; double *dD = nullptr;
     const size_t nn = (size_t)n * n;
-    CK(cudaMalloc(&dC, sizeof(int64_t) * n));
-    CK(cudaMalloc(&dS, sizeof(int64_t) * nn));
-    CK(cudaMalloc(&dD, sizeof(double) * nn));
+    int rs = scratch(ctx, 9, sizeof(int64_t) * n, (void **)&dC); if (rs) return rs;       // kept across calls: no malloc per step
+    rs = scratch(ctx, 10, sizeof(int64_t) * nn, (void **)&dS); if (rs) return rs;
+    rs = scratch(ctx, 11, sizeof(double) * nn, (void **)&dD); if (rs) return rs;
     CK(cudaMemcpyAsync(dC, C, sizeof(int64_t) * n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(dS, S, sizeof(int64_t) * nn, cudaMemcpyHostToDevice, ctx->stream));
     const int threads = 256;
@@ -1034,7 +1035,46 @@ extern "C" int snacc_ncd(snacc_ctx *ctx, const int64_t *C, const int64_t *S, int
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(D, dD, sizeof(double) * nn, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    cudaFree(dC); cudaFree(dS); cudaFree(dD);
+    return SNACC_OK;
+}
+
+// downstream of the distance matrix: metrify (misc.py:20-25) + UPGMA (distmatrix_to_tree.py:9-15) -> scipy's linkage matrix
+extern "C" int snacc_upgma(snacc_ctx *ctx, const double *D, int32_t n, int metrify, double *Z)
+{
+    if (!ctx) return SNACC_ERR_ARG;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->err.clear();
+    if (n < 2 || !D || !Z) FAIL(SNACC_ERR_ARG, "snacc_upgma: needs a matrix of at least 2 x 2");
+    NvtxRange nvtx_("snacc_b200: metrify + upgma");
+    CK(cudaSetDevice(ctx->device));
+    const size_t nn = (size_t)n * n;
+    double *dD = nullptr, *dM = nullptr, *dZ = nullptr, *d_nnv = nullptr;
+    int32_t *d_size = nullptr, *d_label = nullptr, *d_nni = nullptr, *d_todo = nullptr;
+    uint8_t *d_active = nullptr;
+    auto release = [&]() {
+        cudaFree(dD); cudaFree(dM); cudaFree(dZ); cudaFree(d_nnv); cudaFree(d_size); cudaFree(d_label); cudaFree(d_nni);
+        cudaFree(d_todo); cudaFree(d_active);
+    };
+#define UCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { release(); \
+        ctx->err = std::string(#call " failed: ") + cudaGetErrorString(e_); return SNACC_ERR_CUDA; } } while (0)
+    UCK(cudaMalloc(&dD, sizeof(double) * nn));
+    UCK(cudaMalloc(&dM, sizeof(double) * nn));
+    UCK(cudaMalloc(&dZ, sizeof(double) * 4 * (size_t)(n - 1)));
+    UCK(cudaMalloc(&d_nnv, sizeof(double) * n));
+    UCK(cudaMalloc(&d_size, sizeof(int32_t) * n));
+    UCK(cudaMalloc(&d_label, sizeof(int32_t) * n));
+    UCK(cudaMalloc(&d_nni, sizeof(int32_t) * n));
+    UCK(cudaMalloc(&d_todo, sizeof(int32_t) * (n + 1)));
+    UCK(cudaMalloc(&d_active, (size_t)n));
+    UCK(cudaMemcpyAsync(dD, D, sizeof(double) * nn, cudaMemcpyHostToDevice, ctx->stream));
+    metrify_kernel<<<(unsigned)std::min<size_t>((nn + 255) / 256, 148 * 8), 256, 0, ctx->stream>>>(dD, n, metrify ? 1 : 0, dM);
+    UCK(cudaGetLastError());
+    upgma_kernel<<<1, UPGMA_THREADS, 0, ctx->stream>>>(dM, n, dZ, d_size, d_label, d_nni, d_nnv, d_active, d_todo);
+    UCK(cudaGetLastError());
+    UCK(cudaMemcpyAsync(Z, dZ, sizeof(double) * 4 * (size_t)(n - 1), cudaMemcpyDeviceToHost, ctx->stream));
+    UCK(cudaStreamSynchronize(ctx->stream));
+#undef UCK
+    release();
     return SNACC_OK;
 }
 

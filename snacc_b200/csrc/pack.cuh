@@ -66,6 +66,10 @@ __global__ void pk_hist_kernel(const uint8_t *__restrict__ corpus, const uint64_
     __shared__ unsigned int h[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) h[i] = 0;
     __syncthreads();
+    // A genome uses four byte values almost everywhere, so counting straight into shared memory would serialise every
+    // warp on four addresses.  Each thread keeps four (value, count) pairs in registers -- the first four distinct
+    // values it meets -- and only the bytes that match none of them go to the shared counters.
+    uint32_t cv0 = 0x100, cv1 = 0x100, cv2 = 0x100, cv3 = 0x100, cn0 = 0, cn1 = 0, cn2 = 0, cn3 = 0;
     // work item = (sequence, 64 KiB slice)
     for (int32_t s = blockIdx.y; s < n_seqs; s += gridDim.y) {
         const uint8_t *p = corpus + off[s];
@@ -76,10 +80,27 @@ __global__ void pk_hist_kernel(const uint8_t *__restrict__ corpus, const uint64_
                 const uint4 q = __ldg(reinterpret_cast<const uint4 *>(p + i));
                 const uint32_t w[4] = {q.x, q.y, q.z, q.w};
                 const uint32_t cnt = tmin(16u, end - i);
-                for (uint32_t b = 0; b < cnt; ++b) atomicAdd(&h[(w[b >> 2] >> (8 * (b & 3))) & 0xff], 1u);
+#pragma unroll
+                for (uint32_t b = 0; b < 16; ++b) {
+                    if (b >= cnt) break;
+                    const uint32_t v = (w[b >> 2] >> (8 * (b & 3))) & 0xff;
+                    if (v == cv0) ++cn0;
+                    else if (v == cv1) ++cn1;
+                    else if (v == cv2) ++cn2;
+                    else if (v == cv3) ++cn3;
+                    else if (cv0 == 0x100) { cv0 = v; cn0 = 1; }
+                    else if (cv1 == 0x100) { cv1 = v; cn1 = 1; }
+                    else if (cv2 == 0x100) { cv2 = v; cn2 = 1; }
+                    else if (cv3 == 0x100) { cv3 = v; cn3 = 1; }
+                    else atomicAdd(&h[v], 1u);
+                }
             }
         }
     }
+    if (cn0) atomicAdd(&h[cv0], cn0);
+    if (cn1) atomicAdd(&h[cv1], cn1);
+    if (cn2) atomicAdd(&h[cv2], cn2);
+    if (cn3) atomicAdd(&h[cv3], cn3);
     __syncthreads();
     for (int i = threadIdx.x; i < 256; i += blockDim.x)
         if (h[i]) atomicAdd(&hist[i], (unsigned long long)h[i]);

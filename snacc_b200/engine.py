@@ -46,6 +46,7 @@ def load_library():
     lib.snacc_pair_sizes.argtypes = [vp, ctypes.c_int, vp, vp, i64, vp]
     lib.snacc_tile_sizes.argtypes = [vp, ctypes.c_int, i32, i32, i32, i32, vp]
     lib.snacc_ncd.argtypes = [vp, vp, vp, i32, ctypes.c_int, i32, vp]
+    lib.snacc_upgma.argtypes = [vp, vp, i32, ctypes.c_int, vp]
     lib.snacc_last_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
     lib.snacc_set_option.argtypes = [vp, ctypes.c_char_p, i64]
     lib.snacc_get_stat.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]
@@ -196,6 +197,17 @@ class Engine:
         D = np.zeros((n, n), dtype=np.float64)
         self._check(self._lib.snacc_ncd(self._h, C.ctypes.data, S.ctypes.data, n, int(formula), int(bias), D.ctypes.data))
         return D
+
+    def upgma(self, D, metrify=True):
+        """scipy-style linkage matrix ((n-1) x 4) of average-linkage clustering of the distance matrix D, computed on
+        the device; ``metrify`` first symmetrises D and zeroes its diagonal (reference misc.py:20-25)"""
+        D = np.ascontiguousarray(D, dtype=np.float64)
+        n = D.shape[0]
+        if D.ndim != 2 or D.shape[1] != n or n < 2:
+            raise ValueError("D must be a square matrix with at least two rows")
+        Z = np.zeros((n - 1, 4), dtype=np.float64)
+        self._check(self._lib.snacc_upgma(self._h, D.ctypes.data, n, int(bool(metrify)), Z.ctypes.data))
+        return Z
 
     # ---- instrumentation ----
     def last_kernel_ms(self):

@@ -571,3 +571,34 @@ def test_lz4_full_size_genomes_with_flagged_bases(engine):
                     np.concatenate([np.tile(np.arange(n), n), np.full(n, -1)]), "lz4")
     assert np.array_equal(S, ref[:n * n].reshape(n, n))
     assert np.array_equal(C, ref[n * n:])
+
+
+@pytest.mark.parametrize("n", [2, 3, 8, 97, 600])
+def test_metrify_and_upgma_on_the_device_equal_scipy(engine, n):
+    """metrify (misc.py:20-25) + UPGMA (distmatrix_to_tree.py:9-15) on the device: scipy's linkage
+    matrix (ids and leaf counts identical, heights to 1e-12) and the reference's Newick string byte for byte"""
+    from oracle import tree_oracle
+    from snacc_b200 import distmatrix_to_tree as d2t
+    rng = np.random.default_rng(n)
+    pts = rng.random((n, 6))
+    D = np.sqrt(((pts[:, None, :] - pts[None, :, :]) ** 2).sum(-1)) * (1 + 0.05 * rng.random((n, n)))   # asymmetric, NCD-like
+    np.fill_diagonal(D, 0.9 + 0.1 * rng.random(n))                                                    # non-zero diagonal
+    Zref = tree_oracle.hierarchical(tree_oracle.metrify(D))
+    Z = d2t.linkage_from_distances(D, engine=engine)
+    assert np.array_equal(Z[:, [0, 1, 3]], Zref[:, [0, 1, 3]])
+    assert np.allclose(Z[:, 2], Zref[:, 2], rtol=1e-12, atol=0)
+    assert np.array_equal(d2t.hierarchical(tree_oracle.metrify(D), engine=engine), Z)
+    names = [f"genome_{i}.fasta" for i in range(n)]
+    assert d2t.newick_from_linkage(Z, names) == tree_oracle.newick(Zref, names)
+
+
+def test_tree_from_the_cli_csv(engine, golden_dir, tmp_path):
+    """distmatrix_to_tree.main on the CSV the CLI writes (the on-disk contract, cli.py:138-142 -> misc.py:15-17)"""
+    from oracle import tree_oracle
+    from snacc_b200 import distmatrix_to_tree as d2t
+    from snacc_b200.misc import read_dist_values_names
+    csv = Path(golden_dir) / "reference_cli_lz4.csv"
+    out = tmp_path / "tree.nwk"
+    d2t.main(str(csv), None, str(out))
+    names, D = read_dist_values_names(str(csv))
+    assert out.read_text() == tree_oracle.newick(tree_oracle.hierarchical(tree_oracle.metrify(D)), names)

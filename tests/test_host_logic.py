@@ -279,3 +279,15 @@ def test_direct_csv_writer_is_byte_identical_to_the_pandas_route(tmp_path):
     out = tmp_path / "out.csv"
     gcli.write_distance_csv(files, D, out)
     assert out.read_bytes() == ref.read_bytes()
+
+
+def test_newick_writer_equals_the_reference_recursion():
+    """newick_from_linkage (no scipy) against the reference's to_tree + get_newick recursion on scipy linkages"""
+    from oracle import tree_oracle
+    from snacc_b200 import distmatrix_to_tree as d2t
+    rng = np.random.default_rng(4)
+    for n in (2, 3, 9, 150):
+        D = tree_oracle.metrify(rng.random((n, n)))
+        Z = tree_oracle.hierarchical(D)
+        names = [f"g{i}" for i in range(n)]
+        assert d2t.newick_from_linkage(Z, names) == tree_oracle.newick(Z, names)

@@ -119,3 +119,21 @@ def test_skew_transform_known_answer():
     x = np.array([0.0, 0.25, 0.5])
     assert np.array_equal(f_inv(x), x / (1 - x))
     assert np.array_equal(f_arctanh(x), np.arctanh(x))
+
+
+def test_lzma_and_bzip2_oracle_is_pinned_to_the_reference(golden_dir):
+    """SURVEY.md 8f rank 4 (not on the GPU path yet): the oracle for the reference's other two codecs equals what the
+    unmodified reference returned on the committed fixtures (oracle/make_golden_f4.py), sizes and NCD"""
+    import json
+    import os
+    from pathlib import Path
+    from oracle import snacc_oracle
+    gold = json.load(open(os.path.join(golden_dir, "reference_sizes_lzma_bzip2.json")))
+    files = [Path(golden_dir) / "fasta" / f for f in gold["files"]]
+    for algo in ("lzma", "bzip2"):
+        for rc in (False, True):
+            want = gold["cases"][f"{algo}{'_rc' if rc else ''}"]
+            C, S = snacc_oracle.size_tables(files, algo, rc)
+            assert (C + gold["bias"]).tolist() == want["C"]
+            assert (S + gold["bias"]).tolist() == want["S"]
+            assert np.array_equal(snacc_oracle.ncd_from_sizes(C, S), np.array(want["D"]))
