@@ -639,7 +639,9 @@ SNACC_HD bool pk_turbo_lean(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView 
     constexpr uint32_t VMASK = KIND == 0 ? 0xffffffffu : 0xffffu;   // what a slot keeps of a position
     const uint32_t lx = v.lx, rlo = v.rlo, rspan = v.rspan;
     uint32_t p = st.phase == PK_SEARCH ? st.fip : st.ip;
-    uint32_t anchor = st.anchor, nb = st.nb, op = st.op;
+    // (the skip counter is not carried: in search mode with step 1 it is 63 + the number of pending literals -- 64 at the
+    // first probe after a match or a block start, one more per miss -- so "nb < 128" is a bound on the pending literals)
+    uint32_t anchor = st.anchor, op = st.op;
     const uint32_t lim = tmin(stop, st.mfl1 > 16 ? st.mfl1 - 16 : 0u);
     // output budget: PK_UNROLL iterations add at most that many x (token + offset + length byte) + the literals pending
     // at the vote + 11 bases each
@@ -672,7 +674,7 @@ SNACC_HD bool pk_turbo_lean(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView 
         // only change slowly is tested here, with the slack that many iterations can use up.
         const uint32_t pend0 = p - anchor;
         const bool live = !fin && p < stop;
-        bool run = live && !blocked && op + pend0 <= op_lim && nb <= 120 - UNROLL && pend0 <= 200;
+        bool run = live && !blocked && op + pend0 <= op_lim && pend0 <= 57 - UNROLL;
         const bool can = run && p < lim;
         stuck = live && !can;
         if (pk_any(mask, stuck) || !pk_any(mask, can)) break;
@@ -722,7 +724,7 @@ SNACC_HD bool pk_turbo_lean(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView 
             const bool commit = go & !bail, ch = commit & hit;
             k = tmin(k, kmax);
             const uint32_t lit = pend - k;
-            const uint32_t add = 3 + lit + (lit >= 15 ? 1u : 0u);   // token + offset + literals (lit <= 200: one length byte at most)
+            const uint32_t add = 3 + lit + (lit >= 15 ? 1u : 0u);   // token + offset + literals (lit <= 57: one length byte at most)
             const uint32_t d = commit ? (hit ? common : 1u) : 0u;   // the next probe is at p + d
             const uint32_t pn = p + d;
             // first insert: slot of p <- p.  KIND 2: the lookup of p read the epoch word last and nothing has been
@@ -761,7 +763,6 @@ SNACC_HD bool pk_turbo_lean(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView 
             if (commit) ++pk_turbo_steps;
 #endif
             op += ch ? add : 0u;
-            nb = commit ? (hit ? nb : (pend ? nb + 1 : 64u)) : nb;
             anchor = ch ? pn : anchor;
             m = mn; near = nn; sa = san; ea = ean; eb = in; ew = ewn; p = pn;
         }
@@ -769,7 +770,7 @@ SNACC_HD bool pk_turbo_lean(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView 
 #undef PK_TLD
 #undef PK_TST_IF
     if (work && st.phase <= PK_RETEST) {
-        if (p != anchor) { st.phase = PK_SEARCH; st.fip = p; st.step = 1; st.nb = nb; }
+        if (p != anchor) { st.phase = PK_SEARCH; st.fip = p; st.step = 1; st.nb = 63 + (p - anchor); }
         else             { st.phase = PK_RETEST; st.ip = p; }
         st.anchor = anchor; st.op = op;
     }

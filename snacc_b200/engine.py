@@ -190,11 +190,16 @@ class Engine:
             raise ValueError("prefix records do not match the sequence list")
         self._check(self._lib.snacc_import_prefix(self._h, _codec(algorithm), seqs.ctypes.data, seqs.size, records.ctypes.data))
 
-    def ncd(self, C, S, formula=0, bias=GETSIZEOF_BIAS):
+    def ncd(self, C, S, formula=0, bias=GETSIZEOF_BIAS, out=None):
         C = np.ascontiguousarray(C, dtype=np.int64)
         S = np.ascontiguousarray(S, dtype=np.int64)
         n = C.size
-        D = np.zeros((n, n), dtype=np.float64)
+        if out is None:
+            D = np.empty((n, n), dtype=np.float64)
+        elif out.dtype != np.float64 or out.shape != (n, n) or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 (n, n) array")
+        else:
+            D = out
         self._check(self._lib.snacc_ncd(self._h, C.ctypes.data, S.ctypes.data, n, int(formula), int(bias), D.ctypes.data))
         return D
 

@@ -263,10 +263,12 @@ def ncd_host(C, S, fast_mode=False, bias=GETSIZEOF_BIAS):
 MAX_JOBS_PER_CALL = 1 << 24
 
 
-def sizes_matrix(engine, algorithm, fast_mode=False, rows_per_call=None, stats=None):
+def sizes_matrix(engine, algorithm, fast_mode=False, rows_per_call=None, stats=None, band_out=None):
     """C (all singles) and S (all ordered pairs, or the mirrored upper triangle in fast mode) for the corpus already
     uploaded to ``engine``, sharded over the process group when there is one.  Every rank returns the full result.
-    ``stats`` (a dict) receives the library's kernel times and launch counts of this rank."""
+    ``stats`` (a dict) receives the library's kernel times and launch counts of this rank; ``band_out``: an int64
+    (n, width of this rank's band) array to receive the rank's column band (a caller that repeats the job -- bench.py --
+    passes the same page-locked buffer every time instead of having a new one pinned per call)."""
     dist = _dist()
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
     n = engine.n_seqs
@@ -306,7 +308,7 @@ def sizes_matrix(engine, algorithm, fast_mode=False, rows_per_call=None, stats=N
     note(main=False)
     if not fast_mode:
         a, b = int(bounds[rank]), int(bounds[rank + 1])
-        S_cols = _result_buffer(n, b - a)
+        S_cols = band_out if band_out is not None and band_out.shape == (n, b - a) else _result_buffer(n, b - a)
         step = rows_per_call or max(1, n)
         if b > a:
             for r0 in range(0, n, step):
