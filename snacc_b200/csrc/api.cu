@@ -63,10 +63,11 @@ struct snacc_ctx {
     PkAlphabet alphabet;
     uint32_t nslot5 = 1024;                // distinct hash buckets the 1024 5-mers of the alphabet reach
     int64_t last_packed_jobs = 0, last_bytewise_jobs = 0;
+    int64_t pk_segments = 0, last_pk_segments = 1;     // tile segments of the linked pair kernel: 0 = choose per launch
 
     // working memory
     uint8_t *d_work = nullptr; size_t work_bytes = 0;
-    void *d_scratch[12] = {nullptr}; size_t scratch_cap[12] = {0};   // per-call argument arrays, grown on demand, never
+    void *d_scratch[14] = {nullptr}; size_t scratch_cap[14] = {0};   // per-call argument arrays, grown on demand, never
                                                                    // freed between calls (all use is ordered on `stream`)
     unsigned long long *d_counter = nullptr;
     int32_t *d_jobx = nullptr, *d_joby = nullptr; int64_t job_cap = 0;
@@ -680,6 +681,33 @@ static void pk_split(std::vector<PkTile> &tiles, int32_t y, size_t first, size_t
     }
 }
 
+// How many segments to cut the tiles of a linked-regime launch into (PkSegStore): the launch takes
+// ceil(tiles * k / SMs) / k tile times, so k > 1 pays when tiles / SMs has a large fractional part relative to its
+// value (320 tiles on 148 SMs: 3 -> 2.25 tile times with k = 8).  Every tile needs at least 2 k ring states, and the
+// records (2 KB per stream, + a 16 KB overflow table with flagged bases) must stay modest.
+static int pk_choose_segments(const snacc_ctx *ctx, const PkGeometry &g, const std::vector<PkTile> &tiles)
+{
+    uint32_t min_runs = 0xffffffffu;
+    for (const PkTile &t : tiles) {
+        PkRing rg; uint32_t w0, w1;
+        rg.start(ctx->h_len[t.y], w0, w1, g.exc ? PK_RING_COVER_EXC : PK_RING_WORDS);
+        min_runs = std::min(min_runs, rg.runs());
+    }
+    const size_t per_stream = (size_t)g.nslot * 2 + ((g.nslot + 31) / 32) * 4 + sizeof(PkState) + 4 +
+                              (g.exc ? PK_OVF_ENTRIES * sizeof(uint32_t) : 0);
+    if (tiles.size() * g.T * per_stream > ((size_t)6 << 30)) return 1;
+    if (ctx->pk_segments > 0) return (int)std::min<int64_t>(ctx->pk_segments, std::max<uint32_t>(1, min_runs / 2));
+    const double sms = (double)ctx->sm_count, nt = (double)tiles.size();
+    int best = 1;
+    double best_t = std::ceil(nt / sms);
+    for (int k : {2, 4, 8}) {
+        if ((uint32_t)(2 * k) > min_runs) break;
+        const double t = std::ceil(nt * k / sms) / k;
+        if (t < best_t * 0.985) { best = k; best_t = t; }
+    }
+    return best;
+}
+
 // launch lz4_pk_pair_kernel on prepared tiles; tout empty = rectangle mode (out_stride, col0)
 static int pk_launch(snacc_ctx *ctx, bool u16, const PkGeometry &g, const std::vector<PkTile> &tiles,
                      const std::vector<int32_t> &tx, const std::vector<int64_t> &tout, int64_t out_stride, int32_t col0,
@@ -698,15 +726,30 @@ static int pk_launch(snacc_ctx *ctx, bool u16, const PkGeometry &g, const std::v
     unsigned long long *counter = ctx->d_counter + (u16 ? 1 : 2);
     CK(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), ctx->stream));
     const PkCorpus pc{ctx->d_pk_words, ctx->d_pk_woff, ctx->d_len};
-    const int grid = (int)std::min<size_t>(tiles.size(), (size_t)ctx->sm_count);
     const int32_t nt = (int32_t)tiles.size();
+    const int n_seg = u16 ? 1 : pk_choose_segments(ctx, g, tiles);
+    ctx->last_pk_segments = n_seg;
+    const int grid = (int)std::min<size_t>(tiles.size() * n_seg, (size_t)ctx->sm_count);
+    PkSegStore ss{};
+    if (n_seg > 1) {
+        // the records of every stream of the launch, carved out of one array; flags zeroed per launch
+        const size_t ns = tiles.size() * g.T, nw = (g.nslot + 31) / 32;
+        const size_t b_tab = (ns * g.nslot * 2 + 15) & ~(size_t)15, b_ep = (ns * nw * 4 + 15) & ~(size_t)15,
+                     b_st = ns * sizeof(PkState), b_eb = ns * 4;
+        uint8_t *base = nullptr;
+        rs = scratch(ctx, 12, b_tab + b_ep + b_st + b_eb, (void **)&base); if (rs) return rs;
+        ss.tab = (uint16_t *)base; ss.ep = (uint32_t *)(base + b_tab); ss.st = (PkState *)(base + b_tab + b_ep);
+        ss.eb = (uint32_t *)(base + b_tab + b_ep + b_st);
+        rs = scratch(ctx, 13, sizeof(int32_t) * tiles.size(), (void **)&ss.flag); if (rs) return rs;
+        CK(cudaMemsetAsync(ss.flag, 0, sizeof(int32_t) * tiles.size(), ctx->stream));
+    }
     CK(cudaEventRecord(ctx->evm0, ctx->stream));
     PkExcCorpus xc{};
-    if (g.exc) { rs = pk_exc_corpus(ctx, (size_t)grid * g.T, &xc); if (rs) return rs; }
+    if (g.exc) { rs = pk_exc_corpus(ctx, n_seg > 1 ? tiles.size() * g.T : (size_t)grid * g.T, &xc); if (rs) return rs; }
 #define PK_GO(KIND_, LANES_, EXC_, lut_) do {                                                                        \
         CK(cudaFuncSetAttribute(lz4_pk_pair_kernel<KIND_, LANES_, EXC_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem)); \
         lz4_pk_pair_kernel<KIND_, LANES_, EXC_><<<grid, g.warps * 32, g.smem, ctx->stream>>>(                          \
-            pc, xc, d_tiles, nt, d_tx, d_tout, ctx->d_ck_tab, ctx->d_ck_state, lut_, g.nslot, out_stride, col0, counter, ctx->d_out); \
+            pc, xc, d_tiles, nt, d_tx, d_tout, ctx->d_ck_tab, ctx->d_ck_state, lut_, g.nslot, out_stride, col0, counter, ctx->d_out, n_seg, ss); \
     } while (0)
     if (u16) PK_GO(1, PK_S_LANES, false, ctx->d_alias4);
     else if (g.exc && g.lanes == 26) PK_GO(2, 26, true, ctx->d_alias5);
@@ -1094,6 +1137,7 @@ extern "C" int snacc_get_stat(const snacc_ctx *ctx, const char *name, double *ou
     if (!strcmp(name, "launches")) { *out = (double)ctx->last_launches; return SNACC_OK; }
     if (!strcmp(name, "packed_jobs")) { *out = (double)ctx->last_packed_jobs; return SNACC_OK; }
     if (!strcmp(name, "bytewise_jobs")) { *out = (double)ctx->last_bytewise_jobs; return SNACC_OK; }
+    if (!strcmp(name, "lz4_segments")) { *out = (double)ctx->last_pk_segments; return SNACC_OK; }
     if (!strcmp(name, "deflate_serial_jobs")) { *out = (double)ctx->dfl.serial_jobs; return SNACC_OK; }
     return SNACC_ERR_ARG;
 }
@@ -1104,6 +1148,7 @@ extern "C" int snacc_set_option(snacc_ctx *ctx, const char *name, int64_t value)
     std::lock_guard<std::mutex> lock(ctx->mu);
     if (!strcmp(name, "streams_in_flight")) { ctx->streams_in_flight = value; return SNACC_OK; }
     if (!strcmp(name, "lz4_packed")) { ctx->use_packed = value ? 1 : 0; return SNACC_OK; }
+    if (!strcmp(name, "lz4_segments")) { ctx->pk_segments = value < 0 ? 0 : value; return SNACC_OK; }
     if (!strcmp(name, "deflate_canonical")) { ctx->dfl.use_canon = value ? 1 : 0; return SNACC_OK; }
     if (!strcmp(name, "deflate_index6")) { ctx->dfl.use_index6 = value ? 1 : 0; return SNACC_OK; }
     if (!strcmp(name, "deflate_junction")) { ctx->dfl.junction_impl = value == 2 ? 2 : 3; return SNACC_OK; }

@@ -901,6 +901,22 @@ struct PkRing {
         w0 = 0; w1 = hi_w;
     }
     SNACC_HD bool complete() const { return hi_w >= yw_total; }
+    // a stream over y is `runs()` calls of pk_run, one per ring state: the first fill, then one per advance()
+    SNACC_HD uint32_t runs() const
+    {
+        const uint32_t ff = first_fill();
+        return yw_total <= ff ? 1u : 1u + (yw_total - ff + PK_CHUNK_BASES / 32 - 1) / (PK_CHUNK_BASES / 32);
+    }
+    // the ring as it is before run r >= 1 (after r advances), for a CTA that takes a stream over from another one
+    // (tile segments): [w0, w1) = every word resident at that point
+    SNACC_HD void restart(uint32_t ly, uint32_t r, uint32_t &w0, uint32_t &w1, uint32_t cover_ = PK_RING_WORDS)
+    {
+        cover = cover_;
+        yw_total = pk_words(ly);
+        hi_w = tmin(yw_total, first_fill() + r * (PK_CHUNK_BASES / 32));
+        w1 = hi_w;
+        w0 = hi_w > PK_RING_WORDS ? hi_w - PK_RING_WORDS : 0u;
+    }
     SNACC_HD void advance(uint32_t &w0, uint32_t &w1)
     {
         w0 = hi_w;
@@ -968,6 +984,20 @@ struct PkExcCorpus {
 // checkpoint storage: slot = seq * 2 + (linked ? 1 : 0); table stored as u32[1024] in both regimes
 constexpr uint32_t PK_CKPT_TAB = 1024;
 
+// Tile segments (linked regime): a tile's pass over y is cut at ring-refill boundaries into n_seg segments that are
+// separate work items, so that the last round of a launch is 1/n_seg of a tile long instead of a whole tile (a launch
+// of 320 tiles on 148 SMs takes 2.25 tile times with 8 segments instead of 3).  At a cut every stream's table, epoch
+// plane and state go to HBM (2 KB per stream) and flag[tile] is raised; the CTA that draws the next segment waits for
+// the flag -- work items are drawn segment-major from one counter and every CTA of the grid is resident, so the
+// producer of a segment is always running or finished.
+struct PkSegStore {
+    uint16_t *tab;               // [tile * T + stream][nslot]
+    uint32_t *ep;                // [tile * T + stream][nw]
+    PkState *st;                 // [tile * T + stream]
+    uint32_t *eb;                // [tile * T + stream]  epoch_base | (1 if the job left the packed path)
+    int32_t *flag;               // [tile]  segments finished
+};
+
 // cooperative ring fill: y words [w0, w1) -> ring; w0, w1 even
 __device__ __forceinline__ void pk_ring_fill(uint64_t *ring, const uint64_t *yw, uint32_t w0, uint32_t w1)
 {
@@ -1003,7 +1033,8 @@ __global__ void __launch_bounds__(384, 1)
 lz4_pk_pair_kernel(PkCorpus pc, PkExcCorpus xc, const PkTile *__restrict__ tiles, int32_t n_tiles, const int32_t *__restrict__ tile_x,
                    const int64_t *__restrict__ tile_out, const uint32_t *__restrict__ ck_tab,
                    const PkState *__restrict__ ck_state, const uint16_t *__restrict__ lut_g, uint32_t nslot,
-                   int64_t out_stride, int32_t col0, unsigned long long *__restrict__ counter, int64_t *__restrict__ out)
+                   int64_t out_stride, int32_t col0, unsigned long long *__restrict__ counter, int64_t *__restrict__ out,
+                   int32_t n_seg, PkSegStore ss)
 {
     typedef PkTab<KIND, LANES> Tab;
     constexpr bool U16 = Tab::U16;
@@ -1034,14 +1065,34 @@ lz4_pk_pair_kernel(PkCorpus pc, PkExcCorpus xc, const PkTile *__restrict__ tiles
         __syncthreads();
         if (threadIdx.x == 0) s_tile = (int32_t)atomicAdd(counter, 1ull);
         __syncthreads();
-        const int32_t tile = s_tile;
-        if (tile >= n_tiles) break;
+        const int32_t item = s_tile;                       // work items: segment-major
+        if (item >= n_tiles * n_seg) break;
+        const int32_t tile = item % n_tiles, seg = item / n_tiles;
         const PkTile td = tiles[tile];
         const uint32_t ly = pc.len[td.y];
         const uint64_t *yw = pc.words + pc.woff[td.y];
         PkRing rg;
         uint32_t w0, w1;
         rg.start(ly, w0, w1, EXC ? PK_RING_COVER_EXC : PK_RING_WORDS);
+        // this item's runs [r, r1) of the tile's pass over y (host: n_seg <= runs of every tile)
+        const uint32_t runs = rg.runs();
+        uint32_t r = (uint32_t)((uint64_t)runs * seg / n_seg);
+        const uint32_t r1 = (uint32_t)((uint64_t)runs * (seg + 1) / n_seg);
+        const size_t seg_base = (size_t)tile * (n_warps * LANES);         // the tile's records in ss
+        // EXC: a stream's overflow table stays where it is between segments (one per stream of the launch, not per
+        // resident stream)
+        const size_t ovf_base = n_seg > 1 ? seg_base : (size_t)blockIdx.x * (n_warps * LANES);
+        if (seg > 0) {
+            if (threadIdx.x == 0) {
+                int32_t f;
+                do {
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(ss.flag + tile) : "memory");
+                    if (f < seg) __nanosleep(256);
+                } while (f < seg);
+            }
+            __syncthreads();
+            rg.restart(ly, r, w0, w1, EXC ? PK_RING_COVER_EXC : PK_RING_WORDS);
+        }
         pk_ring_fill(ring, yw, w0, w1);
         const uint32_t *ymask = EXC ? xc.mask + xc.moff[td.y] : nullptr;
         if (EXC) pk_dring_build(ring, rg, ymask);
@@ -1060,11 +1111,18 @@ lz4_pk_pair_kernel(PkCorpus pc, PkExcCorpus xc, const PkTile *__restrict__ tiles
         for (int k = 0; k < LANES; ++k) {
             const int32_t sl = (int32_t)(warp * LANES + k);
             if (sl >= td.count) break;
-            const int32_t x = tile_x[td.first + sl];
-            const uint32_t *src = ck_tab + (size_t)(2 * x + (U16 ? 0 : 1)) * PK_CKPT_TAB;
             Tab tk = tab;
             tk.t = tabs + (size_t)warp * (nslot * LANES) + k;
             tk.ep = eps + (size_t)warp * (nw * LANES) + k;
+            if (KIND == 2 && seg > 0) {                        // the records the previous segment left
+                const uint16_t *s16 = ss.tab + (seg_base + sl) * nslot;
+                const uint32_t *s32 = ss.ep + (seg_base + sl) * nw;
+                for (uint32_t e = lane; e < nslot; e += 32) tk.t[e * LANES] = s16[e];
+                for (uint32_t wd = lane; wd < nw; wd += 32) tk.ep[wd * LANES] = s32[wd];
+                continue;
+            }
+            const int32_t x = tile_x[td.first + sl];
+            const uint32_t *src = ck_tab + (size_t)(2 * x + (U16 ? 0 : 1)) * PK_CKPT_TAB;
             const uint32_t bs = ck_state[2 * x + (U16 ? 0 : 1)].bs;
             if (KIND == 2) {
                 // one lane per epoch word so that the read-modify-writes of import_slot never collide
@@ -1075,7 +1133,7 @@ lz4_pk_pair_kernel(PkCorpus pc, PkExcCorpus xc, const PkTile *__restrict__ tiles
             }
             if (EXC) {                                         // the stream's overflow table starts as its x's
                 const uint4 *so = reinterpret_cast<const uint4 *>(xc.ck_ovf + (size_t)x * PK_OVF_ENTRIES);
-                uint4 *dd = reinterpret_cast<uint4 *>(xc.ovf_work + ((size_t)blockIdx.x * (n_warps * LANES) + sl) * PK_OVF_ENTRIES);
+                uint4 *dd = reinterpret_cast<uint4 *>(xc.ovf_work + (ovf_base + sl) * PK_OVF_ENTRIES);
                 for (uint32_t e = lane; e < PK_OVF_ENTRIES / 4; e += 32) dd[e] = so[e];
             }
         }
@@ -1087,11 +1145,18 @@ lz4_pk_pair_kernel(PkCorpus pc, PkExcCorpus xc, const PkTile *__restrict__ tiles
             n = v.lx + ly;
             if (EXC) {
                 xv.s.x = xc.bytes + xc.boff[x]; xv.s.y = xc.bytes + xc.boff[td.y]; xv.s.lx = v.lx; xv.s.n = n;
-                xv.ovf = xc.ovf_work + ((size_t)blockIdx.x * (n_warps * LANES) + slot) * PK_OVF_ENTRIES;
+                xv.ovf = xc.ovf_work + (ovf_base + slot) * PK_OVF_ENTRIES;
             }
-            bail = !pk_resume(st, n);
-            if (bail) st.phase = PK_DONE;
-            tab.epoch_base = st.bs;                // the imported bits refer to the checkpoint's open block
+            if (KIND == 2 && seg > 0) {
+                st = ss.st[seg_base + slot];
+                const uint32_t eb = ss.eb[seg_base + slot];
+                bail = eb & 1u;
+                tab.epoch_base = eb & ~1u;
+            } else {
+                bail = !pk_resume(st, n);
+                if (bail) st.phase = PK_DONE;
+                tab.epoch_base = st.bs;            // the imported bits refer to the checkpoint's open block
+            }
         }
         for (;;) {
             __syncthreads();                       // ring (and on the first pass the tables) visible
@@ -1101,11 +1166,33 @@ lz4_pk_pair_kernel(PkCorpus pc, PkExcCorpus xc, const PkTile *__restrict__ tiles
             const uint32_t stop = stop_q == 0xffffffffu ? 0xffffffffu : v.lx + stop_q;
             if constexpr (EXC) pk_run_exc<KIND, LANES>(st, tab, v, xv, n, stop, rg.hi_w * 32, 0xffffffffu);
             else pk_run<KIND, LANES>(st, tab, v, nullptr, n, stop, 0xffffffffu);
-            if (rg.complete()) break;
+            if (++r >= r1) break;                  // r1 == runs: the ring is complete
             __syncthreads();                       // everyone is done reading the slots about to be replaced
             rg.advance(w0, w1);
             pk_ring_fill(ring, yw, w0, w1);
             if (EXC) pk_dring_build(ring, rg, ymask);
+        }
+        if (KIND == 2 && seg + 1 < n_seg) {
+            // hand the tile's streams to whoever draws the next segment
+            __syncwarp();
+            for (int k = 0; k < LANES; ++k) {
+                const int32_t sl = (int32_t)(warp * LANES + k);
+                if (sl >= td.count) break;
+                const typename Tab::T *tk = tabs + (size_t)warp * (nslot * LANES) + k;
+                const uint32_t *ek = eps + (size_t)warp * (nw * LANES) + k;
+                uint16_t *d16 = ss.tab + (seg_base + sl) * nslot;
+                uint32_t *d32 = ss.ep + (seg_base + sl) * nw;
+                for (uint32_t e = lane; e < nslot; e += 32) d16[e] = (uint16_t)tk[e * LANES];
+                for (uint32_t wd = lane; wd < nw; wd += 32) d32[wd] = ek[wd * LANES];
+            }
+            if (has) {
+                ss.st[seg_base + slot] = st;
+                ss.eb[seg_base + slot] = tab.epoch_base | (bail ? 1u : 0u);
+            }
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(ss.flag + tile), "r"(seg + 1) : "memory");
+            continue;
         }
         if (has) {
             // explicit output index per job, or (rectangle mode) row-major position of (x, y) in the rectangle

@@ -101,6 +101,9 @@ template <int KIND> static std::vector<uint16_t> emu_lut(const uint16_t *raw)
     return std::vector<uint16_t>(raw, raw + PkTab<KIND, 1>::ENTRIES);
 }
 
+static int emu_segments = 1;
+extern "C" void emu_set_segments(int k) { emu_segments = k < 1 ? 1 : k; }
+
 // returns the size, -1 when the packed pair path bails out, -2 when the input is not packable
 extern "C" int64_t emu_lz4_packed(const uint8_t *x, uint32_t lx, const uint8_t *y, int64_t ly_)
 {
@@ -173,7 +176,39 @@ extern "C" int64_t emu_lz4_packed(const uint8_t *x, uint32_t lx, const uint8_t *
         std::vector<uint32_t> ep((nslot + 31) / 32, 0);
         PkTab<2, 1> t17; t17.t = lo.data(); t17.ep = ep.data(); t17.nslot = nslot; t17.epoch_base = ck.st.bs; t17.lut = lut17.data();
         for (uint32_t e = 0; e < nslot; ++e) t17.import_slot(e, ck.tab[e], ck.st.bs);
-        emu_run<2, false>(st, t17, nullptr, v, rg, ring, yw, n, 0, 0, nullptr);
+        if (emu_segments > 1 && rg.runs() >= (uint32_t)emu_segments) {
+            // tile segments (PkSegStore): at a cut, everything but the stream's records is thrown away and the ring is
+            // rebuilt by PkRing::restart, as when another CTA draws the next segment
+            const uint32_t runs = rg.runs();
+            for (int seg = 0; seg < emu_segments; ++seg) {
+                uint32_t r = (uint32_t)((uint64_t)runs * seg / emu_segments);
+                const uint32_t r1 = (uint32_t)((uint64_t)runs * (seg + 1) / emu_segments);
+                if (seg > 0) {
+                    std::fill(ring.begin(), ring.end(), 0x5a5a5a5a5a5a5a5aull);
+                    rg.restart(ly, r, w0, w1);
+                    ring_fill_host(ring, yw, w0, w1);
+                }
+                for (;;) {
+                    rg.view(v);
+                    const uint32_t sq = rg.stop_q();
+                    pk_run<2, 1>(st, t17, v, nullptr, n, sq == 0xffffffffu ? sq : v.lx + sq, 1u);
+                    if (++r >= r1) break;
+                    rg.advance(w0, w1);
+                    ring_fill_host(ring, yw, w0, w1);
+                }
+                if (seg + 1 < emu_segments) {
+                    const std::vector<uint16_t> s_lo = lo; const std::vector<uint32_t> s_ep = ep;
+                    const PkState s_st = st; const uint32_t s_eb = t17.epoch_base;
+                    std::fill(lo.begin(), lo.end(), (uint16_t)0xdead); std::fill(ep.begin(), ep.end(), 0xdeadbeefu);
+                    st = PkState(); t17.epoch_base = 12345;
+                    lo = s_lo; ep = s_ep; st = s_st; t17.epoch_base = s_eb;
+                    t17.t = lo.data(); t17.ep = ep.data();
+                }
+            }
+            if (!rg.complete()) return -4;
+        } else {
+            emu_run<2, false>(st, t17, nullptr, v, rg, ring, yw, n, 0, 0, nullptr);
+        }
     }
     return (int64_t)(st.total + lz4_frame_overhead(n));
 }

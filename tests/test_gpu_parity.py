@@ -573,6 +573,30 @@ def test_lz4_full_size_genomes_with_flagged_bases(engine):
     assert np.array_equal(C, ref[n * n:])
 
 
+@pytest.mark.parametrize("flagged", [False, True])
+def test_lz4_tile_segments(engine, flagged):
+    """Tiles of the linked pair kernel cut into segments that different CTAs continue (PkSegStore, option lz4_segments):
+    sizes == liblz4 for every pair, with mixed lengths (different numbers of ring states per tile), with and without
+    flagged bases (their overflow tables then persist per stream)"""
+    from snacc_b200 import synth
+    g = synth.phylogeny(7, 600000, seed=21) + synth.phylogeny(4, 331000, seed=22)
+    if flagged:
+        g = [_sprinkle(s, 1e-4, 90 + i) for i, s in enumerate(g)]
+    n = len(g)
+    engine.upload_sequences(g)
+    engine.single_sizes("lz4")
+    ref = _ref_jobs(g, np.repeat(np.arange(n), n), np.tile(np.arange(n), n), "lz4").reshape(n, n)
+    try:
+        for k in (3, 2, 8):
+            engine.set_option("lz4_segments", k)
+            S = engine.tile_sizes("lz4", 0, n, 0, n)
+            assert np.array_equal(S, ref), (k, np.argwhere(S != ref)[:10].tolist())
+            assert engine.stat("lz4_segments") == min(k, 4)       # 331 kbp = 8 ring states: at most 4 segments
+            assert engine.stat("packed_jobs") == n * n
+    finally:
+        engine.set_option("lz4_segments", 0)
+
+
 @pytest.mark.parametrize("n", [2, 3, 8, 97, 600])
 def test_metrify_and_upgma_on_the_device_equal_scipy(engine, n):
     """metrify (misc.py:20-25) + UPGMA (distmatrix_to_tree.py:9-15) on the device: scipy's linkage

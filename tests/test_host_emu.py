@@ -144,6 +144,23 @@ def test_lz4_packed_related_genomes(emu):
             assert _call2(emu.emu_lz4_packed, a, b) == lib.ref_lz4f_size(np.concatenate([a, b]))
 
 
+def test_lz4_packed_tile_segments(emu):
+    """PkSegStore / PkRing::restart: a pair stream cut at ring-refill boundaries and continued from its saved table,
+    epoch plane and state on a rebuilt ring gives liblz4's size (what lz4_pk_pair_kernel does with n_seg > 1)"""
+    from snacc_b200 import synth
+    emu.emu_set_segments.argtypes = [ctypes.c_int]
+    g = synth.phylogeny(3, 420000, seed=11)
+    cases = [(g[0], g[1]), (g[2][:70000], g[0]), (g[1][:100], np.concatenate([g[2], g[0]])),
+             (_four_symbol_vector("longrep", 150000, 5), _four_symbol_vector("repeat", 300000, 6))]
+    try:
+        for k in (2, 3, 4, 8):
+            emu.emu_set_segments(k)
+            for x, y in cases:
+                assert _call2(emu.emu_lz4_packed, x, y) == lib.ref_lz4f_size(np.concatenate([x, y])), (k, len(x), len(y))
+    finally:
+        emu.emu_set_segments(1)
+
+
 @pytest.mark.parametrize("kind", VECTOR_KINDS)
 def test_lz4_byte_exact_step_on_any_bytes(emu, kind):
     """pk_step_exact alone (the path probes near non-alphabet bytes take): true-byte hash, alphabet buckets in the slot
