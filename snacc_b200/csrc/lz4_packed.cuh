@@ -429,7 +429,7 @@ SNACC_HD bool pk_step_exact(PkState &st, PkTab<KIND, STRIDE> &tab, const PkExact
 }
 
 #if defined(PK_COUNT_STEPS)
-static uint64_t pk_general_steps = 0, pk_lean_steps = 0, pk_turbo_steps = 0;
+static uint64_t pk_general_steps = 0, pk_lean_steps = 0, pk_turbo_steps = 0, pk_batch_steps = 0;
 #endif
 // ---- inner-loop helpers ------------------------------------------------------------------------
 // 16 bases starting at base index k of a packed array viewed as 32-bit words
@@ -777,6 +777,139 @@ SNACC_HD bool pk_turbo_lean(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView 
     return stuck;
 }
 
+// ---- singles pass: 64 probes at a time ---------------------------------------------------------------------------
+// A sequence on its own is ONE dependency chain, and the singles pass sits in front of every pair tile (0.16 s of a
+// c4 step with the scalar loop above, the same on 1 or 8 GPUs).  In the singles kernel the whole warp works on it:
+// every lane does, for the probes at P + lane and P + 32 + lane, everything the loop above does that does not depend
+// on the probes before -- the window, the slot, the candidate as the table has it at the start of the batch, the
+// 12-base compare forwards and the 4-base compare backwards -- and packs the outcome into one word.  Then all lanes
+// walk the chain together: the probe at p takes the word of position p - P (one shuffle), and the next probe is d
+// further; that shuffle and add are all that is left on the dependency chain, the bookkeeping of op / anchor and the
+// two inserts hang off it.  A lane's candidate is stale once a probe of the same batch has written its slot (slot of
+// p, slot of pn - 2 -- both in the word): every lane compares the slots the walk inserts into with its own and raises
+// a flag that the walk reads with a second shuffle; the walk stops in front of a stale position -- and at anything else
+// the scalar loop does not cover either -- and pk_run lets the scalar loop do a few probes before the next batch.
+// Same state, same table reads and writes as the scalar loop.
+constexpr uint32_t PKB_D = 0xfu, PKB_HIT = 0x10u, PKB_K_SHIFT = 5, PKB_BAIL = 0x100u, PKB_IDX_SHIFT = 9, PKB_IDX2_SHIFT = 19;
+constexpr uint32_t PKB_WINDOW = 64, PKB_HOP_MAX = 52;       // a hop from position l touches positions up to l + 11
+
+// the probe at q on its own
+template <int KIND>
+SNACC_HD uint32_t pk_batch_probe(const PkTab<KIND, 1> &tab, const PkView &v, uint32_t q, uint32_t &idx)
+{
+    constexpr uint32_t MASK = PkTab<KIND, 1>::MASK, RMASK = (2 * PK_RING_WORDS - 1) * 4;
+    const pk_sptr ring_a = pk_sptr_of(v.ring);
+    const uint32_t qp4 = q - 4 - v.lx, jp = (qp4 >> 2) & RMASK;
+    const uint32_t wa = pk_lds32(ring_a + jp), wb = pk_lds32(ring_a + jp + 4), wc = pk_lds32(ring_a + jp + 8);
+    const uint32_t Ws = pk_fsr(wa, wb, qp4 * 2), Wt = pk_fsr(wb, wc, qp4 * 2);
+    idx = tab.lut[pk_fsr(Ws, Wt, 8) & MASK];
+    uint32_t m;
+    const bool near = tab.lookup_idx(idx, q, m);
+    const uint32_t qm4 = m - 4 - v.lx, jm = (qm4 >> 2) & RMASK;
+    const uint32_t ca = pk_lds32(ring_a + jm), cb = pk_lds32(ring_a + jm + 4);
+    const uint32_t x = Ws ^ pk_fsr(ca, cb, qm4 * 2);
+    const bool inring = (uint32_t)(qm4 - v.rlo) <= v.rspan + 32;
+    uint32_t common = pk_ctz32((x >> 8) | 0x01000000u) >> 1;           // forwards from q, at most 12
+    common = near ? common : 0;
+    const uint32_t k = pk_clz32((x << 24) | 0x00800000u) >> 1;         // backwards from q - 1, at most 4
+    const bool hit = common >= 4;
+    // not for the walk: candidate outside the ring, match of 12+ bases, a catch-up that may end at the stream start
+    const bool bail = (near && !inring) || common > 11 || (hit && m < 64);
+    return (hit ? common & PKB_D : 1u) | (hit ? PKB_HIT : 0u) | (k << PKB_K_SHIFT) | (bail ? PKB_BAIL : 0u) | (idx << PKB_IDX_SHIFT);
+}
+
+template <int KIND>
+SNACC_HD void pk_batch_run(PkState &st, PkTab<KIND, 1> &tab, const PkView &v, uint32_t stop)
+{
+    typedef typename PkTab<KIND, 1>::T T;
+    if (st.phase > PK_RETEST || (st.phase == PK_SEARCH && st.step != 1)) return;
+    uint32_t p = st.phase == PK_SEARCH ? st.fip : st.ip;
+    uint32_t anchor = st.anchor, op = st.op;
+    const uint32_t p_in = p;
+    const uint32_t lim = tmin(stop, st.mfl1 > 16 ? st.mfl1 - 16 : 0u);
+    constexpr uint32_t OP_SLACK = 80 + 15 * PKB_WINDOW;
+    const uint32_t op_lim = st.budget > OP_SLACK ? st.budget - OP_SLACK : 0u;
+#ifdef __CUDA_ARCH__
+    const uint32_t lane = threadIdx.x & 31;
+    const pk_sptr tab_a = pk_sptr_of(tab.t);
+#endif
+    for (;;) {
+        const uint32_t P = p;
+        if (P + PKB_WINDOW > lim || op + (P - anchor) > op_lim || (uint32_t)(P - 4 - v.lx - v.rlo) > v.rspan) break;
+        // ---- every lane: its two probes; the slot of q + d - 2 (second insert of a hit at q) comes from the lane that owns it
+#ifdef __CUDA_ARCH__
+        uint32_t idxA, idxB;
+        uint32_t packA = pk_batch_probe<KIND>(tab, v, P + lane, idxA);
+        uint32_t packB = pk_batch_probe<KIND>(tab, v, P + 32 + lane, idxB);
+        {
+            const uint32_t la = lane + (packA & PKB_D) - 2, lb = lane + (packB & PKB_D) - 2;       // (a miss: d = 1, unused)
+            const uint32_t a_lo = __shfl_sync(0xffffffffu, idxA, la & 31), a_hi = __shfl_sync(0xffffffffu, idxB, la & 31);
+            const uint32_t b_hi = __shfl_sync(0xffffffffu, idxB, lb & 31);
+            packA |= ((la & 32) ? a_hi : a_lo) << PKB_IDX2_SHIFT;
+            packB |= b_hi << PKB_IDX2_SHIFT;                          // (lb >= 32: beyond the window, never hopped from)
+        }
+        const pk_sptr saA = tab_a + idxA * (uint32_t)sizeof(T), saB = tab_a + idxB * (uint32_t)sizeof(T);
+        uint32_t staleA = 0, staleB = 0;
+#define PKB_PACK(l) __shfl_sync(0xffffffffu, ((l) & 32) ? packB : packA, (l) & 31)
+#define PKB_STALE(l) __shfl_sync(0xffffffffu, ((l) & 32) ? staleB : staleA, (l) & 31)
+#else
+        uint32_t pack[PKB_WINDOW], idx[PKB_WINDOW], stale[PKB_WINDOW];
+        for (uint32_t l = 0; l < PKB_WINDOW; ++l) { pack[l] = pk_batch_probe<KIND>(tab, v, P + l, idx[l]); stale[l] = 0; }
+        for (uint32_t l = 0; l < PKB_WINDOW; ++l) pack[l] |= idx[(l + (pack[l] & PKB_D) - 2) & (PKB_WINDOW - 1)] << PKB_IDX2_SHIFT;
+#define PKB_PACK(l) pack[(l) & (PKB_WINDOW - 1)]
+#define PKB_STALE(l) stale[(l) & (PKB_WINDOW - 1)]
+#endif
+        // ---- the walk, uniform over the warp.  l runs ahead on its own (d comes straight out of the shuffled word);
+        // everything that changes state is predicated on `ok`, which drops for good at the first position the walk
+        // cannot take, and p / anchor / op stay where they were then.
+        uint32_t l = 0;
+        bool ok = true;
+        do {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t pk = PKB_PACK(l);
+                const uint32_t stl = PKB_STALE(l);
+                const uint32_t d = pk & PKB_D, kk = (pk >> PKB_K_SHIFT) & 7, pend = p - anchor;
+                const bool hit = (pk & PKB_HIT) != 0;
+                const bool bad = (stl != 0) | ((pk & PKB_BAIL) != 0) | (pend > 56) | (hit & (kk == 4) & (pend > 4)) | (l > PKB_HOP_MAX);
+                ok = ok & !bad;
+                const bool gh = ok & hit;
+                const uint32_t i1 = (pk >> PKB_IDX_SHIFT) & 1023, i2 = (pk >> PKB_IDX2_SHIFT) & 1023;
+                const uint32_t pn = p + d, l2 = l + d - 2;
+#ifdef __CUDA_ARCH__
+                staleA |= (uint32_t)(ok & ((idxA == i1) | (hit & (idxA == i2))));
+                staleB |= (uint32_t)(ok & ((idxB == i1) | (hit & (idxB == i2))));
+                const pk_sptr s1 = (l & 32) ? saB : saA, s2 = (l2 & 32) ? saB : saA;
+                if (KIND == 0) { pk_sts32_if(ok & (lane == (l & 31)), s1, p); pk_sts32_if(gh & (lane == (l2 & 31)), s2, pn - 2); }
+                else           { pk_sts16_if(ok & (lane == (l & 31)), s1, p); pk_sts16_if(gh & (lane == (l2 & 31)), s2, pn - 2); }
+#else
+                if (ok) {
+                    for (uint32_t j = 0; j < PKB_WINDOW; ++j) stale[j] |= (idx[j] == i1) | (hit & (idx[j] == i2));
+                    tab.t[i1] = (T)p;
+                    if (hit) tab.t[i2] = (T)(pn - 2);
+#if defined(PK_COUNT_STEPS)
+                    ++pk_batch_steps;
+#endif
+                }
+#endif
+                const uint32_t lit = pend - tmin(kk, pend);
+                op += gh ? 3 + lit + (lit >= 15 ? 1u : 0u) : 0u;
+                anchor = gh ? pn : anchor;
+                p = ok ? pn : p;
+                l += d;
+            }
+        } while (ok);
+#undef PKB_PACK
+#undef PKB_STALE
+        if (p == P) break;
+    }
+    if (p != p_in) {
+        if (p != anchor) { st.phase = PK_SEARCH; st.fip = p; st.step = 1; st.nb = 63 + (p - anchor); }
+        else             { st.phase = PK_RETEST; st.ip = p; }
+        st.anchor = anchor; st.op = op;
+    }
+}
+
 #ifdef __CUDA_ARCH__
 // KIND 2 epoch boundary (PkTab::new_epoch) done by the whole warp for every lane that stands at a block start: 32
 // slots per lane and step instead of one lane walking its ~900 slots while the others wait
@@ -809,12 +942,27 @@ __device__ __forceinline__ void pk_epoch_coop(const PkState &st, PkTab<2, STRIDE
 
 // Run the streams of the warp (lanes in `mask`, one stream each) until each one's next position reaches
 // its `stop` or it is done: turbo bursts, separated by one general pk_step for the lanes that ended the burst.
-template <int KIND, int STRIDE, bool EXC = false>
+// BATCH (singles pass, KIND 0 / 1, one stream for the whole warp -- on the device every lane of the warp calls this
+// with the same state): pk_batch_run in front, the scalar loop for the probes a batch stops at.
+template <int KIND, int STRIDE, bool EXC = false, bool BATCH = false>
 SNACC_HD void pk_run(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView &v, const PkExact *xv, uint32_t n, uint32_t stop, uint32_t mask)
 {
     for (;;) {
         bool work = st.phase != PK_DONE && pk_next_pos(st) < stop;
         if (!pk_any(mask, work)) return;
+        if constexpr (BATCH && STRIDE == 1 && KIND != 2 && !EXC) {
+            pk_batch_run<KIND>(st, tab, v, stop);
+            work = st.phase != PK_DONE && pk_next_pos(st) < stop;
+            if (!work) return;
+            const bool stuck = pk_turbo_lean<KIND, STRIDE, EXC>(st, tab, v, tmin(stop, pk_next_pos(st) + 24), mask, work);
+            if (stuck && st.phase != PK_DONE && pk_next_pos(st) < stop) {
+#if defined(PK_COUNT_STEPS) && !defined(__CUDA_ARCH__)
+                ++pk_general_steps;
+#endif
+                pk_step_general<KIND, STRIDE>(st, tab, v, n);
+            }
+            continue;
+        }
         // only the lanes that ended the burst take a general step: a round then costs one lane's path, not the divergent
         // paths of all 26 (measured: the general steps were 13 % of the pair kernel's time, mostly block ends, which the
         // lanes reach at unrelated times)
@@ -1216,14 +1364,15 @@ __device__ void pk_single_run(PkState &st, PkTab<KIND, 1> &tab, PkView &v, PkRin
                               uint32_t n, uint32_t xend, uint32_t snap_bs, PkState *snap_st, uint32_t *snap_tab,
                               PkExact *xv, uint32_t *snap_ovf)
 {
-    // CTA-uniform control flow: thread 0 parses, all threads take part in ring refills
+    // CTA-uniform control flow: warp 0 parses -- all its lanes carry the same state and run the same code, so that the
+    // batches of pk_batch_run have the whole warp -- and all threads take part in ring refills
     __shared__ uint32_t s_more;
     for (;;) {
         __syncthreads();
         rg.view(v);
         if (EXC) v.dring = reinterpret_cast<const uint32_t *>(ring + rg.dring_word());
         const uint32_t stop = rg.stop_q();
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < 32) {
             bool touched = false;
             while (st.phase != PK_DONE && pk_next_pos(st) < stop) {
                 if (DETECT) {
@@ -1238,15 +1387,16 @@ __device__ void pk_single_run(PkState &st, PkTab<KIND, 1> &tab, PkView &v, PkRin
                     // stop at the start of the last block: its state is where the prefix pass resumes
                     if (st.phase == PK_BLOCK_START && st.bs == snap_bs) {
                         *snap_st = st;
-                        for (uint32_t e = 0; e < PkTab<KIND, 1>::ENTRIES; ++e) snap_tab[e] = tab.t[e];
-                        if (EXC && snap_ovf) for (uint32_t e = 0; e < PK_OVF_ENTRIES; ++e) snap_ovf[e] = xv->ovf[e];
+                        for (uint32_t e = threadIdx.x; e < PkTab<KIND, 1>::ENTRIES; e += 32) snap_tab[e] = tab.t[e];
+                        if (EXC && snap_ovf) for (uint32_t e = threadIdx.x; e < PK_OVF_ENTRIES; e += 32) snap_ovf[e] = xv->ovf[e];
+                        __syncwarp();
                         snap_st = nullptr;
                     } else {
                         limit = tmin(stop, snap_bs);
                     }
                 }
-                if constexpr (EXC && KIND != 1) pk_run_exc<KIND, 1>(st, tab, v, *xv, n, limit, rg.hi_w * 32, 1u);
-                else pk_run<KIND, 1>(st, tab, v, nullptr, n, limit, 1u);
+                if constexpr (EXC && KIND != 1) pk_run_exc<KIND, 1>(st, tab, v, *xv, n, limit, rg.hi_w * 32, 0xffffffffu);
+                else pk_run<KIND, 1, false, true>(st, tab, v, nullptr, n, limit, 0xffffffffu);
             }
             s_more = (!touched && st.phase != PK_DONE && !rg.complete()) ? 1u : 0u;
         }

@@ -65,6 +65,8 @@ static void ring_fill_host(std::vector<uint64_t> &ring, const std::vector<uint64
 }
 
 struct EmuCkpt { PkState st; std::vector<uint32_t> tab; };
+static int emu_batch = 0;            // 1: the KIND 0 / 1 streams run pk_batch_run (the singles kernel's 32-probe batches)
+extern "C" void emu_set_batch(int on) { emu_batch = on; }
 
 // run a stream until DONE (or until DETECT touches); mirrors pk_single_run / the pair kernel loop
 template <int KIND, bool DETECT>
@@ -86,7 +88,8 @@ static bool emu_run(PkState &st, PkTab<KIND, 1> &tab, std::vector<uint32_t> *tab
                 if (st.phase == PK_BLOCK_START && st.bs == snap_bs) { snap->st = st; snap->tab = *tab32; snap = nullptr; }
                 else limit = tmin(stop, snap_bs);
             }
-            pk_run<KIND, 1>(st, tab, v, nullptr, n, limit, 1u);
+            if (emu_batch) pk_run<KIND, 1, false, true>(st, tab, v, nullptr, n, limit, 1u);
+            else pk_run<KIND, 1>(st, tab, v, nullptr, n, limit, 1u);
         }
         if (st.phase == PK_DONE || rg.complete()) return false;
         uint32_t w0, w1;
@@ -625,4 +628,4 @@ extern "C" int64_t emu_flush_compact_fuzz(uint32_t seed, int32_t cases, int32_t 
 
 // step counters of the packed LZ4 parse since the library was loaded: [0] general steps (pk_step), [1] steps inside the
 // speculative loop (pk_turbo)
-extern "C" void emu_lz4_step_counts(uint64_t *out) { out[0] = pk_general_steps; out[1] = pk_turbo_steps; }
+extern "C" void emu_lz4_step_counts(uint64_t *out) { out[0] = pk_general_steps; out[1] = pk_turbo_steps; out[2] = pk_batch_steps; }

@@ -161,6 +161,43 @@ def test_lz4_packed_tile_segments(emu):
         emu.emu_set_segments(1)
 
 
+def test_lz4_singles_batches_of_32_probes(emu):
+    """pk_batch_run (the singles kernel's warp-wide batches: 32 probes looked up at once, the chain walked over their
+    results, stale lanes detected) against liblz4: singles in both regimes and the single-block pair streams, random,
+    repetitive and related inputs; and it is the path that does the work"""
+    from snacc_b200 import synth
+    emu.emu_set_batch.argtypes = [ctypes.c_int]
+    emu.emu_lz4_step_counts.argtypes = [ctypes.c_void_p]
+    cnt0, cnt1 = (ctypes.c_uint64 * 3)(), (ctypes.c_uint64 * 3)()
+    bad = []
+    emu.emu_set_batch(1)
+    try:
+        for lx in [1, 13, 40, 700, 11000, 65535, 65536, 65537, 70000, 131073, 300000]:
+            for kind in ["rand", "run", "period", "two", "skew", "repeat", "longrep"]:
+                x = _dna(lx, lx) if kind == "rand" else _four_symbol_vector(kind, lx, lx)
+                if _call2(emu.emu_lz4_packed, x, None) != lib.ref_lz4f_size(x):
+                    bad.append(("single", kind, lx))
+            for ly in [16, 300, 9000, 30000]:
+                x, y = _dna(lx, lx), _dna(ly, ly + 3)
+                if lx + ly <= 65536 and _call2(emu.emu_lz4_packed, x, y) != lib.ref_lz4f_size(np.concatenate([x, y])):
+                    bad.append(("pair", lx, ly))
+        g = synth.phylogeny(3, 500000, seed=8)
+        emu.emu_lz4_step_counts(cnt0)
+        for a in g:
+            if _call2(emu.emu_lz4_packed, a, None) != lib.ref_lz4f_size(a):
+                bad.append(("genome", len(a)))
+        emu.emu_lz4_step_counts(cnt1)
+        for a in g[:2]:
+            for b in g[:2]:
+                if _call2(emu.emu_lz4_packed, a, b) != lib.ref_lz4f_size(np.concatenate([a, b])):
+                    bad.append(("genome pair",))
+    finally:
+        emu.emu_set_batch(0)
+    assert not bad, bad[:10]
+    general, scalar, batch = (int(cnt1[i] - cnt0[i]) for i in range(3))
+    assert batch > 50 * (general + scalar), (general, scalar, batch)      # singles of genomes: ~99.9 % of the probes
+
+
 @pytest.mark.parametrize("kind", VECTOR_KINDS)
 def test_lz4_byte_exact_step_on_any_bytes(emu, kind):
     """pk_step_exact alone (the path probes near non-alphabet bytes take): true-byte hash, alphabet buckets in the slot
