@@ -316,6 +316,7 @@ def run_workload(args, cfg_name, n, L, seed, legs, env, want_host_stages):
     my_w = int(bounds[rank + 1] - bounds[rank])
     S_band = torch.empty((n, my_w), dtype=torch.int64, pin_memory=True).numpy() if not args.fast_mode else None
     D_buf = torch.empty((n, n), dtype=torch.float64, pin_memory=True).numpy()
+    S_full = torch.empty((n, n), dtype=torch.int64, pin_memory=True).numpy() if world > 1 and not args.fast_mode else None
 
     def run_step(cdc, e2e):
         """one full pass through the product path: [e2e: corpus from pinned host memory,] C(i) for every sequence, S for
@@ -334,7 +335,7 @@ def run_workload(args, cfg_name, n, L, seed, legs, env, want_host_stages):
             eng.set_option("invalidate_caches", 1)       # nothing (prefix checkpoints ...) survives from the last step
         st = {}
         band = args.band or (1024 if cfg_name == "c3" else None)
-        C, S = sharding.sizes_matrix(eng, cdc, args.fast_mode, band, st, band_out=S_band)
+        C, S = sharding.sizes_matrix(eng, cdc, args.fast_mode, band, st, band_out=S_band, full_out=S_full)
         D = eng.ncd(C, S, formula=1 if args.fast_mode else 0, out=D_buf)   # K4: float64 epilogue kernel, result read back
         st["launches"] = st.get("launches", 0) + 1
         st["check"] = int(S[::7, ::5].sum() + C.sum()) ^ int(np.float64(D[::7, ::5].sum()).view(np.int64) & 0xffff)
@@ -445,7 +446,7 @@ def run_workload(args, cfg_name, n, L, seed, legs, env, want_host_stages):
     if want_host_stages and rank == 0:
         host_s = host_stages(host_np, so, n, None)
     eng.close()
-    del corpus_host, band_bytes, host_np, S_band, D_buf
+    del corpus_host, band_bytes, host_np, S_band, D_buf, S_full
     torch.cuda.empty_cache()
     return reports, gen_s, host_s, parity_failed
 

@@ -786,16 +786,17 @@ SNACC_HD bool pk_turbo_lean(PkState &st, PkTab<KIND, STRIDE> &tab, const PkView 
 // walk the chain together: the probe at p takes the word of position p - P (one shuffle), and the next probe is d
 // further; that shuffle and add are all that is left on the dependency chain, the bookkeeping of op / anchor and the
 // two inserts hang off it.  A lane's candidate is stale once a probe of the same batch has written its slot (slot of
-// p, slot of pn - 2 -- both in the word): every lane compares the slots the walk inserts into with its own and raises
-// a flag that the walk reads with a second shuffle; the walk stops in front of a stale position -- and at anything else
-// the scalar loop does not cover either -- and pk_run lets the scalar loop do a few probes before the next batch.
+// p, slot of pn - 2): the walk reads the slot again (its index is in the word) and compares it with what the lane saw
+// (a second shuffle); it stops in front of a stale position -- and at anything else the scalar loop does not cover
+// either -- and pk_run lets the scalar loop do a few probes before the next batch.
 // Same state, same table reads and writes as the scalar loop.
-constexpr uint32_t PKB_D = 0xfu, PKB_HIT = 0x10u, PKB_K_SHIFT = 5, PKB_BAIL = 0x100u, PKB_IDX_SHIFT = 9, PKB_IDX2_SHIFT = 19;
+constexpr uint32_t PKB_D = 0xfu, PKB_HIT = 0x10u, PKB_K_SHIFT = 5, PKB_BAIL = 0x100u, PKB_IDX_SHIFT = 9, PKB_IDX2_SHIFT = 19,
+                   PKB_K4 = 1u << 29;
 constexpr uint32_t PKB_WINDOW = 64, PKB_HOP_MAX = 52;       // a hop from position l touches positions up to l + 11
 
-// the probe at q on its own
+// the probe at q = P + l on its own
 template <int KIND>
-SNACC_HD uint32_t pk_batch_probe(const PkTab<KIND, 1> &tab, const PkView &v, uint32_t q, uint32_t &idx)
+SNACC_HD uint32_t pk_batch_probe(const PkTab<KIND, 1> &tab, const PkView &v, uint32_t q, uint32_t l, uint32_t &idx, uint32_t &seen)
 {
     constexpr uint32_t MASK = PkTab<KIND, 1>::MASK, RMASK = (2 * PK_RING_WORDS - 1) * 4;
     const pk_sptr ring_a = pk_sptr_of(v.ring);
@@ -805,6 +806,7 @@ SNACC_HD uint32_t pk_batch_probe(const PkTab<KIND, 1> &tab, const PkView &v, uin
     idx = tab.lut[pk_fsr(Ws, Wt, 8) & MASK];
     uint32_t m;
     const bool near = tab.lookup_idx(idx, q, m);
+    seen = tab.t[idx];                                                 // (KIND 0 / 1: the slot is the candidate position)
     const uint32_t qm4 = m - 4 - v.lx, jm = (qm4 >> 2) & RMASK;
     const uint32_t ca = pk_lds32(ring_a + jm), cb = pk_lds32(ring_a + jm + 4);
     const uint32_t x = Ws ^ pk_fsr(ca, cb, qm4 * 2);
@@ -813,9 +815,11 @@ SNACC_HD uint32_t pk_batch_probe(const PkTab<KIND, 1> &tab, const PkView &v, uin
     common = near ? common : 0;
     const uint32_t k = pk_clz32((x << 24) | 0x00800000u) >> 1;         // backwards from q - 1, at most 4
     const bool hit = common >= 4;
-    // not for the walk: candidate outside the ring, match of 12+ bases, a catch-up that may end at the stream start
-    const bool bail = (near && !inring) || common > 11 || (hit && m < 64);
-    return (hit ? common & PKB_D : 1u) | (hit ? PKB_HIT : 0u) | (k << PKB_K_SHIFT) | (bail ? PKB_BAIL : 0u) | (idx << PKB_IDX_SHIFT);
+    // not for the walk: candidate outside the ring, match of 12+ bases, a catch-up that may end at the stream start,
+    // and the positions a hop must not start from (its second insert would lie beyond the window)
+    const bool bail = (near && !inring) || common > 11 || (hit && m < 64) || l > PKB_HOP_MAX;
+    return (hit ? common & PKB_D : 1u) | (hit ? PKB_HIT : 0u) | (k << PKB_K_SHIFT) | (bail ? PKB_BAIL : 0u) | (idx << PKB_IDX_SHIFT) |
+           (hit && k == 4 ? PKB_K4 : 0u);
 }
 
 template <int KIND>
@@ -838,53 +842,54 @@ SNACC_HD void pk_batch_run(PkState &st, PkTab<KIND, 1> &tab, const PkView &v, ui
         if (P + PKB_WINDOW > lim || op + (P - anchor) > op_lim || (uint32_t)(P - 4 - v.lx - v.rlo) > v.rspan) break;
         // ---- every lane: its two probes; the slot of q + d - 2 (second insert of a hit at q) comes from the lane that owns it
 #ifdef __CUDA_ARCH__
-        uint32_t idxA, idxB;
-        uint32_t packA = pk_batch_probe<KIND>(tab, v, P + lane, idxA);
-        uint32_t packB = pk_batch_probe<KIND>(tab, v, P + 32 + lane, idxB);
+        uint32_t idxA, idxB, seenA, seenB;
+        uint32_t packA = pk_batch_probe<KIND>(tab, v, P + lane, lane, idxA, seenA);
+        uint32_t packB = pk_batch_probe<KIND>(tab, v, P + 32 + lane, 32 + lane, idxB, seenB);
         {
             const uint32_t la = lane + (packA & PKB_D) - 2, lb = lane + (packB & PKB_D) - 2;       // (a miss: d = 1, unused)
             const uint32_t a_lo = __shfl_sync(0xffffffffu, idxA, la & 31), a_hi = __shfl_sync(0xffffffffu, idxB, la & 31);
             const uint32_t b_hi = __shfl_sync(0xffffffffu, idxB, lb & 31);
             packA |= ((la & 32) ? a_hi : a_lo) << PKB_IDX2_SHIFT;
-            packB |= b_hi << PKB_IDX2_SHIFT;                          // (lb >= 32: beyond the window, never hopped from)
+            packB |= b_hi << PKB_IDX2_SHIFT;                          // (lb >= 32: only for positions no hop starts from)
         }
-        const pk_sptr saA = tab_a + idxA * (uint32_t)sizeof(T), saB = tab_a + idxB * (uint32_t)sizeof(T);
-        uint32_t staleA = 0, staleB = 0;
 #define PKB_PACK(l) __shfl_sync(0xffffffffu, ((l) & 32) ? packB : packA, (l) & 31)
-#define PKB_STALE(l) __shfl_sync(0xffffffffu, ((l) & 32) ? staleB : staleA, (l) & 31)
+#define PKB_SEEN(l) __shfl_sync(0xffffffffu, ((l) & 32) ? seenB : seenA, (l) & 31)
 #else
-        uint32_t pack[PKB_WINDOW], idx[PKB_WINDOW], stale[PKB_WINDOW];
-        for (uint32_t l = 0; l < PKB_WINDOW; ++l) { pack[l] = pk_batch_probe<KIND>(tab, v, P + l, idx[l]); stale[l] = 0; }
+        uint32_t pack[PKB_WINDOW], idx[PKB_WINDOW], seen[PKB_WINDOW];
+        for (uint32_t l = 0; l < PKB_WINDOW; ++l) pack[l] = pk_batch_probe<KIND>(tab, v, P + l, l, idx[l], seen[l]);
         for (uint32_t l = 0; l < PKB_WINDOW; ++l) pack[l] |= idx[(l + (pack[l] & PKB_D) - 2) & (PKB_WINDOW - 1)] << PKB_IDX2_SHIFT;
 #define PKB_PACK(l) pack[(l) & (PKB_WINDOW - 1)]
-#define PKB_STALE(l) stale[(l) & (PKB_WINDOW - 1)]
+#define PKB_SEEN(l) seen[(l) & (PKB_WINDOW - 1)]
 #endif
         // ---- the walk, uniform over the warp.  l runs ahead on its own (d comes straight out of the shuffled word);
         // everything that changes state is predicated on `ok`, which drops for good at the first position the walk
-        // cannot take, and p / anchor / op stay where they were then.
+        // cannot take, and p / anchor / op stay where they were then.  (While ok holds l <= 63: hops start at l <= 52.)
         uint32_t l = 0;
         bool ok = true;
         do {
+            ok = ok & (p - anchor <= 52);                   // at most 4 more literals before the next test: step stays 1
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const uint32_t pk = PKB_PACK(l);
-                const uint32_t stl = PKB_STALE(l);
+                const uint32_t sn = PKB_SEEN(l);
                 const uint32_t d = pk & PKB_D, kk = (pk >> PKB_K_SHIFT) & 7, pend = p - anchor;
                 const bool hit = (pk & PKB_HIT) != 0;
-                const bool bad = (stl != 0) | ((pk & PKB_BAIL) != 0) | (pend > 56) | (hit & (kk == 4) & (pend > 4)) | (l > PKB_HOP_MAX);
-                ok = ok & !bad;
-                const bool gh = ok & hit;
                 const uint32_t i1 = (pk >> PKB_IDX_SHIFT) & 1023, i2 = (pk >> PKB_IDX2_SHIFT) & 1023;
-                const uint32_t pn = p + d, l2 = l + d - 2;
+                const uint32_t pn = p + d;
+                // stale: the slot no longer holds what the lane saw (an insert of this batch; positions only grow)
 #ifdef __CUDA_ARCH__
-                staleA |= (uint32_t)(ok & ((idxA == i1) | (hit & (idxA == i2))));
-                staleB |= (uint32_t)(ok & ((idxB == i1) | (hit & (idxB == i2))));
-                const pk_sptr s1 = (l & 32) ? saB : saA, s2 = (l2 & 32) ? saB : saA;
-                if (KIND == 0) { pk_sts32_if(ok & (lane == (l & 31)), s1, p); pk_sts32_if(gh & (lane == (l2 & 31)), s2, pn - 2); }
-                else           { pk_sts16_if(ok & (lane == (l & 31)), s1, p); pk_sts16_if(gh & (lane == (l2 & 31)), s2, pn - 2); }
+                const uint32_t now = KIND == 0 ? pk_lds32(tab_a + i1 * 4) : pk_lds16(tab_a + i1 * 2);
+#else
+                const uint32_t now = tab.t[i1];
+#endif
+                ok = ok & ((pk & PKB_BAIL) == 0) & !(((pk & PKB_K4) != 0) & (pend > 4)) & (now == sn);
+                const bool gh = ok & hit;
+#ifdef __CUDA_ARCH__
+                // the inserts: every lane stores the same value to the same address
+                if (KIND == 0) { pk_sts32_if(ok, tab_a + i1 * 4, p); pk_sts32_if(gh, tab_a + i2 * 4, pn - 2); }
+                else           { pk_sts16_if(ok, tab_a + i1 * 2, p); pk_sts16_if(gh, tab_a + i2 * 2, pn - 2); }
 #else
                 if (ok) {
-                    for (uint32_t j = 0; j < PKB_WINDOW; ++j) stale[j] |= (idx[j] == i1) | (hit & (idx[j] == i2));
                     tab.t[i1] = (T)p;
                     if (hit) tab.t[i2] = (T)(pn - 2);
 #if defined(PK_COUNT_STEPS)
@@ -900,7 +905,7 @@ SNACC_HD void pk_batch_run(PkState &st, PkTab<KIND, 1> &tab, const PkView &v, ui
             }
         } while (ok);
 #undef PKB_PACK
-#undef PKB_STALE
+#undef PKB_SEEN
         if (p == P) break;
     }
     if (p != p_in) {

@@ -223,8 +223,26 @@ def _all_gather_padded(local, dist, device=None):
     return [out[r * cap:r * cap + sizes[r]] for r in range(world)]
 
 
-def gather_cols(S_cols, bounds, n, dist, device=None):
-    """all ranks get the full n x n matrix from per-rank column bands [bounds[r], bounds[r+1])"""
+def gather_cols(S_cols, bounds, n, dist, device=None, out=None):
+    """all ranks get the full n x n matrix from per-rank column bands [bounds[r], bounds[r+1]).  With a CUDA device (NCCL)
+    the bands are gathered and laid side by side on the device and the matrix comes back in one copy into page-locked
+    memory (the c3 matrix is 800 MB: transposing it on the host cost more than computing it on 8 GPUs)."""
+    if device is not None and getattr(device, "type", None) == "cuda":
+        import torch
+        world = dist.get_world_size()
+        widths = [int(bounds[r + 1]) - int(bounds[r]) for r in range(world)]
+        wmax = max(max(widths), 1)
+        local = torch.from_numpy(np.ascontiguousarray(S_cols, dtype=np.int64).reshape(n, -1))
+        pad = torch.zeros((n, wmax), dtype=torch.int64, device=device)
+        if local.shape[1]:
+            pad[:, :local.shape[1]].copy_(local, non_blocking=True)
+        out = torch.empty((world, n, wmax), dtype=torch.int64, device=device)
+        with _nvtx("snacc_b200: result all-gather"):
+            dist.all_gather_into_tensor(out, pad)
+        S_dev = torch.cat([out[r, :, :widths[r]] for r in range(world) if widths[r]], dim=1)
+        S = out if out is not None and out.shape == (n, n) and out.dtype == np.int64 else _result_buffer(n, n)
+        torch.from_numpy(S).copy_(S_dev)
+        return S
     parts = _all_gather_padded(np.ascontiguousarray(S_cols.T), dist, device)     # transposed: a band is contiguous
     S = np.zeros((n, n), dtype=np.int64)
     for r, p in enumerate(parts):
@@ -263,12 +281,13 @@ def ncd_host(C, S, fast_mode=False, bias=GETSIZEOF_BIAS):
 MAX_JOBS_PER_CALL = 1 << 24
 
 
-def sizes_matrix(engine, algorithm, fast_mode=False, rows_per_call=None, stats=None, band_out=None):
+def sizes_matrix(engine, algorithm, fast_mode=False, rows_per_call=None, stats=None, band_out=None, full_out=None):
     """C (all singles) and S (all ordered pairs, or the mirrored upper triangle in fast mode) for the corpus already
     uploaded to ``engine``, sharded over the process group when there is one.  Every rank returns the full result.
     ``stats`` (a dict) receives the library's kernel times and launch counts of this rank; ``band_out``: an int64
     (n, width of this rank's band) array to receive the rank's column band (a caller that repeats the job -- bench.py --
-    passes the same page-locked buffer every time instead of having a new one pinned per call)."""
+    passes the same page-locked buffer every time instead of having a new one pinned per call); ``full_out``: the same
+    for the gathered (n, n) matrix under a process group."""
     dist = _dist()
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
     n = engine.n_seqs
@@ -318,7 +337,7 @@ def sizes_matrix(engine, algorithm, fast_mode=False, rows_per_call=None, stats=N
         if stats is not None:
             stats["jobs"] = n * (b - a)
             stats["bytes"] = float(n * lengths[a:b].sum() + (b - a) * lengths.sum())
-        S = gather_cols(S_cols, bounds, n, dist, dev) if dist else S_cols
+        S = gather_cols(S_cols, bounds, n, dist, dev, out=full_out) if dist else S_cols
     else:
         xs, ys = triangle_jobs(shares[rank])
         vals = np.zeros(xs.size, dtype=np.int64)
