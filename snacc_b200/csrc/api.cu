@@ -1139,6 +1139,7 @@ extern "C" int snacc_get_stat(const snacc_ctx *ctx, const char *name, double *ou
     if (!strcmp(name, "bytewise_jobs")) { *out = (double)ctx->last_bytewise_jobs; return SNACC_OK; }
     if (!strcmp(name, "lz4_segments")) { *out = (double)ctx->last_pk_segments; return SNACC_OK; }
     if (!strcmp(name, "deflate_serial_jobs")) { *out = (double)ctx->dfl.serial_jobs; return SNACC_OK; }
+    if (!strcmp(name, "deflate_parallel_prep_seqs")) { *out = (double)ctx->dfl.parallel_prep_seqs; return SNACC_OK; }
     return SNACC_ERR_ARG;
 }
 
@@ -1151,6 +1152,7 @@ extern "C" int snacc_set_option(snacc_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "lz4_segments")) { ctx->pk_segments = value < 0 ? 0 : value; return SNACC_OK; }
     if (!strcmp(name, "deflate_canonical")) { ctx->dfl.use_canon = value ? 1 : 0; return SNACC_OK; }
     if (!strcmp(name, "deflate_index6")) { ctx->dfl.use_index6 = value ? 1 : 0; return SNACC_OK; }
+    if (!strcmp(name, "deflate_parallel_prep")) { ctx->dfl.use_parallel_prep = value ? 1 : 0; return SNACC_OK; }
     if (!strcmp(name, "deflate_junction")) { ctx->dfl.junction_impl = value == 2 ? 2 : 3; return SNACC_OK; }
     if (!strcmp(name, "invalidate_caches")) {
         // forget every per-sequence precomputation (prefix checkpoints ...) so the next sizes call

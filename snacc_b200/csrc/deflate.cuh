@@ -1109,6 +1109,108 @@ static __host__ __device__ int dfl_parse(const DflStream &d, const DflFView &fv,
     return done ? 1 : synced ? 2 : 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// the parse of a sequence alone, in parallel
+// ------------------------------------------------------------------------------------------------
+// The serial parse of a 5 Mbp sequence is ~1.4 M dependent loop iterations: 0.46 s on one thread, however many GPUs
+// share the corpus (dfl_prep_kernel).  But right after a match the state of deflate_slow is just the position (see
+// "canonical symbol stream" above), so the parse started ANYWHERE with that state falls in with the true parse at the
+// first position where both end a match, and emits the same symbols from there on.  The sequence is therefore cut into
+// chunks of DFL_CHUNK bytes, one thread each:
+//   scan   thread k parses from its chunk start s_k to s_{k+1} + DFL_CHUNK_OV and notes, as two bitmaps, where its
+//          matches end inside [s_k, s_k + OV) and inside [s_{k+1}, s_{k+1} + OV);
+//   sync   y_{k+1} = the first position of [s_{k+1}, s_{k+1} + OV) where chunk k (true there: y_k < s_k + OV << s_{k+1})
+//          and chunk k+1 both end a match; y_0 = 0;
+//   count  thread k parses [y_k, y_{k+1}) and counts its symbols; a scan over the chunks gives every chunk its place;
+//   emit   thread k parses [y_k, y_{k+1}) again and writes its symbols there.
+// Everything stays below E = n - DFL_TAIL, where zlib's window schedule is the regular one the F tables assume; the
+// blocks (every 16 383 symbols), the size, the checkpoint and the last DFL_TAIL bytes are then done per sequence by
+// dfl_alone_kernel, exactly as a pair stream does them (dfl_canon_blocks + the serial parser for the tail).  A
+// sequence where two neighbouring chunks never meet inside the overlap (long periodic runs: match ends of period 258
+// that are out of phase) takes the serial kernel instead.
+constexpr uint32_t DFL_CHUNK = 8192, DFL_CHUNK_OV = 1024, DFL_CHUNK_WORDS = DFL_CHUNK_OV / 32;
+constexpr uint32_t DFL_PAR_MIN = 16 * DFL_CHUNK;            // shorter sequences: serial kernel
+constexpr uint32_t DFL_NOWIN = 0x80000000u;                 // a window start no position (< 2^31) is within OV of
+
+SNACC_HD uint32_t dfl_chunk_end(uint32_t n) { return n - DFL_TAIL; }                         // E
+SNACC_HD uint32_t dfl_chunk_count(uint32_t n) { return dfl_chunk_end(n) / DFL_CHUNK; }       // the last chunk is [s, E): up to 2 chunks long
+
+struct DflLite {
+    int mode;                          // 0 scan, 1 count, 2 emit
+    uint32_t head_lo, tail_lo;         // scan: windows [head_lo, +OV), [tail_lo, +OV) (DFL_NOWIN: none)
+    uint32_t *head, *tail;             //       their bitmaps (DFL_CHUNK_WORDS words each, zeroed by the caller)
+    uint32_t until;                    // count / emit: stop right after the match that ends here (DFL_NONE: run to `stop`)
+    uint32_t count;                    // symbols seen (count / emit)
+    uint32_t *end; uint16_t *code; uint32_t cap;     // emit: destination of symbol 0 and the slots left
+};
+
+// deflate_slow over F in the regular window schedule from the loop top at `from` (which follows a match, or is the
+// stream start), without tallies and block flushes.  Returns false when an emit ran out of slots.
+static __host__ __device__ bool dfl_lite_parse(const DflStream &d, const uint32_t *F, const uint32_t *Q, const DflConfig &c,
+                                                uint32_t from, uint32_t stop, DflLite &o)
+{
+    uint32_t strstart = from, match_start = 0, match_length = DFL_MIN_MATCH - 1, match_available = 0;
+    for (;;) {
+        if (strstart >= stop) break;
+        const uint32_t prev_length = match_length, prev_match = match_start;
+        match_length = DFL_MIN_MATCH - 1;
+        if (prev_length < (uint32_t)c.max_lazy) {
+            uint32_t f = SNACC_LDG(F + strstart);
+            if (prev_length >= (uint32_t)c.good_length && (f & DFL_QDIFF)) {
+                if (Q) f = SNACC_LDG(Q + strstart);
+                else dfl_longest(d, strstart, dfl_window_base(strstart), (uint32_t)c.max_chain, (uint32_t)c.nice_length, 0xffffffffu, &f);
+            }
+            f &= ~DFL_QDIFF;
+            const uint32_t len = f >> 16, dist = f & 0xffff;
+            if (len > prev_length) {
+                match_length = len; match_start = strstart - dist;
+                if (len == DFL_MIN_MATCH && dist > DFL_TOO_FAR) match_length = DFL_MIN_MATCH - 1;
+            }
+        }
+        if (prev_length >= DFL_MIN_MATCH && match_length <= prev_length) {
+            const uint32_t dist1 = strstart - 1 - prev_match - 1;
+            strstart += prev_length - 1;
+            match_available = 0;
+            match_length = DFL_MIN_MATCH - 1;
+            if (o.mode == 0) {
+                if (strstart - o.head_lo < DFL_CHUNK_OV) o.head[(strstart - o.head_lo) >> 5] |= 1u << ((strstart - o.head_lo) & 31);
+                if (strstart - o.tail_lo < DFL_CHUNK_OV) o.tail[(strstart - o.tail_lo) >> 5] |= 1u << ((strstart - o.tail_lo) & 31);
+            } else {
+                if (o.mode == 2) {
+                    if (o.count >= o.cap) return false;
+                    o.end[o.count] = strstart;
+                    o.code[o.count] = (uint16_t)(((uint32_t)dfl_length_code(prev_length - DFL_MIN_MATCH) + 257) | ((uint32_t)dfl_dist_code(dist1) << 9));
+                }
+                ++o.count;
+                if (strstart == o.until) break;
+            }
+        } else if (match_available) {
+            if (o.mode == 2) {
+                if (o.count >= o.cap) return false;
+                o.end[o.count] = strstart;
+                o.code[o.count] = (uint16_t)(ld8(d.s, strstart - 1) | (DFL_LIT << 9));
+            }
+            if (o.mode) ++o.count;
+            strstart++;
+        } else {
+            match_available = 1;
+            strstart++;
+        }
+    }
+    return true;
+}
+
+// y_k of chunk k >= 1 from the two bitmaps that look at [s_k, s_k + OV): DFL_NONE when the chunks never meet there
+SNACC_HD uint32_t dfl_chunk_sync(const uint32_t *tail_prev, const uint32_t *head, uint32_t s_k)
+{
+    for (uint32_t w = 0; w < DFL_CHUNK_WORDS; ++w) {
+        const uint32_t m = tail_prev[w] & head[w];
+        if (m) return s_k + w * 32 + (uint32_t)SNACC_FFS32(m) - 1;
+    }
+    return DFL_NONE;
+}
+
 #if defined(DFL_CHECK_COMPACT)
 static int64_t dfl_compact_checked = 0, dfl_compact_mismatch = 0;     // host emulation only (tests/host_emu.cu)
 #endif
@@ -1117,10 +1219,13 @@ static int64_t dfl_compact_checked = 0, dfl_compact_mismatch = 0;     // host em
 // canonical match ending at or before ly - DFL_TAIL.  Returns 1 when it advanced, 0 when there was nothing
 // to skip, -1 when a block would consider the stored form (the job then takes the full serial parse).
 // accA/accB: two scratch rows of DFL_L_CODES + DFL_D_CODES counters.
+// (k_sync = DFL_NONE: the stream IS the canonical one from its first symbol -- the sequence alone, dfl_alone_kernel;
+// t_end_out: number of canonical symbols accounted for.)
 template <class TallyT>
 static __host__ __device__ int dfl_canon_blocks(const DflCanon &cn, uint32_t lx, uint32_t n, uint32_t k_sync, DflParseState &st,
                                                 TallyT *lfreq, int lstride, TallyT *dfreq, int dstride, DflTrees &tr,
-                                                uint32_t *accA, uint32_t *accB, DflCompactTrees *ct = nullptr)
+                                                uint32_t *accA, uint32_t *accB, DflCompactTrees *ct = nullptr,
+                                                uint32_t *t_end_out = nullptr)
 {
     const uint32_t ly = n - lx, lim = ly - DFL_TAIL;
     uint32_t lo = 0, hi = cn.n_sym;                        // first symbol that ends beyond lim
@@ -1130,10 +1235,13 @@ static __host__ __device__ int dfl_canon_blocks(const DflCanon &cn, uint32_t lx,
     }
     if (lo == 0) return 0;
     uint32_t kt = lo - 1;
-    while (kt > k_sync && (SNACC_LDG(cn.code + kt) >> 9) == DFL_LIT) --kt;
-    if (kt <= k_sync) return 0;
-    uint32_t t = k_sync + 1;
+    const uint32_t t_first = k_sync + 1;                   // (DFL_NONE + 1 = 0)
+    if (kt < t_first) return 0;
+    while (kt > t_first && (SNACC_LDG(cn.code + kt) >> 9) == DFL_LIT) --kt;
+    if ((SNACC_LDG(cn.code + kt) >> 9) == DFL_LIT) return 0;
+    uint32_t t = t_first;
     const uint32_t t_end = kt + 1;
+    if (t_end_out) *t_end_out = t_end;
     uint32_t *a = accA, *b = accB;
     dfl_cum_at(cn, t, a);
     for (;;) {
@@ -1701,6 +1809,144 @@ dfl_prep_kernel(DflCorpus c, const int32_t *__restrict__ seqs, int32_t n_seqs, i
     }
 }
 
+// ---- K3d'': the same products as dfl_prep_kernel for long sequences, in parallel (see "the parse of a sequence
+// alone, in parallel").  Chunk k of the i-th listed sequence uses entry coff[i] + k of the per-chunk arrays.
+struct DflChunkArgs {
+    const int32_t *seqs; const uint64_t *coff; int32_t n_seqs;
+    uint32_t *head, *tail;             // per chunk: DFL_CHUNK_WORDS words each
+    uint32_t *ysync, *cnt, *off;       // per chunk: y_k, symbols of [y_k, y_{k+1}), their first slot
+    int32_t *fail;                     // per listed sequence: chunks that never met / overflow / stored-block candidate
+};
+
+__global__ void __launch_bounds__(128)
+dfl_chunk_scan_kernel(DflCorpus c, DflChunkArgs a, int level, const uint32_t *__restrict__ F, const uint32_t *__restrict__ FQ)
+{
+    const DflConfig cfg = dfl_config(level);
+    for (int32_t i = blockIdx.y; i < a.n_seqs; i += gridDim.y) {
+        const int32_t sq = a.seqs[i];
+        const DflStream d = dfl_make(c, sq, -1);
+        const uint32_t n = d.s.n, K = dfl_chunk_count(n), E = dfl_chunk_end(n);
+        const uint32_t *f = F + c.poff[sq], *q = FQ ? FQ + c.poff[sq] : nullptr;
+        for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+            DflLite o;
+            o.mode = 0; o.until = DFL_NONE; o.count = 0; o.end = nullptr; o.code = nullptr; o.cap = 0;
+            o.head = a.head + (a.coff[i] + k) * DFL_CHUNK_WORDS;
+            o.tail = a.tail + (a.coff[i] + k) * DFL_CHUNK_WORDS;
+            for (uint32_t w = 0; w < DFL_CHUNK_WORDS; ++w) o.head[w] = o.tail[w] = 0;
+            const uint32_t s_k = k * DFL_CHUNK, s_next = s_k + DFL_CHUNK;
+            const bool last = k + 1 == K;
+            o.head_lo = k ? s_k : DFL_NOWIN;
+            o.tail_lo = last ? DFL_NOWIN : s_next;
+            const uint32_t stop = last ? (k ? tmin(s_k + DFL_CHUNK_OV, E) : 0u) : tmin(s_next + DFL_CHUNK_OV, E);
+            dfl_lite_parse(d, f, q, cfg, s_k, stop, o);
+        }
+    }
+}
+
+template <int MODE>      // 1: sync points + symbol counts, 2: emit
+__global__ void __launch_bounds__(128)
+dfl_chunk_pass_kernel(DflCorpus c, DflChunkArgs a, int level, const uint32_t *__restrict__ F, const uint32_t *__restrict__ FQ,
+                      DflCanonPool cp)
+{
+    const DflConfig cfg = dfl_config(level);
+    for (int32_t i = blockIdx.y; i < a.n_seqs; i += gridDim.y) {
+        if (MODE == 2 && a.fail[i]) continue;
+        const int32_t sq = a.seqs[i];
+        const DflStream d = dfl_make(c, sq, -1);
+        const uint32_t n = d.s.n, K = dfl_chunk_count(n), E = dfl_chunk_end(n);
+        const uint32_t *f = F + c.poff[sq], *q = FQ ? FQ + c.poff[sq] : nullptr;
+        for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+            const uint64_t e = a.coff[i] + k;
+            const bool last = k + 1 == K;
+            uint32_t y_k, y_next;
+            if (MODE == 1) {
+                y_k = k ? dfl_chunk_sync(a.tail + (e - 1) * DFL_CHUNK_WORDS, a.head + e * DFL_CHUNK_WORDS, k * DFL_CHUNK) : 0u;
+                y_next = last ? DFL_NONE : dfl_chunk_sync(a.tail + e * DFL_CHUNK_WORDS, a.head + (e + 1) * DFL_CHUNK_WORDS, (k + 1) * DFL_CHUNK);
+                a.ysync[e] = y_k;
+                if (y_k == DFL_NONE || (!last && y_next == DFL_NONE)) { a.fail[i] = 1; a.cnt[e] = 0; continue; }
+            } else {
+                y_k = a.ysync[e];
+                y_next = last ? DFL_NONE : a.ysync[e + 1];
+            }
+            DflLite o;
+            o.mode = MODE; o.until = y_next; o.count = 0;
+            o.head = o.tail = nullptr; o.head_lo = o.tail_lo = DFL_NOWIN;
+            o.end = nullptr; o.code = nullptr; o.cap = 0;
+            if (MODE == 2) {
+                o.end = cp.end + cp.soff[sq] + a.off[e]; o.code = cp.code + cp.soff[sq] + a.off[e]; o.cap = a.cnt[e];
+            }
+            dfl_lite_parse(d, f, q, cfg, y_k, E, o);
+            if (MODE == 1) a.cnt[e] = o.count;
+        }
+    }
+}
+
+// every chunk's first slot; the sequence's symbol count (0 and fail when the symbols do not fit)
+__global__ void dfl_chunk_offsets_kernel(DflCorpus c, DflChunkArgs a, DflCanonPool cp)
+{
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_seqs) return;
+    const int32_t sq = a.seqs[i];
+    const uint32_t K = dfl_chunk_count(c.len[sq]);
+    uint64_t acc = 0;
+    for (uint32_t k = 0; k < K; ++k) { a.off[a.coff[i] + k] = (uint32_t)acc; acc += a.cnt[a.coff[i] + k]; }
+    if (acc > cp.cap[sq]) a.fail[i] = 1;
+    cp.n_sym[sq] = a.fail[i] ? 0u : (uint32_t)acc;
+}
+
+// blocks, size, checkpoint and tail of every listed sequence whose canonical stream stands (up to E) and whose
+// cumulative histograms are built: what a pair stream does after its synchronisation point, from symbol 0
+constexpr int DFL_ALONE_THREADS = 32;
+struct DflAloneSmem {
+    DflTrees tr;
+    uint32_t accA[DFL_L_CODES + DFL_D_CODES], accB[DFL_L_CODES + DFL_D_CODES];
+    uint16_t lf[DFL_L_CODES], df[DFL_D_CODES];
+};
+__global__ void __launch_bounds__(DFL_ALONE_THREADS)
+dfl_alone_kernel(DflCorpus c, DflChunkArgs a, int level, const uint32_t *__restrict__ F, const uint32_t *__restrict__ FQ,
+                 DflCkpt *__restrict__ ckpt, DflCanonPool cp)
+{
+    extern __shared__ __align__(16) uint8_t alone_raw[];
+    DflAloneSmem &sm = *reinterpret_cast<DflAloneSmem *>(alone_raw);
+    const DflConfig cfg = dfl_config(level);
+    for (int32_t i = blockIdx.x; i < a.n_seqs; i += gridDim.x) {
+        if (a.fail[i]) continue;
+        const int32_t sq = a.seqs[i];
+        __syncthreads();
+        for (uint32_t k = threadIdx.x; k < DFL_L_CODES; k += blockDim.x) sm.lf[k] = k == 256 ? 1 : 0;
+        for (uint32_t k = threadIdx.x; k < DFL_D_CODES; k += blockDim.x) sm.df[k] = 0;
+        __syncthreads();
+        if (threadIdx.x) continue;
+        const DflStream d = dfl_make(c, sq, -1);
+        const uint32_t n = d.s.n, jx0 = dfl_jx0(n);
+        DflFView fv;
+        fv.fx = fv.fy = fv.fj = F + c.poff[sq]; fv.jx0 = fv.jend = fv.lx = n;
+        fv.qx = FQ ? FQ + c.poff[sq] : nullptr; fv.qy = fv.qj = fv.qx;
+        const DflCanon cn = dfl_canon_of(cp, sq);
+        DflParseState st;
+        dfl_parse_fresh(st);
+        uint32_t t_end = 0;
+        const int b = dfl_canon_blocks(cn, 0, n, DFL_NONE, st, sm.lf, 1, sm.df, 1, sm.tr, sm.accA, sm.accB,
+                                       (DflCompactTrees *)nullptr, &t_end);
+        if (b <= 0) { a.fail[i] = 1; cp.n_sym[sq] = 0; continue; }       // (a block zlib might store: the serial kernel decides)
+        DflRec rec{cp.end + cp.soff[sq], cp.code + cp.soff[sq], cp.cap[sq], t_end};
+        bool ck_done = false;
+        for (;;) {
+            const uint32_t stop = ck_done ? 0xffffffffu : jx0;
+            if (dfl_parse(d, fv, cfg, st, sm.lf, 1, sm.df, 1, sm.tr, stop, &rec) == 1) break;
+            if (!ck_done && st.strstart >= jx0) {
+                DflCkpt &ck = ckpt[sq];
+                ck.st = st;
+                for (int k = 0; k < DFL_L_CODES; ++k) ck.lfreq[k] = sm.lf[k];
+                for (int k = 0; k < DFL_D_CODES; ++k) ck.dfreq[k] = sm.df[k];
+                ck_done = true;
+            }
+        }
+        cp.n_sym[sq] = rec.n == DFL_NONE ? 0u : rec.n;
+        cp.seq_size[sq] = (int64_t)(st.bits >> 3);
+    }
+}
+
 // K3e: cumulative symbol histograms of the canonical streams.  Step 1: histogram of every complete chunk of
 // DFL_CUM_G symbols into row chunk+1; step 2: running sum down the rows (row 0 = zeros).
 __global__ void __launch_bounds__(64)
@@ -1764,6 +2010,8 @@ struct DeflateState {
     uint32_t *d_rx_hist = nullptr; size_t rx_cap = 0;   // radix-sort digit totals (dfl_build_index)
     uint32_t *d_bstart6 = nullptr, *d_order6 = nullptr; uint64_t order6_cap = 0;   // 6-byte index: starts per sequence, window buffer
     int use_index6 = 1;                            // 0: dfl_match_kernel always walks the 3-byte chain (tests)
+    int use_parallel_prep = 1;                     // 0: every sequence alone is parsed by the serial kernel (tests, A/B)
+    int64_t parallel_prep_seqs = 0;                // sequences the chunked path finished in the last call
     std::vector<uint8_t> indexed;                  // per sequence
     uint32_t *d_F[2] = {nullptr, nullptr};         // level 9, level 6
     uint32_t *d_FQ = nullptr;                      // level 6 only: quartered-chain table
@@ -2094,30 +2342,94 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
     int rc = 0;
     if (!need_prep.empty()) {
         NvtxRange nvtx_("snacc_b200: deflate sequence parses (sizes, checkpoints, canonical streams)");
-        {
+        // long sequences: chunks in parallel (dfl_chunk_*_kernel), then cumulative rows, then dfl_alone_kernel; the
+        // others -- and whatever the parallel path gives up on -- take the serial kernel
+        std::vector<int32_t> par, ser;
+        for (int32_t i : need_prep) (st.use_parallel_prep && dc.h_len[i] >= DFL_PAR_MIN ? par : ser).push_back(i);
+        auto run_serial = [&](const std::vector<int32_t> &list) -> int {
+            if (list.empty()) return 0;
             int32_t *d_list = nullptr;
-            if (dfl_upload(err, stream, need_prep, &d_list)) return -1;
+            if (dfl_upload(err, stream, list, &d_list)) return -1;
             DCK(cudaFuncSetAttribute(dfl_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DflPrepSmem)));
-            dfl_prep_kernel<<<(unsigned)std::min<size_t>(need_prep.size(), 148 * 5), DFL_PREP_THREADS, sizeof(DflPrepSmem), stream>>>(
-                c, d_list, (int32_t)need_prep.size(), level, st.d_F[li], FQ, st.d_ckpt[li], cp);
+            dfl_prep_kernel<<<(unsigned)std::min<size_t>(list.size(), 148 * 5), DFL_PREP_THREADS, sizeof(DflPrepSmem), stream>>>(
+                c, d_list, (int32_t)list.size(), level, st.d_F[li], FQ, st.d_ckpt[li], cp);
             DCK(cudaGetLastError());
             ++*launches;
             DCK(cudaStreamSynchronize(stream));
             cudaFree(d_list);
-        }
-        if (!rc) {
+            return 0;
+        };
+        auto run_cum = [&](const std::vector<int32_t> &list) -> int {
+            if (list.empty()) return 0;
             int32_t *d_list = nullptr;
-            if (dfl_upload(err, stream, need_prep, &d_list)) return -1;
+            if (dfl_upload(err, stream, list, &d_list)) return -1;
             uint32_t max_rows = 1;
-            for (int32_t i : need_prep) max_rows = std::max(max_rows, dc.h_len[i] / 4 / DFL_CUM_G + 8);
-            dim3 grid(std::min(max_rows, 2048u), (unsigned)std::min<size_t>(need_prep.size(), 64));
-            dfl_cum_chunk_kernel<<<grid, 64, 0, stream>>>(cp, d_list, (int32_t)need_prep.size());
-            dfl_cum_scan_kernel<<<(unsigned)std::min<size_t>(need_prep.size(), 148 * 4), DFL_CUM_W, 0, stream>>>(
-                cp, d_list, (int32_t)need_prep.size());
+            for (int32_t i : list) max_rows = std::max(max_rows, dc.h_len[i] / 4 / DFL_CUM_G + 8);
+            dim3 grid(std::min(max_rows, 2048u), (unsigned)std::min<size_t>(list.size(), 64));
+            dfl_cum_chunk_kernel<<<grid, 64, 0, stream>>>(cp, d_list, (int32_t)list.size());
+            dfl_cum_scan_kernel<<<(unsigned)std::min<size_t>(list.size(), 148 * 4), DFL_CUM_W, 0, stream>>>(
+                cp, d_list, (int32_t)list.size());
             DCK(cudaGetLastError());
             *launches += 2;
             DCK(cudaStreamSynchronize(stream));
             cudaFree(d_list);
+            return 0;
+        };
+        st.parallel_prep_seqs = 0;
+        if (!par.empty()) {
+            // per-chunk scratch of the listed sequences (2 x 128 B of bitmaps + 12 B per 8 KiB chunk)
+            std::vector<uint64_t> coff(par.size() + 1, 0);
+            uint32_t max_k = 1;
+            for (size_t k = 0; k < par.size(); ++k) {
+                const uint32_t K = dfl_chunk_count(dc.h_len[par[k]]);
+                coff[k + 1] = coff[k] + K; max_k = std::max(max_k, K);
+            }
+            const uint64_t tot = coff.back();
+            int32_t *d_list = nullptr; uint64_t *d_coff = nullptr; uint32_t *d_w = nullptr; int32_t *d_fail = nullptr;
+            if (dfl_upload(err, stream, par, &d_list)) return -1;
+            auto free_all = [&]() { cudaFree(d_list); cudaFree(d_coff); cudaFree(d_w); cudaFree(d_fail); };
+            if (cudaMalloc(&d_coff, sizeof(uint64_t) * coff.size()) != cudaSuccess ||
+                cudaMalloc(&d_w, sizeof(uint32_t) * tot * (2 * DFL_CHUNK_WORDS + 3)) != cudaSuccess ||
+                cudaMalloc(&d_fail, sizeof(int32_t) * par.size()) != cudaSuccess) { free_all(); err = "cudaMalloc (chunk scratch) failed"; return -1; }
+            cudaMemcpyAsync(d_coff, coff.data(), sizeof(uint64_t) * coff.size(), cudaMemcpyHostToDevice, stream);
+            cudaMemsetAsync(d_fail, 0, sizeof(int32_t) * par.size(), stream);
+            DflChunkArgs a{d_list, d_coff, (int32_t)par.size(), d_w, d_w + tot * DFL_CHUNK_WORDS, d_w + tot * 2 * DFL_CHUNK_WORDS,
+                           d_w + tot * (2 * DFL_CHUNK_WORDS + 1), d_w + tot * (2 * DFL_CHUNK_WORDS + 2), d_fail};
+            dim3 grid((max_k + 127) / 128, (unsigned)std::min<size_t>(par.size(), 65535));
+            dfl_chunk_scan_kernel<<<grid, 128, 0, stream>>>(c, a, level, st.d_F[li], FQ);
+            dfl_chunk_pass_kernel<1><<<grid, 128, 0, stream>>>(c, a, level, st.d_F[li], FQ, cp);
+            dfl_chunk_offsets_kernel<<<(unsigned)((par.size() + 63) / 64), 64, 0, stream>>>(c, a, cp);
+            dfl_chunk_pass_kernel<2><<<grid, 128, 0, stream>>>(c, a, level, st.d_F[li], FQ, cp);
+            *launches += 4;
+            std::vector<int32_t> fail(par.size(), 0);
+            if (cudaGetLastError() != cudaSuccess ||
+                cudaMemcpyAsync(fail.data(), d_fail, sizeof(int32_t) * par.size(), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+                cudaStreamSynchronize(stream) != cudaSuccess) { free_all(); err = "deflate chunk kernels failed"; return -1; }
+            std::vector<int32_t> ok;
+            for (size_t k = 0; k < par.size(); ++k) (fail[k] ? ser : ok).push_back(par[k]);
+            if (run_serial(ser) || run_cum(need_prep)) { free_all(); return -1; }
+            ser.clear();
+            if (!ok.empty()) {
+                // the sequences that stand: compact list (fail flags restart at 0)
+                cudaMemcpyAsync(d_list, ok.data(), sizeof(int32_t) * ok.size(), cudaMemcpyHostToDevice, stream);
+                cudaMemsetAsync(d_fail, 0, sizeof(int32_t) * ok.size(), stream);
+                a.n_seqs = (int32_t)ok.size();
+                cudaFuncSetAttribute(dfl_alone_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DflAloneSmem));
+                dfl_alone_kernel<<<(unsigned)std::min<size_t>(ok.size(), 148 * 8), DFL_ALONE_THREADS, sizeof(DflAloneSmem), stream>>>(
+                    c, a, level, st.d_F[li], FQ, st.d_ckpt[li], cp);
+                ++*launches;
+                fail.assign(ok.size(), 0);
+                if (cudaGetLastError() != cudaSuccess ||
+                    cudaMemcpyAsync(fail.data(), d_fail, sizeof(int32_t) * ok.size(), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+                    cudaStreamSynchronize(stream) != cudaSuccess) { free_all(); err = "dfl_alone_kernel failed"; return -1; }
+                std::vector<int32_t> redo;
+                for (size_t k = 0; k < ok.size(); ++k) if (fail[k]) redo.push_back(ok[k]);
+                st.parallel_prep_seqs = (int64_t)(ok.size() - redo.size());
+                if (run_serial(redo) || run_cum(redo)) { free_all(); return -1; }
+            }
+            free_all();
+        } else {
+            if (run_serial(ser) || run_cum(need_prep)) return -1;
         }
     }
     if (rc) { /* fall through to cleanup */ }
