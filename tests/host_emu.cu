@@ -579,6 +579,105 @@ extern "C" int64_t emu_deflate_size_ex(const uint8_t *x, uint32_t lx, const uint
     return result;
 }
 
+// The sequence alone through the chunked path (dfl_chunk_*_kernel + dfl_alone_kernel): scan / sync / count / emit
+// with chunks of DFL_CHUNK bytes, cumulative rows, dfl_canon_blocks from symbol 0, serial tail.  Returns the raw
+// deflate size, -1 when the stitched symbol stream differs from the serial parse's, -2 when the sizes differ, -3 when
+// the sequence is too short for the path; info[0] = 1 when the chunked path stood (0: it gave the sequence up --
+// chunks that never meet, or a block zlib might store), info[1] = chunks.
+extern "C" int64_t emu_deflate_chunked(const uint8_t *x, uint32_t lx, int level, int32_t *info)
+{
+    const DflConfig cfg = dfl_config(level);
+    info[0] = info[1] = 0;
+    if (lx < DFL_PAR_MIN) return -3;
+    uint8_t *px = padded_copy(x, lx);
+    EmuIndex ix = emu_index(px, lx);
+    DflStream dx; dx.s.x = px; dx.s.lx = lx; dx.s.y = px + lx; dx.s.n = lx; dx.pair = false;
+    dx.ix.order = ix.order.data(); dx.ix.bstart = ix.bstart.data(); dx.iy = dx.ix;
+    const bool want_q = level != 9;
+    EmuSeq ex = emu_F_single(dx, cfg, want_q);
+    const uint32_t *F = ex.F.data(), *Q = want_q ? ex.FQ.data() : nullptr;
+    DflFView fv; fv.fx = fv.fy = fv.fj = F; fv.jx0 = fv.jend = fv.lx = lx; fv.qx = fv.qy = fv.qj = Q;
+    const uint32_t cap = (lx / 4 + 1024 + DFL_CUM_G - 1) / DFL_CUM_G * DFL_CUM_G;
+    // serial reference
+    std::vector<uint32_t> rend(cap + 16); std::vector<uint16_t> rcode(cap + 16);
+    DflRec rec{rend.data(), rcode.data(), cap, 0};
+    DflTrees *tr = new DflTrees();
+    std::vector<uint16_t> lf(DFL_L_CODES, 0), df(DFL_D_CODES, 0);
+    DflParseState st; dfl_parse_fresh(st); lf[256] = 1;
+    dfl_parse(dx, fv, cfg, st, lf.data(), 1, df.data(), 1, *tr, 0xffffffffu, &rec);
+    const int64_t serial_size = (int64_t)(st.bits >> 3);
+    int64_t result = serial_size;
+    // chunked
+    const uint32_t K = dfl_chunk_count(lx), E = dfl_chunk_end(lx);
+    info[1] = (int32_t)K;
+    std::vector<uint32_t> head((size_t)K * DFL_CHUNK_WORDS, 0), tail((size_t)K * DFL_CHUNK_WORDS, 0), ys(K, 0), cnt(K, 0), off(K, 0);
+    for (uint32_t k = 0; k < K; ++k) {
+        DflLite o; o.mode = 0; o.until = DFL_NONE; o.count = 0; o.end = nullptr; o.code = nullptr; o.cap = 0;
+        o.head = head.data() + (size_t)k * DFL_CHUNK_WORDS; o.tail = tail.data() + (size_t)k * DFL_CHUNK_WORDS;
+        const uint32_t s_k = k * DFL_CHUNK, s_next = s_k + DFL_CHUNK;
+        const bool last = k + 1 == K;
+        o.head_lo = k ? s_k : DFL_NOWIN; o.tail_lo = last ? DFL_NOWIN : s_next;
+        const uint32_t stop = last ? (k ? tmin(s_k + DFL_CHUNK_OV, E) : 0u) : tmin(s_next + DFL_CHUNK_OV, E);
+        dfl_lite_parse(dx, F, Q, cfg, s_k, stop, o);
+    }
+    bool ok = true;
+    for (uint32_t k = 0; k < K; ++k) {
+        ys[k] = k ? dfl_chunk_sync(tail.data() + (size_t)(k - 1) * DFL_CHUNK_WORDS, head.data() + (size_t)k * DFL_CHUNK_WORDS, k * DFL_CHUNK) : 0u;
+        if (ys[k] == DFL_NONE) ok = false;
+    }
+    std::vector<uint32_t> cend(cap + 16, 0); std::vector<uint16_t> ccode(cap + 16, 0);
+    uint32_t total = 0;
+    if (ok) {
+        for (int mode = 1; mode <= 2 && ok; ++mode) {
+            uint32_t acc = 0;
+            for (uint32_t k = 0; k < K; ++k) {
+                DflLite o; o.mode = mode; o.until = k + 1 < K ? ys[k + 1] : DFL_NONE; o.count = 0;
+                o.head = o.tail = nullptr; o.head_lo = o.tail_lo = DFL_NOWIN;
+                o.end = cend.data() + off[k]; o.code = ccode.data() + off[k]; o.cap = mode == 2 ? cnt[k] : 0;
+                if (!dfl_lite_parse(dx, F, Q, cfg, ys[k], E, o)) ok = false;
+                if (mode == 1) { cnt[k] = o.count; off[k] = acc; acc += o.count; }
+                else if (o.count != cnt[k]) ok = false;
+            }
+            if (mode == 1) { total = acc; if (total > cap) ok = false; }
+        }
+    }
+    if (ok) {
+        // the stitched stream is the serial one, symbol for symbol
+        if (total > rec.n) result = -1;
+        for (uint32_t k = 0; k < total && result >= 0; ++k) if (cend[k] != rend[k] || ccode[k] != rcode[k]) result = -1;
+        // cumulative rows, then blocks from symbol 0 and the serial tail (dfl_alone_kernel)
+        std::vector<uint32_t> cum((size_t)(cap / DFL_CUM_G + 1) * DFL_CUM_W, 0);
+        for (uint32_t r = 1; r <= total / DFL_CUM_G; ++r) {
+            uint32_t *row = cum.data() + (size_t)r * DFL_CUM_W;
+            for (uint32_t c = 0; c < DFL_CUM_W; ++c) row[c] = (row - DFL_CUM_W)[c];
+            for (uint32_t k = (r - 1) * DFL_CUM_G; k < r * DFL_CUM_G; ++k) {
+                const uint32_t cd = ccode[k];
+                row[cd & 511]++;
+                if ((cd >> 9) != DFL_LIT) row[DFL_L_CODES + (cd >> 9)]++;
+            }
+        }
+        DflCanon cn{cend.data(), ccode.data(), cum.data(), total};
+        std::vector<uint32_t> accA(DFL_L_CODES + DFL_D_CODES), accB(DFL_L_CODES + DFL_D_CODES);
+        std::fill(lf.begin(), lf.end(), 0); std::fill(df.begin(), df.end(), 0); lf[256] = 1;
+        dfl_parse_fresh(st);
+        uint32_t t_end = 0;
+        const int b = dfl_canon_blocks(cn, 0, lx, DFL_NONE, st, lf.data(), 1, df.data(), 1, *tr, accA.data(), accB.data(),
+                                       (DflCompactTrees *)nullptr, &t_end);
+        if (b > 0) {
+            DflRec rec2{cend.data(), ccode.data(), cap, t_end};
+            if (dfl_parse(dx, fv, cfg, st, lf.data(), 1, df.data(), 1, *tr, dfl_jx0(lx), &rec2) == 0)
+                dfl_parse(dx, fv, cfg, st, lf.data(), 1, df.data(), 1, *tr, 0xffffffffu, &rec2);
+            if (result >= 0 && (int64_t)(st.bits >> 3) != serial_size) result = -2;
+            if (result >= 0 && rec2.n != rec.n) result = -1;
+            for (uint32_t k = 0; k < rec.n && result >= 0; ++k) if (cend[k] != rend[k] || ccode[k] != rcode[k]) result = -1;
+            info[0] = 1;
+        }
+    }
+    delete tr;
+    free(px);
+    return result;
+}
+
 extern "C" int64_t emu_deflate_size(const uint8_t *x, uint32_t lx, const uint8_t *y, int64_t ly_, int level)
 {
     return emu_deflate_size_ex(x, lx, y, ly_, level, 1, nullptr);

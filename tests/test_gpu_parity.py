@@ -520,6 +520,38 @@ def test_deflate_prefix_records_exchange(engine, algo):
     engine.set_option("invalidate_caches", 1)
 
 
+@pytest.mark.parametrize("algo", ["gzip", "zlib"])
+def test_deflate_sequence_alone_in_parallel_chunks(engine, algo):
+    """the sequence-alone products (size, checkpoint, canonical stream) from the chunked path (dfl_chunk_*_kernel +
+    dfl_alone_kernel) and from the serial kernel are the same bytes: sizes == zlib, prefix records identical, and pair
+    streams built on either equal zlib's; periodic inputs that the chunked path gives up still come out right"""
+    from snacc_b200 import synth
+    g = synth.phylogeny(5, 700_000, seed=12) + [synth_vector("dna", 140_000, 3), synth_vector("dna", 90_000, 4),
+                                                np.tile(synth_vector("dna", 517, 5), 600), synth_vector("run", 300_000, 6)]
+    n = len(g)
+    engine.upload_sequences(g)
+    allseq = np.arange(n, dtype=np.int32)
+    ref_c = np.array([_ref_len(s, algo) for s in g])
+    out = {}
+    try:
+        for mode in (1, 0):
+            engine.set_option("invalidate_caches", 1)
+            engine.set_option("deflate_parallel_prep", mode)
+            C = engine.single_sizes(algo)
+            assert np.array_equal(C, ref_c), (mode, np.flatnonzero(C != ref_c).tolist())
+            stood = engine.stat("deflate_parallel_prep_seqs")
+            assert (stood >= 6) if mode else (stood == 0), (mode, stood)
+            xs, ys = np.repeat(allseq, 3), np.tile(np.array([0, 5, 7], dtype=np.int32), n)
+            out[mode] = (engine.export_prefix(algo, allseq).copy(), engine.pair_sizes(algo, xs, ys))
+    finally:
+        engine.set_option("deflate_parallel_prep", 1)
+        engine.set_option("invalidate_caches", 1)
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1])
+    ref = np.array([_ref_len(np.concatenate([g[a], g[b]]), algo) for a, b in zip(xs, ys)])
+    assert np.array_equal(out[1][1], ref)
+
+
 def _sprinkle(seq, rate, seed, alt=b"NNNNRYKMSWacgtn", runs=3):
     """what real assemblies contain: a fraction `rate` of the bases replaced by N / IUPAC / lower-case bytes, a few N runs"""
     rng = np.random.default_rng(seed)

@@ -39,6 +39,8 @@ def emu():
     e.emu_deflate_size_ex.restype = ctypes.c_int64
     e.emu_deflate_size_ex.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_void_p]
+    e.emu_deflate_chunked.restype = ctypes.c_int64
+    e.emu_deflate_chunked.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int, ctypes.c_void_p]
     return e
 
 
@@ -374,3 +376,26 @@ def test_deflate_shortcuts_on_repetitive_inputs(emu):
             if r != ref or mism:
                 bad.append((x.size, y.size, level, ref, r, mism))
     assert not bad, bad
+
+
+@pytest.mark.parametrize("level", [9, 6])
+def test_deflate_sequence_alone_in_parallel_chunks(emu, level):
+    """dfl_chunk_*_kernel + dfl_alone_kernel emulated: chunks of 8 KiB parsed independently from a 'just emitted a match'
+    state fall in with the true parse inside the overlap; the stitched symbol stream equals the serial parse's symbol
+    for symbol and the size (blocks from the cumulative rows + serial tail) equals zlib's.  Inputs where neighbouring
+    chunks never meet (periodic runs) are given up -- never a wrong stream."""
+    from snacc_b200 import synth
+    g = synth.phylogeny(2, 300000, seed=31)
+    cases = [("genome", g[0], True), ("genome", g[1], True), ("random", _dna(140000, 3), True),
+             ("lower", _four_symbol_vector("lower", 200000, 5), True), ("skew", _four_symbol_vector("skew", 160000, 6), None),
+             ("repeat", _four_symbol_vector("repeat", 180000, 7), None), ("run", _four_symbol_vector("run", 150000, 8), None),
+             ("period", _four_symbol_vector("period", 150000, 9), None),
+             ("bytes", np.frombuffer(np.random.default_rng(4).bytes(150000), dtype=np.uint8).copy(), None)]
+    info = (ctypes.c_int32 * 2)()
+    for name, x, must_stand in cases:
+        got = emu.emu_deflate_chunked(x.ctypes.data, len(x), level, info)
+        assert got == lib.ref_deflate_size(x, level), (name, len(x), got, list(info))
+        if must_stand:
+            assert info[0] == 1, (name, list(info))
+    short = _dna(1000, 1)
+    assert emu.emu_deflate_chunked(short.ctypes.data, len(short), level, info) == -3
