@@ -314,9 +314,9 @@ def run_workload(args, cfg_name, n, L, seed, legs, env, want_host_stages):
     # page-locked result buffers, reused by every step (pinning 800 MB per step would cost more than the c3 kernels)
     bounds = sharding.band_bounds(lengths, world)
     my_w = int(bounds[rank + 1] - bounds[rank])
-    S_band = torch.empty((n, my_w), dtype=torch.int64, pin_memory=True).numpy() if not args.fast_mode else None
+    S_band = sharding.pinned_array((n, my_w), np.int64) if not args.fast_mode else None
     D_buf = torch.empty((n, n), dtype=torch.float64, pin_memory=True).numpy()
-    S_full = torch.empty((n, n), dtype=torch.int64, pin_memory=True).numpy() if world > 1 and not args.fast_mode else None
+    S_full = sharding.pinned_array((n, n), np.int64) if world > 1 and not args.fast_mode else None
 
     def run_step(cdc, e2e):
         """one full pass through the product path: [e2e: corpus from pinned host memory,] C(i) for every sequence, S for

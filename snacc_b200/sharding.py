@@ -17,6 +17,8 @@ call.  With ``torch.distributed`` uninitialised this is the single-GPU path.
 """
 import os
 
+import weakref
+
 import numpy as np
 
 from . import fasta
@@ -232,7 +234,7 @@ def gather_cols(S_cols, bounds, n, dist, device=None, out=None):
         world = dist.get_world_size()
         widths = [int(bounds[r + 1]) - int(bounds[r]) for r in range(world)]
         wmax = max(max(widths), 1)
-        local = torch.from_numpy(np.ascontiguousarray(S_cols, dtype=np.int64).reshape(n, -1))
+        local = _tensor_of(np.ascontiguousarray(S_cols, dtype=np.int64).reshape(n, -1))
         pad = torch.zeros((n, wmax), dtype=torch.int64, device=device)
         if local.shape[1]:
             pad[:, :local.shape[1]].copy_(local, non_blocking=True)
@@ -241,7 +243,7 @@ def gather_cols(S_cols, bounds, n, dist, device=None, out=None):
             dist.all_gather_into_tensor(out, pad)
         S_dev = torch.cat([out[r, :, :widths[r]] for r in range(world) if widths[r]], dim=1)
         S = out if out is not None and out.shape == (n, n) and out.dtype == np.int64 else _result_buffer(n, n)
-        torch.from_numpy(S).copy_(S_dev)
+        _tensor_of(S).copy_(S_dev)
         return S
     parts = _all_gather_padded(np.ascontiguousarray(S_cols.T), dist, device)     # transposed: a band is contiguous
     S = np.zeros((n, n), dtype=np.int64)
@@ -252,13 +254,34 @@ def gather_cols(S_cols, bounds, n, dist, device=None, out=None):
     return S
 
 
+_PINNED = weakref.WeakValueDictionary()        # data pointer of a page-locked numpy array -> the torch tensor that owns it
+
+
+def pinned_array(shape, dtype=np.int64):
+    """page-locked host array (numpy view of a pinned torch tensor); torch copies to / from it go by DMA because the
+    tensor is remembered (``torch.from_numpy`` alone would treat the memory as pageable and stage the copy)"""
+    import torch
+    t = torch.empty(tuple(shape), dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+    a = t.numpy()
+    _PINNED[a.ctypes.data] = t
+    return a
+
+
+def _tensor_of(a):
+    import torch
+    t = _PINNED.get(a.ctypes.data)
+    if t is not None and tuple(t.shape) == tuple(a.shape) and t.numpy().dtype == a.dtype:
+        return t
+    return torch.from_numpy(a)
+
+
 def _result_buffer(rows, cols):
     """int64 (rows, cols) host array the library copies sizes into: page-locked when torch + CUDA are there (the c3 matrix
     is 800 MB; a pageable destination halves the copy rate)"""
     try:
         import torch
         if torch.cuda.is_available() and rows * cols >= (1 << 20):
-            return torch.empty((rows, cols), dtype=torch.int64, pin_memory=True).numpy()
+            return pinned_array((rows, cols), np.int64)
     except Exception:
         pass
     return np.zeros((rows, cols), dtype=np.int64)
