@@ -1153,6 +1153,7 @@ extern "C" int snacc_set_option(snacc_ctx *ctx, const char *name, int64_t value)
     if (!strcmp(name, "deflate_canonical")) { ctx->dfl.use_canon = value ? 1 : 0; return SNACC_OK; }
     if (!strcmp(name, "deflate_index6")) { ctx->dfl.use_index6 = value ? 1 : 0; return SNACC_OK; }
     if (!strcmp(name, "deflate_parallel_prep")) { ctx->dfl.use_parallel_prep = value ? 1 : 0; return SNACC_OK; }
+    if (!strcmp(name, "deflate_tail_index")) { ctx->dfl.use_tail_index = value ? 1 : 0; return SNACC_OK; }
     if (!strcmp(name, "deflate_junction")) { ctx->dfl.junction_impl = value == 2 ? 2 : 3; return SNACC_OK; }
     if (!strcmp(name, "invalidate_caches")) {
         // forget every per-sequence precomputation (prefix checkpoints ...) so the next sizes call

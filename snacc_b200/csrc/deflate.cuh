@@ -1338,7 +1338,11 @@ struct DflCorpus {
     // transient 6-byte index of whole sequences (DflIndex6): order6 is a window buffer addressed like `order`
     uint32_t *order6;
     uint32_t *bstart6;           // per sequence DFL_HASH + 1 entries
+    // first position of the 3-byte index: 0, or len - DFL_XTAIL for a sequence that is only ever the x of pair streams
+    // here (its record came from another rank): the junction walks reach at most 264 + 32 768 positions back from its end
+    const uint32_t *ifrom;
 };
+constexpr uint32_t DFL_XTAIL = 40960;
 
 SNACC_HD Stream dfl_make_stream(const DflCorpus &c, int32_t x, int32_t y)
 {
@@ -1370,6 +1374,13 @@ __device__ __forceinline__ DflStream dfl_make(const DflCorpus &c, int32_t x, int
 // across tiles from the scanned per-tile digit totals (dfl_radix_scan_kernel).
 constexpr uint32_t DFL_RX_TILE = 8192, DFL_RX_THREADS = 1024, DFL_RX_ROUNDS = DFL_RX_TILE / DFL_RX_THREADS;
 template <int KIND> SNACC_HD uint32_t dfl_index_count(uint32_t len) { return KIND == 0 ? (len >= 3 ? len - 2 : 0) : (len >= 6 ? len - 5 : 0); }
+// first indexed position / number of index entries of sequence sq (the 6-byte index is always whole)
+template <int KIND> __device__ __forceinline__ uint32_t dfl_index_first(const DflCorpus &c, int32_t sq) { return KIND == 0 ? c.ifrom[sq] : 0u; }
+template <int KIND> __device__ __forceinline__ uint32_t dfl_index_n(const DflCorpus &c, int32_t sq)
+{
+    const uint32_t n = dfl_index_count<KIND>(c.len[sq]), f = dfl_index_first<KIND>(c, sq);
+    return n > f ? n - f : 0u;
+}
 template <int KIND> __device__ __forceinline__ uint32_t dfl_index_hash(const uint8_t *p, uint32_t i)
 {
     return KIND == 0 ? dfl_hash3(p[i], p[i + 1], p[i + 2]) : dfl_hash6w(ldu64(p + i));
@@ -1386,7 +1397,7 @@ dfl_radix_kernel(DflCorpus c, const int32_t *__restrict__ seqs, uint32_t max_til
     __shared__ uint16_t wcnt[32][256];
     __shared__ uint32_t toff[256];
     const int32_t slot = blockIdx.y, sq = seqs[slot];
-    const uint32_t n = dfl_index_count<KIND>(c.len[sq]);
+    const uint32_t n = dfl_index_n<KIND>(c, sq), first = dfl_index_first<KIND>(c, sq);
     const uint32_t tile = blockIdx.x;
     if (tile * DFL_RX_TILE >= n) return;
     const uint8_t *p = c.corpus + c.off[sq];
@@ -1400,7 +1411,7 @@ dfl_radix_kernel(DflCorpus c, const int32_t *__restrict__ seqs, uint32_t max_til
     for (uint32_t r = 0; r < DFL_RX_ROUNDS; ++r) {
         const uint32_t idx = tile * DFL_RX_TILE + w * (32 * DFL_RX_ROUNDS) + r * 32 + lane;
         const bool ok = idx < n;
-        pos[r] = ok ? (PASS == 0 ? idx : src[idx]) : 0;
+        pos[r] = ok ? (PASS == 0 ? first + idx : src[idx]) : 0;
         const uint32_t h = ok ? dfl_index_hash<KIND>(p, pos[r]) : 0;
         dg[r] = ok ? (PASS == 0 ? (h & 255u) : (h >> 8)) : 0x10000u + lane;
         const uint32_t peers = __match_any_sync(0xffffffffu, dg[r]);
@@ -1452,7 +1463,7 @@ __global__ void __launch_bounds__(256)
 dfl_index_bounds_kernel(DflCorpus c, const int32_t *__restrict__ seqs)
 {
     const int32_t sq = seqs[blockIdx.y];
-    const uint32_t n = dfl_index_count<KIND>(c.len[sq]);
+    const uint32_t n = dfl_index_n<KIND>(c, sq);
     const uint8_t *p = c.corpus + c.off[sq];
     const uint32_t *order = (KIND == 0 ? c.order : c.order6) + c.poff[sq];
     uint32_t *bstart = (KIND == 0 ? c.bstart : c.bstart6) + (size_t)sq * (DFL_HASH + 1);
@@ -1468,7 +1479,7 @@ dfl_index_fill_kernel(DflCorpus c, const int32_t *__restrict__ seqs, int phase)
     // phase 0: all starts unmarked; phase 1 (after dfl_index_bounds_kernel): suffix minimum
     __shared__ uint32_t part[1024];
     const int32_t sq = seqs[blockIdx.x];
-    const uint32_t n = dfl_index_count<KIND>(c.len[sq]);
+    const uint32_t n = dfl_index_n<KIND>(c, sq);
     uint32_t *bstart = (KIND == 0 ? c.bstart : c.bstart6) + (size_t)sq * (DFL_HASH + 1);
     const uint32_t per = DFL_HASH / 1024;
     if (phase == 0) {
@@ -1540,6 +1551,7 @@ dfl_head_kernel(DflCorpus c, const int32_t *__restrict__ seqs, int32_t n_seqs)
             hcnt[h] = lo < hi ? dfl_lower_bound(order, lo, hi, DFL_JY) - lo : 0;
             tc[h] = (uint16_t)(lo < hi ? hi - dfl_lower_bound(order, lo, hi, tail_from) : 0);
         }
+        if (c.ifrom[sq]) continue;                           // tail-only index (x role): no head order
         __syncthreads();
         // exclusive scan over DFL_HASH counters: 32 per thread
         const uint32_t per = DFL_HASH / 1024;
@@ -2007,10 +2019,12 @@ struct DeflateState {
     uint32_t *d_order = nullptr, *d_bstart = nullptr;
     uint16_t *d_head_order = nullptr, *d_head_visit[2] = {nullptr, nullptr};
     uint16_t *d_tail_cnt = nullptr, *d_tail6_order = nullptr, *d_tail6_start = nullptr;
+    uint32_t *d_ifrom = nullptr; std::vector<uint32_t> h_ifrom;     // first position of every 3-byte index (DflCorpus::ifrom)
     uint32_t *d_rx_hist = nullptr; size_t rx_cap = 0;   // radix-sort digit totals (dfl_build_index)
     uint32_t *d_bstart6 = nullptr, *d_order6 = nullptr; uint64_t order6_cap = 0;   // 6-byte index: starts per sequence, window buffer
     int use_index6 = 1;                            // 0: dfl_match_kernel always walks the 3-byte chain (tests)
     int use_parallel_prep = 1;                     // 0: every sequence alone is parsed by the serial kernel (tests, A/B)
+    int use_tail_index = 1;                        // 0: x-role sequences get the whole 3-byte index too (tests, A/B)
     int64_t parallel_prep_seqs = 0;                // sequences the chunked path finished in the last call
     std::vector<uint8_t> indexed;                  // per sequence
     uint32_t *d_F[2] = {nullptr, nullptr};         // level 9, level 6
@@ -2045,8 +2059,8 @@ static inline void deflate_free_corpus(DeflateState &st)
     cudaFree(st.d_FQ); st.d_FQ = nullptr;
     cudaFree(st.d_soff); cudaFree(st.d_roff); cudaFree(st.d_cap);
     cudaFree(st.d_head_order); st.d_head_order = nullptr;
-    cudaFree(st.d_tail_cnt); cudaFree(st.d_tail6_order); cudaFree(st.d_tail6_start);
-    st.d_tail_cnt = st.d_tail6_order = st.d_tail6_start = nullptr;
+    cudaFree(st.d_tail_cnt); cudaFree(st.d_tail6_order); cudaFree(st.d_tail6_start); cudaFree(st.d_ifrom);
+    st.d_tail_cnt = st.d_tail6_order = st.d_tail6_start = nullptr; st.d_ifrom = nullptr; st.h_ifrom.clear();
     cudaFree(st.d_bstart6); cudaFree(st.d_order6); st.d_bstart6 = st.d_order6 = nullptr; st.order6_cap = 0;
     cudaFree(st.d_rx_hist); st.d_rx_hist = nullptr; st.rx_cap = 0;
     for (int l = 0; l < 2; ++l) { cudaFree(st.d_head_visit[l]); st.d_head_visit[l] = nullptr; }
@@ -2113,7 +2127,10 @@ static int dfl_build_index(DeflateState &st, const DflCorpus &c, const std::vect
 {
     if (list.empty()) return 0;
     uint32_t mx = 0;
-    for (int32_t i : list) mx = std::max(mx, dfl_index_count<KIND>(h_len[i]));
+    for (int32_t i : list) {
+        const uint32_t cnt = dfl_index_count<KIND>(h_len[i]), first = KIND == 0 ? st.h_ifrom[i] : 0u;
+        mx = std::max(mx, cnt > first ? cnt - first : 0u);
+    }
     const uint32_t max_tiles = std::max(1u, dfl_rx_tiles(mx));
     const size_t need = list.size() * 256 * (size_t)max_tiles;
     if (st.rx_cap < need) {
@@ -2181,6 +2198,9 @@ static int deflate_ensure_alloc(DeflateState &st, const DeflateCorpus &dc, int l
         DCK(cudaMalloc(&st.d_bstart6, sizeof(uint32_t) * (size_t)ns * (DFL_HASH + 1)));
         DCK(cudaMalloc(&st.d_tail6_order, sizeof(uint16_t) * (size_t)ns * DFL_T6));
         DCK(cudaMalloc(&st.d_tail6_start, sizeof(uint16_t) * (size_t)ns * (DFL_H6 + 1)));
+        DCK(cudaMalloc(&st.d_ifrom, sizeof(uint32_t) * (size_t)ns));
+        DCK(cudaMemsetAsync(st.d_ifrom, 0, sizeof(uint32_t) * (size_t)ns, stream));
+        st.h_ifrom.assign(ns, 0);
         st.indexed.assign(ns, 0);
         for (int l = 0; l < 2; ++l) { st.have_F[l].assign(ns, 0); st.have_prep[l].assign(ns, 0); st.have_ckpt[l].assign(ns, 0); }
     }
@@ -2245,7 +2265,7 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
     if (deflate_ensure_alloc(st, dc, level, stream, err)) return -1;
     uint32_t *FQ = level != 9 ? st.d_FQ : nullptr;
     DflCorpus c{dc.d_corpus, dc.d_off, dc.d_len, st.d_poff, st.d_order, st.d_bstart, st.d_head_order, st.d_head_visit[li],
-                st.d_tail_cnt, st.d_tail6_order, st.d_tail6_start, nullptr, st.d_bstart6};
+                st.d_tail_cnt, st.d_tail6_order, st.d_tail6_start, nullptr, st.d_bstart6, st.d_ifrom};
     DflCanonPool cp{st.d_sym_end[li], st.d_sym_code[li], st.d_cum[li], st.d_soff, st.d_cap, st.d_roff, st.d_nsym[li],
                     st.d_seq_size[li]};
 
@@ -2261,9 +2281,16 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
         for (int32_t i = 0; i < ns; ++i) {
             if (!used[i]) continue;
             const bool full = (used[i] & 2) || !st.have_ckpt[li][i];
-            if (ys && !st.indexed[i]) { need_idx.push_back(i); st.indexed[i] = 1; st.have_F[0][i] = st.have_F[1][i] = 0; }
-            if (!full) continue;
-            if (!st.indexed[i]) { need_idx.push_back(i); st.indexed[i] = 1; st.have_F[0][i] = st.have_F[1][i] = 0; }
+            // indexed: 0 none, 1 the last DFL_XTAIL positions only (enough for the x of a pair stream), 2 whole sequence
+            if (!full) {
+                if (ys && !st.indexed[i]) {
+                    need_idx.push_back(i); st.indexed[i] = 1; st.have_F[0][i] = st.have_F[1][i] = 0;
+                    st.h_ifrom[i] = st.use_tail_index && dc.h_len[i] > DFL_XTAIL ? dc.h_len[i] - DFL_XTAIL : 0;
+                    if (!st.h_ifrom[i]) st.indexed[i] = 2;
+                }
+                continue;
+            }
+            if (st.indexed[i] < 2) { need_idx.push_back(i); st.indexed[i] = 2; st.h_ifrom[i] = 0; st.have_F[0][i] = st.have_F[1][i] = 0; }
             if (!st.have_F[li][i]) { need_f.push_back(i); st.have_F[li][i] = 1; st.have_prep[li][i] = 0; }
             if (!st.have_prep[li][i]) { need_prep.push_back(i); st.have_prep[li][i] = 1; st.have_ckpt[li][i] = 1; }
         }
@@ -2274,6 +2301,7 @@ static int deflate_run(DeflateState &st, const DeflateCorpus &dc, int level, con
         NvtxRange nvtx_("snacc_b200: deflate index (radix sort, head/tail packs)");
         int32_t *d_list = nullptr;
         if (dfl_upload(err, stream, need_idx, &d_list)) return -1;
+        DCK(cudaMemcpyAsync(st.d_ifrom, st.h_ifrom.data(), sizeof(uint32_t) * st.h_ifrom.size(), cudaMemcpyHostToDevice, stream));
         // the F slices of this level double as sort scratch; they are recomputed right below
         for (size_t a0 = 0; a0 < need_idx.size(); a0 += 64) {
             std::vector<int32_t> part(need_idx.begin() + a0, need_idx.begin() + std::min(need_idx.size(), a0 + 64));

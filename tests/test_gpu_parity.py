@@ -517,6 +517,22 @@ def test_deflate_prefix_records_exchange(engine, algo):
     S = engine.pair_sizes(algo, xs, ys)
     ref = np.array([_ref_len(np.concatenate([g[a], g[b]]), algo) for a, b in zip(xs, ys)])
     assert np.array_equal(S, ref)
+    # the same with the whole 3-byte index for the x-only sequences (default: their last 40 KiB only), and then a
+    # sequence that was x-only becomes a y (its index is rebuilt whole)
+    try:
+        engine.set_option("invalidate_caches", 1)
+        engine.set_option("deflate_tail_index", 0)
+        engine.import_prefix(algo, theirs, recs)
+        assert np.array_equal(engine.pair_sizes(algo, xs, ys), ref)
+    finally:
+        engine.set_option("deflate_tail_index", 1)
+    engine.set_option("invalidate_caches", 1)
+    engine.import_prefix(algo, theirs, recs)
+    assert np.array_equal(engine.pair_sizes(algo, xs, ys), ref)
+    xs2, ys2 = np.arange(n), np.full(n, 0)                        # sequence 0 (x-only so far) as y
+    ref2 = np.array([_ref_len(np.concatenate([g[a], g[0]]), algo) for a in xs2])
+    assert np.array_equal(engine.pair_sizes(algo, xs2, ys2), ref2)
+    assert np.array_equal(engine.pair_sizes(algo, xs, ys), ref)
     engine.set_option("invalidate_caches", 1)
 
 
