@@ -127,14 +127,17 @@ int snacc_upgma(snacc_ctx *ctx, const double *D, int32_t n, int metrify, double 
 int snacc_last_kernel_ms(const snacc_ctx *ctx, double *ms, int64_t *launches);
 /* named statistics of the last sizes call: "main_kernel_ms" (dominant kernel only), "total_kernel_ms",
  * "launches", "packed_jobs", "bytewise_jobs", "deflate_serial_jobs" (pair streams of a deflate call that took
- * the full serial parse after their canonical-stream shortcut met a block that might be stored) */
+ * the full serial parse after their canonical-stream shortcut met a block that might be stored),
+ * "deflate_parallel_prep_seqs" (sequences whose parse alone was done in parallel chunks), "lz4_segments"
+ * (segments per tile of the last linked-regime LZ4 pair launch) */
 int snacc_get_stat(const snacc_ctx *ctx, const char *name, double *out);
 /* tunables: 0 = default.  `streams_in_flight` bounds the number of concurrently parsed streams;
  * `invalidate_caches` (any value) drops every per-sequence precomputation so the next call redoes it;
  * `lz4_packed` 0 forces the byte-wise LZ4 kernels; `deflate_canonical` 0 makes every deflate pair stream take
  * the full serial parse instead of the canonical symbol stream of y; `deflate_junction` 2 computes every junction
  * table without the 6-byte-index shortcut, `deflate_index6` 0 every match table from the 3-byte chain walk
- * (all four are for tests: same results). */
+ * `deflate_parallel_prep` 0 parses every sequence alone serially, `deflate_tail_index` 0 builds the whole 3-byte
+ * index for x-only sequences, `lz4_segments` k forces k segments per LZ4 tile (all for tests: same results). */
 int snacc_set_option(snacc_ctx *ctx, const char *name, int64_t value);
 
 #ifdef __cplusplus
