@@ -702,7 +702,7 @@ static int pk_choose_segments(const snacc_ctx *ctx, const PkGeometry &g, const s
     double best_t = std::ceil(nt / sms);
     for (int k : {2, 4, 8}) {
         if ((uint32_t)(2 * k) > min_runs) break;
-        const double t = std::ceil(nt * k / sms) / k;
+        const double t = std::max(1.0, std::ceil(nt * k / sms) / k);      // (the segments of one tile run one after the other)
         if (t < best_t * 0.985) { best = k; best_t = t; }
     }
     return best;
