@@ -78,8 +78,43 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.lines, self.proc, self.index = [], None, index
+        self.nvml = None
+
+    def _nvml_loop(self):
+        # the same counters nvidia-smi prints, read through NVML in this process every 200 ms
+        import pynvml as nv
+        h = self.nvml
+        names = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)]
+        while not self.quit.wait(0.2 if self.lines else 0.0):
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.lines.append(",".join([str(sm), str(mx), f"{pw:.1f}"] + ["Active" if rs & bit else "Not Active" for _, bit in names]))
+            except Exception:
+                break
 
     def start(self):
+        # NVML in-process when the bindings are there (no second process attaching to the driver during the timed region);
+        # nvidia-smi otherwise, or when SNACC_BENCH_NVIDIA_SMI is set
+        if not os.environ.get("SNACC_BENCH_NVIDIA_SMI"):
+            try:
+                import pynvml as nv
+                nv.nvmlInit()
+                self.nvml = nv.nvmlDeviceGetHandleByIndex(self.index)
+                self.quit = threading.Event()
+                self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+                self.thread.start()
+                self.source = "NVML (pynvml), 200 ms"
+                return
+            except Exception:
+                self.nvml = None
+        self.source = "nvidia-smi -lms 200"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "200"],
@@ -94,13 +129,17 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
-        if not self.proc:
+        if self.nvml is not None:
+            self.quit.set()
+            self.thread.join(timeout=2)
+        elif not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
@@ -116,7 +155,7 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": getattr(self, "source", "nvidia-smi")}
 
 
 def host_cores():
@@ -335,10 +374,17 @@ def run_workload(args, cfg_name, n, L, seed, legs, env, want_host_stages):
             eng.set_option("invalidate_caches", 1)       # nothing (prefix checkpoints ...) survives from the last step
         st = {}
         band = args.band or (1024 if cfg_name == "c3" else None)
+        t0 = time.perf_counter()
         C, S = sharding.sizes_matrix(eng, cdc, args.fast_mode, band, st, band_out=S_band, full_out=S_full)
+        t1 = time.perf_counter()
         D = eng.ncd(C, S, formula=1 if args.fast_mode else 0, out=D_buf)   # K4: float64 epilogue kernel, result read back
+        t2 = time.perf_counter()
         st["launches"] = st.get("launches", 0) + 1
         st["check"] = int(S[::7, ::5].sum() + C.sum()) ^ int(np.float64(D[::7, ::5].sum()).view(np.int64) & 0xffff)
+        if os.environ.get("SNACC_BENCH_TRACE"):
+            print(f"[trace rank {rank}] {cfg_name} {cdc} e2e={int(e2e)}: sizes_matrix {1e3 * (t1 - t0):.0f} ms (kernels "
+                  f"{st.get('kernel_ms', 0):.0f}, gather {1e3 * st.get('gather_s', 0):.0f}), ncd {1e3 * (t2 - t1):.0f} ms, "
+                  f"checksum {1e3 * (time.perf_counter() - t2):.0f} ms", file=sys.stderr, flush=True)
         st["h2d"] = h2d
         st["C"], st["S"] = C, S
         return st

@@ -16,6 +16,7 @@ to the ranks longest-processing-time first by their byte count and each rank run
 call.  With ``torch.distributed`` uninitialised this is the single-GPU path.
 """
 import os
+import time
 
 import weakref
 
@@ -235,13 +236,20 @@ def gather_cols(S_cols, bounds, n, dist, device=None, out=None):
         widths = [int(bounds[r + 1]) - int(bounds[r]) for r in range(world)]
         wmax = max(max(widths), 1)
         local = _tensor_of(np.ascontiguousarray(S_cols, dtype=np.int64).reshape(n, -1))
-        pad = torch.zeros((n, wmax), dtype=torch.int64, device=device)
+        # the device buffers are kept between calls (one shape at a time): a job that is repeated -- bench.py -- must not
+        # depend on what the caching allocator can reuse
+        key = (str(device), world, n, wmax)
+        if _GATHER_BUF.get("key") != key:
+            _GATHER_BUF.clear()
+            _GATHER_BUF.update(key=key, pad=torch.zeros((n, wmax), dtype=torch.int64, device=device),
+                               out=torch.empty((world, n, wmax), dtype=torch.int64, device=device),
+                               S=torch.empty((n, n), dtype=torch.int64, device=device))
+        pad, gathered, S_dev = _GATHER_BUF["pad"], _GATHER_BUF["out"], _GATHER_BUF["S"]
         if local.shape[1]:
             pad[:, :local.shape[1]].copy_(local, non_blocking=True)
-        out = torch.empty((world, n, wmax), dtype=torch.int64, device=device)
         with _nvtx("snacc_b200: result all-gather"):
-            dist.all_gather_into_tensor(out, pad)
-        S_dev = torch.cat([out[r, :, :widths[r]] for r in range(world) if widths[r]], dim=1)
+            dist.all_gather_into_tensor(gathered, pad)
+        torch.cat([gathered[r, :, :widths[r]] for r in range(world) if widths[r]], dim=1, out=S_dev)
         S = out if out is not None and out.shape == (n, n) and out.dtype == np.int64 else _result_buffer(n, n)
         _tensor_of(S).copy_(S_dev)
         return S
@@ -254,6 +262,7 @@ def gather_cols(S_cols, bounds, n, dist, device=None, out=None):
     return S
 
 
+_GATHER_BUF = {}                               # gather_cols: device buffers of the last shape
 _PINNED = weakref.WeakValueDictionary()        # data pointer of a page-locked numpy array -> the torch tensor that owns it
 
 
@@ -360,7 +369,10 @@ def sizes_matrix(engine, algorithm, fast_mode=False, rows_per_call=None, stats=N
         if stats is not None:
             stats["jobs"] = n * (b - a)
             stats["bytes"] = float(n * lengths[a:b].sum() + (b - a) * lengths.sum())
+        t_g = time.perf_counter()
         S = gather_cols(S_cols, bounds, n, dist, dev, out=full_out) if dist else S_cols
+        if stats is not None:
+            stats["gather_s"] = time.perf_counter() - t_g
     else:
         xs, ys = triangle_jobs(shares[rank])
         vals = np.zeros(xs.size, dtype=np.int64)
