@@ -399,3 +399,22 @@ def test_deflate_sequence_alone_in_parallel_chunks(emu, level):
             assert info[0] == 1, (name, list(info))
     short = _dna(1000, 1)
     assert emu.emu_deflate_chunked(short.ctypes.data, len(short), level, info) == -3
+
+
+@pytest.mark.parametrize("level", [9, 6])
+def test_deflate_parallel_chunks_length_boundaries(emu, level):
+    """the chunk grid at its edges: the shortest sequence the path takes (16 chunks), lengths where n - 1 KiB falls on, just
+    before and just after a chunk boundary (the last chunk is then one to two chunks long), and a repeat that straddles a
+    chunk start (a match that begins in one chunk and ends in the next)"""
+    info = (ctypes.c_int32 * 2)()
+    base = _dna(160000, 77)
+    for n in [131072, 131073, 16 * 8192 + 1024 - 1, 16 * 8192 + 1024, 16 * 8192 + 1024 + 1, 17 * 8192 + 1023, 18 * 8192 + 1025]:
+        x = base[:n].copy()
+        got = emu.emu_deflate_chunked(x.ctypes.data, len(x), level, info)
+        assert got == lib.ref_deflate_size(x, level), (n, got, list(info))
+        assert info[0] == 1 and info[1] == (n - 1024) // 8192, (n, list(info))
+    x = base[:150000].copy()
+    for s in (8192 * 3, 8192 * 7, 8192 * 11):                 # 300-byte copies of earlier text across three chunk starts
+        x[s - 150:s + 150] = x[s - 5150:s - 4850]
+    got = emu.emu_deflate_chunked(x.ctypes.data, len(x), level, info)
+    assert got == lib.ref_deflate_size(x, level) and info[0] == 1, (got, list(info))
