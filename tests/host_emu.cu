@@ -313,15 +313,28 @@ static void emu_run_x(PkState &st, PkTab<KIND, 1> &tab, PkView &v, const PkExact
 {
     PkRing rg; uint32_t w0, w1;
     rg.start(y.len, w0, w1, PK_RING_COVER_EXC); ring_fill_x(ring, rg, y, w0, w1);
-    for (;;) {
-        rg.view(v);
-        v.dring = reinterpret_cast<const uint32_t *>(ring.data() + rg.dring_word());
-        const uint32_t sq = rg.stop_q();
-        const uint32_t stop = tmin(limit, sq == 0xffffffffu ? sq : v.lx + sq);
-        pk_run_exc<KIND, 1>(st, tab, v, xv, n, stop, rg.hi_w * 32, 1u);
-        if (st.phase == PK_DONE || rg.complete() || pk_next_pos(st) >= limit) return;
-        rg.advance(w0, w1);
-        ring_fill_x(ring, rg, y, w0, w1);
+    // tile segments (emu_set_segments; pair streams only): at a cut the ring is thrown away and rebuilt by
+    // PkRing::restart, as when another CTA draws the next segment (table, state and overflow table stay where they are)
+    const uint32_t runs = rg.runs(), k = (KIND == 2 && limit == 0xffffffffu && emu_segments > 1 && runs >= (uint32_t)emu_segments) ? emu_segments : 1;
+    uint32_t r = 0;
+    for (uint32_t seg = 0; seg < k; ++seg) {
+        const uint32_t r1 = (uint32_t)((uint64_t)runs * (seg + 1) / k);
+        if (seg > 0) {
+            std::fill(ring.begin(), ring.end(), 0x5a5a5a5a5a5a5a5aull);
+            rg.restart(y.len, r, w0, w1, PK_RING_COVER_EXC);
+            ring_fill_x(ring, rg, y, w0, w1);
+        }
+        for (;;) {
+            rg.view(v);
+            v.dring = reinterpret_cast<const uint32_t *>(ring.data() + rg.dring_word());
+            const uint32_t sq = rg.stop_q();
+            const uint32_t stop = tmin(limit, sq == 0xffffffffu ? sq : v.lx + sq);
+            pk_run_exc<KIND, 1>(st, tab, v, xv, n, stop, rg.hi_w * 32, 1u);
+            if (k == 1 && (st.phase == PK_DONE || rg.complete() || pk_next_pos(st) >= limit)) return;
+            if (++r >= r1) break;
+            rg.advance(w0, w1);
+            ring_fill_x(ring, rg, y, w0, w1);
+        }
     }
 }
 

@@ -253,6 +253,24 @@ def test_lz4_packed_path_with_flagged_bases(emu, rate):
     assert not bad, bad[:10]
 
 
+def test_lz4_tile_segments_with_flagged_bases(emu):
+    """tile segments on the EXC path: the ring AND the dirty ring inside it are rebuilt at a cut (PkRing::restart with the
+    EXC cover), table / state / overflow table carry over"""
+    from snacc_b200 import synth
+    emu.emu_set_segments.argtypes = [ctypes.c_int]
+    g = synth.phylogeny(3, 420000, seed=23)
+    seqs = [_sprinkle(s, r, 50 + i) for i, (s, r) in enumerate(zip(g, [1e-4, 1e-3, 1e-5]))]
+    seqs[0][131070:131075] = ord("N"); seqs[1][-2:] = ord("n")
+    try:
+        for k in (2, 3, 8):
+            emu.emu_set_segments(k)
+            for i, j in [(0, 1), (1, 0), (2, 1), (1, 2)]:
+                x, y = seqs[i][:150000], seqs[j]
+                assert _call2(emu.emu_lz4_packed_exc, x, y) == lib.ref_lz4f_size(np.concatenate([x, y])), (k, i, j)
+    finally:
+        emu.emu_set_segments(1)
+
+
 def test_lz4_packed_refuses_more_than_four_symbols(emu):
     assert _call2(emu.emu_lz4_packed, np.frombuffer(b"ACGTNACGTNACGTNACGT", dtype=np.uint8), None) == -2
 
