@@ -58,6 +58,13 @@ int snacc_version(void);                                  /* 10000*major + 100*m
  * the first max_recs records.  Returns the number of records (>= 0) or a negative snacc_status. */
 int64_t snacc_fasta_parse(const uint8_t *raw, uint64_t n, uint8_t *out, uint64_t *out_len, uint64_t *rec_len,
                           int64_t max_recs);
+/* Host-side helper, no GPU involved (replaces the pandas pivot + to_csv of cli.py:138-142 for matrices too large for a
+ * DataFrame of N^2 Python objects): writes `header_line` and then, for r = 0..n-1, the line
+ * row_labels[order[r]] , D[order[r]][order[0]] , ... , D[order[r]][order[n-1]]  with every double as Python's repr()
+ * prints it (shortest round-trip digits; NaN = empty cell, as to_csv).  Labels arrive already quoted (csv.QUOTE_MINIMAL).
+ * `threads` <= 0: all host threads.  Returns SNACC_OK or SNACC_ERR_ARG (bad argument / I/O error). */
+int snacc_csv_write(const char *path, const char *header_line, const char *const *row_labels, const double *D, int64_t n,
+                    const int32_t *order, int threads);
 const char *snacc_last_error(const snacc_ctx *ctx);       /* NUL-terminated, owned by ctx; "" if none */
 
 /* replaces: ThreadPoolExecutor construction, cli.py:104 */

@@ -12,6 +12,8 @@ import sys
 from datetime import datetime
 from pathlib import Path
 
+import os
+
 import click
 import numpy as np
 
@@ -56,12 +58,37 @@ def write_distance_csv(files, D, output):
         quote.writerow([str(pth)])
         return cell.getvalue()
 
+    labels = [label(f) for f in files]
+    header = ",".join(["file"] + [labels[j] for j in order])
+    if _write_csv_native(output, header, labels, D, order):
+        return
     with open(output, "w", newline="") as f:
-        f.write(",".join(["file"] + [label(files[j]) for j in order]) + "\n")
+        f.write(header + "\n")
         for i in order:
             row = D[i, order]
             vals = [("" if v != v else repr(v)) for v in row.tolist()]                  # NaN -> empty cell, like to_csv
-            f.write(label(files[i]) + "," + ",".join(vals) + "\n")
+            f.write(labels[i] + "," + ",".join(vals) + "\n")
+
+
+def _write_csv_native(output, header, labels, D, order):
+    """snacc_csv_write of libsnacc_b200.so (a host function of the C ABI, all host threads): the same bytes as the loop
+    above, 10^8 cells (c3) in seconds instead of most of a minute.  False when the library is not built -- formatting is
+    host work either way."""
+    import ctypes
+    from .engine import SnaccGpuError, load_library
+    try:
+        lib = load_library()
+        fn = lib.snacc_csv_write
+    except (SnaccGpuError, OSError, AttributeError):
+        return False
+    n = len(labels)
+    Dc = np.ascontiguousarray(D, dtype=np.float64)
+    arr = (ctypes.c_char_p * max(n, 1))(*[s.encode("utf-8") for s in labels])
+    od = np.ascontiguousarray(order, dtype=np.int32)
+    rc = fn(os.fsencode(str(output)), header.encode("utf-8"), arr, Dc.ctypes.data, n, od.ctypes.data, 0)
+    if rc != 0:
+        raise OSError(f"snacc_csv_write failed for {output}")
+    return True
 
 
 def _parse_bool(ctx, param, value):

@@ -7,6 +7,10 @@
 #include <stdlib.h>
 #include <string>
 #include <vector>
+#include <charconv>
+#include <thread>
+#include <cmath>
+#include <cstdio>
 #include <algorithm>
 #include <mutex>
 
@@ -175,6 +179,103 @@ struct FastaScan {
     }
 };
 }  // namespace
+
+// ---- CSV of the distance matrix (host side, no GPU) -----------------------------------------------------------------
+// What DataFrame.pivot(...).to_csv writes for the reference (cli.py:138-142): one row per file, cells = the float64 as
+// Python's repr() prints it -- the shortest digit string that reads back to the same double, fixed notation when the
+// decimal exponent is in (-4, 16], exponent notation (two exponent digits at least) otherwise, ".0" appended to whole
+// numbers, NaN as an empty cell.  std::to_chars produces the shortest digits; the layout rules are applied here.
+namespace {
+static char *csv_put_double(char *o, double v)
+{
+    if (v != v) return o;                                         // NaN: empty cell
+    if (v == HUGE_VAL || v == -HUGE_VAL) { if (v < 0) *o++ = '-'; memcpy(o, "inf", 3); return o + 3; }
+    char buf[40];
+    // scientific, shortest round trip: [-]d[.ddd]e[+-]XX
+    const std::to_chars_result r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::scientific);
+    const char *p = buf, *end = r.ptr;
+    if (*p == '-') { *o++ = '-'; ++p; }
+    const char *e = p;
+    while (e < end && *e != 'e') ++e;
+    char digits[24]; int nd = 0;
+    for (const char *q = p; q < e; ++q) if (*q != '.') digits[nd++] = *q;
+    int ex = 0;
+    {
+        const char *q = e + 1; bool neg = false;
+        if (*q == '-') { neg = true; ++q; } else if (*q == '+') ++q;
+        for (; q < end; ++q) ex = ex * 10 + (*q - '0');
+        if (neg) ex = -ex;
+    }
+    const int decpt = ex + 1;                                     // value = 0.d1d2... x 10^decpt
+    if (decpt > -4 && decpt <= 16) {
+        if (decpt <= 0) {
+            *o++ = '0'; *o++ = '.';
+            for (int k = 0; k < -decpt; ++k) *o++ = '0';
+            memcpy(o, digits, (size_t)nd); o += nd;
+        } else if (decpt >= nd) {
+            memcpy(o, digits, (size_t)nd); o += nd;
+            for (int k = nd; k < decpt; ++k) *o++ = '0';
+            *o++ = '.'; *o++ = '0';
+        } else {
+            memcpy(o, digits, (size_t)decpt); o += decpt;
+            *o++ = '.';
+            memcpy(o, digits + decpt, (size_t)(nd - decpt)); o += nd - decpt;
+        }
+    } else {
+        *o++ = digits[0];
+        if (nd > 1) { *o++ = '.'; memcpy(o, digits + 1, (size_t)(nd - 1)); o += nd - 1; }
+        *o++ = 'e';
+        int x = decpt - 1;
+        if (x < 0) { *o++ = '-'; x = -x; } else *o++ = '+';
+        if (x >= 100) { *o++ = (char)('0' + x / 100); x %= 100; *o++ = (char)('0' + x / 10); *o++ = (char)('0' + x % 10); }
+        else { *o++ = (char)('0' + x / 10); *o++ = (char)('0' + x % 10); }
+    }
+    return o;
+}
+}  // namespace
+
+extern "C" int snacc_csv_write(const char *path, const char *header_line, const char *const *row_labels, const double *D,
+                               int64_t n, const int32_t *order, int threads)
+{
+    if (!path || !header_line || !row_labels || !D || !order || n < 0) return SNACC_ERR_ARG;
+    FILE *f = fopen(path, "wb");
+    if (!f) return SNACC_ERR_ARG;
+    bool ok = fputs(header_line, f) >= 0 && fputc('\n', f) != EOF;
+    // rows are formatted in blocks by a few threads, each into its own buffer, and written in order
+    const int T = (int)std::max<int64_t>(1, std::min<int64_t>(threads > 0 ? threads : (int)std::thread::hardware_concurrency(), 64));
+    const int64_t rows_per_block = std::max<int64_t>(1, std::min<int64_t>(256, (4 << 20) / std::max<int64_t>(1, n)));
+    const int64_t per_round = rows_per_block * T;
+    std::vector<std::vector<char>> bufs((size_t)T);
+    for (int64_t r0 = 0; r0 < n && ok; r0 += per_round) {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < T; ++t) {
+            const int64_t a = r0 + t * rows_per_block, b = std::min<int64_t>(n, a + rows_per_block);
+            bufs[(size_t)t].clear();
+            if (a >= b) continue;
+            pool.emplace_back([&, t, a, b]() {
+                std::vector<char> &buf = bufs[(size_t)t];
+                size_t labels = 0;
+                for (int64_t r = a; r < b; ++r) labels += strlen(row_labels[order[r]]);
+                buf.resize(labels + (size_t)(b - a) * ((size_t)n * 26 + 2));
+                char *o = buf.data();
+                for (int64_t r = a; r < b; ++r) {
+                    const int32_t i = order[r];
+                    const size_t ll = strlen(row_labels[i]);
+                    memcpy(o, row_labels[i], ll); o += ll;
+                    const double *row = D + (size_t)i * (size_t)n;
+                    for (int64_t c = 0; c < n; ++c) { *o++ = ','; o = csv_put_double(o, row[order[c]]); }
+                    *o++ = '\n';
+                }
+                buf.resize((size_t)(o - buf.data()));
+            });
+        }
+        for (std::thread &th : pool) th.join();
+        for (int t = 0; t < T && ok; ++t)
+            if (!bufs[(size_t)t].empty()) ok = fwrite(bufs[(size_t)t].data(), 1, bufs[(size_t)t].size(), f) == bufs[(size_t)t].size();
+    }
+    ok = (fclose(f) == 0) && ok;
+    return ok ? SNACC_OK : SNACC_ERR_ARG;
+}
 
 extern "C" int64_t snacc_fasta_parse(const uint8_t *raw, uint64_t n, uint8_t *out, uint64_t *out_len, uint64_t *rec_len,
                                      int64_t max_recs)

@@ -54,6 +54,8 @@ def load_library():
     lib.snacc_prefix_record_bytes.argtypes = [vp, ctypes.c_int]
     lib.snacc_export_prefix.argtypes = [vp, ctypes.c_int, vp, i64, vp]
     lib.snacc_import_prefix.argtypes = [vp, ctypes.c_int, vp, i64, vp]
+    lib.snacc_csv_write.restype = ctypes.c_int
+    lib.snacc_csv_write.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_char_p), vp, i64, vp, ctypes.c_int]
     lib.snacc_fasta_parse.restype = i64
     lib.snacc_fasta_parse.argtypes = [vp, ctypes.c_uint64, vp, ctypes.POINTER(ctypes.c_uint64), vp, i64]
     _lib = lib

@@ -281,6 +281,32 @@ def test_direct_csv_writer_is_byte_identical_to_the_pandas_route(tmp_path):
     assert out.read_bytes() == ref.read_bytes()
 
 
+def test_native_csv_writer_formats_every_double_like_repr(tmp_path, monkeypatch):
+    """snacc_csv_write (C ABI, host threads) against the Python loop and against pandas: zeros, whole numbers, the
+    fixed / exponent switch at 1e-4 and 1e16, subnormals, the largest double, NaN (empty cell), infinities, random
+    doubles over 600 binary orders of magnitude"""
+    import pandas as pd
+    from snacc_b200.engine import load_library
+    assert hasattr(load_library(), "snacc_csv_write")
+    rng = np.random.default_rng(2)
+    n = 60
+    D = rng.random((n, n))
+    special = [0.0, -0.0, 1.0, 0.5, 1e-5, 1e-4, 0.0001234, 9.999e-5, 1e15, 1e16, 9.999999999999998e15, 1e17, 5e-324, 1e-323,
+               2.2250738585072014e-308, 1.7976931348623157e308, float("nan"), float("inf"), -float("inf"), -1.5e-7, 0.1, 1 / 3,
+               1e22, 1e21, 100.0, 1234567.0, 0.30000000000000004, 12345678.9, -123456789012345680.0]
+    D.flat[:len(special)] = special
+    D[5] = np.exp(rng.uniform(-50, 50, n)); D[6] = -np.exp(rng.uniform(-700, 700, n)); D[7] = rng.integers(-10**6, 10**6, n)
+    files = [Path(f"/d/g,{i}.fa") if i % 9 == 0 else Path(f"/d/g{i:02d}.fa") for i in range(n)]
+    native, plain, ref = tmp_path / "native.csv", tmp_path / "plain.csv", tmp_path / "ref.csv"
+    gcli.write_distance_csv(files, D, native)
+    monkeypatch.setattr(gcli, "_write_csv_native", lambda *a: False)
+    gcli.write_distance_csv(files, D, plain)
+    assert native.read_bytes() == plain.read_bytes()
+    rows = [(files[i], files[j], D[i][j]) for i in range(n) for j in range(n)]
+    pd.DataFrame(rows, columns=["file", "file2", "ncd"]).pivot(index="file", columns="file2", values="ncd").to_csv(ref)
+    assert native.read_bytes() == ref.read_bytes()
+
+
 def test_newick_writer_equals_the_reference_recursion():
     """newick_from_linkage (no scipy) against the reference's to_tree + get_newick recursion on scipy linkages"""
     from oracle import tree_oracle
